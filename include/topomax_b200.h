@@ -1,0 +1,136 @@
+/* libtopomax_b200 -- C ABI of the B200-native FEM elasticity inner loop of topomax.
+ *
+ * The reference (Emilinya/topomax) has no FFI: its seam is the Python classes
+ * FEMSolver / ElasticityProblem / HelmholtzFilter, which call dolfin.  This header is the
+ * boundary a binding for that seam links against; every entry point names the reference
+ * code whose arithmetic it replaces.  Conventions:
+ *   - plain C types only; every array argument is a CUDA DEVICE pointer owned by the caller
+ *     (the Python host passes torch.Tensor.data_ptr()); element type = the engine dtype;
+ *   - the engine owns only scratch memory; no ownership is transferred;
+ *   - every function returns 0 on success, a negative TM_ERR_* code otherwise, and
+ *     tm_last_error() returns the message of the last failure on the calling thread;
+ *   - work is enqueued on the stream given to tm_set_stream (default: the legacy stream);
+ *     functions that return scalars synchronise that stream before returning.
+ *
+ * Layouts:
+ *   P1 fields (rho, psi, xi, G):  (ny+1) x (nx+1) vertex grid, row-major, v = iy*(nx+1)+ix
+ *   P2 fields (u, b):  (2ny+1) x (2nx+1) half-step lattice, row-major, 2 interleaved
+ *                      components per node, dof = 2*(j*(2nx+1)+i) + comp
+ */
+#ifndef TOPOMAX_B200_H
+#define TOPOMAX_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tm_engine_s* tm_handle;
+
+enum { TM_OK = 0, TM_ERR_INVALID = -1, TM_ERR_UNSUPPORTED = -2, TM_ERR_CUDA = -3,
+       TM_ERR_NOT_CONVERGED = -4 };
+
+enum { TM_F64 = 0, TM_F32 = 1 };
+enum { TM_SIDE_LEFT = 1, TM_SIDE_RIGHT = 2, TM_SIDE_TOP = 4, TM_SIDE_BOTTOM = 8 };
+enum { TM_PRECOND_JACOBI = 0, TM_PRECOND_MULTIGRID = 1 };
+
+/* integer / real options for tm_set_option */
+enum {
+    TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
+    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps  (default 3)           */
+    TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
+    TM_OPT_MG_COARSE_CELLS = 4 /* stop coarsening at max(nx,ny) <= this (default 2)      */
+};
+
+/* Mesh, material and filter of one problem.
+ * reference: FEM_src/solver.py:38-49 (RectangleMesh((0,0),(W,H),nx,ny), "right" diagonal),
+ * FEM_src/elasisity_problem.py:93-99 (Lame constants), src/penalizers.py:32-34 (minimum),
+ * FEM_src/filter.py:15-38 (epsilon), FEM_src/elasisity_problem.py:183-192 (fixed sides). */
+typedef struct {
+    int nx, ny;
+    double width, height;
+    double lame_lambda, lame_mu;
+    double simp_min;
+    double filter_radius;
+    int fixed_sides; /* TM_SIDE_* bitmask */
+    int dtype;       /* TM_F64 / TM_F32 */
+    int device;      /* CUDA device ordinal */
+} tm_config;
+
+/* reference: designs/definitions.py Force / Traction, evaluated by BodyForce.eval and
+ * TractionExpression.eval (FEM_src/elasisity_problem.py:26-33, :47-70). */
+typedef struct {
+    int has_force;
+    double force_center[2], force_radius, force_value[2];
+    int ntractions;         /* <= 8 */
+    int traction_side[8];   /* one TM_SIDE_* each */
+    double traction_center[8], traction_length[8], traction_value[8][2];
+} tm_loads;
+
+int tm_create(const tm_config* cfg, tm_handle* out);
+int tm_destroy(tm_handle h);
+int tm_set_stream(tm_handle h, void* cuda_stream);
+int tm_set_option(tm_handle h, int option, double value);
+const char* tm_last_error(void);
+const char* tm_version(void);
+
+/* b = int f_h.v dx + int t_h.v ds (not yet zeroed on the fixed sides).
+ * reference: l_func, FEM_src/elasisity_problem.py:120-124, assembled once by
+ * SmartMumpsSolver.__init__ (FEM_src/pde_solver.py:102-104). */
+int tm_load_vector(tm_handle h, const tm_loads* loads, void* b);
+
+/* Helmholtz filter  (eps^2 K1 + M1) out = rhs.
+ * rhs_kind 0: `in` is a nodal P1 function, rhs = M1 in   (HelmholtzFilter.apply on a Function)
+ * rhs_kind 1: `in` is an assembled right-hand side       (apply on a UFL expression)
+ * reference: FEM_src/filter.py:27-41 + SmartMumpsSolver.solve, FEM_src/pde_solver.py:106-133. */
+int tm_filter_apply(tm_handle h, int rhs_kind, const void* in, void* out, double rtol, int maxit,
+                    int* iters, double* relres);
+
+/* y = K(xi) x with identity rows on the fixed sides; penalty must be 3.
+ * reference: a_func, FEM_src/elasisity_problem.py:112-118 assembled in
+ * FEM_src/pde_solver.py:117-119, bc.apply :125. */
+int tm_elast_matvec(tm_handle h, const void* xi, double penalty, const void* x, void* y);
+/* dinv = 1 / diag K(xi) (1 on fixed dofs) */
+int tm_elast_diag(tm_handle h, const void* xi, double penalty, void* dinv);
+
+/* u = K(xi)^-1 b with u = 0 on the fixed sides, by preconditioned CG to ||r|| <= rtol ||b||.
+ * flags bit 0: use the incoming u as initial guess.
+ * reference: ElasticityProblem.forward, FEM_src/elasisity_problem.py:168-169 ->
+ * SmartMumpsSolver.solve, FEM_src/pde_solver.py:106-133 (LUSolver("mumps")). */
+int tm_state_solve(tm_handle h, const void* xi, double penalty, const void* b, void* u,
+                   double rtol, int maxit, int flags, int* iters, double* relres);
+
+/* *out = u . b  (compliance; reference: FEM_src/elasisity_problem.py:161-164) */
+int tm_dot_p2(tm_handle h, const void* u, const void* b, double* out);
+
+/* out_i = int -r'(xi_h)(lambda (div u)^2 + 2 mu eps(u):eps(u)) phi_i dx  (assembled P1 rhs)
+ * reference: calculate_objective_gradient, FEM_src/elasisity_problem.py:146-150 */
+int tm_sens_rhs(tm_handle h, const void* xi, double penalty, const void* u, void* out);
+
+/* half = psi - alpha G            reference: Solver.step, src/solver.py:191-192 */
+int tm_md_halfstep(tm_handle h, const void* psi, const void* grad, double alpha, void* half);
+/* vol = int expit(half+c), dvol = int expit'(half+c)   reference: Solver.project,
+ * src/solver.py:158-162 with FEMSolver.integrate, FEM_src/solver.py:81-84 */
+int tm_md_volume(tm_handle h, const void* half, double c, double* vol, double* dvol);
+/* psi = half + c, rho = expit(psi), *delta_sq = int (rho - expit(psi_prev))^2, *vol = int rho
+ * reference: src/solver.py:186,262,286-288 */
+int tm_md_apply(tm_handle h, const void* half, double c, const void* psi_prev, void* psi,
+                void* rho, double* delta_sq, double* vol);
+/* *out = int values dx (nodal quadrature)   reference: FEM_src/solver.py:81-84 */
+int tm_integrate(tm_handle h, const void* values, double* out);
+
+/* statistics of the last tm_state_solve: out[0] iterations, [1] V-cycles, [2] fine-level
+ * operator applications, [3] levels, [4] lambda_max estimate of level 0 */
+int tm_last_solve_stats(tm_handle h, double* out, int n);
+
+/* Diagnostics for the parity tests: the multigrid hierarchy built for xi.
+ *   op 0: out = A_level in          op 1: out(level) = P in(level+1)
+ *   op 2: out(level+1) = P^T in(level)   op 3: out = V-cycle(in) on level 0
+ *   op 4: out = A_coarsest^-1 in    op 5: out = inverse diagonal of the level
+ * tm_mg_level_info: info6 = {nx, ny, dl, dr, db, dt} of `level`; *nlevels = level count. */
+int tm_mg_debug(tm_handle h, const void* xi, int op, int level, const void* in, void* out);
+int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

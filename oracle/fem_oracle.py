@@ -349,3 +349,18 @@ def solve_spd(A, b, free=None):
     x = np.zeros_like(b)
     x[idx] = spla.splu(Aff, permc_spec="MMD_AT_PLUS_A").solve(b[idx])
     return x
+
+
+def l2_error_p1(mesh, xi, exact, nq=6):
+    """|| xi_h - exact ||_L2 by quadrature (the role of df.errornorm in tests/test_filter.py)."""
+    pts, wts = triangle_rule(nq)
+    X, Y = np.meshgrid(mesh.xv, mesh.yv, indexing="xy")
+    X, Y = X.ravel(), Y.ravel()
+    err = 0.0
+    for t in ("A", "B"):
+        area, _ = mesh.geom[t]
+        v = mesh.tri_v[t]
+        for q, w in zip(pts, wts):
+            xq, yq, fq = X[v] @ q, Y[v] @ q, xi[v] @ q
+            err += w * area * np.sum((fq - exact(xq, yq)) ** 2)
+    return np.sqrt(err)

@@ -1,0 +1,162 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+host mirror of the reference interface behaves like the reference's (parser, schedules, exit
+rules, record formats) and the product path refuses to run without a GPU."""
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_header_symbol(repo_root):
+    from topomax_b200 import _lib
+    from topomax_b200 import build as tm_build
+
+    tm_build.build()
+    lib = _lib.load_library()
+    header = open(os.path.join(repo_root, "include", "topomax_b200.h")).read()
+    declared = set(re.findall(r"\b(tm_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.tm_version()
+
+
+def test_sass_is_sm100a(repo_root):
+    import subprocess
+    so = os.path.join(repo_root, "topomax_b200", "libtopomax_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_parse_design(repo_root, tmp_path):
+    """reference tests/test_design_parser.py:6-49"""
+    import json
+    from designs.definitions import ElasticityParameters, Side
+    from designs.design_parser import parse_design
+
+    dom, prm = parse_design(os.path.join(repo_root, "designs", "cantilever.json"))
+    assert isinstance(prm, ElasticityParameters)
+    assert dom.width == 3 and dom.height == 1 and dom.penalties == [3]
+    assert prm.body_force.region.radius == 0.05 and prm.body_force.region.center == (2.9, 0.5)
+    assert prm.body_force.value == (0, -1)
+    assert prm.fixed_sides == [Side.LEFT] and prm.tractions is None
+
+    raw = json.load(open(os.path.join(repo_root, "designs", "cantilever.json")))
+    raw["Elasticity"]["objective"] = "MinimizeCompliance"  # ignored extra key
+    ok = tmp_path / "extra.json"
+    ok.write_text(json.dumps(raw))
+    parse_design(str(ok))
+    raw["Elasticity"]["problem_parameters"]["body_force"]["value"] = [0.0, -1.0, 0]
+    bad = tmp_path / "broken.json"
+    bad.write_text(json.dumps(raw))
+    with pytest.raises(ValueError):
+        parse_design(str(bad))
+    fluid = {"Fluid": {"domain_parameters": dict(width=1.5, height=1, fem_step_size=1, dem_step_size=1,
+                                                 penalties=[0.01, 0.1], volume_fraction=1 / 3),
+                       "problem_parameters": {"viscosity": 1.0, "flows": [
+                           {"side": "Left", "center": 0.25, "length": 1 / 6, "rate": 1.0}]}}}
+    fl = tmp_path / "fluid.json"
+    fl.write_text(json.dumps(fluid))
+    dom, prm = parse_design(str(fl))
+    assert dom.penalties == [0.01, 0.1] and prm.flows[0].side == Side.LEFT
+    with pytest.raises(ValueError):
+        Side.from_string("Front")
+
+
+def test_no_cpu_fallback(repo_root):
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from topomax_b200.engine import Engine
+    from topomax_b200.fem_solver import FEMSolver
+    with pytest.raises(RuntimeError):
+        Engine(4, 4, 1.0, 1.0)
+    with pytest.raises(RuntimeError):
+        FEMSolver(10, os.path.join(repo_root, "designs", "triangle.json"))
+
+
+def test_product_package_never_imports_oracle(repo_root):
+    for base, _, files in os.walk(os.path.join(repo_root, "topomax_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                assert "oracle" not in src, f
+
+
+class _ToySolver:
+    """exercises the generic Solver loop with a quadratic toy problem (no GPU)"""
+
+
+def test_generic_solver_schedules_and_exit_rules(tmp_path, repo_root):
+    from src.problem import Problem
+    from src.solver import Solver, expit, logit
+    from src.utils import IterationData, SolverResult
+
+    class Quadratic(Problem):
+        def __init__(self, n):
+            self.target = np.linspace(0.2, 0.8, n)
+            self.rho = None
+            self.penalization = None
+
+        def set_penalization(self, p):
+            self.penalization = p
+
+        def calculate_objective(self, rho):
+            self.rho = rho.copy()
+            return float(np.mean((rho - self.target) ** 2))
+
+        def calculate_objective_gradient(self):
+            if self.rho is None:
+                raise ValueError("objective first")
+            return 2 * (self.rho - self.target) / len(self.rho)
+
+        def forward(self, rho):
+            return rho
+
+    class Toy(Solver):
+        def get_name(self): return "TOY"
+        def get_step_size(self): return 1.0
+        def prepare_domain(self): self.n = 21
+        def create_rho(self, vf): return np.full(self.n, vf)
+        def create_problem(self, _): return Quadratic(self.n)
+        def to_array(self, rho): return rho.copy()
+        def set_from_array(self, rho, values): rho[:] = values
+        def integrate(self, values): return float(np.mean(values) * self.width * self.height)
+        def save_rho(self, rho, file_root):
+            np.save(file_root + "_rho.npy", rho)
+            return os.path.basename(file_root + "_rho.npy")
+
+    s = Toy(512, os.path.join(repo_root, "designs", "short_cantilever.json"), str(tmp_path), skip_multiple=7)
+    assert (s.N, s.full_N) == (102, 510)  # reference src/solver.py:66-67 truncation
+    assert s.tolerance(0) == 25e-5 and s.tolerance(100) == 1e-2
+    assert s.step_size_at_iter(4) == 5.0
+    assert s.penalty_formatter(3.0) == "3.0"
+    s.verbose = False
+    s.solve()
+    r = s.last_result
+    assert r["exit_condition"] in ("Convergence treshold reached", "Objective is not decreasing")
+    assert abs(s.integrate(s.rho) - s.volume) < 1e-9  # volume constraint holds
+    out = tmp_path / "TOY" / "short_cantilever" / "data"
+    k = r["k_final"]
+    rec = pickle.load(open(out / f"N=510_p=3.0_k={k}.dat", "rb"))
+    assert isinstance(rec, IterationData) and rec.iteration == k
+    assert type(rec).__module__ == "src.utils"
+    res = pickle.load(open(out / "N=510_p=3.0_result.dat", "rb"))
+    assert isinstance(res, SolverResult) and res.iterations == len(r["objectives"]) == k + 1
+    assert Solver.stop_condition([1.0, float("nan")], 0) == "Objective is NaN"
+    assert Solver.stop_condition([1.0, 2.5], 0) == "Objective is increasing"
+    assert Solver.stop_condition([1.0] + [1.5] * 51, 50) == "Objective is not decreasing"
+    assert np.allclose(expit(logit(np.array([0.3]))), 0.3)
+
+
+def test_projection_falls_back_to_brent():
+    from topomax_b200.solver import find_volume_shift
+    # derivative that sends Newton away: flat tails
+    f = lambda c: np.tanh(50 * (c - 1.5))
+    df = lambda c: 50 / np.cosh(50 * (c - 1.5)) ** 2
+    assert abs(find_volume_shift(f, df) - 1.5) < 1e-9
+    with pytest.raises(ValueError):
+        find_volume_shift(lambda c: 1.0, lambda c: 0.0)

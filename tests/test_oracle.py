@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.fem_oracle import StructuredMesh, solve_spd, triangle_rule
+from oracle.fem_oracle import StructuredMesh, l2_error_p1, solve_spd, triangle_rule
 from oracle.md_oracle import OracleSolver
 
 
@@ -46,21 +46,6 @@ def test_negative_control_other_diagonal_differs(repo_root, golden_dir):
     assert np.abs(rho - rho[:, ::-1]).max() > 1e-3
 
 
-def _l2_error_p1_vs_exact(mesh, xi, exact, nq=6):
-    """|| xi_h - exact ||_L2 by quadrature (df.errornorm role)."""
-    pts, wts = triangle_rule(nq)
-    X, Y = np.meshgrid(mesh.xv, mesh.yv, indexing="xy")
-    X, Y = X.ravel(), Y.ravel()
-    err = 0.0
-    for t in ("A", "B"):
-        area, _ = mesh.geom[t]
-        v = mesh.tri_v[t]
-        for q, w in zip(pts, wts):
-            xq, yq, fq = X[v] @ q, Y[v] @ q, xi[v] @ q
-            err += w * area * np.sum((fq - exact(xq, yq)) ** 2)
-    return np.sqrt(err)
-
-
 def test_filter_identity_and_convergence():
     """tests/test_filter.py:25-60, including the un-converted Polynomial.fit coefficient quirk
     of tests/utils.py:11-33."""
@@ -80,7 +65,7 @@ def test_filter_identity_and_convergence():
         X, Y = np.meshgrid(m.xv, m.yv, indexing="xy")
         rho = ((8 * eps * eps * np.pi**2 + 1) * np.cos(2 * np.pi * X) * np.cos(2 * np.pi * Y)).ravel()
         xi = solve_spd(eps * eps * K + M, M @ rho)
-        return _l2_error_p1_vs_exact(m, xi, lambda x, y: np.cos(2 * np.pi * x) * np.cos(2 * np.pi * y))
+        return l2_error_p1(m, xi, lambda x, y: np.cos(2 * np.pi * x) * np.cos(2 * np.pi * y))
 
     Ns = list(range(10, 91, 10))
     errors = [err(N) for N in Ns]

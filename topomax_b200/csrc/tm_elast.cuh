@@ -1,0 +1,325 @@
+// Matrix-free penalised stiffness operator  y = K(xi) x  on the vector-P2 lattice
+// (replaces dolfin's assembly of FEM_src/elasisity_problem.py:112-118 in
+// FEM_src/pde_solver.py:117-119 and its Dirichlet treatment in :125).
+//
+// Thread mapping ("march and shuffle"): one thread per CELL COLUMN, marching upwards through
+// the cell rows of its strip.  Each cell (two triangles, element matrices never formed: see
+// tm_element.cuh) is evaluated exactly once, entirely in registers:
+//   * contributions to the cell's right-hand lattice column travel to lane+1 by __shfl_up,
+//   * contributions to the cell's top lattice row are carried to the next march step,
+// so every lattice node is written once, by its owner, with no atomics and no shared memory,
+// and the summation order is fixed (bit-reproducible).  A warp owns 31 cell columns; lane 0
+// re-evaluates the last column of the warp to its left (32/31 redundant flops), and a strip
+// re-evaluates the cell row below it ((H+1)/H).
+//
+// Loads: a warp reads 65 consecutive (u_x,u_y) pairs per lattice row (coalesced 16-byte
+// vector loads); the density is read once per cell row.  The epilogue fuses what follows the
+// matvec in the solvers so the vectors are not re-read:
+//   EP_PLAIN  y = A x
+//   EP_DOT    y = A x, and the grid-wide  x . A x   (PCG)
+//   EP_RESID  y = b - A x
+//   EP_CHEB   r = b - A x;  d = c1 d + c2 D^-1 r;  y = x + d   (one Chebyshev-Jacobi step)
+// Dirichlet nodes are identity rows/columns (symmetric elimination; same solution as the
+// reference's bc.apply because the prescribed value is zero).
+#pragma once
+
+#include "tm_common.cuh"
+#include "tm_tables.h"
+
+namespace tmx {
+
+enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3 };
+
+template <typename T>
+struct Vec2;
+template <>
+struct Vec2<double> {
+    using type = double2;
+};
+template <>
+struct Vec2<float> {
+    using type = float2;
+};
+
+template <typename T>
+struct ApplyArgs {
+    const T* x;     // input lattice vector
+    T* y;           // output lattice vector (must not alias x)
+    const T* b;     // EP_RESID / EP_CHEB
+    const T* dinv;  // EP_CHEB: inverse diagonal
+    T* d;           // EP_CHEB: Chebyshev direction, updated in place
+    T c1, c2;       // EP_CHEB coefficients
+    ReduceScratch rs;
+    double* dot_out;  // EP_DOT
+    int rows_per_strip;
+};
+
+constexpr int kApplyWarps = 4;  // warps (column groups) per block
+
+template <typename T, bool STORED_W, int EP>
+__global__ void __launch_bounds__(kApplyWarps * 32, 2)
+elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
+    using V2 = typename Vec2<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int cgroup = blockIdx.x * kApplyWarps + (threadIdx.x >> 5);
+    const int ix = cgroup * 31 + lane - 1;  // cell column of this thread
+    const int iy0 = blockIdx.y * a.rows_per_strip;
+    const int iy1 = min(g.ny, iy0 + a.rows_per_strip);
+    const bool warp_active = (cgroup * 31 - 1) < g.nx + 1 && (cgroup * 31) <= g.nx;
+    const bool cell_ok = ix >= 0 && ix < g.nx;
+    const bool owner = lane >= 1 && ix <= g.nx;  // writes lattice columns 2ix (and 2ix+1)
+    const bool own_c1 = owner && ix < g.nx;
+
+    double dot = 0.0;
+
+    if (warp_active) {
+        const V2* __restrict__ xv = reinterpret_cast<const V2*>(a.x);
+        V2* __restrict__ yv = reinterpret_cast<V2*>(a.y);
+        const int Lx = g.Lx;
+        const int i0 = 2 * ix;
+        bool colok[3], colfix[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            colok[c] = ix >= 0 && (i0 + c) <= 2 * g.nx && (cell_ok || c == 0);
+            colfix[c] = (i0 + c) <= g.dl || (i0 + c) >= g.dr;
+        }
+
+        T X[9][2];  // raw input of the cell's 3x3 lattice block
+#pragma unroll
+        for (int q = 0; q < 9; ++q) X[q][0] = X[q][1] = T(0);
+        T xiv[4] = {T(0), T(0), T(0), T(0)};  // density at v0 v1 v2 v3 (level 0)
+        T carry[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+
+        const int iy_start = iy0 > 0 ? iy0 - 1 : 0;
+        // lattice row 2*iy_start enters as the "top row of the previous step"
+        {
+            const size_t row = (size_t)(2 * iy_start) * Lx;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (colok[c]) {
+                    const V2 v = xv[row + i0 + c];
+                    X[6 + c][0] = v.x;
+                    X[6 + c][1] = v.y;
+                }
+            if (!STORED_W && cell_ok) {
+                xiv[2] = g.xi[(size_t)iy_start * (g.nx + 1) + ix];
+                xiv[3] = g.xi[(size_t)iy_start * (g.nx + 1) + ix + 1];
+            }
+        }
+
+        for (int iy = iy_start; iy < iy1; ++iy) {
+            const int j0 = 2 * iy;
+            // shift: previous top row becomes the bottom row
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                X[c][0] = X[6 + c][0];
+                X[c][1] = X[6 + c][1];
+            }
+            xiv[0] = xiv[2];
+            xiv[1] = xiv[3];
+#pragma unroll
+            for (int r = 1; r < 3; ++r) {
+                const size_t row = (size_t)(j0 + r) * Lx;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (colok[c]) {
+                        const V2 v = xv[row + i0 + c];
+                        X[3 * r + c][0] = v.x;
+                        X[3 * r + c][1] = v.y;
+                    }
+            }
+            T acc[9][2];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) acc[q][0] = acc[q][1] = T(0);
+            if (cell_ok) {
+                T wA[6], wB[6];
+                if (STORED_W) {
+                    const size_t plane = (size_t)g.nx * g.ny;
+                    const size_t cidx = (size_t)iy * g.nx + ix;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        wA[k] = g.W[k * plane + cidx];
+                        wB[k] = g.W[(6 + k) * plane + cidx];
+                    }
+                } else {
+                    xiv[2] = g.xi[(size_t)(iy + 1) * (g.nx + 1) + ix];
+                    xiv[3] = g.xi[(size_t)(iy + 1) * (g.nx + 1) + ix + 1];
+                    moments_from_xi<T>(xiv[0], xiv[1], xiv[3], g.simp_min, wA);
+                    moments_from_xi<T>(xiv[0], xiv[2], xiv[3], g.simp_min, wB);
+                }
+                T Xm[9][2];  // Dirichlet columns of the operator: masked input
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const bool rowfix = (j0 + r) <= g.db || (j0 + r) >= g.dt;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const bool f = rowfix || colfix[c];
+                        Xm[3 * r + c][0] = f ? T(0) : X[3 * r + c][0];
+                        Xm[3 * r + c][1] = f ? T(0) : X[3 * r + c][1];
+                    }
+                }
+                cell_apply<T>(Xm, wA, wB, g.mat, acc);
+            }
+            // right lattice column of the cell -> owner of that column (lane + 1)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    T recv = __shfl_up_sync(0xffffffffu, acc[3 * r + 2][k], 1);
+                    if (lane == 0) recv = T(0);
+                    acc[3 * r][k] += recv;
+                }
+            // rows j0 (now complete) and j0+1 of the owned columns
+            if (iy >= iy0 && owner) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int j = j0 + r;
+                    const bool rowfix = j <= g.db || j >= g.dt;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c == 1 && !own_c1) continue;
+                        T v0 = acc[3 * r + c][0], v1 = acc[3 * r + c][1];
+                        if (r == 0) {
+                            v0 += carry[c][0];
+                            v1 += carry[c][1];
+                        }
+                        const T x0 = X[3 * r + c][0], x1 = X[3 * r + c][1];
+                        if (rowfix || colfix[c]) {
+                            v0 = x0;
+                            v1 = x1;
+                        }
+                        const size_t n = (size_t)j * Lx + i0 + c;
+                        V2 out;
+                        if (EP == EP_PLAIN || EP == EP_DOT) {
+                            out.x = v0;
+                            out.y = v1;
+                            if (EP == EP_DOT) dot += (double)x0 * (double)v0 + (double)x1 * (double)v1;
+                        } else {
+                            const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
+                            const T r0 = bb.x - v0, r1 = bb.y - v1;
+                            if (EP == EP_RESID) {
+                                out.x = r0;
+                                out.y = r1;
+                            } else {
+                                const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
+                                V2 dd;
+                                dd.x = a.c2 * di.x * r0;
+                                dd.y = a.c2 * di.y * r1;
+                                if (a.c1 != T(0)) {
+                                    const V2 dold = reinterpret_cast<const V2*>(a.d)[n];
+                                    dd.x += a.c1 * dold.x;
+                                    dd.y += a.c1 * dold.y;
+                                }
+                                reinterpret_cast<V2*>(a.d)[n] = dd;
+                                out.x = x0 + dd.x;
+                                out.y = x1 + dd.y;
+                            }
+                        }
+                        yv[n] = out;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                carry[c][0] = acc[6 + c][0];
+                carry[c][1] = acc[6 + c][1];
+            }
+        }
+        // the lattice's top row belongs to the last strip
+        if (iy1 == g.ny && owner) {
+            const int j = 2 * g.ny;
+            const bool rowfix = j <= g.db || j >= g.dt;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c == 1 && !own_c1) continue;
+                T v0 = carry[c][0], v1 = carry[c][1];
+                const T x0 = X[6 + c][0], x1 = X[6 + c][1];
+                if (rowfix || colfix[c]) {
+                    v0 = x0;
+                    v1 = x1;
+                }
+                const size_t n = (size_t)j * Lx + i0 + c;
+                V2 out;
+                if (EP == EP_PLAIN || EP == EP_DOT) {
+                    out.x = v0;
+                    out.y = v1;
+                    if (EP == EP_DOT) dot += (double)x0 * (double)v0 + (double)x1 * (double)v1;
+                } else {
+                    const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
+                    const T r0 = bb.x - v0, r1 = bb.y - v1;
+                    if (EP == EP_RESID) {
+                        out.x = r0;
+                        out.y = r1;
+                    } else {
+                        const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
+                        V2 dd;
+                        dd.x = a.c2 * di.x * r0;
+                        dd.y = a.c2 * di.y * r1;
+                        if (a.c1 != T(0)) {
+                            const V2 dold = reinterpret_cast<const V2*>(a.d)[n];
+                            dd.x += a.c1 * dold.x;
+                            dd.y += a.c1 * dold.y;
+                        }
+                        reinterpret_cast<V2*>(a.d)[n] = dd;
+                        out.x = x0 + dd.x;
+                        out.y = x1 + dd.y;
+                    }
+                }
+                yv[n] = out;
+            }
+        }
+    }
+    if (EP == EP_DOT) {
+        double v[1] = {dot};
+        double* const outs[1] = {a.dot_out};
+        grid_reduce<1>(v, a.rs, outs);
+    }
+}
+
+// Jacobi diagonal by node-centric gather: dinv = 1 / diag(K), 1 on Dirichlet nodes.
+// diag entry of a triangle-local dof = sum_m Q[type][local][comp][m] * w[m] with Q a constant
+// table (filled by the host from tri_apply on unit vectors).
+template <typename T, bool STORED_W>
+__global__ void elast_diag_kernel(const LevelGeom<T> g, const DiagTable tab, T* __restrict__ dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.Lx || j >= g.Ly) return;
+    const size_t n = (size_t)j * g.Lx + i;
+    if (g.fixed(i, j)) {
+        dinv[2 * n] = T(1);
+        dinv[2 * n + 1] = T(1);
+        return;
+    }
+    double d0 = 0.0, d1 = 0.0;
+    const int cx_lo = i > 0 ? (i - 1) >> 1 : 0, cx_hi = min(g.nx - 1, i >> 1);
+    const int cy_lo = j > 0 ? (j - 1) >> 1 : 0, cy_hi = min(g.ny - 1, j >> 1);
+    for (int cy = cy_lo; cy <= cy_hi; ++cy)
+        for (int cx = cx_lo; cx <= cx_hi; ++cx) {
+            const int q = 3 * (j - 2 * cy) + (i - 2 * cx);
+#pragma unroll
+            for (int type = 0; type < 2; ++type) {
+                const int kl = cell_to_tri_local(type, q);
+                if (kl < 0) continue;
+                T w[6];
+                if (STORED_W) {
+                    const size_t plane = (size_t)g.nx * g.ny;
+                    const size_t cidx = (size_t)cy * g.nx + cx;
+                    for (int k = 0; k < 6; ++k) w[k] = g.W[(6 * type + k) * plane + cidx];
+                } else {
+                    const T x0 = g.xi[(size_t)cy * (g.nx + 1) + cx];
+                    const T x3 = g.xi[(size_t)(cy + 1) * (g.nx + 1) + cx + 1];
+                    const T x1 = type == 0 ? g.xi[(size_t)cy * (g.nx + 1) + cx + 1]
+                                           : g.xi[(size_t)(cy + 1) * (g.nx + 1) + cx];
+                    moments_from_xi<T>(x0, x1, x3, g.simp_min, w);
+                }
+                for (int m = 0; m < 6; ++m) {
+                    d0 += tab.Q[type][kl][0][m] * (double)w[m];
+                    d1 += tab.Q[type][kl][1][m] * (double)w[m];
+                }
+            }
+        }
+    dinv[2 * n] = T(1.0 / d0);
+    dinv[2 * n + 1] = T(1.0 / d1);
+}
+
+}  // namespace tmx

@@ -1,0 +1,951 @@
+// libtopomax_b200: engine (workspace, solvers) and the C ABI of include/topomax_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/topomax_b200.h"
+#include "tm_elast.cuh"
+#include "tm_mg.cuh"
+#include "tm_p1.cuh"
+#include "tm_vec.cuh"
+
+namespace tmx {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const char* last_error() { return g_error.c_str(); }
+
+struct Unsupported {
+    std::string what;
+};
+struct Invalid {
+    std::string what;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void ensure(size_t count) {
+        if (n >= count && p) return;
+        release();
+        TM_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+};
+
+struct SolveStats {
+    int iters = 0;
+    double relres = 0.0;
+    bool converged = false;
+};
+
+class EngineBase {
+   public:
+    virtual ~EngineBase() {}
+    virtual void set_stream(cudaStream_t s) = 0;
+    virtual void set_option(int opt, double value) = 0;
+    virtual void load_vector(const tm_loads& loads, void* b) = 0;
+    virtual SolveStats filter_apply(int kind, const void* in, void* out, double rtol, int maxit) = 0;
+    virtual void elast_matvec(const void* xi, double p, const void* x, void* y) = 0;
+    virtual void elast_diag(const void* xi, double p, void* dinv) = 0;
+    virtual SolveStats state_solve(const void* xi, double p, const void* b, void* u, double rtol,
+                                   int maxit, int flags) = 0;
+    virtual double dot_p2(const void* u, const void* b) = 0;
+    virtual void sens_rhs(const void* xi, double p, const void* u, void* out) = 0;
+    virtual void md_halfstep(const void* psi, const void* g, double alpha, void* half) = 0;
+    virtual void md_volume(const void* half, double c, double* vol, double* dvol) = 0;
+    virtual void md_apply(const void* half, double c, const void* psi_prev, void* psi, void* rho,
+                          double* delta_sq, double* vol) = 0;
+    virtual double integrate(const void* values) = 0;
+    virtual void last_stats(double* out, int n) = 0;
+    virtual void mg_debug(const void* xi, int op, int level, const void* in, void* out) = 0;
+    virtual int mg_level_info(int level, int* info) = 0;
+    int device = 0;
+};
+
+template <typename T>
+class Engine : public EngineBase {
+   public:
+    explicit Engine(const tm_config& cfg) : cfg_(cfg) {
+        device = cfg.device;
+        nx_ = cfg.nx;
+        ny_ = cfg.ny;
+        if (nx_ < 1 || ny_ < 1) throw Invalid{"nx, ny must be >= 1"};
+        if (!(cfg.width > 0) || !(cfg.height > 0)) throw Invalid{"width/height must be > 0"};
+        hx_ = cfg.width / nx_;
+        hy_ = cfg.height / ny_;
+        n1_ = (size_t)(nx_ + 1) * (ny_ + 1);
+        n2_ = (size_t)(2 * nx_ + 1) * (2 * ny_ + 1);
+        nu_ = 2 * n2_;
+
+        TM_CUDA(cudaSetDevice(device));
+        TM_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device));
+
+        // P1 element matrices (reference: FEM_src/filter.py:27-33; exact for P1)
+        p1_.nx = nx_; p1_.ny = ny_; p1_.hx = hx_; p1_.hy = hy_;
+        const double area = 0.5 * hx_ * hy_;
+        const double gA[3][2] = {{-1 / hx_, 0}, {1 / hx_, -1 / hy_}, {0, 1 / hy_}};
+        const double gB[3][2] = {{0, -1 / hy_}, {-1 / hx_, 1 / hy_}, {1 / hx_, 0}};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                p1_.Ke[0][i][j] = area * (gA[i][0] * gA[j][0] + gA[i][1] * gA[j][1]);
+                p1_.Ke[1][i][j] = area * (gB[i][0] * gB[j][0] + gB[i][1] * gB[j][1]);
+                p1_.Me[i][j] = area / 12.0 * (i == j ? 2.0 : 1.0);
+            }
+
+        g0_ = make_level_geom(nx_, ny_);
+        g0_.dl = (cfg.fixed_sides & TM_SIDE_LEFT) ? 0 : -1;
+        g0_.db = (cfg.fixed_sides & TM_SIDE_BOTTOM) ? 0 : -1;
+        g0_.dr = (cfg.fixed_sides & TM_SIDE_RIGHT) ? 2 * nx_ : INT_MAX;
+        g0_.dt = (cfg.fixed_sides & TM_SIDE_TOP) ? 2 * ny_ : INT_MAX;
+
+        const Material<double> matd = make_material<double>(cfg.lame_lambda, cfg.lame_mu, hx_, hy_);
+        diag_tab_ = make_diag_table(matd);
+        tr_tab_ = make_transfer_table();
+        co_tab_ = make_coarsen_table();
+
+        rs_.capacity = 1 << 20;
+        TM_CUDA(cudaMalloc(&rs_.partials, sizeof(double) * 2 * rs_.capacity));
+        TM_CUDA(cudaMalloc(&rs_.counter, sizeof(unsigned int)));
+        TM_CUDA(cudaMemset(rs_.counter, 0, sizeof(unsigned int)));
+        TM_CUDA(cudaMalloc(&sc_, sizeof(double) * SC_COUNT));
+        TM_CUDA(cudaMemset(sc_, 0, sizeof(double) * SC_COUNT));
+        TM_CUDA(cudaMallocHost(&h_sc_, sizeof(double) * 128));
+    }
+
+    ~Engine() override {
+        cudaSetDevice(device);
+        cudaFree(rs_.partials);
+        cudaFree(rs_.counter);
+        cudaFree(sc_);
+        cudaFree(eig_sc_);
+        cudaFreeHost(h_sc_);
+    }
+
+    void set_stream(cudaStream_t s) override { stream_ = s; }
+
+    void set_option(int opt, double value) override {
+        switch (opt) {
+            case TM_OPT_PRECOND: precond_ = (int)value; break;
+            case TM_OPT_CHEB_DEGREE: cheb_degree_ = std::max(1, (int)value); break;
+            case TM_OPT_CHECK_EVERY: check_every_ = std::max(0, (int)value); break;
+            case TM_OPT_MG_COARSE_CELLS:
+                coarse_cells_ = std::min(4, std::max(1, (int)value));
+                levels_.clear();
+                break;
+            case 100: cheb_ratio_ = value; break;
+            case 101: eig_safety_ = value; break;
+            default: throw Invalid{"unknown option " + std::to_string(opt)};
+        }
+    }
+
+    // ------------------------------------------------------------------ loads
+    void load_vector(const tm_loads& in, void* b) override {
+        LoadSpec s;
+        std::memset(&s, 0, sizeof(s));
+        s.nx = nx_; s.ny = ny_; s.W = cfg_.width; s.H = cfg_.height;
+        s.has_force = in.has_force;
+        s.fcx = in.force_center[0]; s.fcy = in.force_center[1]; s.frad = in.force_radius;
+        s.fx = in.force_value[0]; s.fy = in.force_value[1];
+        if (in.ntractions < 0 || in.ntractions > 8) throw Invalid{"ntractions must be in 0..8"};
+        // the reference compares the node coordinate with the side coordinate exactly
+        // (FEM_src/elasisity_problem.py:54-66); ((n*W)/n == W) can fail for odd W
+        const bool right_ok = ((double)nx_ * cfg_.width) / (double)nx_ == cfg_.width;
+        const bool top_ok = ((double)ny_ * cfg_.height) / (double)ny_ == cfg_.height;
+        for (int t = 0; t < in.ntractions; ++t) {
+            int side;
+            switch (in.traction_side[t]) {
+                case TM_SIDE_LEFT: side = 0; break;
+                case TM_SIDE_RIGHT: side = 1; break;
+                case TM_SIDE_TOP: side = 2; break;
+                case TM_SIDE_BOTTOM: side = 3; break;
+                default: throw Invalid{"Malformed side: " + std::to_string(in.traction_side[t])};
+            }
+            if ((side == 1 && !right_ok) || (side == 2 && !top_ok)) continue;
+            const int k = s.ntractions++;
+            s.tside[k] = side;
+            s.tlo[k] = in.traction_center[t] - in.traction_length[t] / 2;
+            s.thi[k] = in.traction_center[t] + in.traction_length[t] / 2;
+            s.tx[k] = in.traction_value[t][0];
+            s.ty[k] = in.traction_value[t][1];
+        }
+        // exact P2 mass matrix of a triangle of area |T| (vertices 0..2, mids 01,12,02)
+        const double area = 0.5 * hx_ * hy_;
+        const int opposite_mid[3] = {4, 5, 3};  // mid(12) opposite v0, mid(02) opp v1, mid(01) opp v2
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+                double v;
+                if (i < 3 && j < 3) v = (i == j) ? 1.0 / 30 : -1.0 / 180;
+                else if (i >= 3 && j >= 3) v = (i == j) ? 8.0 / 45 : 4.0 / 45;
+                else {
+                    const int vert = i < 3 ? i : j, mid = i < 3 ? j : i;
+                    v = (opposite_mid[vert] == mid) ? -1.0 / 45 : 0.0;
+                }
+                s.M2[i][j] = area * v;
+            }
+        dim3 blk(32, 8), grd(ceil_div(2 * nx_ + 1, 32), ceil_div(2 * ny_ + 1, 8));
+        load_vector_kernel<T><<<grd, blk, 0, stream_>>>(s, (T*)b);
+        TM_CHECK_LAUNCH();
+    }
+
+    // ------------------------------------------------------------------ filter
+    SolveStats filter_apply(int kind, const void* in_, void* out_, double rtol, int maxit) override {
+        const T* in = (const T*)in_;
+        T* out = (T*)out_;
+        const double alpha = cfg_.filter_radius * cfg_.filter_radius, beta = 1.0;
+        f_r_.ensure(n1_); f_p_.ensure(n1_); f_Ap_.ensure(n1_); f_rhs_.ensure(n1_);
+        if (!f_dinv_ready_) {
+            f_dinv_.ensure(n1_);
+            p1_diag_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(p1_, alpha, beta, f_dinv_.p);
+            TM_CHECK_LAUNCH();
+            f_dinv_ready_ = true;
+        }
+        const T* rhs;
+        if (kind == 0) {
+            p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
+            rhs = f_rhs_.p;
+            // initial guess: the unfiltered field itself
+            if (out != in) TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            p1_apply(alpha, beta, out, f_Ap_.p, nullptr);
+            waxpby_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(n1_, 1.0, rhs, -1.0, f_Ap_.p, f_r_.p);
+            TM_CHECK_LAUNCH();
+        } else if (kind == 1) {
+            rhs = in;
+            TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
+            TM_CUDA(cudaMemcpyAsync(f_r_.p, rhs, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        } else {
+            throw Invalid{"rhs_kind must be 0 or 1"};
+        }
+        auto apply_dot = [&](const T* p, T* Ap) { p1_apply(alpha, beta, p, Ap, sc_ + SC_PAP); };
+        auto precond = [&](const T*) -> const T* { return nullptr; };
+        const int check = check_every_ > 0 ? check_every_ : 10;
+        return pcg(n1_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, f_dinv_.p, apply_dot, precond, true, rtol,
+                   maxit, check);
+    }
+
+    // ------------------------------------------------------------------ elasticity operator
+    void check_penalty(double p) {
+        if (p != 3.0)
+            throw Unsupported{"penalty p=" + std::to_string(p) +
+                              ": the closed-form SIMP moments are implemented for p = 3 only"};
+    }
+
+    void elast_matvec(const void* xi, double p, const void* x, void* y) override {
+        check_penalty(p);
+        if (x == y) throw Invalid{"tm_elast_matvec: x and y must not alias"};
+        LevelGeom<T> g = g0_;
+        g.xi = (const T*)xi;
+        ApplyArgs<T> a = apply_args();
+        a.x = (const T*)x;
+        a.y = (T*)y;
+        launch_apply(g, false, EP_PLAIN, a);
+    }
+
+    void elast_diag(const void* xi, double p, void* dinv) override {
+        check_penalty(p);
+        LevelGeom<T> g = g0_;
+        g.xi = (const T*)xi;
+        launch_diag(g, false, (T*)dinv);
+    }
+
+    SolveStats state_solve(const void* xi_, double p, const void* b_, void* u_, double rtol,
+                           int maxit, int flags) override {
+        check_penalty(p);
+        const T* xi = (const T*)xi_;
+        const T* b = (const T*)b_;
+        T* u = (T*)u_;
+        s_r_.ensure(nu_); s_p_.ensure(nu_); s_Ap_.ensure(nu_); s_b_.ensure(nu_);
+        stats_fine_applies_ = 0;
+        stats_vcycles_ = 0;
+
+        LevelGeom<T> g = g0_;
+        g.xi = xi;
+        mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, b, s_b_.p);
+        TM_CHECK_LAUNCH();
+
+        bool use_mg = precond_ == TM_PRECOND_MULTIGRID;
+        if (use_mg) {
+            if (levels_.empty()) build_levels();
+            if (levels_.size() < 2) use_mg = false;
+        }
+        const T* dinv = nullptr;
+        if (use_mg) {
+            setup_hierarchy(xi);
+        } else {
+            s_dinv_.ensure(nu_);
+            launch_diag(g, false, s_dinv_.p);
+            dinv = s_dinv_.p;
+        }
+
+        if (flags & 1) {
+            mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, u, u);
+            TM_CHECK_LAUNCH();
+            ApplyArgs<T> a = apply_args();
+            a.x = u; a.y = s_r_.p; a.b = s_b_.p;
+            launch_apply(g, false, EP_RESID, a);
+        } else {
+            TM_CUDA(cudaMemsetAsync(u, 0, nu_ * sizeof(T), stream_));
+            TM_CUDA(cudaMemcpyAsync(s_r_.p, s_b_.p, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        }
+
+        auto apply_dot = [&](const T* pp, T* Ap) {
+            ApplyArgs<T> a = apply_args();
+            a.x = pp; a.y = Ap; a.dot_out = sc_ + SC_PAP;
+            launch_apply(g, false, EP_DOT, a);
+        };
+        auto precond = [&](const T* r) -> const T* { return use_mg ? vcycle(r) : nullptr; };
+        int check = check_every_;
+        if (check <= 0) check = use_mg ? 1 : 25;
+        SolveStats st = pcg(nu_, s_b_.p, u, s_r_.p, s_p_.p, s_Ap_.p, dinv, apply_dot, precond, !use_mg,
+                            rtol, maxit, check);
+        stats_iters_ = st.iters;
+        return st;
+    }
+
+    double dot_p2(const void* u, const void* b) override {
+        dot_kernel<T><<<grid1d(nu_), kVecThreads, 0, stream_>>>(nu_, (const T*)u, (const T*)b, rs_,
+                                                               sc_ + SC_TMP);
+        TM_CHECK_LAUNCH();
+        read_scalars();
+        return h_sc_[SC_TMP];
+    }
+
+    void sens_rhs(const void* xi, double p, const void* u, void* out) override {
+        check_penalty(p);
+        LevelGeom<T> g = g0_;
+        g.xi = (const T*)xi;
+        sens_rhs_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, (const T*)u, (T*)out);
+        TM_CHECK_LAUNCH();
+    }
+
+    // ------------------------------------------------------------------ mirror descent
+    void md_halfstep(const void* psi, const void* g, double alpha, void* half) override {
+        waxpby_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(n1_, 1.0, (const T*)psi, -alpha,
+                                                                  (const T*)g, (T*)half);
+        TM_CHECK_LAUNCH();
+    }
+
+    void md_volume(const void* half, double c, double* vol, double* dvol) override {
+        md_volume_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(p1_, (const T*)half, c, rs_,
+                                                                     sc_ + SC_TMP);
+        TM_CHECK_LAUNCH();
+        read_scalars();
+        *vol = h_sc_[SC_TMP];
+        *dvol = h_sc_[SC_TMP + 1];
+    }
+
+    void md_apply(const void* half, double c, const void* psi_prev, void* psi, void* rho,
+                  double* delta_sq, double* vol) override {
+        md_apply_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(
+            p1_, (const T*)half, c, (const T*)psi_prev, (T*)psi, (T*)rho, rs_, sc_ + SC_TMP);
+        TM_CHECK_LAUNCH();
+        read_scalars();
+        *delta_sq = h_sc_[SC_TMP];
+        *vol = h_sc_[SC_TMP + 1];
+    }
+
+    double integrate(const void* values) override {
+        p1_integrate_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(p1_, (const T*)values, rs_,
+                                                                        sc_ + SC_TMP);
+        TM_CHECK_LAUNCH();
+        read_scalars();
+        return h_sc_[SC_TMP];
+    }
+
+    void last_stats(double* out, int n) override {
+        const double v[5] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
+                             (double)levels_.size(), levels_.empty() ? 0.0 : levels_[0].lmax};
+        for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
+    }
+
+    // diagnostics (tests): multigrid internals on the hierarchy built for xi
+    void mg_debug(const void* xi, int op, int level, const void* in_, void* out_) override {
+        if (levels_.empty()) build_levels();
+        const int nl = (int)levels_.size();
+        if (nl < 2) throw Invalid{"no multigrid hierarchy for this mesh"};
+        if (level < 0 || level >= nl) throw Invalid{"bad level"};
+        setup_hierarchy((const T*)xi);
+        const T* in = (const T*)in_;
+        T* out = (T*)out_;
+        Level& L = levels_[level];
+        dim3 blk(32, 8);
+        if (op == 0) {
+            if (level == nl - 1) throw Invalid{"coarsest level has no matrix-free operator exposed"};
+            ApplyArgs<T> a = apply_args();
+            a.x = in; a.y = out;
+            launch_apply(L.g, level > 0, EP_PLAIN, a);
+        } else if (op == 1) {
+            if (level + 1 >= nl) throw Invalid{"no coarser level"};
+            Level& C = levels_[level + 1];
+            TM_CUDA(cudaMemsetAsync(out, 0, L.nu * sizeof(T), stream_));
+            dim3 grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
+            mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, in, out);
+            TM_CHECK_LAUNCH();
+        } else if (op == 2) {
+            if (level + 1 >= nl) throw Invalid{"no coarser level"};
+            Level& C = levels_[level + 1];
+            dim3 grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
+            mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, in, out);
+            TM_CHECK_LAUNCH();
+        } else if (op == 3) {
+            const T* z = vcycle(in);
+            TM_CUDA(cudaMemcpyAsync(out, z, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        } else if (op == 4) {
+            if (level != nl - 1) throw Invalid{"op 4 is the coarsest-level direct solve"};
+            mg_coarse_solve_kernel<T><<<1, 128, 0, stream_>>>((int)L.nu, coarse_A_.p, in, out);
+            TM_CHECK_LAUNCH();
+        } else if (op == 5) {
+            if (level == nl - 1) throw Invalid{"coarsest level has no diagonal"};
+            TM_CUDA(cudaMemcpyAsync(out, L.dinv.p, L.nu * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        } else {
+            throw Invalid{"unknown mg_debug op"};
+        }
+        TM_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    int mg_level_info(int level, int* info) override {
+        if (levels_.empty()) build_levels();
+        if (level < 0 || level >= (int)levels_.size()) return (int)levels_.size();
+        const LevelGeom<T>& g = levels_[level].g;
+        info[0] = g.nx; info[1] = g.ny; info[2] = g.dl; info[3] = g.dr; info[4] = g.db; info[5] = g.dt;
+        return (int)levels_.size();
+    }
+
+   private:
+    // ------------------------------------------------------------------ helpers
+    LevelGeom<T> make_level_geom(int nx, int ny) const {
+        LevelGeom<T> g;
+        g.nx = nx; g.ny = ny; g.Lx = 2 * nx + 1; g.Ly = 2 * ny + 1;
+        g.dl = -1; g.db = -1; g.dr = INT_MAX; g.dt = INT_MAX;
+        g.xi = nullptr; g.W = nullptr;
+        g.simp_min = (T)cfg_.simp_min;
+        g.mat = make_material<T>(cfg_.lame_lambda, cfg_.lame_mu, hx_, hy_);
+        return g;
+    }
+
+    int grid1d(size_t n) const {
+        const size_t want = (n + kVecThreads - 1) / kVecThreads;
+        return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)num_sms_ * 8));
+    }
+    dim3 grid2d_p1() const { return dim3(ceil_div(nx_ + 1, 32), ceil_div(ny_ + 1, 8)); }
+
+    void read_scalars() {
+        TM_CUDA(cudaMemcpyAsync(h_sc_, sc_, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    ApplyArgs<T> apply_args() const {
+        ApplyArgs<T> a;
+        std::memset(&a, 0, sizeof(a));
+        a.rs = rs_;
+        return a;
+    }
+
+    void launch_apply(const LevelGeom<T>& g, bool stored, int ep, ApplyArgs<T> a) {
+        const int ncg = ceil_div(g.nx + 1, 31);
+        const int bx = ceil_div(ncg, kApplyWarps);
+        // enough blocks for ~2 waves at 2 resident blocks per SM, strips of 8..64 cell rows
+        int strips = ceil_div(4L * num_sms_, bx);
+        strips = std::min(strips, std::max(1, g.ny / 8));
+        strips = std::max(strips, ceil_div(g.ny, 64));
+        a.rows_per_strip = ceil_div(g.ny, strips);
+        strips = ceil_div(g.ny, a.rows_per_strip);
+        dim3 grd(bx, strips), blk(kApplyWarps * 32);
+        if ((long)bx * strips > rs_.capacity) throw Invalid{"reduction scratch too small"};
+#define TM_LAUNCH_APPLY(ST, EPV) \
+    elast_apply_kernel<T, ST, EPV><<<grd, blk, 0, stream_>>>(g, a)
+        if (!stored) {
+            switch (ep) {
+                case EP_PLAIN: TM_LAUNCH_APPLY(false, EP_PLAIN); break;
+                case EP_DOT: TM_LAUNCH_APPLY(false, EP_DOT); break;
+                case EP_RESID: TM_LAUNCH_APPLY(false, EP_RESID); break;
+                default: TM_LAUNCH_APPLY(false, EP_CHEB); break;
+            }
+        } else {
+            switch (ep) {
+                case EP_PLAIN: TM_LAUNCH_APPLY(true, EP_PLAIN); break;
+                case EP_DOT: TM_LAUNCH_APPLY(true, EP_DOT); break;
+                case EP_RESID: TM_LAUNCH_APPLY(true, EP_RESID); break;
+                default: TM_LAUNCH_APPLY(true, EP_CHEB); break;
+            }
+        }
+#undef TM_LAUNCH_APPLY
+        TM_CHECK_LAUNCH();
+        if (g.nx == nx_ && g.ny == ny_) ++stats_fine_applies_;
+    }
+
+    void launch_diag(const LevelGeom<T>& g, bool stored, T* dinv) {
+        dim3 blk(32, 8), grd(ceil_div(g.Lx, 32), ceil_div(g.Ly, 8));
+        if (stored)
+            elast_diag_kernel<T, true><<<grd, blk, 0, stream_>>>(g, diag_tab_, dinv);
+        else
+            elast_diag_kernel<T, false><<<grd, blk, 0, stream_>>>(g, diag_tab_, dinv);
+        TM_CHECK_LAUNCH();
+    }
+
+    void p1_apply(double alpha, double beta, const T* x, T* y, double* dot_out) {
+        dim3 grd = grid2d_p1();
+        if ((long)grd.x * grd.y > rs_.capacity) throw Invalid{"reduction scratch too small"};
+        if (dot_out)
+            p1_apply_kernel<T, true><<<grd, dim3(32, 8), 0, stream_>>>(p1_, alpha, beta, x, y, rs_, dot_out);
+        else
+            p1_apply_kernel<T, false><<<grd, dim3(32, 8), 0, stream_>>>(p1_, alpha, beta, x, y, rs_, nullptr);
+        TM_CHECK_LAUNCH();
+    }
+
+    // ------------------------------------------------------------------ PCG
+    // Solves A x = b given r = b - A x on entry.  precond(r) returns z = M^-1 r, or nullptr
+    // when `jacobi` (then z = dinv r is fused into the vector kernels).
+    template <class ApplyDot, class Precond>
+    SolveStats pcg(size_t n, const T* b, T* x, T* r, T* p, T* Ap, const T* dinv, ApplyDot apply_dot,
+                   Precond precond, bool jacobi, double rtol, int maxit, int check) {
+        SolveStats st;
+        const int g1 = grid1d(n);
+        dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, b, b, rs_, sc_ + SC_BB);
+        TM_CHECK_LAUNCH();
+        int cur = 0;
+        if (jacobi) {
+            pcg_start_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, p, r, dinv, rs_);
+        } else {
+            const T* z = precond(r);
+            pcg_start_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, p, r, z, rs_);
+        }
+        TM_CHECK_LAUNCH();
+        read_scalars();
+        const double bb = h_sc_[SC_BB];
+        if (!(bb > 0.0)) {
+            TM_CUDA(cudaMemsetAsync(x, 0, n * sizeof(T), stream_));
+            st.converged = true;
+            return st;
+        }
+        st.relres = std::sqrt(h_sc_[SC_RR] / bb);
+        if (st.relres <= rtol) {
+            st.converged = true;
+            return st;
+        }
+        for (int k = 0; k < maxit; ++k) {
+            apply_dot(p, Ap);
+            if (jacobi) {
+                pcg_update_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, x, r, p,
+                                                                           Ap, dinv, rs_);
+                TM_CHECK_LAUNCH();
+            } else {
+                pcg_update_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, x, r,
+                                                                            p, Ap, nullptr, rs_);
+                TM_CHECK_LAUNCH();
+            }
+            st.iters = k + 1;
+            const bool do_check = ((k + 1) % check == 0) || (k + 1 == maxit);
+            if (do_check) {
+                read_scalars();
+                st.relres = std::sqrt(h_sc_[SC_RR] / bb);
+                if (!(st.relres == st.relres)) break;  // NaN: give up
+                if (st.relres <= rtol) {
+                    st.converged = true;
+                    break;
+                }
+            }
+            if (jacobi) {
+                pcg_direction_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p, r,
+                                                                              dinv);
+            } else {
+                const T* z = precond(r);
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, r, z, rs_, sc_ + (cur ^ 1));
+                TM_CHECK_LAUNCH();
+                pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p,
+                                                                               r, z);
+            }
+            TM_CHECK_LAUNCH();
+            cur ^= 1;
+        }
+        return st;
+    }
+
+    // ------------------------------------------------------------------ multigrid
+    struct Level {
+        LevelGeom<T> g;
+        size_t nu = 0;
+        DevBuf<T> W, dinv, x, xalt, b, d, tmp, eig;
+        bool eig_ready = false;
+        double lmax = 0.0;
+    };
+
+    void build_levels() {
+        levels_.clear();
+        int nx = nx_, ny = ny_;
+        LevelGeom<T> g = g0_;
+        while (true) {
+            levels_.emplace_back();
+            Level& L = levels_.back();
+            L.g = g;
+            L.nu = 2 * (size_t)g.Lx * g.Ly;
+            if (std::max(nx, ny) <= coarse_cells_) break;
+            const int nxc = (nx + 1) / 2, nyc = (ny + 1) / 2;
+            if (nxc == nx && nyc == ny) break;  // 1x1: cannot coarsen
+            LevelGeom<T> c = make_level_geom(nxc, nyc);
+            c.dl = g.dl; c.db = g.db;  // near sides stay aligned (0 or free)
+            c.dr = g.dr == INT_MAX ? INT_MAX : 2 * (g.dr / 4);
+            c.dt = g.dt == INT_MAX ? INT_MAX : 2 * (g.dt / 4);
+            g = c; nx = nxc; ny = nyc;
+        }
+        const size_t nl = levels_.size();
+        if (nl < 2) return;
+        if (2 * (size_t)levels_.back().g.Lx * levels_.back().g.Ly > (size_t)kCoarseMaxDofs)
+            throw Invalid{"coarsest multigrid level too large"};
+        for (size_t l = 0; l < nl; ++l) {
+            Level& L = levels_[l];
+            const bool coarsest = (l + 1 == nl);
+            if (l > 0) {
+                L.W.ensure(12 * (size_t)L.g.nx * L.g.ny);
+                L.g.W = L.W.p;
+                L.b.ensure(L.nu);
+            }
+            L.x.ensure(L.nu);
+            if (!coarsest) {
+                L.dinv.ensure(L.nu); L.xalt.ensure(L.nu); L.d.ensure(L.nu);
+                L.tmp.ensure(L.nu); L.eig.ensure(L.nu);
+            }
+        }
+        const size_t nc = levels_.back().nu;
+        coarse_A_.ensure(nc * nc);
+        if (!eig_sc_) TM_CUDA(cudaMalloc(&eig_sc_, sizeof(double) * 64));
+    }
+
+    void setup_hierarchy(const T* xi) {
+        const size_t nl = levels_.size();
+        levels_[0].g.xi = xi;
+        for (size_t l = 1; l < nl; ++l) {
+            Level& F = levels_[l - 1];
+            Level& C = levels_[l];
+            dim3 blk(32, 8), grd(ceil_div(C.g.nx, 32), ceil_div(C.g.ny, 8));
+            if (l == 1)
+                mg_coarsen_moments_kernel<T, false><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, co_tab_, C.W.p);
+            else
+                mg_coarsen_moments_kernel<T, true><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, co_tab_, C.W.p);
+            TM_CHECK_LAUNCH();
+        }
+        if (nl > 32) throw Invalid{"too many multigrid levels"};
+        for (size_t l = 0; l + 1 < nl; ++l) {
+            Level& L = levels_[l];
+            launch_diag(L.g, l > 0, L.dinv.p);
+            // lambda_max(D^-1 A) by power iteration, warm-started across solves
+            const int g1 = grid1d(L.nu);
+            int its = 4;
+            if (!L.eig_ready) {
+                mg_seed_vector_kernel<T><<<grid1d(L.nu / 2), kVecThreads, 0, stream_>>>(L.g, L.eig.p);
+                TM_CHECK_LAUNCH();
+                its = 10;
+                L.eig_ready = true;
+            }
+            double* slots = eig_sc_ + 2 * l;
+            dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.nu, L.eig.p, L.eig.p, rs_, slots + 1);
+            TM_CHECK_LAUNCH();
+            for (int it = 0; it < its; ++it) {
+                ApplyArgs<T> a = apply_args();
+                a.x = L.eig.p; a.y = L.tmp.p;
+                launch_apply(L.g, l > 0, EP_PLAIN, a);
+                // eig <- dinv .* tmp / ||eig_old||   (normalised by the previous norm)
+                normalize_scale_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.nu, L.dinv.p, L.tmp.p, L.eig.p, slots + 1);
+                TM_CHECK_LAUNCH();
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.nu, L.eig.p, L.eig.p, rs_, slots + 1);
+                TM_CHECK_LAUNCH();
+            }
+        }
+        {
+            Level& C = levels_[nl - 1];
+            mg_coarse_factor_kernel<T><<<1, 256, 0, stream_>>>(C.g, coarse_A_.p);
+            TM_CHECK_LAUNCH();
+        }
+        TM_CUDA(cudaMemcpyAsync(h_sc_ + SC_COUNT, eig_sc_, sizeof(double) * 2 * (nl - 1),
+                                cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (size_t l = 0; l + 1 < nl; ++l) {
+            // after normalising by the previous norm, ||eig||^2 -> lambda^2
+            const double lam = std::sqrt(h_sc_[SC_COUNT + 2 * l + 1]);
+            if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"multigrid: eigenvalue estimate failed"};
+            levels_[l].lmax = lam;
+        }
+    }
+
+    // Chebyshev-Jacobi smoothing of A x = b on level l; xin == nullptr means zero initial guess
+    T* smooth(size_t l, const T* b, T* xin) {
+        Level& L = levels_[l];
+        const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
+        const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+        double rho = 1.0 / sigma;
+        T* cur;
+        int k0 = 0;
+        if (!xin) {
+            cheb_first_kernel<T><<<grid1d(L.nu), kVecThreads, 0, stream_>>>(L.nu, 1.0 / theta, L.dinv.p, b,
+                                                                        L.d.p, L.x.p);
+            TM_CHECK_LAUNCH();
+            cur = L.x.p;
+            k0 = 1;
+        } else {
+            cur = xin;
+        }
+        for (int k = k0; k < cheb_degree_; ++k) {
+            double c1, c2;
+            if (k == 0) {
+                c1 = 0.0;
+                c2 = 1.0 / theta;
+            } else {
+                const double rho_new = 1.0 / (2.0 * sigma - rho);
+                c1 = rho_new * rho;
+                c2 = 2.0 * rho_new / delta;
+                rho = rho_new;
+            }
+            T* other = (cur == L.x.p) ? L.xalt.p : L.x.p;
+            ApplyArgs<T> a = apply_args();
+            a.x = cur; a.y = other; a.b = b; a.dinv = L.dinv.p; a.d = L.d.p;
+            a.c1 = (T)c1; a.c2 = (T)c2;
+            launch_apply(L.g, l > 0, EP_CHEB, a);
+            cur = other;
+        }
+        return cur;
+    }
+
+    // z = V(r): one symmetric V-cycle with zero initial guess
+    const T* vcycle(const T* r) {
+        const size_t nl = levels_.size();
+        std::vector<T*> xs(nl, nullptr);
+        std::vector<const T*> bs(nl, nullptr);
+        bs[0] = r;
+        for (size_t l = 0; l + 1 < nl; ++l) {
+            Level& L = levels_[l];
+            Level& C = levels_[l + 1];
+            xs[l] = smooth(l, bs[l], nullptr);
+            ApplyArgs<T> a = apply_args();
+            a.x = xs[l]; a.y = L.tmp.p; a.b = bs[l];
+            launch_apply(L.g, l > 0, EP_RESID, a);
+            dim3 blk(32, 8), grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
+            mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, L.tmp.p, C.b.p);
+            TM_CHECK_LAUNCH();
+            bs[l + 1] = C.b.p;
+        }
+        {
+            Level& C = levels_[nl - 1];
+            mg_coarse_solve_kernel<T><<<1, 128, 0, stream_>>>((int)C.nu, coarse_A_.p, bs[nl - 1], C.x.p);
+            TM_CHECK_LAUNCH();
+            xs[nl - 1] = C.x.p;
+        }
+        for (size_t l = nl - 1; l-- > 0;) {
+            Level& L = levels_[l];
+            Level& C = levels_[l + 1];
+            dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
+            mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, xs[l + 1], xs[l]);
+            TM_CHECK_LAUNCH();
+            xs[l] = smooth(l, bs[l], xs[l]);
+        }
+        ++stats_vcycles_;
+        return xs[0];
+    }
+
+    // ------------------------------------------------------------------ state
+    tm_config cfg_;
+    cudaStream_t stream_ = nullptr;
+    int nx_, ny_, num_sms_ = 148;
+    double hx_, hy_;
+    size_t n1_, n2_, nu_;
+    P1Geom p1_;
+    LevelGeom<T> g0_;
+    DiagTable diag_tab_;
+    TransferTable tr_tab_;
+    CoarsenTable co_tab_;
+    ReduceScratch rs_{};
+    double* sc_ = nullptr;
+    double* eig_sc_ = nullptr;
+    double* h_sc_ = nullptr;
+
+    int precond_ = TM_PRECOND_MULTIGRID, cheb_degree_ = 3, check_every_ = 0, coarse_cells_ = 2;
+    double cheb_ratio_ = 10.0, eig_safety_ = 1.1;
+
+    DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_;
+    bool f_dinv_ready_ = false;
+    DevBuf<T> s_r_, s_p_, s_Ap_, s_b_, s_dinv_;
+    std::vector<Level> levels_;
+    DevBuf<double> coarse_A_;
+
+    long stats_fine_applies_ = 0, stats_vcycles_ = 0;
+    int stats_iters_ = 0;
+};
+
+}  // namespace tmx
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+struct tm_engine_s {
+    std::unique_ptr<tmx::EngineBase> impl;
+};
+
+namespace {
+template <class F>
+int guarded(tm_handle h, F&& f) {
+    try {
+        if (h) {
+            cudaError_t e = cudaSetDevice(h->impl->device);
+            if (e != cudaSuccess) {
+                tmx::set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+                return TM_ERR_CUDA;
+            }
+        }
+        f();
+        return TM_OK;
+    } catch (const tmx::CudaFailure& e) {
+        tmx::set_error(e.what);
+        return TM_ERR_CUDA;
+    } catch (const tmx::Unsupported& e) {
+        tmx::set_error(e.what);
+        return TM_ERR_UNSUPPORTED;
+    } catch (const tmx::Invalid& e) {
+        tmx::set_error(e.what);
+        return TM_ERR_INVALID;
+    } catch (const std::exception& e) {
+        tmx::set_error(e.what());
+        return TM_ERR_INVALID;
+    }
+}
+#define TM_REQUIRE_HANDLE(h)                      \
+    if (!(h) || !(h)->impl) {                     \
+        tmx::set_error("null engine handle");     \
+        return TM_ERR_INVALID;                    \
+    }
+}  // namespace
+
+extern "C" {
+
+const char* tm_last_error(void) { return tmx::last_error(); }
+const char* tm_version(void) { return "topomax_b200 0.1 (sm_100a)"; }
+
+int tm_create(const tm_config* cfg, tm_handle* out) {
+    if (!cfg || !out) {
+        tmx::set_error("tm_create: null argument");
+        return TM_ERR_INVALID;
+    }
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw tmx::CudaFailure{std::string("no CUDA device available: ") + cudaGetErrorString(e)};
+        if (cfg->device < 0 || cfg->device >= ndev) throw tmx::Invalid{"bad device ordinal"};
+        auto* h = new tm_engine_s;
+        try {
+            if (cfg->dtype == TM_F64) h->impl.reset(new tmx::Engine<double>(*cfg));
+            else if (cfg->dtype == TM_F32) h->impl.reset(new tmx::Engine<float>(*cfg));
+            else throw tmx::Invalid{"dtype must be TM_F64 or TM_F32"};
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+
+int tm_destroy(tm_handle h) {
+    if (!h) return TM_OK;
+    delete h;
+    return TM_OK;
+}
+
+int tm_set_stream(tm_handle h, void* s) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->set_stream((cudaStream_t)s); });
+}
+int tm_set_option(tm_handle h, int option, double value) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->set_option(option, value); });
+}
+int tm_load_vector(tm_handle h, const tm_loads* loads, void* b) {
+    TM_REQUIRE_HANDLE(h);
+    if (!loads || !b) { tmx::set_error("tm_load_vector: null argument"); return TM_ERR_INVALID; }
+    return guarded(h, [&] { h->impl->load_vector(*loads, b); });
+}
+int tm_filter_apply(tm_handle h, int rhs_kind, const void* in, void* out, double rtol, int maxit,
+                    int* iters, double* relres) {
+    TM_REQUIRE_HANDLE(h);
+    tmx::SolveStats st;
+    int rc = guarded(h, [&] { st = h->impl->filter_apply(rhs_kind, in, out, rtol, maxit); });
+    if (iters) *iters = st.iters;
+    if (relres) *relres = st.relres;
+    if (rc == TM_OK && !st.converged) {
+        tmx::set_error("filter PCG did not converge: relres " + std::to_string(st.relres));
+        return TM_ERR_NOT_CONVERGED;
+    }
+    return rc;
+}
+int tm_elast_matvec(tm_handle h, const void* xi, double penalty, const void* x, void* y) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->elast_matvec(xi, penalty, x, y); });
+}
+int tm_elast_diag(tm_handle h, const void* xi, double penalty, void* dinv) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->elast_diag(xi, penalty, dinv); });
+}
+int tm_state_solve(tm_handle h, const void* xi, double penalty, const void* b, void* u, double rtol,
+                   int maxit, int flags, int* iters, double* relres) {
+    TM_REQUIRE_HANDLE(h);
+    tmx::SolveStats st;
+    int rc = guarded(h, [&] { st = h->impl->state_solve(xi, penalty, b, u, rtol, maxit, flags); });
+    if (iters) *iters = st.iters;
+    if (relres) *relres = st.relres;
+    if (rc == TM_OK && !st.converged) {
+        tmx::set_error("state PCG did not converge: relres " + std::to_string(st.relres));
+        return TM_ERR_NOT_CONVERGED;
+    }
+    return rc;
+}
+int tm_dot_p2(tm_handle h, const void* u, const void* b, double* out) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { *out = h->impl->dot_p2(u, b); });
+}
+int tm_sens_rhs(tm_handle h, const void* xi, double penalty, const void* u, void* out) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->sens_rhs(xi, penalty, u, out); });
+}
+int tm_md_halfstep(tm_handle h, const void* psi, const void* grad, double alpha, void* half) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->md_halfstep(psi, grad, alpha, half); });
+}
+int tm_md_volume(tm_handle h, const void* half, double c, double* vol, double* dvol) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->md_volume(half, c, vol, dvol); });
+}
+int tm_md_apply(tm_handle h, const void* half, double c, const void* psi_prev, void* psi, void* rho,
+                double* delta_sq, double* vol) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->md_apply(half, c, psi_prev, psi, rho, delta_sq, vol); });
+}
+int tm_integrate(tm_handle h, const void* values, double* out) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { *out = h->impl->integrate(values); });
+}
+int tm_last_solve_stats(tm_handle h, double* out, int n) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->last_stats(out, n); });
+}
+
+int tm_mg_debug(tm_handle h, const void* xi, int op, int level, const void* in, void* out) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->mg_debug(xi, op, level, in, out); });
+}
+int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { *nlevels = h->impl->mg_level_info(level, info6); });
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// Geometric multigrid for the penalised stiffness operator (the preconditioner that takes
+// LUSolver("mumps")'s place, reference: FEM_src/pde_solver.py:130-131).
+//
+// Hierarchy: P2 spaces on uniformly coarsened right-diagonal meshes are NESTED (each coarse
+// triangle is the union of 4 fine triangles of the same family), so the Galerkin coarse
+// operator P^T K P is again "the P2 stiffness operator with coefficient r(xi)", and because
+// grad(phi_coarse) is affine on a coarse triangle it is determined EXACTLY by six moments
+// int r lambda_a lambda_b per coarse triangle.  Coarse levels therefore run the very same
+// matrix-free kernel (tm_elast.cuh, STORED_W=true) on 12 numbers per cell, and the moments
+// are restricted level to level by a fixed 3x3 congruence per sub-triangle.
+//
+// Grids whose cell counts are odd are coarsened with ceil(n/2): the coarse mesh overhangs the
+// domain, the overhanging fine triangles contribute zero moments, transfers skip the missing
+// fine nodes.  The coarse spaces stay nested subspaces (restrictions to the domain).  Fixed
+// sides on the far end are pulled in to the last coarse column whose functions vanish on the
+// fine Dirichlet nodes (dr' = 2*floor(dr/4)).
+#pragma once
+
+#include "tm_common.cuh"
+#include "tm_tables.h"
+
+namespace tmx {
+
+// fine moments of triangle `type` of fine cell (cx,cy); zero outside the fine mesh
+template <typename T, bool FINE_STORED>
+__device__ __forceinline__ void fine_moments(const LevelGeom<T>& f, int type, int cx, int cy,
+                                             double w[6]) {
+    if (cx >= f.nx || cy >= f.ny) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = 0.0;
+        return;
+    }
+    if (FINE_STORED) {
+        const size_t plane = (size_t)f.nx * f.ny, cidx = (size_t)cy * f.nx + cx;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = (double)f.W[(6 * type + k) * plane + cidx];
+    } else {
+        const double x0 = (double)f.xi[(size_t)cy * (f.nx + 1) + cx];
+        const double x3 = (double)f.xi[(size_t)(cy + 1) * (f.nx + 1) + cx + 1];
+        const double x1 = type == 0 ? (double)f.xi[(size_t)cy * (f.nx + 1) + cx + 1]
+                                    : (double)f.xi[(size_t)(cy + 1) * (f.nx + 1) + cx];
+        moments_from_xi<double>(x0, x1, x3, (double)f.simp_min, w);
+    }
+}
+
+// W_c (SoA, 12 planes of nxc*nyc) from the fine level
+template <typename T, bool FINE_STORED>
+__global__ void mg_coarsen_moments_kernel(const LevelGeom<T> f, int nxc, int nyc,
+                                          const CoarsenTable tab, T* __restrict__ Wc) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= nxc || J >= nyc) return;
+    const size_t plane = (size_t)nxc * nyc, cidx = (size_t)J * nxc + I;
+    for (int ctype = 0; ctype < 2; ++ctype) {
+        double acc[3][3] = {};
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int s = 4 * ctype + s4;
+            double w[6];
+            fine_moments<T, FINE_STORED>(f, tab.type[s], 2 * I + tab.dx[s], 2 * J + tab.dy[s], w);
+            // acc += M w M^T
+            double tmp[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v += tab.M[s][a][c] * w[moment_slot(c, d)];
+                    tmp[a][d] = v;
+                }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) v += tmp[a][d] * tab.M[s][b][d];
+                    acc[a][b] += v;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = a; b < 3; ++b)
+                Wc[(6 * ctype + moment_slot(a, b)) * plane + cidx] = (T)(0.25 * acc[a][b]);
+    }
+}
+
+// weight of coarse lattice node (I,J) at fine lattice node (i,j); 0 if unrelated
+__device__ __forceinline__ double transfer_weight(const TransferTable& tab, int nxc, int nyc, int i,
+                                                  int j, int I, int J) {
+    const int cx = min(i >> 2, nxc - 1), cy = min(j >> 2, nyc - 1);
+    const int qx = I - 2 * cx, qy = J - 2 * cy;
+    if (qx < 0 || qx > 2 || qy < 0 || qy > 2) return 0.0;
+    return tab.Pw[5 * (j - 4 * cy) + (i - 4 * cx)][3 * qy + qx];
+}
+
+// bc = P^T r  (zero on coarse Dirichlet nodes)
+template <typename T>
+__global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
+                                   const TransferTable tab, const T* __restrict__ r,
+                                   T* __restrict__ bc) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= c.Lx || J >= c.Ly) return;
+    double a0 = 0.0, a1 = 0.0;
+    if (!c.fixed(I, J)) {
+        for (int dj = -3; dj <= 3; ++dj) {
+            const int j = 2 * J + dj;
+            if (j < 0 || j >= f.Ly) continue;
+            for (int di = -3; di <= 3; ++di) {
+                const int i = 2 * I + di;
+                if (i < 0 || i >= f.Lx) continue;
+                const double w = transfer_weight(tab, c.nx, c.ny, i, j, I, J);
+                if (w == 0.0) continue;
+                const size_t n = (size_t)j * f.Lx + i;
+                a0 += w * (double)r[2 * n];
+                a1 += w * (double)r[2 * n + 1];
+            }
+        }
+    }
+    const size_t N = (size_t)J * c.Lx + I;
+    bc[2 * N] = (T)a0;
+    bc[2 * N + 1] = (T)a1;
+}
+
+// x += P xc  (fine Dirichlet nodes untouched)
+template <typename T>
+__global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
+                                      const TransferTable tab, const T* __restrict__ xc,
+                                      T* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= f.Lx || j >= f.Ly) return;
+    if (f.fixed(i, j)) return;
+    const int cx = min(i >> 2, c.nx - 1), cy = min(j >> 2, c.ny - 1);
+    const double* pw = tab.Pw[5 * (j - 4 * cy) + (i - 4 * cx)];
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const double w = pw[q];
+        if (w == 0.0) continue;
+        const size_t N = (size_t)(2 * cy + q / 3) * c.Lx + (2 * cx + q % 3);
+        a0 += w * (double)xc[2 * N];
+        a1 += w * (double)xc[2 * N + 1];
+    }
+    const size_t n = (size_t)j * f.Lx + i;
+    x[2 * n] = (T)((double)x[2 * n] + a0);
+    x[2 * n + 1] = (T)((double)x[2 * n + 1] + a1);
+}
+
+// ---------------------------------------------------------------------------------------
+// coarsest level: dense Cholesky in one block (n = 2*Lx*Ly <= kCoarseMaxDofs)
+// ---------------------------------------------------------------------------------------
+constexpr int kCoarseMaxDofs = 2 * 9 * 9;
+
+// A (n x n, row-major, double) <- dense K of the coarsest level, then A = L L^T in place (lower)
+template <typename T>
+__global__ void mg_coarse_factor_kernel(const LevelGeom<T> g, double* __restrict__ A) {
+    const int n = 2 * g.Lx * g.Ly;
+    Material<double> mat;
+    mat.A11 = (double)g.mat.A11; mat.A22 = (double)g.mat.A22; mat.A12 = (double)g.mat.A12;
+    mat.A33 = (double)g.mat.A33; mat.kappa = (double)g.mat.kappa;
+    for (int col = threadIdx.x; col < n; col += blockDim.x) {
+        for (int row = 0; row < n; ++row) A[(size_t)row * n + col] = 0.0;
+        const int node = col >> 1, comp = col & 1;
+        const int ni = node % g.Lx, nj = node / g.Lx;
+        if (g.fixed(ni, nj)) {
+            A[(size_t)col * n + col] = 1.0;
+            continue;
+        }
+        for (int cy = 0; cy < g.ny; ++cy)
+            for (int cx = 0; cx < g.nx; ++cx) {
+                const int li = ni - 2 * cx, lj = nj - 2 * cy;
+                if (li < 0 || li > 2 || lj < 0 || lj > 2) continue;
+                double X[9][2] = {}, acc[9][2] = {}, wA[6], wB[6];
+                X[3 * lj + li][comp] = 1.0;
+                const size_t plane = (size_t)g.nx * g.ny, cidx = (size_t)cy * g.nx + cx;
+                for (int k = 0; k < 6; ++k) {
+                    wA[k] = (double)g.W[k * plane + cidx];
+                    wB[k] = (double)g.W[(6 + k) * plane + cidx];
+                }
+                cell_apply<double>(X, wA, wB, mat, acc);
+                for (int q = 0; q < 9; ++q) {
+                    const int i = 2 * cx + q % 3, j = 2 * cy + q / 3;
+                    if (g.fixed(i, j)) continue;
+                    const size_t rown = (size_t)j * g.Lx + i;
+                    A[(2 * rown) * n + col] += acc[q][0];
+                    A[(2 * rown + 1) * n + col] += acc[q][1];
+                }
+            }
+    }
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (threadIdx.x == 0) A[(size_t)k * n + k] = sqrt(A[(size_t)k * n + k]);
+        __syncthreads();
+        const double dk = A[(size_t)k * n + k];
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + k] /= dk;
+        __syncthreads();
+        const int m = n - k - 1;
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int i = k + 1 + e / m, j = k + 1 + e % m;
+            if (j <= i) A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        }
+        __syncthreads();
+    }
+}
+
+// x = (L L^T)^-1 b, one block
+template <typename T>
+__global__ void mg_coarse_solve_kernel(int n, const double* __restrict__ L,
+                                       const T* __restrict__ b, T* __restrict__ x) {
+    __shared__ double y[kCoarseMaxDofs];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = (double)b[i];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {  // forward: L y = b
+        if (threadIdx.x == 0) y[k] /= L[(size_t)k * n + k];
+        __syncthreads();
+        const double yk = y[k];
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) y[i] -= L[(size_t)i * n + k] * yk;
+        __syncthreads();
+    }
+    for (int k = n - 1; k >= 0; --k) {  // backward: L^T x = y
+        if (threadIdx.x == 0) y[k] /= L[(size_t)k * n + k];
+        __syncthreads();
+        const double yk = y[k];
+        for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] -= L[(size_t)k * n + i] * yk;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = (T)y[i];
+}
+
+// deterministic pseudo-random start vector for the power iteration (zero on Dirichlet nodes)
+template <typename T>
+__global__ void mg_seed_vector_kernel(const LevelGeom<T> g, T* __restrict__ v) {
+    const size_t n2 = (size_t)g.Lx * g.Ly;
+    for (size_t n = blockIdx.x * (size_t)blockDim.x + threadIdx.x; n < n2;
+         n += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(n / g.Lx), i = (int)(n - (size_t)j * g.Lx);
+        const bool f = g.fixed(i, j);
+        for (int c = 0; c < 2; ++c) {
+            unsigned int h = (unsigned int)(2 * n + c) * 2654435761u;
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            v[2 * n + c] = f ? T(0) : (T)(0.5 + (double)(h & 0xffffu) / 65536.0);
+        }
+    }
+}
+
+}  // namespace tmx

@@ -1,0 +1,98 @@
+"""Elastic compliance problem on the GPU engine (reference: FEM_src/elasisity_problem.py:76-196,
+FEM_src/problem.py:13-36).
+
+Same public surface as the reference class -- ``filter``, ``u``, ``filtered_rho``, ``penalizer``,
+``lamé_mu``, ``lamé_lda``, ``body_force``, ``traction_term``, ``domain_size``,
+``set_penalization`` / ``calculate_objective`` / ``calculate_objective_gradient`` / ``forward`` --
+with dolfin's assemble + MUMPS replaced by the kernels behind ``Engine``.
+"""
+from __future__ import annotations
+
+from .designs.definitions import DomainParameters, ElasticityParameters
+from .engine import Engine
+from .filter import AssembledP1Form, HelmholtzFilter
+from .mesh import Function, FunctionSpace, RectangleMesh
+from .penalizers import ElasticPenalizer
+from .problem import Problem
+
+
+class ElasticityProblem(Problem):
+    """Elastic compliance topology optimization problem."""
+
+    def __init__(self, mesh: RectangleMesh, control_space: FunctionSpace,
+                 domain_parameters: DomainParameters, elasticity_parameters: ElasticityParameters,
+                 *, state_rtol: float = 1e-10, state_max_iterations: int = 200000,
+                 filter_rtol: float = 1e-13, preconditioner: str = "multigrid",
+                 warm_start: bool = True):
+        self.parameters = elasticity_parameters
+        self.domain_size = (domain_parameters.width, domain_parameters.height)
+        self.mesh = mesh
+        self.control_space = control_space
+
+        self.Young_modulus = self.parameters.young_modulus
+        self.Poisson_ratio = self.parameters.poisson_ratio
+        self.penalizer = ElasticPenalizer()
+        # Lamé parameters exactly as the reference computes them (plane-strain-type lambda)
+        self.lamé_mu = self.Young_modulus / (2 * (1 + self.Poisson_ratio))
+        self.lamé_lda = self.lamé_mu * self.Poisson_ratio / (0.5 - self.Poisson_ratio)
+
+        self.engine = Engine(
+            mesh.nx, mesh.ny, mesh.width, mesh.height,
+            lame_lambda=self.lamé_lda, lame_mu=self.lamé_mu, simp_min=self.penalizer.minimum,
+            filter_radius=self.parameters.filter_radius, fixed_sides=self.parameters.fixed_sides,
+            dtype=control_space.dtype_name, device=control_space.device,
+        )
+        from . import _lib
+        self.engine.set_option(_lib.OPT_PRECOND, _lib.PRECOND_MULTIGRID if preconditioner == "multigrid"
+                               else _lib.PRECOND_JACOBI)
+        self.preconditioner = preconditioner
+        self.state_rtol = state_rtol
+        self.state_max_iterations = state_max_iterations
+        self.warm_start = warm_start
+
+        self.solution_space = FunctionSpace(mesh, "CG", 2, dtype=control_space.dtype_name,
+                                            device=self.engine.device)
+        self.body_force = self.parameters.body_force
+        self.traction_term = self.parameters.tractions or []
+        # load vector, assembled once like SmartMumpsSolver(l_has_no_args=True)
+        self.load = self.engine.load_vector(self.body_force, self.traction_term)
+
+        self.filter = HelmholtzFilter(self.parameters.filter_radius, control_space,
+                                      engine=self.engine, rtol=filter_rtol)
+        self.u: Function | None = None
+        self.filtered_rho: Function | None = None
+        self.solve_log: list[dict] = []
+
+    # ------------------------------------------------------------------ Problem interface
+    def set_penalization(self, penalization: float):
+        if self.penalizer is None:
+            raise ValueError("Classes deriving from Problem must set a penalizer in their initializer")
+        self.penalizer.set_penalization(penalization)
+
+    def forward(self, rho: Function) -> Function:
+        """State solve  K(rho) u = b, u = 0 on the fixed sides; ``rho`` is the filtered density."""
+        p = self.penalizer.assert_has_penalization()
+        warm = self.warm_start and self.u is not None
+        u0 = self.u.tensor.clone() if warm else None
+        u, info = self.engine.state_solve(rho.tensor, self.load, p, rtol=self.state_rtol,
+                                          maxit=self.state_max_iterations, u=u0, warm_start=warm)
+        stats = self.engine.last_solve_stats()
+        stats["relative_residual"] = info.relative_residual
+        self.solve_log.append(stats)
+        return Function(self.solution_space, u)
+
+    def calculate_objective(self, rho: Function) -> float:
+        """Compliance  phi(rho) = int u.f dx + int u.t ds = u . b."""
+        self.filtered_rho = self.filter.apply(rho)
+        self.u = self.forward(self.filtered_rho)
+        return float(self.engine.dot_p2(self.u.tensor, self.load))
+
+    def calculate_objective_gradient(self) -> Function:
+        """Filtered  -r'(xi) (lambda |div u|^2 + 2 mu |eps(u)|^2)."""
+        if self.filtered_rho is None or self.u is None:
+            raise ValueError(
+                "You must call calculate_objective before calling calculate_objective_gradient"
+            )
+        p = self.penalizer.assert_has_penalization()
+        rhs = self.engine.sens_rhs(self.filtered_rho.tensor, self.u.tensor, p)
+        return self.filter.apply(AssembledP1Form(self.control_space, rhs))

@@ -1,0 +1,204 @@
+"""``FEMSolver``: the reference's FEM back-end of the optimiser on the GPU engine
+(reference: FEM_src/solver.py:15-89 driven by src/solver.py:208-302).
+
+Two equivalent loops:
+* ``solve()``          -- device resident: psi, rho, the gradient and the volume projection stay
+                          in HBM; per iteration only scalars cross PCIe (rho is copied to the
+                          host only when an iteration is saved).
+* ``solve_generic()``  -- the reference's base-class loop over the numpy hooks
+                          (``to_array`` / ``set_from_array`` / ``integrate``), for callers that
+                          drive the hooks themselves.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .designs.definitions import ElasticityParameters, FluidParameters
+from .elasticity_problem import ElasticityProblem
+from .mesh import Function, FunctionSpace, RectangleMesh
+from .printer import Printer
+from .solver import MAX_ITERATIONS, Solver, find_volume_shift
+from .utils import Timer
+
+
+def save_function(f: Function, filename: str, problem: str):
+    """Pickle ``{N, domain_size, problem, vector}`` (reference: FEM_src/utils.py:47-70).
+    ``vector`` is stored in this package's row-major vertex order, not dolfin's dof order."""
+    mesh = f.function_space().mesh()
+    n = 1 / (mesh.hmin() / np.sqrt(2))
+    data = {
+        "N": int(round(n)),
+        "domain_size": mesh.domain_size,
+        "problem": problem,
+        "vector": f.vector()[:].astype(np.float64),
+    }
+    with open(filename, "wb") as fh:
+        pickle.dump(data, fh)
+
+
+def load_function(filename: str, *, dtype: str = "float64", device=None):
+    """Inverse of ``save_function`` for ``problem == 'design'`` (reference: FEM_src/utils.py:73-109)."""
+    with open(filename, "rb") as fh:
+        data = pickle.load(fh)
+    if data["problem"] != "design":
+        raise ValueError(f"load_function got unsupported problem: {data['problem']}")
+    w, h = data["domain_size"]
+    mesh = RectangleMesh(w, h, int(w * data["N"]), int(h * data["N"]))
+    space = FunctionSpace(mesh, "CG", 1, dtype=dtype, device=device)
+    f = Function(space)
+    f.vector()[:] = data["vector"]
+    return f, mesh, space
+
+
+class FEMSolver(Solver):
+    def __init__(self, N: int, design_file: str, data_path: str = "output", skip_multiple: int = 1,
+                 *, dtype: str = "float64", device=None, problem_options: dict | None = None,
+                 verbose: bool = True):
+        self.dtype_name = dtype
+        self.device = torch.device(device) if device is not None else None
+        self.problem_options = dict(problem_options or {})
+        super().__init__(N, design_file, data_path, skip_multiple)
+        self.verbose = verbose
+        self.problem: ElasticityProblem = self.problem
+
+    # ------------------------------------------------------------------ hooks
+    def get_name(self):
+        return "FEM"
+
+    def get_step_size(self):
+        return self.parameters.fem_step_size
+
+    def prepare_domain(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("FEMSolver needs a CUDA device: topomax_b200 has no CPU fallback")
+        if self.device is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.mesh = RectangleMesh(self.width, self.height,
+                                  int(self.width * self.N), int(self.height * self.N))
+        self.control_space = FunctionSpace(self.mesh, "CG", 1, dtype=self.dtype_name, device=self.device)
+
+    def create_rho(self, volume_fraction: float):
+        rho = Function(self.control_space)
+        rho.tensor.fill_(volume_fraction)
+        return rho
+
+    def create_problem(self, problem_parameters):
+        if isinstance(problem_parameters, ElasticityParameters):
+            return ElasticityProblem(self.mesh, self.control_space, self.parameters,
+                                     problem_parameters, **self.problem_options)
+        if isinstance(problem_parameters, FluidParameters):
+            raise NotImplementedError(
+                "the fluid problem is outside the accelerated path (SURVEY.md section 8f)")
+        raise ValueError(
+            f"Got unknown problem '{self.parameters.problem}' "
+            f"with problem parameters of type '{type(problem_parameters)}'"
+        )
+
+    def to_array(self, rho: Function) -> np.ndarray:
+        return rho.vector()[:]
+
+    def set_from_array(self, rho: Function, values: np.ndarray):
+        rho.vector()[:] = values
+
+    def integrate(self, values: np.ndarray) -> float:
+        t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.rho.tensor.dtype).to(self.device)
+        return self.problem.engine.integrate(t)
+
+    def save_rho(self, rho: Function, file_root: str):
+        rho_file = file_root + "_rho.dat"
+        save_function(rho, rho_file, "design")
+        return os.path.basename(rho_file)
+
+    # ------------------------------------------------------------------ device-resident step
+    def step_device(self, previous_psi: torch.Tensor, step_size: float, psi_out: torch.Tensor,
+                    rho_out: torch.Tensor):
+        """One mirror-descent step on the device (reference: Solver.step/project,
+        src/solver.py:149-194).  Returns sqrt(int (rho_new - expit(psi_prev))^2)."""
+        engine = self.problem.engine
+        gradient = self.problem.calculate_objective_gradient()
+        half = engine.md_halfstep(previous_psi, gradient.tensor, step_size)
+        c = find_volume_shift(
+            lambda c: engine.md_volume(half, c)[0] - self.volume,
+            lambda c: engine.md_volume(half, c)[1],
+        )
+        delta_sq, _ = engine.md_apply(half, c, previous_psi, psi_out, rho_out)
+        return float(np.sqrt(delta_sq))
+
+    def solve_generic(self):
+        """The base-class loop through the numpy hooks."""
+        return Solver.solve(self)
+
+    def solve(self, fixed_iterations: int | None = None):
+        """Device-resident loop; same schedule, stop rules, prints and files as Solver.solve.
+        ``fixed_iterations`` runs exactly that many steps without the stop rules (used to
+        compare designs "after a fixed iteration count")."""
+        total_timer, timer = Timer(), Timer()
+        rho = self.rho.tensor
+        psi = torch.log(rho / (1.0 - rho))
+        previous_psi = torch.empty_like(psi)
+
+        for penalty in self.parameters.penalties:
+            self.problem.set_penalization(penalty)
+            printer = Printer(self.verbose)
+            if self.verbose:
+                print(f"{'Penalty: ' + str(penalty):^{printer.title_length()}}")
+            printer.print_title()
+
+            timer.restart()
+            objectives = [self.problem.calculate_objective(self.rho)]
+            times = [timer.get_time_seconds()]
+            printer.set(iteration=0, objective=objectives[0], seconds=times[0])
+            deltas = []
+
+            k = 0
+            exit_condition = "Iteration did not converge"
+            n_iterations = MAX_ITERATIONS if fixed_iterations is None else fixed_iterations
+            for k in range(n_iterations):
+                printer.print_values()
+                if k % self.skip_multiple == 0 and fixed_iterations is None:
+                    self.save_iteration(self.rho, objectives[-1], k, penalty)
+
+                timer.restart()
+                previous_psi.copy_(psi)
+                try:
+                    difference = self.step_device(previous_psi, self.step_size_at_iter(k), psi, rho)
+                except ValueError as e:
+                    exit_condition = str(e)
+                    if self.verbose:
+                        print(f"EXIT: {exit_condition}!")
+                    break
+
+                objectives.append(self.problem.calculate_objective(self.rho))
+                times.append(timer.get_time_seconds())
+                printer.set(iteration=k + 1, objective=objectives[-1], seconds=times[-1],
+                            tolerance=self.tolerance(k), delta_rho=difference)
+                deltas.append(difference)
+                if fixed_iterations is not None:
+                    continue
+
+                stop = self.stop_condition(objectives, k)
+                if stop is None and difference < self.tolerance(k):
+                    stop = "Convergence treshold reached"
+                if stop is not None:
+                    exit_condition = stop
+                    printer.exit(stop)
+                    break
+            else:
+                if fixed_iterations is None:
+                    printer.exit(exit_condition)
+                else:
+                    exit_condition = ""
+
+            if fixed_iterations is None:
+                self.save_iteration(self.rho, objectives[-1], k + 1, penalty)
+                self.save_result(objectives, times, penalty, exit_condition)
+            self.last_result = dict(objectives=objectives, times=times, k_final=k + 1,
+                                    exit_condition=exit_condition, penalty=penalty, deltas=deltas)
+
+        if self.verbose:
+            print(f"\nTopology optimization took {total_timer.get_time_string()}")
+        return self.last_result

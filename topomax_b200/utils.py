@@ -1,0 +1,76 @@
+"""Result records, timer and root-finding helper of the optimiser
+(reference: src/utils.py:12-60,138-157).  The two records are pickled into the output tree;
+their ``__module__`` is set to the reference's ``src.utils`` so that files written here are
+readable by the reference's tools (``plot.py``) and vice versa (see ``src/utils.py`` shim)."""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+from scipy import optimize
+
+
+@dataclass
+class IterationData:
+    domain_size: tuple[float, float]
+    objective: float
+    iteration: int
+    rho_file: str
+    penalty: float
+
+
+@dataclass
+class SolverResult:
+    exit_condition: str
+    min_objective: float
+    objectives: list[float]
+    iterations: int
+    min_index: int
+    times: list[float]
+
+
+IterationData.__module__ = "src.utils"
+SolverResult.__module__ = "src.utils"
+
+
+class Timer:
+    def __init__(self):
+        self.restart()
+
+    def restart(self):
+        self.start_time = time.time()
+
+    def get_time_seconds(self) -> float:
+        return time.time() - self.start_time
+
+    def get_time_string(self) -> str:
+        return prettify_seconds(self.get_time_seconds())
+
+
+def prettify_seconds(seconds: float) -> str:
+    whole = int(seconds)
+    ms = (seconds - whole) * 1000
+    if whole == 0:
+        return f"{ms:.3g}ms"
+    h, rem = divmod(whole, 3600)
+    m, s = divmod(rem, 60)
+    parts = []
+    if h:
+        parts.append(f"{h:d}h")
+    if h or m:
+        parts.append(f"{m:d}m")
+    parts.append(f"{s:d}s")
+    parts.append(f"{ms:.0f}ms")
+    return " ".join(parts)
+
+
+def smart_brentq(f, initial_radius: float, max_radius: float):
+    """Brent's method on [-r, r], doubling r from ``initial_radius`` until f changes sign;
+    ValueError once r exceeds ``max_radius`` (reference: src/utils.py:138-157)."""
+    r = initial_radius
+    while r <= max_radius:
+        try:
+            return optimize.brentq(f, -r, r, full_output=True)
+        except ValueError:
+            r *= 2
+    raise ValueError("f(-max_radius) and f(max_radius) must have different signs!")
