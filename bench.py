@@ -1,0 +1,388 @@
+"""Benchmark of the hot path: mirror-descent iterations per second (BASELINE.json metric).
+
+A "step" is one full mirror-descent iteration of the reference's optimiser loop
+(src/solver.py:247-294): filtered sensitivity (1 Helmholtz solve) -> latent step + volume
+projection -> Helmholtz filter -> SIMP state solve -> compliance.  Steps W .. W+K-1 of the real
+optimisation are timed, so the density field evolves exactly as in a run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # CUDA arm
+    python bench.py --impl reference [--steps K] [--warmup W]        # CPU arm (oracle port)
+
+Workload at N=1: designs/short_cantilever.json at N=512 (configs[1] of BASELINE.json; the
+reference's N truncation makes it nx=1020, ny=510, 4 167 722 displacement dofs), fp64.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DESIGN = "short_cantilever"
+FULL_N = 512
+METRIC = "mirror_descent_iters_per_sec"
+UNIT = "iter/s"
+
+
+def workload_description(design, full_n, nx, ny):
+    n_u = 2 * (2 * nx + 1) * (2 * ny + 1)
+    return {
+        "workload": f"designs/{design}.json N={full_n} (nx={nx}, ny={ny}; vector-P2 / P1, fp64)",
+        "n_cells": nx * ny, "n_density_dofs": (nx + 1) * (ny + 1), "n_displacement_dofs": n_u,
+    }
+
+
+def mesh_of(design_path, full_n):
+    from topomax_b200.designs.design_parser import parse_design
+    dom, _ = parse_design(design_path)
+    n = int(full_n / min(dom.width, dom.height))
+    return int(dom.width * n), int(dom.height * n)
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks and throttle reasons during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.device_index), "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                except ValueError:
+                    continue
+                for name, flag in zip(names, f[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+        finally:
+            try:
+                os.remove(self.path)
+            except OSError:
+                pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=smax, reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (assembly + sparse direct solves)
+# --------------------------------------------------------------------------------------
+def oracle_iteration_seconds(design_path, sample_n, steps, warmup):
+    """Times `steps` mirror-descent iterations of the oracle at resolution sample_n."""
+    from oracle.md_oracle import OracleSolver, expit, logit
+
+    s = OracleSolver(sample_n, design_path)
+    s.problem.set_penalization(s.design["penalties"][0])
+    psi = logit(s.rho)
+    s.problem.calculate_objective(s.rho)
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        psi = s.step(psi.copy(), s.step_size_at_iter(k))
+        s.rho = expit(psi)
+        s.problem.calculate_objective(s.rho)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+    return times, s
+
+
+def pick_sample_n(full_n, steps_total, budget_s):
+    # sparse LU with nested dissection on a 2-D mesh: ~17 s at N=256 here, flops ~ N^3
+    for n in (full_n, 384, 256, 192, 128, 96, 64):
+        if n > full_n:
+            continue
+        est = 22.0 * (n / 256.0) ** 3 + 3.0 * (n / 256.0) ** 2
+        if est * steps_total <= budget_s:
+            return n
+    return 64
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    design_path = os.path.join(ROOT, "designs", f"{args.design}.json")
+    nx, ny = mesh_of(design_path, args.N)
+    warmup = min(args.warmup, 1)
+    sample_n = args.sample_n or pick_sample_n(args.N, warmup + args.steps, 240.0)
+    times, s = oracle_iteration_seconds(design_path, sample_n, args.steps, warmup)
+    total = sum(times)
+    value = len(times) / total
+    sample = (f"{len(times)} mirror-descent iteration(s) of the scipy oracle (CSR assembly + SuperLU with "
+              f"nested-dissection ordering in MUMPS' role) on designs/{args.design}.json at N={sample_n} "
+              f"(nx={s.mesh.nx}, ny={s.mesh.ny}, {s.mesh.nu} displacement dofs"
+              + ("" if sample_n == args.N else f"; bounded sample: the metric workload is N={args.N}") + ")")
+    cfg = workload_description(args.design, args.N, nx, ny)
+    cfg["reference_sample_N"] = sample_n
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count(),
+                         "split_seconds": {k: round(v, 3) for k, v in s.problem.timings.items()}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (CUDA arm) needs a GPU; use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from topomax_b200 import _lib
+    from topomax_b200.fem_solver import FEMSolver
+    from topomax_b200.solver import expit, logit
+
+    design_path = os.path.join(ROOT, "designs", f"{args.design}.json")
+    tmp = tempfile.mkdtemp(prefix="tm_bench_")
+    solver = FEMSolver(args.N, design_path, data_path=tmp, verbose=False, dtype=args.dtype,
+                       problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol})
+    problem, engine = solver.problem, solver.problem.engine
+    nx, ny = solver.mesh.nx, solver.mesh.ny
+    n1, nu = engine.n1, engine.nu
+    esize = 8 if args.dtype == "float64" else 4
+    problem.set_penalization(solver.parameters.penalties[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop: W warm-up + K timed mirror-descent iterations
+    rho = solver.rho.tensor
+    psi = torch.log(rho / (1.0 - rho))
+    prev = torch.empty_like(psi)
+    objectives = [problem.calculate_objective(solver.rho)]
+    k = 0
+    for _ in range(args.warmup):
+        prev.copy_(psi)
+        solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
+        objectives.append(problem.calculate_objective(solver.rho))
+        k += 1
+
+    engine.set_option(_lib.OPT_PROFILE, 1)
+    engine.profile_read()
+    log0 = len(problem.solve_log)
+    launches0 = engine.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        prev.copy_(psi)
+        solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
+        objectives.append(problem.calculate_objective(solver.rho))
+        k += 1
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    clocks = sampler.stop()
+    prof = engine.profile_read()
+    engine.set_option(_lib.OPT_PROFILE, 0)
+    launches = engine.launch_count() - launches0
+    solves = problem.solve_log[log0:]
+    pcg_iters = sum(s["iterations"] for s in solves)
+    fine_applies = sum(s["fine_applies"] for s in solves)
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the reference-facing hooks with HOST buffers (numpy in/out):
+    # Solver.step + calculate_objective of src/solver.py, every array crossing PCIe
+    traffic = {"h2d": 0, "d2h": 0}
+    pinned = torch.empty(n1, dtype=rho.dtype).pin_memory()
+
+    def to_device(values):
+        pinned.copy_(torch.from_numpy(np.ascontiguousarray(values, dtype=pinned.numpy().dtype)))
+        traffic["h2d"] += pinned.numel() * esize
+        return pinned.to(rho.device, non_blocking=True)
+
+    def to_host(tensor):
+        traffic["d2h"] += tensor.numel() * esize
+        return tensor.cpu().numpy()
+
+    solver.integrate = lambda values: engine.integrate(to_device(values))
+    solver.to_array = lambda f: to_host(f.tensor)
+    solver.set_from_array = lambda f, values: f.tensor.copy_(to_device(values))
+    psi_host = psi.cpu().numpy().copy()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        psi_host = solver.step(psi_host.copy(), solver.step_size_at_iter(k))
+        solver.set_from_array(solver.rho, expit(psi_host))
+        objectives.append(problem.calculate_objective(solver.rho))
+        k += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the fine-level operator with the fused
+    # Chebyshev-Jacobi epilogue (reads x, b, D^-1, d and xi; writes d, x_new)
+    peak, peak_src = measured_peak_hbm()
+    alg_bytes = {
+        "cheb": (6 * nu + n1) * esize, "resid": (3 * nu + n1) * esize,
+        "dot": (2 * nu + n1) * esize, "plain": (2 * nu + n1) * esize,
+    }
+    dominant = max(prof, key=lambda name: prof[name]["ms"])
+    d = prof[dominant]
+    avg_ms = d["ms"] / max(d["launches"], 1)
+    achieved = alg_bytes[dominant] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    kernel_ms = sum(p["ms"] for p in prof.values())
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src,
+        "kernel": f"elast_apply_kernel<{'double' if esize == 8 else 'float'},xi,EP_{dominant.upper()}>",
+        "algorithmic_bytes_per_launch": alg_bytes[dominant], "avg_launch_ms": avg_ms,
+        "launches_in_timed_region": d["launches"],
+        "share_of_step_time": kernel_ms / elapsed_ms,
+        "per_epilogue": {n: {"ms": p["ms"], "launches": p["launches"],
+                             "GBps": (alg_bytes[n] * p["launches"] / (p["ms"] * 1e-3) / 1e9) if p["ms"] > 0 else None}
+                         for n, p in prof.items()},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_n = args.sample_n or 256
+        times, s = oracle_iteration_seconds(design_path, sample_n, 1, 0)
+        cpu_baseline = {
+            "value": 1.0 / times[0], "unit": UNIT, "cores": 1, "kind": "port",
+            "host_cores_available": os.cpu_count(),
+            "sample": (f"1 mirror-descent iteration of the scipy oracle (CSR assembly + SuperLU, nested "
+                       f"dissection) on designs/{args.design}.json at N={sample_n} (nx={s.mesh.nx}, "
+                       f"ny={s.mesh.ny}, {s.mesh.nu} displacement dofs): a bounded sample, "
+                       f"{(nx * ny) / (s.mesh.nx * s.mesh.ny):.1f}x fewer cells than the GPU workload"),
+            "split_seconds": {k2: round(v, 3) for k2, v in s.problem.timings.items()},
+        }
+
+    cfg = workload_description(args.design, args.N, nx, ny)
+    cfg.update({
+        "preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
+        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (strip sharding: next)",
+        "l2": f"working set of a state solve ~{10 * nu * esize / 1e6:.0f} MB of lattice vectors, larger than the 126 MB L2",
+        "md_iterations_timed": [args.warmup, args.warmup + args.steps],
+    })
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if esize == 8 else "f32",
+        "data": "synthetic", "config": cfg, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": traffic["h2d"] // args.steps,
+                "d2h_bytes_per_step": traffic["d2h"] // args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "pcg": {"iterations_per_step": pcg_iters / args.steps,
+                "dof_iters_per_sec": world * pcg_iters * nu / (elapsed_ms * 1e-3),
+                "fine_operator_applies_per_step": fine_applies / args.steps,
+                "state_solves": len(solves),
+                "last_relative_residual": solves[-1]["relative_residual"] if solves else None},
+        "objective_trace": objectives[: args.warmup + args.steps + 1],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("cuda", "reference"), default="cuda")
+    ap.add_argument("--design", default=DESIGN)
+    ap.add_argument("--N", type=int, default=FULL_N)
+    ap.add_argument("--dtype", choices=("float64", "float32"), default="float64")
+    ap.add_argument("--preconditioner", choices=("multigrid", "jacobi"), default="multigrid")
+    ap.add_argument("--state_rtol", type=float, default=1e-10)
+    ap.add_argument("--sample_n", type=int, default=0, help="resolution of the CPU baseline sample")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

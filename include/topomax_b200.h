@@ -38,7 +38,8 @@ enum {
     TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
     TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps  (default 3)           */
     TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
-    TM_OPT_MG_COARSE_CELLS = 4 /* stop coarsening at max(nx,ny) <= this (default 2)      */
+    TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (default 2)     */
+    TM_OPT_PROFILE = 5       /* 1: time every fine-level operator launch with CUDA events */
 };
 
 /* Mesh, material and filter of one problem.
@@ -121,6 +122,12 @@ int tm_integrate(tm_handle h, const void* values, double* out);
 /* statistics of the last tm_state_solve: out[0] iterations, [1] V-cycles, [2] fine-level
  * operator applications, [3] levels, [4] lambda_max estimate of level 0 */
 int tm_last_solve_stats(tm_handle h, double* out, int n);
+
+/* Measurement support (bench.py): with TM_OPT_PROFILE on, out[0..3] = milliseconds spent in the
+ * fine-level operator kernel per epilogue (plain, dot, residual, Chebyshev) since the last
+ * read, out[4..7] = launch counts.  tm_launch_count: kernels launched by the library so far. */
+int tm_profile_read(tm_handle h, double* out, int n);
+long long tm_launch_count(void);
 
 /* Diagnostics for the parity tests: the multigrid hierarchy built for xi.
  *   op 0: out = A_level in          op 1: out(level) = P in(level+1)

@@ -336,18 +336,73 @@ def lame(E, nu):
     return lda, mu
 
 
-def solve_spd(A, b, free=None):
+def nested_dissection_order(Lx, Ly, leaf=6):
+    """Fill-reducing ordering of the Lx x Ly P2 lattice for the direct solver (MUMPS would get
+    one from METIS/SCOTCH): recursive bisection with single even lattice lines as separators
+    (nodes two lattice steps apart across an even line share no cell, hence no matrix entry)."""
+    pieces = []
+
+    def box(i0, i1, j0, j1):
+        jj, ii = np.meshgrid(np.arange(j0, j1 + 1), np.arange(i0, i1 + 1), indexing="ij")
+        pieces.append((jj * Lx + ii).ravel())
+
+    def split(lo, hi):
+        m = (lo + hi) // 2
+        m -= m & 1
+        if m <= lo:
+            m = lo + (2 if (lo & 1) == 0 else 1)
+        return m
+
+    def rec(i0, i1, j0, j1):
+        w, h = i1 - i0 + 1, j1 - j0 + 1
+        if w <= 0 or h <= 0:
+            return
+        if w <= leaf and h <= leaf:
+            return box(i0, i1, j0, j1)
+        if w >= h:
+            m = split(i0, i1)
+            if m >= i1:
+                return box(i0, i1, j0, j1)
+            rec(i0, m - 1, j0, j1)
+            rec(m + 1, i1, j0, j1)
+            pieces.append(np.arange(j0, j1 + 1) * Lx + m)
+        else:
+            m = split(j0, j1)
+            if m >= j1:
+                return box(i0, i1, j0, j1)
+            rec(i0, i1, j0, m - 1)
+            rec(i0, i1, m + 1, j1)
+            pieces.append(m * Lx + np.arange(i0, i1 + 1))
+
+    rec(0, Lx - 1, 0, Ly - 1)
+    order = np.concatenate(pieces)
+    assert order.size == Lx * Ly
+    return order
+
+
+def solve_spd(A, b, free=None, lattice=None):
     """Sparse direct solve (SuperLU in MUMPS' role, FEM_src/pde_solver.py:130-131).
 
     With ``free`` given, Dirichlet dofs are eliminated symmetrically: identical to the
     reference's row-zero/unit-diagonal ``bc.apply`` because the prescribed value is 0.
+    ``lattice=(Lx, Ly)`` (vector-P2 systems) switches on the nested-dissection ordering, which
+    is what keeps the factorisation affordable beyond ~1e5 dofs.
     """
     if free is None:
         return spla.splu(A.tocsc()).solve(b)
-    idx = np.flatnonzero(free)
-    Aff = A[idx][:, idx].tocsc()
     x = np.zeros_like(b)
-    x[idx] = spla.splu(Aff, permc_spec="MMD_AT_PLUS_A").solve(b[idx])
+    if lattice is not None and A.shape[0] > 20000:
+        nodes = nested_dissection_order(*lattice)
+        idx = np.stack([2 * nodes, 2 * nodes + 1], 1).ravel()
+        idx = idx[free[idx]]
+        Aff = A[idx][:, idx].tocsc()
+        lu = spla.splu(Aff, permc_spec="NATURAL", diag_pivot_thresh=0.0,
+                       options=dict(SymmetricMode=True))
+    else:
+        idx = np.flatnonzero(free)
+        Aff = A[idx][:, idx].tocsc()
+        lu = spla.splu(Aff, permc_spec="MMD_AT_PLUS_A")
+    x[idx] = lu.solve(b[idx])
     return x
 
 

@@ -114,7 +114,7 @@ class OracleElasticityProblem:
         t0 = time.perf_counter()
         K = self.mesh.elasticity_matrix(xi, self.lda, self.mu, self.penalization, self.minimum)
         t1 = time.perf_counter()
-        u = solve_spd(K, self.b_bc, free=~self.fixed)
+        u = solve_spd(K, self.b_bc, free=~self.fixed, lattice=(self.mesh.Lx, self.mesh.Ly))
         t2 = time.perf_counter()
         self.timings["assemble"] += t1 - t0
         self.timings["solve"] += t2 - t1

@@ -16,6 +16,7 @@ TM_F64, TM_F32 = 0, 1
 SIDE_LEFT, SIDE_RIGHT, SIDE_TOP, SIDE_BOTTOM = 1, 2, 4, 8
 PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
 OPT_PRECOND, OPT_CHEB_DEGREE, OPT_CHECK_EVERY, OPT_MG_COARSE_CELLS = 1, 2, 3, 4
+OPT_PROFILE = 5
 OPT_CHEB_RATIO, OPT_EIG_SAFETY = 100, 101
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOT_CONVERGED = -1, -2, -3, -4
@@ -25,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "tm_create", "tm_destroy", "tm_set_stream", "tm_set_option", "tm_last_error", "tm_version",
     "tm_load_vector", "tm_filter_apply", "tm_elast_matvec", "tm_elast_diag", "tm_state_solve",
     "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate",
-    "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info",
+    "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
 )
 
 
@@ -95,6 +96,8 @@ def load_library() -> ctypes.CDLL:
         "tm_md_apply": ([V, V, D, V, V, V, POINTER(D), POINTER(D)], I),
         "tm_integrate": ([V, V, POINTER(D)], I),
         "tm_last_solve_stats": ([V, POINTER(D), I], I),
+        "tm_profile_read": ([V, POINTER(D), I], I),
+        "tm_launch_count": ([], ctypes.c_longlong),
         "tm_mg_debug": ([V, V, I, I, V, V], I),
         "tm_mg_level_info": ([V, I, POINTER(I), POINTER(I)], I),
     }

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <climits>
 #include <cstdint>
 #include <cstdio>
@@ -18,6 +19,8 @@ namespace tmx {
 // ---------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
 const char* last_error();
+// every kernel launch of the library passes through TM_CHECK_LAUNCH (tm_launch_count)
+extern std::atomic<long long> g_launches;
 
 struct CudaFailure {
     std::string what;
@@ -32,7 +35,11 @@ struct CudaFailure {
         }                                                                                      \
     } while (0)
 
-#define TM_CHECK_LAUNCH() TM_CUDA(cudaGetLastError())
+#define TM_CHECK_LAUNCH()            \
+    do {                             \
+        ++::tmx::g_launches;         \
+        TM_CUDA(cudaGetLastError()); \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------
 // lattice description of one multigrid level

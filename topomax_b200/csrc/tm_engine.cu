@@ -1,5 +1,6 @@
 // libtopomax_b200: engine (workspace, solvers) and the C ABI of include/topomax_b200.h.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -14,6 +15,7 @@
 namespace tmx {
 
 static thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 const char* last_error() { return g_error.c_str(); }
 
@@ -73,6 +75,7 @@ class EngineBase {
     virtual void last_stats(double* out, int n) = 0;
     virtual void mg_debug(const void* xi, int op, int level, const void* in, void* out) = 0;
     virtual int mg_level_info(int level, int* info) = 0;
+    virtual void profile_read(double* out, int n) = 0;
     int device = 0;
 };
 
@@ -148,6 +151,7 @@ class Engine : public EngineBase {
                 break;
             case 100: cheb_ratio_ = value; break;
             case 101: eig_safety_ = value; break;
+            case TM_OPT_PROFILE: profile_ = value != 0.0; break;
             default: throw Invalid{"unknown option " + std::to_string(opt)};
         }
     }
@@ -465,6 +469,18 @@ class Engine : public EngineBase {
         strips = ceil_div(g.ny, a.rows_per_strip);
         dim3 grd(bx, strips), blk(kApplyWarps * 32);
         if ((long)bx * strips > rs_.capacity) throw Invalid{"reduction scratch too small"};
+        const bool fine = g.nx == nx_ && g.ny == ny_;
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (fine && profile_) {
+            if (prof_free_.empty()) {
+                TM_CUDA(cudaEventCreate(&ev.first));
+                TM_CUDA(cudaEventCreate(&ev.second));
+            } else {
+                ev = prof_free_.back();
+                prof_free_.pop_back();
+            }
+            TM_CUDA(cudaEventRecord(ev.first, stream_));
+        }
 #define TM_LAUNCH_APPLY(ST, EPV) \
     elast_apply_kernel<T, ST, EPV><<<grd, blk, 0, stream_>>>(g, a)
         if (!stored) {
@@ -484,7 +500,29 @@ class Engine : public EngineBase {
         }
 #undef TM_LAUNCH_APPLY
         TM_CHECK_LAUNCH();
-        if (g.nx == nx_ && g.ny == ny_) ++stats_fine_applies_;
+        if (fine && profile_) {
+            TM_CUDA(cudaEventRecord(ev.second, stream_));
+            prof_pending_.push_back({ep, ev});
+        }
+        if (fine) ++stats_fine_applies_;
+    }
+
+    // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
+    void profile_read(double* out, int n) override {
+        double ms[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (auto& p : prof_pending_) {
+            float t = 0.f;
+            TM_CUDA(cudaEventElapsedTime(&t, p.second.first, p.second.second));
+            ms[p.first] += t;
+            cnt[p.first] += 1;
+            prof_free_.push_back(p.second);
+        }
+        prof_pending_.clear();
+        for (int i = 0; i < 4; ++i) {
+            if (i < n) out[i] = ms[i];
+            if (4 + i < n) out[4 + i] = cnt[i];
+        }
     }
 
     void launch_diag(const LevelGeom<T>& g, bool stored, T* dinv) {
@@ -780,6 +818,9 @@ class Engine : public EngineBase {
     DevBuf<double> coarse_A_;
 
     long stats_fine_applies_ = 0, stats_vcycles_ = 0;
+    bool profile_ = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending_;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free_;
     int stats_iters_ = 0;
 };
 
@@ -939,6 +980,11 @@ int tm_last_solve_stats(tm_handle h, double* out, int n) {
     return guarded(h, [&] { h->impl->last_stats(out, n); });
 }
 
+int tm_profile_read(tm_handle h, double* out, int n) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->profile_read(out, n); });
+}
+long long tm_launch_count(void) { return tmx::g_launches.load(); }
 int tm_mg_debug(tm_handle h, const void* xi, int op, int level, const void* in, void* out) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->mg_debug(xi, op, level, in, out); });

@@ -208,6 +208,17 @@ class Engine:
         return {"iterations": int(buf[0]), "vcycles": int(buf[1]), "fine_applies": int(buf[2]),
                 "levels": int(buf[3]), "lambda_max": buf[4]}
 
+    def profile_read(self) -> dict:
+        """Milliseconds / launch counts of the fine-level operator kernel per epilogue since the
+        last read (needs ``set_option(OPT_PROFILE, 1)``)."""
+        buf = (c_double * 8)()
+        _lib.check(self.lib.tm_profile_read(self._h, buf, 8))
+        names = ("plain", "dot", "resid", "cheb")
+        return {n: {"ms": buf[i], "launches": int(buf[4 + i])} for i, n in enumerate(names)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.tm_launch_count())
+
     # ---------------------------------------------------------------- multigrid diagnostics
     def mg_levels(self):
         """[(nx, ny, dl, dr, db, dt)] per level of the hierarchy."""
