@@ -234,6 +234,9 @@ def run_cuda_arm(args):
     sampler.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    in_profiler = bool(os.environ.get("TM_PROFILER_RANGE"))  # ncu --profile-from-start off
+    if in_profiler:
+        torch.cuda.profiler.start()
     start.record()
     for _ in range(args.steps):
         prev.copy_(psi)
@@ -242,6 +245,8 @@ def run_cuda_arm(args):
         k += 1
     stop.record()
     barrier()
+    if in_profiler:
+        torch.cuda.profiler.stop()
     elapsed_ms = start.elapsed_time(stop)
     clocks = sampler.stop()
     prof = engine.profile_read()

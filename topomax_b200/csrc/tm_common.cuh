@@ -61,10 +61,21 @@ struct LevelGeom {
     const T* W;
     T simp_min;
     Material<T> mat;
+    // Row-strip sharding (one GPU: j_off = 0 and every row is owned).  A rank holds its own
+    // lattice rows plus halo rows as ONE local lattice that kernels treat as a standalone
+    // mesh; they only WRITE rows in [own_j0, own_j1), and the Dirichlet thresholds db/dt
+    // are compared against the global row index j + j_off.
+    int j_off, own_j0, own_j1;
 
     __host__ __device__ bool fixed(int i, int j) const {
-        return i <= dl || i >= dr || j <= db || j >= dt;
+        const int jg = j + j_off;
+        return i <= dl || i >= dr || jg <= db || jg >= dt;
     }
+    __host__ __device__ bool row_fixed(int j) const {
+        const int jg = j + j_off;
+        return jg <= db || jg >= dt;
+    }
+    __host__ __device__ bool owns_row(int j) const { return j >= own_j0 && j < own_j1; }
 };
 
 // ---------------------------------------------------------------------------------------

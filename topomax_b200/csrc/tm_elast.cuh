@@ -56,6 +56,44 @@ struct ApplyArgs {
 
 constexpr int kApplyWarps = 4;  // warps (column groups) per block
 
+// what happens to one owned node once its row of K x is complete (v), x being the input there
+template <typename T, int EP>
+__device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, bool fixed, T v0, T v1,
+                                               T x0, T x1, double& dot) {
+    using V2 = typename Vec2<T>::type;
+    if (fixed) {  // identity row
+        v0 = x0;
+        v1 = x1;
+    }
+    V2 out;
+    if (EP == EP_PLAIN || EP == EP_DOT) {
+        out.x = v0;
+        out.y = v1;
+        if (EP == EP_DOT) dot += (double)x0 * (double)v0 + (double)x1 * (double)v1;
+    } else {
+        const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
+        const T r0 = bb.x - v0, r1 = bb.y - v1;
+        if (EP == EP_RESID) {
+            out.x = r0;
+            out.y = r1;
+        } else {
+            const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
+            V2 dd;
+            dd.x = a.c2 * di.x * r0;
+            dd.y = a.c2 * di.y * r1;
+            if (a.c1 != T(0)) {
+                const V2 dold = reinterpret_cast<const V2*>(a.d)[n];
+                dd.x += a.c1 * dold.x;
+                dd.y += a.c1 * dold.y;
+            }
+            reinterpret_cast<V2*>(a.d)[n] = dd;
+            out.x = x0 + dd.x;
+            out.y = x1 + dd.y;
+        }
+    }
+    reinterpret_cast<V2*>(a.y)[n] = out;
+}
+
 template <typename T, bool STORED_W, int EP>
 __global__ void __launch_bounds__(kApplyWarps * 32, 2)
 elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
@@ -150,7 +188,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                 T Xm[9][2];  // Dirichlet columns of the operator: masked input
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const bool rowfix = (j0 + r) <= g.db || (j0 + r) >= g.dt;
+                    const bool rowfix = g.row_fixed(j0 + r);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const bool f = rowfix || colfix[c];
@@ -174,7 +212,8 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int j = j0 + r;
-                    const bool rowfix = j <= g.db || j >= g.dt;
+                    if (!g.owns_row(j)) continue;
+                    const bool rowfix = g.row_fixed(j);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (c == 1 && !own_c1) continue;
@@ -183,39 +222,8 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                             v0 += carry[c][0];
                             v1 += carry[c][1];
                         }
-                        const T x0 = X[3 * r + c][0], x1 = X[3 * r + c][1];
-                        if (rowfix || colfix[c]) {
-                            v0 = x0;
-                            v1 = x1;
-                        }
-                        const size_t n = (size_t)j * Lx + i0 + c;
-                        V2 out;
-                        if (EP == EP_PLAIN || EP == EP_DOT) {
-                            out.x = v0;
-                            out.y = v1;
-                            if (EP == EP_DOT) dot += (double)x0 * (double)v0 + (double)x1 * (double)v1;
-                        } else {
-                            const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
-                            const T r0 = bb.x - v0, r1 = bb.y - v1;
-                            if (EP == EP_RESID) {
-                                out.x = r0;
-                                out.y = r1;
-                            } else {
-                                const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
-                                V2 dd;
-                                dd.x = a.c2 * di.x * r0;
-                                dd.y = a.c2 * di.y * r1;
-                                if (a.c1 != T(0)) {
-                                    const V2 dold = reinterpret_cast<const V2*>(a.d)[n];
-                                    dd.x += a.c1 * dold.x;
-                                    dd.y += a.c1 * dold.y;
-                                }
-                                reinterpret_cast<V2*>(a.d)[n] = dd;
-                                out.x = x0 + dd.x;
-                                out.y = x1 + dd.y;
-                            }
-                        }
-                        yv[n] = out;
+                        apply_epilogue<T, EP>(a, (size_t)j * Lx + i0 + c, rowfix || colfix[c], v0, v1,
+                                              X[3 * r + c][0], X[3 * r + c][1], dot);
                     }
                 }
             }
@@ -226,46 +234,14 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             }
         }
         // the lattice's top row belongs to the last strip
-        if (iy1 == g.ny && owner) {
+        if (iy1 == g.ny && owner && g.owns_row(2 * g.ny)) {
             const int j = 2 * g.ny;
-            const bool rowfix = j <= g.db || j >= g.dt;
+            const bool rowfix = g.row_fixed(j);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 if (c == 1 && !own_c1) continue;
-                T v0 = carry[c][0], v1 = carry[c][1];
-                const T x0 = X[6 + c][0], x1 = X[6 + c][1];
-                if (rowfix || colfix[c]) {
-                    v0 = x0;
-                    v1 = x1;
-                }
-                const size_t n = (size_t)j * Lx + i0 + c;
-                V2 out;
-                if (EP == EP_PLAIN || EP == EP_DOT) {
-                    out.x = v0;
-                    out.y = v1;
-                    if (EP == EP_DOT) dot += (double)x0 * (double)v0 + (double)x1 * (double)v1;
-                } else {
-                    const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
-                    const T r0 = bb.x - v0, r1 = bb.y - v1;
-                    if (EP == EP_RESID) {
-                        out.x = r0;
-                        out.y = r1;
-                    } else {
-                        const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
-                        V2 dd;
-                        dd.x = a.c2 * di.x * r0;
-                        dd.y = a.c2 * di.y * r1;
-                        if (a.c1 != T(0)) {
-                            const V2 dold = reinterpret_cast<const V2*>(a.d)[n];
-                            dd.x += a.c1 * dold.x;
-                            dd.y += a.c1 * dold.y;
-                        }
-                        reinterpret_cast<V2*>(a.d)[n] = dd;
-                        out.x = x0 + dd.x;
-                        out.y = x1 + dd.y;
-                    }
-                }
-                yv[n] = out;
+                apply_epilogue<T, EP>(a, (size_t)j * Lx + i0 + c, rowfix || colfix[c], carry[c][0],
+                                      carry[c][1], X[6 + c][0], X[6 + c][1], dot);
             }
         }
     }
@@ -283,7 +259,7 @@ template <typename T, bool STORED_W>
 __global__ void elast_diag_kernel(const LevelGeom<T> g, const DiagTable tab, T* __restrict__ dinv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= g.Lx || j >= g.Ly) return;
+    if (i >= g.Lx || j >= g.Ly || !g.owns_row(j)) return;
     const size_t n = (size_t)j * g.Lx + i;
     if (g.fixed(i, j)) {
         dinv[2 * n] = T(1);

@@ -8,6 +8,7 @@
 
 #include "../../include/topomax_b200.h"
 #include "tm_elast.cuh"
+#include "tm_filter_pcg.cuh"
 #include "tm_mg.cuh"
 #include "tm_p1.cuh"
 #include "tm_vec.cuh"
@@ -135,7 +136,13 @@ class Engine : public EngineBase {
         cudaFree(rs_.counter);
         cudaFree(sc_);
         cudaFree(eig_sc_);
+        cudaFree(filter_part_);
         cudaFreeHost(h_sc_);
+        for (auto& p : prof_pending_) prof_free_.push_back(p.second);
+        for (auto& e : prof_free_) {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
     }
 
     void set_stream(cudaStream_t s) override { stream_ = s; }
@@ -152,6 +159,9 @@ class Engine : public EngineBase {
             case 100: cheb_ratio_ = value; break;
             case 101: eig_safety_ = value; break;
             case TM_OPT_PROFILE: profile_ = value != 0.0; break;
+            case 102: blocks_per_sm_target_ = std::max(1, (int)value); break;
+            case 103: min_rows_per_strip_ = std::max(1, (int)value); break;
+            case 104: filter_persistent_ = value != 0.0; break;
             default: throw Invalid{"unknown option " + std::to_string(opt)};
         }
     }
@@ -216,6 +226,45 @@ class Engine : public EngineBase {
             p1_diag_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(p1_, alpha, beta, f_dinv_.p);
             TM_CHECK_LAUNCH();
             f_dinv_ready_ = true;
+        }
+        if (kind != 0 && kind != 1) throw Invalid{"rhs_kind must be 0 or 1"};
+        if (filter_persistent_) {
+            // whole solve in one cooperative launch (tm_filter_pcg.cuh)
+            const T* rhs_p = in;
+            if (kind == 0) {
+                p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
+                rhs_p = f_rhs_.p;
+                if (out != in)
+                    TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            } else {
+                TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
+            }
+            f_p2_.ensure(n1_);
+            if (filter_blocks_ == 0) {
+                int per_sm = 0;
+                TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pcg_kernel<T>, 256, 0));
+                if (per_sm < 1) throw Invalid{"filter_pcg_kernel cannot be made resident"};
+                filter_blocks_ = std::min(per_sm, 4) * num_sms_;
+                TM_CUDA(cudaMalloc(&filter_part_, sizeof(double) * (4 * (size_t)filter_blocks_ + 4)));
+            }
+            const int nb = (int)std::max<size_t>(1, std::min<size_t>(filter_blocks_, (n1_ + 255) / 256));
+            FilterPcgArgs fa;
+            fa.g = p1_; fa.alpha = alpha; fa.beta = beta; fa.rtol = rtol; fa.maxit = maxit;
+            fa.partA = filter_part_;
+            fa.partB = filter_part_ + filter_blocks_;
+            fa.result = filter_part_ + 4 * (size_t)filter_blocks_;
+            const T* dinv_p = f_dinv_.p;
+            T *x_p = out, *r_p = f_r_.p, *Ap_p = f_Ap_.p, *p0_p = f_p_.p, *p1_p = f_p2_.p;
+            void* kargs[] = {&fa, &rhs_p, &dinv_p, &x_p, &r_p, &Ap_p, &p0_p, &p1_p};
+            TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_pcg_kernel<T>, dim3(nb), dim3(256), kargs, 0, stream_));
+            ++g_launches;
+            TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, fa.result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
+            TM_CUDA(cudaStreamSynchronize(stream_));
+            SolveStats st;
+            st.iters = (int)h_sc_[64];
+            st.relres = h_sc_[65];
+            st.converged = h_sc_[66] != 0.0;
+            return st;
         }
         const T* rhs;
         if (kind == 0) {
@@ -434,6 +483,7 @@ class Engine : public EngineBase {
         LevelGeom<T> g;
         g.nx = nx; g.ny = ny; g.Lx = 2 * nx + 1; g.Ly = 2 * ny + 1;
         g.dl = -1; g.db = -1; g.dr = INT_MAX; g.dt = INT_MAX;
+        g.j_off = 0; g.own_j0 = 0; g.own_j1 = g.Ly;
         g.xi = nullptr; g.W = nullptr;
         g.simp_min = (T)cfg_.simp_min;
         g.mat = make_material<T>(cfg_.lame_lambda, cfg_.lame_mu, hx_, hy_);
@@ -461,11 +511,13 @@ class Engine : public EngineBase {
     void launch_apply(const LevelGeom<T>& g, bool stored, int ep, ApplyArgs<T> a) {
         const int ncg = ceil_div(g.nx + 1, 31);
         const int bx = ceil_div(ncg, kApplyWarps);
-        // enough blocks for ~2 waves at 2 resident blocks per SM, strips of 8..64 cell rows
-        int strips = ceil_div(4L * num_sms_, bx);
-        strips = std::min(strips, std::max(1, g.ny / 8));
+        // A strip re-evaluates the cell row below it ((H+1)/H flops) and marches H rows
+        // serially: large meshes get H up to 64, small (latency-bound) levels H down to 1 so
+        // that there are always ~4 blocks per SM to overlap the march latencies.
+        int strips = ceil_div((long)blocks_per_sm_target_ * num_sms_, bx);
+        strips = std::min(strips, g.ny);
         strips = std::max(strips, ceil_div(g.ny, 64));
-        a.rows_per_strip = ceil_div(g.ny, strips);
+        a.rows_per_strip = std::max(min_rows_per_strip_, ceil_div(g.ny, strips));
         strips = ceil_div(g.ny, a.rows_per_strip);
         dim3 grd(bx, strips), blk(kApplyWarps * 32);
         if ((long)bx * strips > rs_.capacity) throw Invalid{"reduction scratch too small"};
@@ -819,6 +871,11 @@ class Engine : public EngineBase {
 
     long stats_fine_applies_ = 0, stats_vcycles_ = 0;
     bool profile_ = false;
+    int blocks_per_sm_target_ = 4, min_rows_per_strip_ = 1;
+    bool filter_persistent_ = true;
+    int filter_blocks_ = 0;
+    double* filter_part_ = nullptr;
+    DevBuf<T> f_p2_;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free_;
     int stats_iters_ = 0;
