@@ -6,7 +6,8 @@
  * code whose arithmetic it replaces.  Conventions:
  *   - plain C types only; every array argument is a CUDA DEVICE pointer owned by the caller
  *     (the Python host passes torch.Tensor.data_ptr()); element type = the engine dtype;
- *   - the engine owns only scratch memory; no ownership is transferred;
+ *   - the engine owns only scratch memory; no ownership is transferred; on a sharded engine
+ *     the non-const field arguments (xi, x, in) get their halo rows refreshed in place;
  *   - every function returns 0 on success, a negative TM_ERR_* code otherwise, and
  *     tm_last_error() returns the message of the last failure on the calling thread;
  *   - work is enqueued on the stream given to tm_set_stream (default: the legacy stream);
@@ -55,6 +56,12 @@ typedef struct {
     int fixed_sides; /* TM_SIDE_* bitmask */
     int dtype;       /* TM_F64 / TM_F32 */
     int device;      /* CUDA device ordinal */
+    /* row-strip sharding, one process per GPU: this engine is rank `rank` of
+     * `nranks` (1 = unsharded).  nx, ny, width, height always describe the GLOBAL mesh; the
+     * library partitions the cell rows itself (tm_local_layout) and every array argument of a
+     * sharded engine is the rank-LOCAL array (owned rows + halo rows).  mg_dist_levels: how
+     * many multigrid levels stay sharded (0 = automatic). */
+    int rank, nranks, mg_dist_levels;
 } tm_config;
 
 /* reference: designs/definitions.py Force / Traction, evaluated by BodyForce.eval and
@@ -74,6 +81,17 @@ int tm_set_option(tm_handle h, int option, double value);
 const char* tm_last_error(void);
 const char* tm_version(void);
 
+/* Sharding plumbing.  Rank 0 calls tm_comm_unique_id (an ncclUniqueId, 128 bytes), the host
+ * broadcasts it (torch.distributed), every rank calls tm_comm_init: the engine then owns an
+ * NCCL communicator for halo rows (ncclSend/Recv), dot products (ncclAllReduce) and the gather
+ * of the first replicated multigrid level (ncclBroadcast).
+ * tm_local_layout: out = {rank, nranks, nx, ny_global, cl0, cl1, c0, c1, owns_top, dist_levels}:
+ * this rank stores cell rows [cl0, cl1) and owns [c0, c1); local P1 arrays are
+ * (cl1-cl0+1) x (nx+1), local P2 arrays (2(cl1-cl0)+1) x (2nx+1) x 2. */
+int tm_comm_unique_id(char* id128);
+int tm_comm_init(tm_handle h, const char* id128);
+int tm_local_layout(tm_handle h, int* out, int n);
+
 /* b = int f_h.v dx + int t_h.v ds (not yet zeroed on the fixed sides).
  * reference: l_func, FEM_src/elasisity_problem.py:120-124, assembled once by
  * SmartMumpsSolver.__init__ (FEM_src/pde_solver.py:102-104). */
@@ -83,21 +101,21 @@ int tm_load_vector(tm_handle h, const tm_loads* loads, void* b);
  * rhs_kind 0: `in` is a nodal P1 function, rhs = M1 in   (HelmholtzFilter.apply on a Function)
  * rhs_kind 1: `in` is an assembled right-hand side       (apply on a UFL expression)
  * reference: FEM_src/filter.py:27-41 + SmartMumpsSolver.solve, FEM_src/pde_solver.py:106-133. */
-int tm_filter_apply(tm_handle h, int rhs_kind, const void* in, void* out, double rtol, int maxit,
+int tm_filter_apply(tm_handle h, int rhs_kind, void* in, void* out, double rtol, int maxit,
                     int* iters, double* relres);
 
 /* y = K(xi) x with identity rows on the fixed sides; penalty must be 3.
  * reference: a_func, FEM_src/elasisity_problem.py:112-118 assembled in
  * FEM_src/pde_solver.py:117-119, bc.apply :125. */
-int tm_elast_matvec(tm_handle h, const void* xi, double penalty, const void* x, void* y);
+int tm_elast_matvec(tm_handle h, void* xi, double penalty, void* x, void* y);
 /* dinv = 1 / diag K(xi) (1 on fixed dofs) */
-int tm_elast_diag(tm_handle h, const void* xi, double penalty, void* dinv);
+int tm_elast_diag(tm_handle h, void* xi, double penalty, void* dinv);
 
 /* u = K(xi)^-1 b with u = 0 on the fixed sides, by preconditioned CG to ||r|| <= rtol ||b||.
  * flags bit 0: use the incoming u as initial guess.
  * reference: ElasticityProblem.forward, FEM_src/elasisity_problem.py:168-169 ->
  * SmartMumpsSolver.solve, FEM_src/pde_solver.py:106-133 (LUSolver("mumps")). */
-int tm_state_solve(tm_handle h, const void* xi, double penalty, const void* b, void* u,
+int tm_state_solve(tm_handle h, void* xi, double penalty, const void* b, void* u,
                    double rtol, int maxit, int flags, int* iters, double* relres);
 
 /* *out = u . b  (compliance; reference: FEM_src/elasisity_problem.py:161-164) */
@@ -134,7 +152,7 @@ long long tm_launch_count(void);
  *   op 2: out(level+1) = P^T in(level)   op 3: out = V-cycle(in) on level 0
  *   op 4: out = A_coarsest^-1 in    op 5: out = inverse diagonal of the level
  * tm_mg_level_info: info6 = {nx, ny, dl, dr, db, dt} of `level`; *nlevels = level count. */
-int tm_mg_debug(tm_handle h, const void* xi, int op, int level, const void* in, void* out);
+int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* out);
 int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels);
 
 #ifdef __cplusplus

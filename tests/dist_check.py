@@ -1,0 +1,96 @@
+"""Sharded path vs single-GPU path on the same inputs.  Launched by tests/test_gpu_sharded.py as
+    python -m torch.distributed.run --nproc-per-node 2 tests/dist_check.py
+Every rank builds the global inputs from the same seed, runs the sharded engine on its strip and
+the gathered result is compared with an unsharded engine on rank 0's GPU."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from topomax_b200 import _lib  # noqa: E402
+from topomax_b200.designs.definitions import Side  # noqa: E402
+from topomax_b200.engine import Engine  # noqa: E402
+from topomax_b200 import sharding as sh  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    report = {}
+    for case, (nx, ny, fixed, ld) in enumerate([(40, 32, [Side.LEFT], 2), (70, 52, [Side.BOTTOM, Side.TOP], 1),
+                                                (96, 64, [Side.LEFT, Side.RIGHT], 3)]):
+        W, H = 0.25 * nx, 0.25 * ny
+        kw = dict(lame_lambda=1.3, lame_mu=0.8, filter_radius=0.3, fixed_sides=fixed)
+        eng = Engine(nx, ny, W, H, rank=rank, nranks=world, dist_levels=ld, **kw)
+        eng.init_comm()
+        ref = Engine(nx, ny, W, H, **kw)
+        rng = np.random.default_rng(100 + case)
+        n1, nu = (nx + 1) * (ny + 1), 2 * (2 * nx + 1) * (2 * ny + 1)
+        xi_g, x_g, rho_g = 0.05 + 0.9 * rng.random(n1), rng.standard_normal(nu), rng.random(n1)
+        rhs_g = rng.standard_normal(n1)
+        t = lambda a: torch.as_tensor(a, dtype=torch.float64).cuda()
+        tag = f"case{case}"
+
+        # operator and diagonal
+        y = sh.gather_p2(eng, eng.elast_matvec(sh.local_p1(eng, xi_g), sh.local_p2(eng, x_g)))
+        y_ref = ref.elast_matvec(t(xi_g), t(x_g)).cpu().numpy()
+        report[tag + "_matvec"] = rel(y, y_ref)
+        d = sh.gather_p2(eng, eng.elast_diag_inverse(sh.local_p1(eng, xi_g)))
+        report[tag + "_diag"] = rel(d, ref.elast_diag_inverse(t(xi_g)).cpu().numpy())
+
+        # filter, both right-hand-side kinds
+        f, info = eng.filter_apply(sh.local_p1(eng, rho_g), assembled=False, rtol=1e-13)
+        f_ref, _ = ref.filter_apply(t(rho_g), assembled=False, rtol=1e-13)
+        report[tag + "_filter0"] = rel(sh.gather_p1(eng, f), f_ref.cpu().numpy())
+        g, _ = eng.filter_apply(sh.local_p1(eng, rhs_g), assembled=True, rtol=1e-13)
+        g_ref, _ = ref.filter_apply(t(rhs_g), assembled=True, rtol=1e-13)
+        report[tag + "_filter1"] = rel(sh.gather_p1(eng, g), g_ref.cpu().numpy())
+
+        # loads, state solve (multigrid and Jacobi), compliance, sensitivity
+        from topomax_b200.designs.definitions import CircularRegion, Force, Traction
+        force = Force(CircularRegion((0.6 * W, 0.5 * H), 0.2 * H), (0.0, -1.0))
+        tr = [Traction(Side.TOP, 0.5 * W, 0.3 * W, (0.0, -3.0))]
+        b = eng.load_vector(force, tr)
+        b_ref = ref.load_vector(force, tr)
+        report[tag + "_load"] = rel(sh.gather_p2(eng, b), b_ref.cpu().numpy())
+        for name, pre in (("mg", _lib.PRECOND_MULTIGRID), ("jacobi", _lib.PRECOND_JACOBI)):
+            eng.set_option(_lib.OPT_PRECOND, pre)
+            ref.set_option(_lib.OPT_PRECOND, pre)
+            u, info = eng.state_solve(sh.local_p1(eng, xi_g), b, rtol=1e-11)
+            u_ref, info_ref = ref.state_solve(t(xi_g), b_ref, rtol=1e-11)
+            ug = sh.gather_p2(eng, u)
+            report[f"{tag}_solve_{name}"] = float(np.linalg.norm(ug - u_ref.cpu().numpy()) /
+                                                  np.linalg.norm(u_ref.cpu().numpy()))
+            report[f"{tag}_iters_{name}"] = [info.iterations, info_ref.iterations]
+        c, c_ref = eng.dot_p2(u, b), ref.dot_p2(u_ref, b_ref)
+        report[tag + "_compliance"] = abs(c - c_ref) / abs(c_ref)
+        s = eng.sens_rhs(sh.local_p1(eng, xi_g), u)
+        s_ref = ref.sens_rhs(t(xi_g), u_ref)
+        report[tag + "_sens"] = rel(sh.gather_p1(eng, s), s_ref.cpu().numpy())
+
+        # mirror-descent reductions
+        half = sh.local_p1(eng, rhs_g)
+        v, dv = eng.md_volume(half, 0.2)
+        v_ref, dv_ref = ref.md_volume(t(rhs_g), 0.2)
+        report[tag + "_volume"] = max(abs(v - v_ref) / abs(v_ref), abs(dv - dv_ref) / abs(dv_ref))
+        report[tag + "_integrate"] = abs(eng.integrate(half) - ref.integrate(t(rhs_g))) / abs(ref.integrate(t(rhs_g)))
+        del eng, ref
+    if rank == 0:
+        print("DIST_REPORT " + json.dumps(report))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,31 @@
+"""Row-strip sharded path (2 GPUs, NCCL halos + all-reduce + replicated coarse multigrid levels)
+against the single-GPU path.  Skipped when fewer than 2 GPUs are visible."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def test_sharded_matches_single_gpu(repo_root):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(repo_root, "tests", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=repo_root)
+    line = [l for l in out.stdout.splitlines() if l.startswith("DIST_REPORT ")]
+    assert line, out.stdout[-2000:] + out.stderr[-4000:]
+    report = json.loads(line[0][len("DIST_REPORT "):])
+    print(report)
+    for key, val in report.items():
+        if "_iters_" in key:
+            assert abs(val[0] - val[1]) <= 3, (key, val)  # same preconditioner up to round-off
+        elif "_solve_" in key or "compliance" in key or "filter" in key or "sens" in key:
+            assert val < 1e-8, (key, val)
+        else:
+            assert val < 1e-12, (key, val)

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "tm_load_vector", "tm_filter_apply", "tm_elast_matvec", "tm_elast_diag", "tm_state_solve",
     "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
+    "tm_comm_unique_id", "tm_comm_init", "tm_local_layout",
 )
 
 
@@ -37,6 +38,7 @@ class TmConfig(Structure):
         ("lame_lambda", c_double), ("lame_mu", c_double),
         ("simp_min", c_double), ("filter_radius", c_double),
         ("fixed_sides", c_int), ("dtype", c_int), ("device", c_int),
+        ("rank", c_int), ("nranks", c_int), ("mg_dist_levels", c_int),
     ]
 
 
@@ -96,6 +98,9 @@ def load_library() -> ctypes.CDLL:
         "tm_md_apply": ([V, V, D, V, V, V, POINTER(D), POINTER(D)], I),
         "tm_integrate": ([V, V, POINTER(D)], I),
         "tm_last_solve_stats": ([V, POINTER(D), I], I),
+        "tm_comm_unique_id": ([ctypes.c_char_p], I),
+        "tm_comm_init": ([V, ctypes.c_char_p], I),
+        "tm_local_layout": ([V, POINTER(I), I], I),
         "tm_profile_read": ([V, POINTER(D), I], I),
         "tm_launch_count": ([], ctypes.c_longlong),
         "tm_mg_debug": ([V, V, I, I, V, V], I),

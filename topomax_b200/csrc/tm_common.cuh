@@ -66,6 +66,7 @@ struct LevelGeom {
     // mesh; they only WRITE rows in [own_j0, own_j1), and the Dirichlet thresholds db/dt
     // are compared against the global row index j + j_off.
     int j_off, own_j0, own_j1;
+    int nyg;  // global cell rows of this level (= ny on one GPU)
 
     __host__ __device__ bool fixed(int i, int j) const {
         const int jg = j + j_off;

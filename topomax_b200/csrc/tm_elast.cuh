@@ -94,8 +94,15 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
     reinterpret_cast<V2*>(a.y)[n] = out;
 }
 
-template <typename T, bool STORED_W, int EP>
-__global__ void __launch_bounds__(kApplyWarps * 32, 2)
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// MINB: resident blocks per SM the register allocation is held to; PF: software prefetch (into
+// L1) of the next march step's input rows and of this step's epilogue operands, which is what
+// hides the HBM latency at the low occupancy a 170-register fp64 kernel runs at.
+template <typename T, bool STORED_W, int EP, int MINB = 2, bool PF = false>
+__global__ void __launch_bounds__(kApplyWarps * 32, MINB)
 elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
     using V2 = typename Vec2<T>::type;
     const int lane = threadIdx.x & 31;
@@ -147,6 +154,24 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 
         for (int iy = iy_start; iy < iy1; ++iy) {
             const int j0 = 2 * iy;
+            if (PF && colok[0]) {
+                if (iy + 1 < iy1) {  // rows j0+3, j0+4 feed the next step (even columns touch every line)
+                    prefetch_l1(&xv[(size_t)(j0 + 3) * Lx + i0]);
+                    prefetch_l1(&xv[(size_t)(j0 + 4) * Lx + i0]);
+                    if (!STORED_W && cell_ok) prefetch_l1(&g.xi[(size_t)(iy + 2) * (g.nx + 1) + ix]);
+                }
+                if ((EP == EP_RESID || EP == EP_CHEB) && iy >= iy0) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const size_t n = (size_t)(j0 + r) * Lx + i0;
+                        prefetch_l1(reinterpret_cast<const V2*>(a.b) + n);
+                        if (EP == EP_CHEB) {
+                            prefetch_l1(reinterpret_cast<const V2*>(a.dinv) + n);
+                            if (a.c1 != T(0)) prefetch_l1(reinterpret_cast<const V2*>(a.d) + n);
+                        }
+                    }
+                }
+            }
             // shift: previous top row becomes the bottom row
 #pragma unroll
             for (int c = 0; c < 3; ++c) {

@@ -1,4 +1,14 @@
-// libtopomax_b200: engine (workspace, solvers) and the C ABI of include/topomax_b200.h.
+// libtopomax_b200: engine (workspace, solvers, row-strip sharding) and the C ABI of
+// include/topomax_b200.h.
+//
+// Sharding model: the mesh is cut into strips of cell rows, one per rank
+// (one process per GPU).  A rank stores its owned lattice rows plus halo rows (2 cell rows
+// below, 1 above) as one local lattice; kernels treat it as a standalone mesh and write only
+// owned rows.  Halo rows are contiguous in memory, so an exchange is plain ncclSend/ncclRecv on
+// the vector itself (4 lattice rows up, 3 down).  Dot products are reduced on the device and
+// summed over ranks in place with ncclAllReduce -- no host round trip.  The top `dist_levels`
+// multigrid levels are sharded; from there down every rank holds the (small) level in full and
+// runs it redundantly, the hand-over being a gather by broadcasts of the restricted residual.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -7,6 +17,7 @@
 #include <vector>
 
 #include "../../include/topomax_b200.h"
+#include "tm_comm.h"
 #include "tm_elast.cuh"
 #include "tm_filter_pcg.cuh"
 #include "tm_mg.cuh"
@@ -45,6 +56,7 @@ struct DevBuf {
         if (n >= count && p) return;
         release();
         TM_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        TM_CUDA(cudaMemset(p, 0, count * sizeof(T)));
         n = count;
     }
 };
@@ -60,12 +72,14 @@ class EngineBase {
     virtual ~EngineBase() {}
     virtual void set_stream(cudaStream_t s) = 0;
     virtual void set_option(int opt, double value) = 0;
+    virtual void comm_init(const char* id128) = 0;
+    virtual void layout(int* out, int n) = 0;
     virtual void load_vector(const tm_loads& loads, void* b) = 0;
-    virtual SolveStats filter_apply(int kind, const void* in, void* out, double rtol, int maxit) = 0;
-    virtual void elast_matvec(const void* xi, double p, const void* x, void* y) = 0;
-    virtual void elast_diag(const void* xi, double p, void* dinv) = 0;
-    virtual SolveStats state_solve(const void* xi, double p, const void* b, void* u, double rtol,
-                                   int maxit, int flags) = 0;
+    virtual SolveStats filter_apply(int kind, void* in, void* out, double rtol, int maxit) = 0;
+    virtual void elast_matvec(void* xi, double p, void* x, void* y) = 0;
+    virtual void elast_diag(void* xi, double p, void* dinv) = 0;
+    virtual SolveStats state_solve(void* xi, double p, const void* b, void* u, double rtol, int maxit,
+                                   int flags) = 0;
     virtual double dot_p2(const void* u, const void* b) = 0;
     virtual void sens_rhs(const void* xi, double p, const void* u, void* out) = 0;
     virtual void md_halfstep(const void* psi, const void* g, double alpha, void* half) = 0;
@@ -74,10 +88,21 @@ class EngineBase {
                           double* delta_sq, double* vol) = 0;
     virtual double integrate(const void* values) = 0;
     virtual void last_stats(double* out, int n) = 0;
-    virtual void mg_debug(const void* xi, int op, int level, const void* in, void* out) = 0;
+    virtual void mg_debug(void* xi, int op, int level, const void* in, void* out) = 0;
     virtual int mg_level_info(int level, int* info) = 0;
     virtual void profile_read(double* out, int n) = 0;
     int device = 0;
+};
+
+// owned / stored cell-row ranges of one rank on one multigrid level
+struct RowRange {
+    int nyg;       // global cell rows of the level
+    int c0, c1;    // owned cell rows [c0, c1)
+    int cl0, cl1;  // stored cell rows [cl0, cl1)  (owned + halo)
+    bool last;     // owns the top lattice row
+    int ny() const { return cl1 - cl0; }
+    int own_j0() const { return 2 * (c0 - cl0); }
+    int own_j1() const { return 2 * (c1 - cl0) + (last ? 1 : 0); }
 };
 
 template <typename T>
@@ -86,35 +111,20 @@ class Engine : public EngineBase {
     explicit Engine(const tm_config& cfg) : cfg_(cfg) {
         device = cfg.device;
         nx_ = cfg.nx;
-        ny_ = cfg.ny;
-        if (nx_ < 1 || ny_ < 1) throw Invalid{"nx, ny must be >= 1"};
+        nyg_ = cfg.ny;
+        rank_ = cfg.rank;
+        nranks_ = std::max(1, cfg.nranks);
+        if (nx_ < 1 || nyg_ < 1) throw Invalid{"nx, ny must be >= 1"};
         if (!(cfg.width > 0) || !(cfg.height > 0)) throw Invalid{"width/height must be > 0"};
+        if (rank_ < 0 || rank_ >= nranks_) throw Invalid{"rank out of range"};
         hx_ = cfg.width / nx_;
-        hy_ = cfg.height / ny_;
-        n1_ = (size_t)(nx_ + 1) * (ny_ + 1);
-        n2_ = (size_t)(2 * nx_ + 1) * (2 * ny_ + 1);
-        nu_ = 2 * n2_;
+        hy_ = cfg.height / nyg_;
+        coarse_cells_ = 2;
+        plan_levels(cfg.mg_dist_levels);
+        derive_local_sizes();
 
         TM_CUDA(cudaSetDevice(device));
         TM_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device));
-
-        // P1 element matrices (reference: FEM_src/filter.py:27-33; exact for P1)
-        p1_.nx = nx_; p1_.ny = ny_; p1_.hx = hx_; p1_.hy = hy_;
-        const double area = 0.5 * hx_ * hy_;
-        const double gA[3][2] = {{-1 / hx_, 0}, {1 / hx_, -1 / hy_}, {0, 1 / hy_}};
-        const double gB[3][2] = {{0, -1 / hy_}, {-1 / hx_, 1 / hy_}, {1 / hx_, 0}};
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                p1_.Ke[0][i][j] = area * (gA[i][0] * gA[j][0] + gA[i][1] * gA[j][1]);
-                p1_.Ke[1][i][j] = area * (gB[i][0] * gB[j][0] + gB[i][1] * gB[j][1]);
-                p1_.Me[i][j] = area / 12.0 * (i == j ? 2.0 : 1.0);
-            }
-
-        g0_ = make_level_geom(nx_, ny_);
-        g0_.dl = (cfg.fixed_sides & TM_SIDE_LEFT) ? 0 : -1;
-        g0_.db = (cfg.fixed_sides & TM_SIDE_BOTTOM) ? 0 : -1;
-        g0_.dr = (cfg.fixed_sides & TM_SIDE_RIGHT) ? 2 * nx_ : INT_MAX;
-        g0_.dt = (cfg.fixed_sides & TM_SIDE_TOP) ? 2 * ny_ : INT_MAX;
 
         const Material<double> matd = make_material<double>(cfg.lame_lambda, cfg.lame_mu, hx_, hy_);
         diag_tab_ = make_diag_table(matd);
@@ -127,11 +137,13 @@ class Engine : public EngineBase {
         TM_CUDA(cudaMemset(rs_.counter, 0, sizeof(unsigned int)));
         TM_CUDA(cudaMalloc(&sc_, sizeof(double) * SC_COUNT));
         TM_CUDA(cudaMemset(sc_, 0, sizeof(double) * SC_COUNT));
+        TM_CUDA(cudaMalloc(&eig_sc_, sizeof(double) * 64));
         TM_CUDA(cudaMallocHost(&h_sc_, sizeof(double) * 128));
     }
 
     ~Engine() override {
         cudaSetDevice(device);
+        if (comm_) nccl().CommDestroy(comm_);
         cudaFree(rs_.partials);
         cudaFree(rs_.counter);
         cudaFree(sc_);
@@ -153,8 +165,11 @@ class Engine : public EngineBase {
             case TM_OPT_CHEB_DEGREE: cheb_degree_ = std::max(1, (int)value); break;
             case TM_OPT_CHECK_EVERY: check_every_ = std::max(0, (int)value); break;
             case TM_OPT_MG_COARSE_CELLS:
+                if (nranks_ > 1) throw Invalid{"TM_OPT_MG_COARSE_CELLS cannot change on a sharded engine"};
                 coarse_cells_ = std::min(4, std::max(1, (int)value));
                 levels_.clear();
+                plan_levels(0);
+                derive_local_sizes();
                 break;
             case 100: cheb_ratio_ = value; break;
             case 101: eig_safety_ = value; break;
@@ -162,15 +177,40 @@ class Engine : public EngineBase {
             case 102: blocks_per_sm_target_ = std::max(1, (int)value); break;
             case 103: min_rows_per_strip_ = std::max(1, (int)value); break;
             case 104: filter_persistent_ = value != 0.0; break;
+            case 105: apply_minb_ = (int)value == 3 ? 3 : 2; break;
+            case 106: apply_prefetch_ = value != 0.0; break;
+            case 107:
+                filter_blocks_per_sm_ = std::max(1, (int)value);
+                if (filter_part_) cudaFree(filter_part_);
+                filter_part_ = nullptr;
+                filter_blocks_ = 0;
+                break;
             default: throw Invalid{"unknown option " + std::to_string(opt)};
         }
+    }
+
+    // ------------------------------------------------------------------ sharding plumbing
+    void comm_init(const char* id128) override {
+        if (nranks_ == 1) return;
+        if (!nccl().load()) throw Invalid{nccl().error};
+        NcclUniqueId id;
+        std::memcpy(id.internal, id128, 128);
+        const int rc = nccl().CommInitRank(&comm_, nranks_, id, rank_);
+        if (rc != 0) throw Invalid{std::string("ncclCommInitRank: ") + nccl().GetErrorString(rc)};
+    }
+
+    void layout(int* out, int n) override {
+        const RowRange& r = ranges_[0];
+        const int v[10] = {rank_, nranks_, nx_, nyg_, r.cl0, r.cl1, r.c0, r.c1, r.last ? 1 : 0, dist_levels_};
+        for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
     }
 
     // ------------------------------------------------------------------ loads
     void load_vector(const tm_loads& in, void* b) override {
         LoadSpec s;
         std::memset(&s, 0, sizeof(s));
-        s.nx = nx_; s.ny = ny_; s.W = cfg_.width; s.H = cfg_.height;
+        s.nx = nx_; s.ny = nyg_; s.W = cfg_.width; s.H = cfg_.height;
+        s.j_off = g0_.j_off; s.Ly_loc = g0_.Ly;
         s.has_force = in.has_force;
         s.fcx = in.force_center[0]; s.fcy = in.force_center[1]; s.frad = in.force_radius;
         s.fx = in.force_value[0]; s.fy = in.force_value[1];
@@ -178,7 +218,7 @@ class Engine : public EngineBase {
         // the reference compares the node coordinate with the side coordinate exactly
         // (FEM_src/elasisity_problem.py:54-66); ((n*W)/n == W) can fail for odd W
         const bool right_ok = ((double)nx_ * cfg_.width) / (double)nx_ == cfg_.width;
-        const bool top_ok = ((double)ny_ * cfg_.height) / (double)ny_ == cfg_.height;
+        const bool top_ok = ((double)nyg_ * cfg_.height) / (double)nyg_ == cfg_.height;
         for (int t = 0; t < in.ntractions; ++t) {
             int side;
             switch (in.traction_side[t]) {
@@ -210,16 +250,17 @@ class Engine : public EngineBase {
                 }
                 s.M2[i][j] = area * v;
             }
-        dim3 blk(32, 8), grd(ceil_div(2 * nx_ + 1, 32), ceil_div(2 * ny_ + 1, 8));
+        dim3 blk(32, 8), grd(ceil_div(g0_.Lx, 32), ceil_div(g0_.Ly, 8));
         load_vector_kernel<T><<<grd, blk, 0, stream_>>>(s, (T*)b);
         TM_CHECK_LAUNCH();
     }
 
     // ------------------------------------------------------------------ filter
-    SolveStats filter_apply(int kind, const void* in_, void* out_, double rtol, int maxit) override {
-        const T* in = (const T*)in_;
+    SolveStats filter_apply(int kind, void* in_, void* out_, double rtol, int maxit) override {
+        T* in = (T*)in_;
         T* out = (T*)out_;
         const double alpha = cfg_.filter_radius * cfg_.filter_radius, beta = 1.0;
+        if (kind != 0 && kind != 1) throw Invalid{"rhs_kind must be 0 or 1"};
         f_r_.ensure(n1_); f_p_.ensure(n1_); f_Ap_.ensure(n1_); f_rhs_.ensure(n1_);
         if (!f_dinv_ready_) {
             f_dinv_.ensure(n1_);
@@ -227,8 +268,7 @@ class Engine : public EngineBase {
             TM_CHECK_LAUNCH();
             f_dinv_ready_ = true;
         }
-        if (kind != 0 && kind != 1) throw Invalid{"rhs_kind must be 0 or 1"};
-        if (filter_persistent_) {
+        if (filter_persistent_ && nranks_ == 1) {
             // whole solve in one cooperative launch (tm_filter_pcg.cuh)
             const T* rhs_p = in;
             if (kind == 0) {
@@ -242,12 +282,14 @@ class Engine : public EngineBase {
             f_p2_.ensure(n1_);
             if (filter_blocks_ == 0) {
                 int per_sm = 0;
-                TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pcg_kernel<T>, 256, 0));
+                TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pcg_kernel<T>,
+                                                                      kFilterThreads, 0));
                 if (per_sm < 1) throw Invalid{"filter_pcg_kernel cannot be made resident"};
-                filter_blocks_ = std::min(per_sm, 4) * num_sms_;
+                filter_blocks_ = std::min(per_sm, filter_blocks_per_sm_) * num_sms_;
                 TM_CUDA(cudaMalloc(&filter_part_, sizeof(double) * (4 * (size_t)filter_blocks_ + 4)));
             }
-            const int nb = (int)std::max<size_t>(1, std::min<size_t>(filter_blocks_, (n1_ + 255) / 256));
+            const int nb = (int)std::max<size_t>(
+                1, std::min<size_t>(filter_blocks_, (n1_ + kFilterThreads - 1) / kFilterThreads));
             FilterPcgArgs fa;
             fa.g = p1_; fa.alpha = alpha; fa.beta = beta; fa.rtol = rtol; fa.maxit = maxit;
             fa.partA = filter_part_;
@@ -256,7 +298,8 @@ class Engine : public EngineBase {
             const T* dinv_p = f_dinv_.p;
             T *x_p = out, *r_p = f_r_.p, *Ap_p = f_Ap_.p, *p0_p = f_p_.p, *p1_p = f_p2_.p;
             void* kargs[] = {&fa, &rhs_p, &dinv_p, &x_p, &r_p, &Ap_p, &p0_p, &p1_p};
-            TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_pcg_kernel<T>, dim3(nb), dim3(256), kargs, 0, stream_));
+            TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_pcg_kernel<T>, dim3(nb), dim3(kFilterThreads),
+                                                kargs, 0, stream_));
             ++g_launches;
             TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, fa.result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
             TM_CUDA(cudaStreamSynchronize(stream_));
@@ -266,27 +309,33 @@ class Engine : public EngineBase {
             st.converged = h_sc_[66] != 0.0;
             return st;
         }
+        // launch-per-operation PCG (sharded runs: the search direction needs a halo exchange)
         const T* rhs;
         if (kind == 0) {
+            exchange_p1(in);
             p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
             rhs = f_rhs_.p;
-            // initial guess: the unfiltered field itself
             if (out != in) TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
             p1_apply(alpha, beta, out, f_Ap_.p, nullptr);
-            waxpby_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(n1_, 1.0, rhs, -1.0, f_Ap_.p, f_r_.p);
+            waxpby_kernel<T><<<grid1d(p1_cnt_), kVecThreads, 0, stream_>>>(
+                p1_cnt_, 1.0, rhs + p1_off_, -1.0, f_Ap_.p + p1_off_, f_r_.p + p1_off_);
             TM_CHECK_LAUNCH();
-        } else if (kind == 1) {
+        } else {
             rhs = in;
             TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
             TM_CUDA(cudaMemcpyAsync(f_r_.p, rhs, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
-        } else {
-            throw Invalid{"rhs_kind must be 0 or 1"};
         }
-        auto apply_dot = [&](const T* p, T* Ap) { p1_apply(alpha, beta, p, Ap, sc_ + SC_PAP); };
-        auto precond = [&](const T*) -> const T* { return nullptr; };
+        auto apply_dot = [&](T* p, T* Ap) {
+            exchange_p1(p);
+            p1_apply(alpha, beta, p, Ap, sc_ + SC_PAP);
+            sum_ranks(sc_ + SC_PAP, 1);
+        };
+        auto precond = [&](T*) -> T* { return nullptr; };
         const int check = check_every_ > 0 ? check_every_ : 10;
-        return pcg(n1_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, f_dinv_.p, apply_dot, precond, true, rtol,
-                   maxit, check);
+        SolveStats st = pcg(p1_off_, p1_cnt_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, f_dinv_.p, apply_dot,
+                            precond, true, rtol, maxit, check);
+        exchange_p1(out);
+        return st;
     }
 
     // ------------------------------------------------------------------ elasticity operator
@@ -296,9 +345,11 @@ class Engine : public EngineBase {
                               ": the closed-form SIMP moments are implemented for p = 3 only"};
     }
 
-    void elast_matvec(const void* xi, double p, const void* x, void* y) override {
+    void elast_matvec(void* xi, double p, void* x, void* y) override {
         check_penalty(p);
         if (x == y) throw Invalid{"tm_elast_matvec: x and y must not alias"};
+        exchange_p1((T*)xi);
+        exchange_p2(0, (T*)x);
         LevelGeom<T> g = g0_;
         g.xi = (const T*)xi;
         ApplyArgs<T> a = apply_args();
@@ -307,33 +358,32 @@ class Engine : public EngineBase {
         launch_apply(g, false, EP_PLAIN, a);
     }
 
-    void elast_diag(const void* xi, double p, void* dinv) override {
+    void elast_diag(void* xi, double p, void* dinv) override {
         check_penalty(p);
+        exchange_p1((T*)xi);
         LevelGeom<T> g = g0_;
         g.xi = (const T*)xi;
         launch_diag(g, false, (T*)dinv);
     }
 
-    SolveStats state_solve(const void* xi_, double p, const void* b_, void* u_, double rtol,
-                           int maxit, int flags) override {
+    SolveStats state_solve(void* xi_, double p, const void* b_, void* u_, double rtol, int maxit,
+                           int flags) override {
         check_penalty(p);
-        const T* xi = (const T*)xi_;
+        T* xi = (T*)xi_;
         const T* b = (const T*)b_;
         T* u = (T*)u_;
         s_r_.ensure(nu_); s_p_.ensure(nu_); s_Ap_.ensure(nu_); s_b_.ensure(nu_);
         stats_fine_applies_ = 0;
         stats_vcycles_ = 0;
 
+        exchange_p1(xi);
         LevelGeom<T> g = g0_;
         g.xi = xi;
         mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, b, s_b_.p);
         TM_CHECK_LAUNCH();
 
-        bool use_mg = precond_ == TM_PRECOND_MULTIGRID;
-        if (use_mg) {
-            if (levels_.empty()) build_levels();
-            if (levels_.size() < 2) use_mg = false;
-        }
+        bool use_mg = precond_ == TM_PRECOND_MULTIGRID && nlevels_ >= 2;
+        if (use_mg && levels_.empty()) build_levels();
         const T* dinv = nullptr;
         if (use_mg) {
             setup_hierarchy(xi);
@@ -346,6 +396,7 @@ class Engine : public EngineBase {
         if (flags & 1) {
             mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, u, u);
             TM_CHECK_LAUNCH();
+            exchange_p2(0, u);
             ApplyArgs<T> a = apply_args();
             a.x = u; a.y = s_r_.p; a.b = s_b_.p;
             launch_apply(g, false, EP_RESID, a);
@@ -354,24 +405,28 @@ class Engine : public EngineBase {
             TM_CUDA(cudaMemcpyAsync(s_r_.p, s_b_.p, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
         }
 
-        auto apply_dot = [&](const T* pp, T* Ap) {
+        auto apply_dot = [&](T* pp, T* Ap) {
+            exchange_p2(0, pp);
             ApplyArgs<T> a = apply_args();
             a.x = pp; a.y = Ap; a.dot_out = sc_ + SC_PAP;
             launch_apply(g, false, EP_DOT, a);
+            sum_ranks(sc_ + SC_PAP, 1);
         };
-        auto precond = [&](const T* r) -> const T* { return use_mg ? vcycle(r) : nullptr; };
+        auto precond = [&](T* r) -> T* { return use_mg ? vcycle(r) : nullptr; };
         int check = check_every_;
         if (check <= 0) check = use_mg ? 1 : 25;
-        SolveStats st = pcg(nu_, s_b_.p, u, s_r_.p, s_p_.p, s_Ap_.p, dinv, apply_dot, precond, !use_mg,
-                            rtol, maxit, check);
+        SolveStats st = pcg(p2_off_, p2_cnt_, s_b_.p, u, s_r_.p, s_p_.p, s_Ap_.p, dinv, apply_dot, precond,
+                            !use_mg, rtol, maxit, check);
+        exchange_p2(0, u);
         stats_iters_ = st.iters;
         return st;
     }
 
     double dot_p2(const void* u, const void* b) override {
-        dot_kernel<T><<<grid1d(nu_), kVecThreads, 0, stream_>>>(nu_, (const T*)u, (const T*)b, rs_,
-                                                               sc_ + SC_TMP);
+        dot_kernel<T><<<grid1d(p2_cnt_), kVecThreads, 0, stream_>>>(
+            p2_cnt_, (const T*)u + p2_off_, (const T*)b + p2_off_, rs_, sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        sum_ranks(sc_ + SC_TMP, 1);
         read_scalars();
         return h_sc_[SC_TMP];
     }
@@ -380,7 +435,8 @@ class Engine : public EngineBase {
         check_penalty(p);
         LevelGeom<T> g = g0_;
         g.xi = (const T*)xi;
-        sens_rhs_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, (const T*)u, (T*)out);
+        sens_rhs_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, p1_.own_iy0, p1_.own_iy1,
+                                                                    (const T*)u, (T*)out);
         TM_CHECK_LAUNCH();
     }
 
@@ -395,6 +451,7 @@ class Engine : public EngineBase {
         md_volume_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(p1_, (const T*)half, c, rs_,
                                                                      sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        sum_ranks(sc_ + SC_TMP, 2);
         read_scalars();
         *vol = h_sc_[SC_TMP];
         *dvol = h_sc_[SC_TMP + 1];
@@ -405,6 +462,7 @@ class Engine : public EngineBase {
         md_apply_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(
             p1_, (const T*)half, c, (const T*)psi_prev, (T*)psi, (T*)rho, rs_, sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        sum_ranks(sc_ + SC_TMP, 2);
         read_scalars();
         *delta_sq = h_sc_[SC_TMP];
         *vol = h_sc_[SC_TMP + 1];
@@ -414,23 +472,43 @@ class Engine : public EngineBase {
         p1_integrate_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(p1_, (const T*)values, rs_,
                                                                         sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        sum_ranks(sc_ + SC_TMP, 1);
         read_scalars();
         return h_sc_[SC_TMP];
     }
 
     void last_stats(double* out, int n) override {
         const double v[5] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
-                             (double)levels_.size(), levels_.empty() ? 0.0 : levels_[0].lmax};
+                             (double)nlevels_, levels_.empty() ? 0.0 : levels_[0].lmax};
         for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
     }
 
-    // diagnostics (tests): multigrid internals on the hierarchy built for xi
-    void mg_debug(const void* xi, int op, int level, const void* in_, void* out_) override {
+    // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
+    void profile_read(double* out, int n) override {
+        double ms[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (auto& p : prof_pending_) {
+            float t = 0.f;
+            TM_CUDA(cudaEventElapsedTime(&t, p.second.first, p.second.second));
+            ms[p.first] += t;
+            cnt[p.first] += 1;
+            prof_free_.push_back(p.second);
+        }
+        prof_pending_.clear();
+        for (int i = 0; i < 4; ++i) {
+            if (i < n) out[i] = ms[i];
+            if (4 + i < n) out[4 + i] = cnt[i];
+        }
+    }
+
+    // diagnostics (tests): multigrid internals on the hierarchy built for xi (single rank)
+    void mg_debug(void* xi, int op, int level, const void* in_, void* out_) override {
+        if (nranks_ > 1) throw Invalid{"tm_mg_debug is a single-rank diagnostic"};
+        if (nlevels_ < 2) throw Invalid{"no multigrid hierarchy for this mesh"};
         if (levels_.empty()) build_levels();
-        const int nl = (int)levels_.size();
-        if (nl < 2) throw Invalid{"no multigrid hierarchy for this mesh"};
+        const int nl = nlevels_;
         if (level < 0 || level >= nl) throw Invalid{"bad level"};
-        setup_hierarchy((const T*)xi);
+        setup_hierarchy((T*)xi);
         const T* in = (const T*)in_;
         T* out = (T*)out_;
         Level& L = levels_[level];
@@ -454,7 +532,9 @@ class Engine : public EngineBase {
             mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, in, out);
             TM_CHECK_LAUNCH();
         } else if (op == 3) {
-            const T* z = vcycle(in);
+            s_r_.ensure(nu_);
+            TM_CUDA(cudaMemcpyAsync(s_r_.p, in, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            const T* z = vcycle(s_r_.p);
             TM_CUDA(cudaMemcpyAsync(out, z, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
         } else if (op == 4) {
             if (level != nl - 1) throw Invalid{"op 4 is the coarsest-level direct solve"};
@@ -470,26 +550,128 @@ class Engine : public EngineBase {
     }
 
     int mg_level_info(int level, int* info) override {
-        if (levels_.empty()) build_levels();
-        if (level < 0 || level >= (int)levels_.size()) return (int)levels_.size();
-        const LevelGeom<T>& g = levels_[level].g;
-        info[0] = g.nx; info[1] = g.ny; info[2] = g.dl; info[3] = g.dr; info[4] = g.db; info[5] = g.dt;
-        return (int)levels_.size();
+        if (level < 0 || level >= nlevels_) return nlevels_;
+        const LevelGeom<T> g = level_geom(level, level >= dist_levels_);
+        info[0] = g.nx; info[1] = g.nyg; info[2] = g.dl; info[3] = g.dr; info[4] = g.db; info[5] = g.dt;
+        return nlevels_;
     }
 
    private:
-    // ------------------------------------------------------------------ helpers
-    LevelGeom<T> make_level_geom(int nx, int ny) const {
+    // ------------------------------------------------------------------ level planning
+    // Global level sizes (ceil halving), Dirichlet thresholds, the number of sharded levels and
+    // the partition of the level-0 cell rows (aligned so that strips nest across levels).
+    void plan_levels(int dist_levels_hint) {
+        lv_nx_.clear(); lv_ny_.clear(); lv_dr_.clear(); lv_dt_.clear();
+        int nx = nx_, ny = nyg_;
+        int dr = (cfg_.fixed_sides & TM_SIDE_RIGHT) ? 2 * nx_ : INT_MAX;
+        int dt = (cfg_.fixed_sides & TM_SIDE_TOP) ? 2 * nyg_ : INT_MAX;
+        while (true) {
+            lv_nx_.push_back(nx); lv_ny_.push_back(ny); lv_dr_.push_back(dr); lv_dt_.push_back(dt);
+            if (std::max(nx, ny) <= coarse_cells_) break;
+            const int nxc = (nx + 1) / 2, nyc = (ny + 1) / 2;
+            if (nxc == nx && nyc == ny) break;  // 1x1: cannot coarsen
+            // far sides: last coarse column/row whose functions vanish on the fine Dirichlet nodes
+            dr = dr == INT_MAX ? INT_MAX : 2 * (dr / 4);
+            dt = dt == INT_MAX ? INT_MAX : 2 * (dt / 4);
+            nx = nxc; ny = nyc;
+        }
+        nlevels_ = (int)lv_nx_.size();
+        if (nlevels_ >= 2 &&
+            2 * (size_t)(2 * lv_nx_.back() + 1) * (2 * lv_ny_.back() + 1) > (size_t)kCoarseMaxDofs)
+            throw Invalid{"coarsest multigrid level too large"};
+        if (nlevels_ > 30) throw Invalid{"too many multigrid levels"};
+
+        // sharded levels: 0 .. dist_levels_-1
+        dist_levels_ = 0;
+        if (nranks_ > 1) {
+            int ld = dist_levels_hint;
+            if (ld <= 0) {
+                ld = 1;
+                while (ld < nlevels_ - 1 && (size_t)lv_nx_[ld] * lv_ny_[ld] > (size_t)262144 &&
+                       (nyg_ >> (ld + 1)) >= 4 * nranks_)
+                    ++ld;
+            }
+            dist_levels_ = std::max(1, std::min(ld, std::max(1, nlevels_ - 1)));
+        }
+        const int align = 1 << dist_levels_;
+        starts_.assign(nranks_ + 1, nyg_);
+        if (nranks_ == 1) {
+            starts_[0] = 0;
+        } else {
+            const int per = ceil_div(ceil_div(nyg_, nranks_), align) * align;
+            for (int r = 0; r < nranks_; ++r) starts_[r] = (int)std::min((long)r * per, (long)nyg_);
+            if (starts_[nranks_ - 1] >= nyg_)
+                throw Invalid{"mesh has too few cell rows for " + std::to_string(nranks_) + " ranks with " +
+                              std::to_string(dist_levels_) + " sharded multigrid levels"};
+        }
+        ranges_.clear();
+        for (int l = 0; l < nlevels_; ++l) ranges_.push_back(row_range(l, rank_, l >= dist_levels_));
+    }
+
+    void derive_local_sizes() {
+        const RowRange& r0 = ranges_[0];
+        ny_ = r0.ny();
+        n1_ = (size_t)(nx_ + 1) * (ny_ + 1);
+        n2_ = (size_t)(2 * nx_ + 1) * (2 * ny_ + 1);
+        nu_ = 2 * n2_;
+        p2_off_ = (size_t)r0.own_j0() * (2 * nx_ + 1) * 2;
+        p2_cnt_ = (size_t)(r0.own_j1() - r0.own_j0()) * (2 * nx_ + 1) * 2;
+        const int oi0 = r0.c0 - r0.cl0, oi1 = r0.c1 - r0.cl0 + (r0.last ? 1 : 0);
+        p1_off_ = (size_t)oi0 * (nx_ + 1);
+        p1_cnt_ = (size_t)(oi1 - oi0) * (nx_ + 1);
+        // P1 element matrices (reference: FEM_src/filter.py:27-33; exact for P1)
+        p1_.nx = nx_; p1_.ny = ny_; p1_.hx = hx_; p1_.hy = hy_;
+        p1_.iy_off = r0.cl0; p1_.ny_global = nyg_; p1_.own_iy0 = oi0; p1_.own_iy1 = oi1;
+        const double area = 0.5 * hx_ * hy_;
+        const double gA[3][2] = {{-1 / hx_, 0}, {1 / hx_, -1 / hy_}, {0, 1 / hy_}};
+        const double gB[3][2] = {{0, -1 / hy_}, {-1 / hx_, 1 / hy_}, {1 / hx_, 0}};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                p1_.Ke[0][i][j] = area * (gA[i][0] * gA[j][0] + gA[i][1] * gA[j][1]);
+                p1_.Ke[1][i][j] = area * (gB[i][0] * gB[j][0] + gB[i][1] * gB[j][1]);
+                p1_.Me[i][j] = area / 12.0 * (i == j ? 2.0 : 1.0);
+            }
+        p1_fill_interior_stencil(p1_);
+        g0_ = level_geom(0, false);
+    }
+
+    RowRange row_range(int l, int rank, bool replicated) const {
+        RowRange r;
+        r.nyg = lv_ny_[l];
+        if (replicated || nranks_ == 1) {
+            r.c0 = 0; r.c1 = r.nyg; r.cl0 = 0; r.cl1 = r.nyg; r.last = true;
+            return r;
+        }
+        r.last = rank == nranks_ - 1;
+        r.c0 = starts_[rank] >> l;
+        r.c1 = r.last ? r.nyg : (starts_[rank + 1] >> l);
+        r.cl0 = std::max(0, r.c0 - 2);
+        r.cl1 = std::min(r.nyg, r.c1 + 1);
+        return r;
+    }
+
+    // rows of the FULL level l that `rank` owns (used to gather the first replicated level)
+    void piece_rows(int l, int rank, int& j0, int& j1) const {
+        const bool last = rank == nranks_ - 1;
+        j0 = 2 * (starts_[rank] >> l);
+        j1 = last ? 2 * lv_ny_[l] + 1 : 2 * (starts_[rank + 1] >> l);
+    }
+
+    LevelGeom<T> level_geom(int l, bool replicated) const {
+        const RowRange r = row_range(l, rank_, replicated);
         LevelGeom<T> g;
-        g.nx = nx; g.ny = ny; g.Lx = 2 * nx + 1; g.Ly = 2 * ny + 1;
-        g.dl = -1; g.db = -1; g.dr = INT_MAX; g.dt = INT_MAX;
-        g.j_off = 0; g.own_j0 = 0; g.own_j1 = g.Ly;
+        g.nx = lv_nx_[l]; g.ny = r.ny(); g.Lx = 2 * g.nx + 1; g.Ly = 2 * g.ny + 1;
+        g.dl = (cfg_.fixed_sides & TM_SIDE_LEFT) ? 0 : -1;
+        g.db = (cfg_.fixed_sides & TM_SIDE_BOTTOM) ? 0 : -1;
+        g.dr = lv_dr_[l]; g.dt = lv_dt_[l];
+        g.j_off = 2 * r.cl0; g.own_j0 = r.own_j0(); g.own_j1 = r.own_j1(); g.nyg = r.nyg;
         g.xi = nullptr; g.W = nullptr;
         g.simp_min = (T)cfg_.simp_min;
         g.mat = make_material<T>(cfg_.lame_lambda, cfg_.lame_mu, hx_, hy_);
         return g;
     }
 
+    // ------------------------------------------------------------------ helpers
     int grid1d(size_t n) const {
         const size_t want = (n + kVecThreads - 1) / kVecThreads;
         return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)num_sms_ * 8));
@@ -499,6 +681,78 @@ class Engine : public EngineBase {
     void read_scalars() {
         TM_CUDA(cudaMemcpyAsync(h_sc_, sc_, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, stream_));
         TM_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    void nccl_check(int rc, const char* what) {
+        if (rc != 0) throw Invalid{std::string(what) + ": " + nccl().GetErrorString(rc)};
+    }
+    void need_comm() {
+        if (!comm_) throw Invalid{"sharded engine used before tm_comm_init"};
+    }
+
+    // in-place sum over ranks of n device doubles
+    void sum_ranks(double* p, int n) {
+        if (nranks_ == 1) return;
+        need_comm();
+        nccl_check(nccl().AllReduce(p, p, (size_t)n, kNcclFloat64, kNcclSum, comm_, stream_), "ncclAllReduce");
+    }
+
+    // halo exchange of a row-major local array: the `up` rows below my top edge go to rank+1,
+    // which stores them in its first rows; `down` rows from my first owned row go to rank-1
+    void exchange_rows(T* v, size_t row_elems, int own0, int own1, int up, int down, bool last) {
+        if (nranks_ == 1) return;
+        need_comm();
+        const int dtype = sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32;
+        nccl_check(nccl().GroupStart(), "ncclGroupStart");
+        if (!last) {
+            nccl().Send(v + (size_t)(own1 - up) * row_elems, (size_t)up * row_elems, dtype, rank_ + 1, comm_, stream_);
+            nccl().Recv(v + (size_t)own1 * row_elems, (size_t)down * row_elems, dtype, rank_ + 1, comm_, stream_);
+        }
+        if (rank_ > 0) {
+            nccl().Send(v + (size_t)own0 * row_elems, (size_t)down * row_elems, dtype, rank_ - 1, comm_, stream_);
+            nccl().Recv(v + (size_t)(own0 - up) * row_elems, (size_t)up * row_elems, dtype, rank_ - 1, comm_, stream_);
+        }
+        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+    }
+    // lattice vector of sharded level l: 4 rows up, 3 rows down
+    void exchange_p2(int l, T* v) {
+        if (nranks_ == 1 || l >= dist_levels_) return;
+        const RowRange& r = ranges_[l];
+        exchange_rows(v, (size_t)(2 * lv_nx_[l] + 1) * 2, r.own_j0(), 2 * (r.c1 - r.cl0), 4, 3, r.last);
+    }
+    // P1 field (level 0): 2 vertex rows each way
+    void exchange_p1(T* v) {
+        if (nranks_ == 1) return;
+        const RowRange& r = ranges_[0];
+        exchange_rows(v, (size_t)nx_ + 1, r.c0 - r.cl0, r.c1 - r.cl0, 2, 2, r.last);
+    }
+    // stored moments of sharded level l >= 1: 12 planes, 2 cell rows up, 1 down
+    void exchange_w(int l, T* W) {
+        if (nranks_ == 1 || l >= dist_levels_) return;
+        const RowRange& r = ranges_[l];
+        const size_t plane = (size_t)lv_nx_[l] * r.ny();
+        for (int k = 0; k < 12; ++k)
+            exchange_rows(W + k * plane, (size_t)lv_nx_[l], r.c0 - r.cl0, r.c1 - r.cl0, 2, 1, r.last);
+    }
+    // every rank contributes its rows of the FULL array (row_elems per row) of level l
+    void gather_rows(int l, T* full, size_t row_elems, bool cell_rows) {
+        if (nranks_ == 1) return;
+        need_comm();
+        const int dtype = sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32;
+        nccl_check(nccl().GroupStart(), "ncclGroupStart");
+        for (int q = 0; q < nranks_; ++q) {
+            int j0, j1;
+            if (cell_rows) {
+                j0 = starts_[q] >> l;
+                j1 = q == nranks_ - 1 ? lv_ny_[l] : (starts_[q + 1] >> l);
+            } else {
+                piece_rows(l, q, j0, j1);
+            }
+            if (j1 <= j0) continue;
+            T* p = full + (size_t)j0 * row_elems;
+            nccl().Broadcast(p, p, (size_t)(j1 - j0) * row_elems, dtype, q, comm_, stream_);
+        }
+        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
     }
 
     ApplyArgs<T> apply_args() const {
@@ -521,7 +775,7 @@ class Engine : public EngineBase {
         strips = ceil_div(g.ny, a.rows_per_strip);
         dim3 grd(bx, strips), blk(kApplyWarps * 32);
         if ((long)bx * strips > rs_.capacity) throw Invalid{"reduction scratch too small"};
-        const bool fine = g.nx == nx_ && g.ny == ny_;
+        const bool fine = g.nx == nx_ && g.nyg == nyg_;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (fine && profile_) {
             if (prof_free_.empty()) {
@@ -533,23 +787,23 @@ class Engine : public EngineBase {
             }
             TM_CUDA(cudaEventRecord(ev.first, stream_));
         }
-#define TM_LAUNCH_APPLY(ST, EPV) \
-    elast_apply_kernel<T, ST, EPV><<<grd, blk, 0, stream_>>>(g, a)
-        if (!stored) {
-            switch (ep) {
-                case EP_PLAIN: TM_LAUNCH_APPLY(false, EP_PLAIN); break;
-                case EP_DOT: TM_LAUNCH_APPLY(false, EP_DOT); break;
-                case EP_RESID: TM_LAUNCH_APPLY(false, EP_RESID); break;
-                default: TM_LAUNCH_APPLY(false, EP_CHEB); break;
-            }
+#define TM_LAUNCH_APPLY(ST, EPV, MB, PFV) \
+    elast_apply_kernel<T, ST, EPV, MB, PFV><<<grd, blk, 0, stream_>>>(g, a)
+#define TM_LAUNCH_APPLY_EP(ST, MB, PFV)                             \
+    switch (ep) {                                                   \
+        case EP_PLAIN: TM_LAUNCH_APPLY(ST, EP_PLAIN, MB, PFV); break; \
+        case EP_DOT: TM_LAUNCH_APPLY(ST, EP_DOT, MB, PFV); break;     \
+        case EP_RESID: TM_LAUNCH_APPLY(ST, EP_RESID, MB, PFV); break; \
+        default: TM_LAUNCH_APPLY(ST, EP_CHEB, MB, PFV); break;        \
+    }
+        if (stored) {
+            TM_LAUNCH_APPLY_EP(true, 2, false)
+        } else if (apply_minb_ == 3) {
+            if (apply_prefetch_) { TM_LAUNCH_APPLY_EP(false, 3, true) } else { TM_LAUNCH_APPLY_EP(false, 3, false) }
         } else {
-            switch (ep) {
-                case EP_PLAIN: TM_LAUNCH_APPLY(true, EP_PLAIN); break;
-                case EP_DOT: TM_LAUNCH_APPLY(true, EP_DOT); break;
-                case EP_RESID: TM_LAUNCH_APPLY(true, EP_RESID); break;
-                default: TM_LAUNCH_APPLY(true, EP_CHEB); break;
-            }
+            if (apply_prefetch_) { TM_LAUNCH_APPLY_EP(false, 2, true) } else { TM_LAUNCH_APPLY_EP(false, 2, false) }
         }
+#undef TM_LAUNCH_APPLY_EP
 #undef TM_LAUNCH_APPLY
         TM_CHECK_LAUNCH();
         if (fine && profile_) {
@@ -557,24 +811,6 @@ class Engine : public EngineBase {
             prof_pending_.push_back({ep, ev});
         }
         if (fine) ++stats_fine_applies_;
-    }
-
-    // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
-    void profile_read(double* out, int n) override {
-        double ms[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
-        TM_CUDA(cudaStreamSynchronize(stream_));
-        for (auto& p : prof_pending_) {
-            float t = 0.f;
-            TM_CUDA(cudaEventElapsedTime(&t, p.second.first, p.second.second));
-            ms[p.first] += t;
-            cnt[p.first] += 1;
-            prof_free_.push_back(p.second);
-        }
-        prof_pending_.clear();
-        for (int i = 0; i < 4; ++i) {
-            if (i < n) out[i] = ms[i];
-            if (4 + i < n) out[4 + i] = cnt[i];
-        }
     }
 
     void launch_diag(const LevelGeom<T>& g, bool stored, T* dinv) {
@@ -597,27 +833,33 @@ class Engine : public EngineBase {
     }
 
     // ------------------------------------------------------------------ PCG
-    // Solves A x = b given r = b - A x on entry.  precond(r) returns z = M^-1 r, or nullptr
-    // when `jacobi` (then z = dinv r is fused into the vector kernels).
+    // Solves A x = b given r = b - A x on entry.  All vectors are local arrays; the flat vector
+    // kernels touch the owned range [off, off+n) only.  precond(r) returns z = M^-1 r, or
+    // nullptr when `jacobi` (then z = dinv r is fused into the vector kernels).
     template <class ApplyDot, class Precond>
-    SolveStats pcg(size_t n, const T* b, T* x, T* r, T* p, T* Ap, const T* dinv, ApplyDot apply_dot,
-                   Precond precond, bool jacobi, double rtol, int maxit, int check) {
+    SolveStats pcg(size_t off, size_t n, const T* b, T* x, T* r, T* p, T* Ap, const T* dinv,
+                   ApplyDot apply_dot, Precond precond, bool jacobi, double rtol, int maxit, int check) {
         SolveStats st;
         const int g1 = grid1d(n);
-        dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, b, b, rs_, sc_ + SC_BB);
+        const T* dv = dinv ? dinv + off : nullptr;
+        dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, b + off, b + off, rs_, sc_ + SC_BB);
         TM_CHECK_LAUNCH();
+        sum_ranks(sc_ + SC_BB, 1);
         int cur = 0;
         if (jacobi) {
-            pcg_start_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, p, r, dinv, rs_);
+            pcg_start_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, p + off, r + off, dv, rs_);
         } else {
             const T* z = precond(r);
-            pcg_start_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, p, r, z, rs_);
+            pcg_start_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, p + off, r + off,
+                                                                       z + off, rs_);
         }
         TM_CHECK_LAUNCH();
+        sum_ranks(sc_ + SC_RR, 1);
+        sum_ranks(sc_ + cur, 1);
         read_scalars();
         const double bb = h_sc_[SC_BB];
         if (!(bb > 0.0)) {
-            TM_CUDA(cudaMemsetAsync(x, 0, n * sizeof(T), stream_));
+            TM_CUDA(cudaMemsetAsync(x + off, 0, n * sizeof(T), stream_));
             st.converged = true;
             return st;
         }
@@ -629,13 +871,16 @@ class Engine : public EngineBase {
         for (int k = 0; k < maxit; ++k) {
             apply_dot(p, Ap);
             if (jacobi) {
-                pcg_update_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, x, r, p,
-                                                                           Ap, dinv, rs_);
+                pcg_update_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(
+                    n, sc_, cur, cur ^ 1, x + off, r + off, p + off, Ap + off, dv, rs_);
                 TM_CHECK_LAUNCH();
+                sum_ranks(sc_ + SC_RR, 1);
+                sum_ranks(sc_ + (cur ^ 1), 1);
             } else {
-                pcg_update_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, x, r,
-                                                                            p, Ap, nullptr, rs_);
+                pcg_update_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(
+                    n, sc_, cur, cur ^ 1, x + off, r + off, p + off, Ap + off, nullptr, rs_);
                 TM_CHECK_LAUNCH();
+                sum_ranks(sc_ + SC_RR, 1);
             }
             st.iters = k + 1;
             const bool do_check = ((k + 1) % check == 0) || (k + 1 == maxit);
@@ -649,14 +894,15 @@ class Engine : public EngineBase {
                 }
             }
             if (jacobi) {
-                pcg_direction_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p, r,
-                                                                              dinv);
+                pcg_direction_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p + off,
+                                                                              r + off, dv);
             } else {
                 const T* z = precond(r);
-                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, r, z, rs_, sc_ + (cur ^ 1));
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, r + off, z + off, rs_, sc_ + (cur ^ 1));
                 TM_CHECK_LAUNCH();
-                pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p,
-                                                                               r, z);
+                sum_ranks(sc_ + (cur ^ 1), 1);
+                pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p + off,
+                                                                               r + off, z + off);
             }
             TM_CHECK_LAUNCH();
             cur ^= 1;
@@ -666,8 +912,10 @@ class Engine : public EngineBase {
 
     // ------------------------------------------------------------------ multigrid
     struct Level {
-        LevelGeom<T> g;
-        size_t nu = 0;
+        LevelGeom<T> g;       // local geometry (own rows = this rank's)
+        LevelGeom<T> gpiece;  // first replicated level only: full geometry, own rows = my piece
+        size_t nu = 0, off = 0, cnt = 0;  // local size; owned flat range
+        bool sharded = false;
         DevBuf<T> W, dinv, x, xalt, b, d, tmp, eig;
         bool eig_ready = false;
         double lmax = 0.0;
@@ -675,32 +923,26 @@ class Engine : public EngineBase {
 
     void build_levels() {
         levels_.clear();
-        int nx = nx_, ny = ny_;
-        LevelGeom<T> g = g0_;
-        while (true) {
-            levels_.emplace_back();
-            Level& L = levels_.back();
-            L.g = g;
-            L.nu = 2 * (size_t)g.Lx * g.Ly;
-            if (std::max(nx, ny) <= coarse_cells_) break;
-            const int nxc = (nx + 1) / 2, nyc = (ny + 1) / 2;
-            if (nxc == nx && nyc == ny) break;  // 1x1: cannot coarsen
-            LevelGeom<T> c = make_level_geom(nxc, nyc);
-            c.dl = g.dl; c.db = g.db;  // near sides stay aligned (0 or free)
-            c.dr = g.dr == INT_MAX ? INT_MAX : 2 * (g.dr / 4);
-            c.dt = g.dt == INT_MAX ? INT_MAX : 2 * (g.dt / 4);
-            g = c; nx = nxc; ny = nyc;
-        }
-        const size_t nl = levels_.size();
-        if (nl < 2) return;
-        if (2 * (size_t)levels_.back().g.Lx * levels_.back().g.Ly > (size_t)kCoarseMaxDofs)
-            throw Invalid{"coarsest multigrid level too large"};
-        for (size_t l = 0; l < nl; ++l) {
+        levels_.resize(nlevels_);
+        for (int l = 0; l < nlevels_; ++l) {
             Level& L = levels_[l];
-            const bool coarsest = (l + 1 == nl);
+            L.sharded = l < dist_levels_;
+            L.g = level_geom(l, !L.sharded);
+            L.gpiece = L.g;
+            L.nu = 2 * (size_t)L.g.Lx * L.g.Ly;
+            L.off = (size_t)L.g.own_j0 * L.g.Lx * 2;
+            L.cnt = (size_t)(L.g.own_j1 - L.g.own_j0) * L.g.Lx * 2;
+            if (nranks_ > 1 && l == dist_levels_) {
+                int j0, j1;
+                piece_rows(l, rank_, j0, j1);
+                L.gpiece.own_j0 = j0;
+                L.gpiece.own_j1 = j1;
+            }
+            const bool coarsest = (l + 1 == nlevels_);
             if (l > 0) {
                 L.W.ensure(12 * (size_t)L.g.nx * L.g.ny);
                 L.g.W = L.W.p;
+                L.gpiece.W = L.W.p;
                 L.b.ensure(L.nu);
             }
             L.x.ensure(L.nu);
@@ -711,28 +953,41 @@ class Engine : public EngineBase {
         }
         const size_t nc = levels_.back().nu;
         coarse_A_.ensure(nc * nc);
-        if (!eig_sc_) TM_CUDA(cudaMalloc(&eig_sc_, sizeof(double) * 64));
     }
 
-    void setup_hierarchy(const T* xi) {
-        const size_t nl = levels_.size();
+    void setup_hierarchy(T* xi) {
+        const int nl = nlevels_;
         levels_[0].g.xi = xi;
-        for (size_t l = 1; l < nl; ++l) {
+        for (int l = 1; l < nl; ++l) {
             Level& F = levels_[l - 1];
             Level& C = levels_[l];
+            const bool gather = nranks_ > 1 && l == dist_levels_;
+            const int cell_off = C.sharded ? ranges_[l].cl0 : 0;
+            int own0 = 0, own1 = C.g.ny;
+            if (C.sharded || gather) {
+                const RowRange rc = row_range(l, rank_, false);  // my share even if C is replicated
+                own0 = rc.c0 - cell_off;
+                own1 = rc.c1 - cell_off;
+            }
             dim3 blk(32, 8), grd(ceil_div(C.g.nx, 32), ceil_div(C.g.ny, 8));
             if (l == 1)
-                mg_coarsen_moments_kernel<T, false><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, co_tab_, C.W.p);
+                mg_coarsen_moments_kernel<T, false><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, cell_off, own0,
+                                                                             own1, co_tab_, C.W.p);
             else
-                mg_coarsen_moments_kernel<T, true><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, co_tab_, C.W.p);
+                mg_coarsen_moments_kernel<T, true><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, cell_off, own0,
+                                                                            own1, co_tab_, C.W.p);
             TM_CHECK_LAUNCH();
+            if (C.sharded) exchange_w(l, C.W.p);
+            if (gather) {
+                const size_t plane = (size_t)C.g.nx * C.g.ny;
+                for (int k = 0; k < 12; ++k) gather_rows(l, C.W.p + k * plane, (size_t)C.g.nx, true);
+            }
         }
-        if (nl > 32) throw Invalid{"too many multigrid levels"};
-        for (size_t l = 0; l + 1 < nl; ++l) {
+        for (int l = 0; l + 1 < nl; ++l) {
             Level& L = levels_[l];
             launch_diag(L.g, l > 0, L.dinv.p);
             // lambda_max(D^-1 A) by power iteration, warm-started across solves
-            const int g1 = grid1d(L.nu);
+            const int g1 = grid1d(L.cnt);
             int its = 4;
             if (!L.eig_ready) {
                 mg_seed_vector_kernel<T><<<grid1d(L.nu / 2), kVecThreads, 0, stream_>>>(L.g, L.eig.p);
@@ -740,18 +995,22 @@ class Engine : public EngineBase {
                 its = 10;
                 L.eig_ready = true;
             }
-            double* slots = eig_sc_ + 2 * l;
-            dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.nu, L.eig.p, L.eig.p, rs_, slots + 1);
+            double* slot = eig_sc_ + 2 * l + 1;
+            dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.cnt, L.eig.p + L.off, L.eig.p + L.off, rs_, slot);
             TM_CHECK_LAUNCH();
+            if (L.sharded) sum_ranks(slot, 1);
             for (int it = 0; it < its; ++it) {
+                exchange_p2(l, L.eig.p);
                 ApplyArgs<T> a = apply_args();
                 a.x = L.eig.p; a.y = L.tmp.p;
                 launch_apply(L.g, l > 0, EP_PLAIN, a);
-                // eig <- dinv .* tmp / ||eig_old||   (normalised by the previous norm)
-                normalize_scale_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.nu, L.dinv.p, L.tmp.p, L.eig.p, slots + 1);
+                // eig <- dinv .* tmp / ||eig_old||
+                normalize_scale_kernel<T><<<g1, kVecThreads, 0, stream_>>>(
+                    L.cnt, L.dinv.p + L.off, L.tmp.p + L.off, L.eig.p + L.off, slot);
                 TM_CHECK_LAUNCH();
-                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.nu, L.eig.p, L.eig.p, rs_, slots + 1);
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.cnt, L.eig.p + L.off, L.eig.p + L.off, rs_, slot);
                 TM_CHECK_LAUNCH();
+                if (L.sharded) sum_ranks(slot, 1);
             }
         }
         {
@@ -762,7 +1021,7 @@ class Engine : public EngineBase {
         TM_CUDA(cudaMemcpyAsync(h_sc_ + SC_COUNT, eig_sc_, sizeof(double) * 2 * (nl - 1),
                                 cudaMemcpyDeviceToHost, stream_));
         TM_CUDA(cudaStreamSynchronize(stream_));
-        for (size_t l = 0; l + 1 < nl; ++l) {
+        for (int l = 0; l + 1 < nl; ++l) {
             // after normalising by the previous norm, ||eig||^2 -> lambda^2
             const double lam = std::sqrt(h_sc_[SC_COUNT + 2 * l + 1]);
             if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"multigrid: eigenvalue estimate failed"};
@@ -771,7 +1030,7 @@ class Engine : public EngineBase {
     }
 
     // Chebyshev-Jacobi smoothing of A x = b on level l; xin == nullptr means zero initial guess
-    T* smooth(size_t l, const T* b, T* xin) {
+    T* smooth(int l, const T* b, T* xin) {
         Level& L = levels_[l];
         const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
         const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
@@ -779,8 +1038,8 @@ class Engine : public EngineBase {
         T* cur;
         int k0 = 0;
         if (!xin) {
-            cheb_first_kernel<T><<<grid1d(L.nu), kVecThreads, 0, stream_>>>(L.nu, 1.0 / theta, L.dinv.p, b,
-                                                                        L.d.p, L.x.p);
+            cheb_first_kernel<T><<<grid1d(L.cnt), kVecThreads, 0, stream_>>>(
+                L.cnt, 1.0 / theta, L.dinv.p + L.off, b + L.off, L.d.p + L.off, L.x.p + L.off);
             TM_CHECK_LAUNCH();
             cur = L.x.p;
             k0 = 1;
@@ -799,6 +1058,7 @@ class Engine : public EngineBase {
                 rho = rho_new;
             }
             T* other = (cur == L.x.p) ? L.xalt.p : L.x.p;
+            exchange_p2(l, cur);
             ApplyArgs<T> a = apply_args();
             a.x = cur; a.y = other; a.b = b; a.dinv = L.dinv.p; a.d = L.d.p;
             a.c1 = (T)c1; a.c2 = (T)c2;
@@ -809,21 +1069,26 @@ class Engine : public EngineBase {
     }
 
     // z = V(r): one symmetric V-cycle with zero initial guess
-    const T* vcycle(const T* r) {
-        const size_t nl = levels_.size();
+    T* vcycle(T* r) {
+        const int nl = nlevels_;
         std::vector<T*> xs(nl, nullptr);
         std::vector<const T*> bs(nl, nullptr);
         bs[0] = r;
-        for (size_t l = 0; l + 1 < nl; ++l) {
+        for (int l = 0; l + 1 < nl; ++l) {
             Level& L = levels_[l];
             Level& C = levels_[l + 1];
             xs[l] = smooth(l, bs[l], nullptr);
+            exchange_p2(l, xs[l]);
             ApplyArgs<T> a = apply_args();
             a.x = xs[l]; a.y = L.tmp.p; a.b = bs[l];
             launch_apply(L.g, l > 0, EP_RESID, a);
+            exchange_p2(l, L.tmp.p);
+            const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
             dim3 blk(32, 8), grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
-            mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, L.tmp.p, C.b.p);
+            mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, gather ? C.gpiece : C.g, tr_tab_, L.tmp.p,
+                                                           C.b.p);
             TM_CHECK_LAUNCH();
+            if (gather) gather_rows(l + 1, C.b.p, (size_t)C.g.Lx * 2, false);
             bs[l + 1] = C.b.p;
         }
         {
@@ -832,9 +1097,10 @@ class Engine : public EngineBase {
             TM_CHECK_LAUNCH();
             xs[nl - 1] = C.x.p;
         }
-        for (size_t l = nl - 1; l-- > 0;) {
+        for (int l = nl - 1; l-- > 0;) {
             Level& L = levels_[l];
             Level& C = levels_[l + 1];
+            exchange_p2(l + 1, xs[l + 1]);
             dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
             mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
@@ -847,9 +1113,13 @@ class Engine : public EngineBase {
     // ------------------------------------------------------------------ state
     tm_config cfg_;
     cudaStream_t stream_ = nullptr;
-    int nx_, ny_, num_sms_ = 148;
+    int nx_, nyg_, ny_ = 0, num_sms_ = 148;
+    int rank_ = 0, nranks_ = 1, dist_levels_ = 0, nlevels_ = 1;
+    NcclComm comm_ = nullptr;
+    std::vector<int> starts_, lv_nx_, lv_ny_, lv_dr_, lv_dt_;
+    std::vector<RowRange> ranges_;
     double hx_, hy_;
-    size_t n1_, n2_, nu_;
+    size_t n1_ = 0, n2_ = 0, nu_ = 0, p2_off_ = 0, p2_cnt_ = 0, p1_off_ = 0, p1_cnt_ = 0;
     P1Geom p1_;
     LevelGeom<T> g0_;
     DiagTable diag_tab_;
@@ -863,7 +1133,7 @@ class Engine : public EngineBase {
     int precond_ = TM_PRECOND_MULTIGRID, cheb_degree_ = 3, check_every_ = 0, coarse_cells_ = 2;
     double cheb_ratio_ = 10.0, eig_safety_ = 1.1;
 
-    DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_;
+    DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_, f_p2_;
     bool f_dinv_ready_ = false;
     DevBuf<T> s_r_, s_p_, s_Ap_, s_b_, s_dinv_;
     std::vector<Level> levels_;
@@ -873,9 +1143,10 @@ class Engine : public EngineBase {
     bool profile_ = false;
     int blocks_per_sm_target_ = 4, min_rows_per_strip_ = 1;
     bool filter_persistent_ = true;
+    int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
+    bool apply_prefetch_ = true;
     int filter_blocks_ = 0;
     double* filter_part_ = nullptr;
-    DevBuf<T> f_p2_;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free_;
     int stats_iters_ = 0;
@@ -927,7 +1198,7 @@ int guarded(tm_handle h, F&& f) {
 extern "C" {
 
 const char* tm_last_error(void) { return tmx::last_error(); }
-const char* tm_version(void) { return "topomax_b200 0.1 (sm_100a)"; }
+const char* tm_version(void) { return "topomax_b200 0.2 (sm_100a)"; }
 
 int tm_create(const tm_config* cfg, tm_handle* out) {
     if (!cfg || !out) {
@@ -968,13 +1239,41 @@ int tm_set_option(tm_handle h, int option, double value) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->set_option(option, value); });
 }
+int tm_comm_unique_id(char* id128) {
+    if (!id128) {
+        tmx::set_error("tm_comm_unique_id: null argument");
+        return TM_ERR_INVALID;
+    }
+    return guarded(nullptr, [&] {
+        if (!tmx::nccl().load()) throw tmx::Invalid{tmx::nccl().error};
+        tmx::NcclUniqueId id;
+        const int rc = tmx::nccl().GetUniqueId(&id);
+        if (rc != 0) throw tmx::Invalid{std::string("ncclGetUniqueId: ") + tmx::nccl().GetErrorString(rc)};
+        std::memcpy(id128, id.internal, 128);
+    });
+}
+int tm_comm_init(tm_handle h, const char* id128) {
+    TM_REQUIRE_HANDLE(h);
+    if (!id128) {
+        tmx::set_error("tm_comm_init: null argument");
+        return TM_ERR_INVALID;
+    }
+    return guarded(h, [&] { h->impl->comm_init(id128); });
+}
+int tm_local_layout(tm_handle h, int* out, int n) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->layout(out, n); });
+}
 int tm_load_vector(tm_handle h, const tm_loads* loads, void* b) {
     TM_REQUIRE_HANDLE(h);
-    if (!loads || !b) { tmx::set_error("tm_load_vector: null argument"); return TM_ERR_INVALID; }
+    if (!loads || !b) {
+        tmx::set_error("tm_load_vector: null argument");
+        return TM_ERR_INVALID;
+    }
     return guarded(h, [&] { h->impl->load_vector(*loads, b); });
 }
-int tm_filter_apply(tm_handle h, int rhs_kind, const void* in, void* out, double rtol, int maxit,
-                    int* iters, double* relres) {
+int tm_filter_apply(tm_handle h, int rhs_kind, void* in, void* out, double rtol, int maxit, int* iters,
+                    double* relres) {
     TM_REQUIRE_HANDLE(h);
     tmx::SolveStats st;
     int rc = guarded(h, [&] { st = h->impl->filter_apply(rhs_kind, in, out, rtol, maxit); });
@@ -986,16 +1285,16 @@ int tm_filter_apply(tm_handle h, int rhs_kind, const void* in, void* out, double
     }
     return rc;
 }
-int tm_elast_matvec(tm_handle h, const void* xi, double penalty, const void* x, void* y) {
+int tm_elast_matvec(tm_handle h, void* xi, double penalty, void* x, void* y) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->elast_matvec(xi, penalty, x, y); });
 }
-int tm_elast_diag(tm_handle h, const void* xi, double penalty, void* dinv) {
+int tm_elast_diag(tm_handle h, void* xi, double penalty, void* dinv) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->elast_diag(xi, penalty, dinv); });
 }
-int tm_state_solve(tm_handle h, const void* xi, double penalty, const void* b, void* u, double rtol,
-                   int maxit, int flags, int* iters, double* relres) {
+int tm_state_solve(tm_handle h, void* xi, double penalty, const void* b, void* u, double rtol, int maxit,
+                   int flags, int* iters, double* relres) {
     TM_REQUIRE_HANDLE(h);
     tmx::SolveStats st;
     int rc = guarded(h, [&] { st = h->impl->state_solve(xi, penalty, b, u, rtol, maxit, flags); });
@@ -1036,13 +1335,12 @@ int tm_last_solve_stats(tm_handle h, double* out, int n) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->last_stats(out, n); });
 }
-
 int tm_profile_read(tm_handle h, double* out, int n) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->profile_read(out, n); });
 }
 long long tm_launch_count(void) { return tmx::g_launches.load(); }
-int tm_mg_debug(tm_handle h, const void* xi, int op, int level, const void* in, void* out) {
+int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* out) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->mg_debug(xi, op, level, in, out); });
 }

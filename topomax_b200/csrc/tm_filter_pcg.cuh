@@ -22,6 +22,8 @@ namespace tmx {
 
 namespace cg = cooperative_groups;
 
+constexpr int kFilterThreads = 512;
+
 struct FilterPcgArgs {
     P1Geom g;
     double alpha, beta;   // operator alpha K1 + beta M1
@@ -81,29 +83,9 @@ __device__ __forceinline__ void store_block_partials(double (&val)[NV], double* 
     __syncthreads();
 }
 
-// row `v=(ix,iy)` of (alpha K1 + beta M1) applied to a field given by a functor f(vertex index)
-template <class F>
-__device__ __forceinline__ double p1_row_apply(const P1Geom& g, double alpha, double beta, int ix,
-                                               int iy, F&& f) {
-    double acc = 0.0;
-    for (int cy = max(iy - 1, 0); cy <= min(iy, g.ny - 1); ++cy)
-        for (int cx = max(ix - 1, 0); cx <= min(ix, g.nx - 1); ++cx) {
-#pragma unroll
-            for (int type = 0; type < 2; ++type) {
-                const int kl = corner_to_tri_local(type, ix - cx, iy - cy);
-                if (kl < 0) continue;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    acc += (alpha * g.Ke[type][kl][k] + beta * g.Me[kl][k]) *
-                           f(tri_vertex(type, k, cx, cy, g.nx));
-            }
-        }
-    return acc;
-}
-
 // x holds the initial guess on entry and the solution on exit; r, Ap, p0, p1 are scratch (n1 each)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFilterThreads)
 filter_pcg_kernel(const FilterPcgArgs a, const T* __restrict__ rhs, const T* __restrict__ dinv,
                   T* x, T* r, T* Ap, T* p0, T* p1) {
     cg::grid_group grid = cg::this_grid();

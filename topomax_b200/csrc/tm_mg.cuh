@@ -21,11 +21,13 @@
 
 namespace tmx {
 
-// fine moments of triangle `type` of fine cell (cx,cy); zero outside the fine mesh
+// fine moments of triangle `type` of fine cell (cx, cyg) -- cyg is the GLOBAL fine cell row;
+// zero outside the fine mesh (overhanging coarse cells)
 template <typename T, bool FINE_STORED>
-__device__ __forceinline__ void fine_moments(const LevelGeom<T>& f, int type, int cx, int cy,
+__device__ __forceinline__ void fine_moments(const LevelGeom<T>& f, int type, int cx, int cyg,
                                              double w[6]) {
-    if (cx >= f.nx || cy >= f.ny) {
+    const int cy = cyg - (f.j_off >> 1);  // local fine cell row
+    if (cx >= f.nx || cyg >= f.nyg || cy < 0 || cy >= f.ny) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) w[k] = 0.0;
         return;
@@ -45,18 +47,22 @@ __device__ __forceinline__ void fine_moments(const LevelGeom<T>& f, int type, in
 
 // W_c (SoA, 12 planes of nxc*nyc) from the fine level
 template <typename T, bool FINE_STORED>
-__global__ void mg_coarsen_moments_kernel(const LevelGeom<T> f, int nxc, int nyc,
-                                          const CoarsenTable tab, T* __restrict__ Wc) {
+__global__ void mg_coarsen_moments_kernel(const LevelGeom<T> f, int nxc, int nyc, int c_cell_off,
+                                          int own_c0, int own_c1, const CoarsenTable tab,
+                                          T* __restrict__ Wc) {
+    // (nxc, nyc): local coarse cells; local coarse cell row 0 is global row c_cell_off; only the
+    // owned rows [own_c0, own_c1) are produced (halo rows arrive by exchange)
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
-    if (I >= nxc || J >= nyc) return;
+    if (I >= nxc || J >= nyc || J < own_c0 || J >= own_c1) return;
+    const int Jg = J + c_cell_off;
     const size_t plane = (size_t)nxc * nyc, cidx = (size_t)J * nxc + I;
     for (int ctype = 0; ctype < 2; ++ctype) {
         double acc[3][3] = {};
         for (int s4 = 0; s4 < 4; ++s4) {
             const int s = 4 * ctype + s4;
             double w[6];
-            fine_moments<T, FINE_STORED>(f, tab.type[s], 2 * I + tab.dx[s], 2 * J + tab.dy[s], w);
+            fine_moments<T, FINE_STORED>(f, tab.type[s], 2 * I + tab.dx[s], 2 * Jg + tab.dy[s], w);
             // acc += M w M^T
             double tmp[3][3];
 #pragma unroll
@@ -102,16 +108,18 @@ __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
                                    T* __restrict__ bc) {
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
-    if (I >= c.Lx || J >= c.Ly) return;
+    if (I >= c.Lx || J >= c.Ly || !c.owns_row(J)) return;
     double a0 = 0.0, a1 = 0.0;
     if (!c.fixed(I, J)) {
+        const int Jg = J + c.j_off;  // global coarse lattice row
         for (int dj = -3; dj <= 3; ++dj) {
-            const int j = 2 * J + dj;
-            if (j < 0 || j >= f.Ly) continue;
+            const int jg = 2 * Jg + dj;  // global fine lattice row
+            const int j = jg - f.j_off;
+            if (jg < 0 || jg > 2 * f.nyg || j < 0 || j >= f.Ly) continue;
             for (int di = -3; di <= 3; ++di) {
                 const int i = 2 * I + di;
                 if (i < 0 || i >= f.Lx) continue;
-                const double w = transfer_weight(tab, c.nx, c.ny, i, j, I, J);
+                const double w = transfer_weight(tab, c.nx, c.nyg, i, jg, I, Jg);
                 if (w == 0.0) continue;
                 const size_t n = (size_t)j * f.Lx + i;
                 a0 += w * (double)r[2 * n];
@@ -131,16 +139,17 @@ __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c
                                       T* __restrict__ x) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= f.Lx || j >= f.Ly) return;
+    if (i >= f.Lx || j >= f.Ly || !f.owns_row(j)) return;
     if (f.fixed(i, j)) return;
-    const int cx = min(i >> 2, c.nx - 1), cy = min(j >> 2, c.ny - 1);
-    const double* pw = tab.Pw[5 * (j - 4 * cy) + (i - 4 * cx)];
+    const int jg = j + f.j_off;  // global fine lattice row
+    const int cx = min(i >> 2, c.nx - 1), cy = min(jg >> 2, c.nyg - 1);
+    const double* pw = tab.Pw[5 * (jg - 4 * cy) + (i - 4 * cx)];
     double a0 = 0.0, a1 = 0.0;
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
         const double w = pw[q];
         if (w == 0.0) continue;
-        const size_t N = (size_t)(2 * cy + q / 3) * c.Lx + (2 * cx + q % 3);
+        const size_t N = (size_t)(2 * cy + q / 3 - c.j_off) * c.Lx + (2 * cx + q % 3);
         a0 += w * (double)xc[2 * N];
         a1 += w * (double)xc[2 * N + 1];
     }
@@ -239,7 +248,7 @@ __global__ void mg_seed_vector_kernel(const LevelGeom<T> g, T* __restrict__ v) {
         const int j = (int)(n / g.Lx), i = (int)(n - (size_t)j * g.Lx);
         const bool f = g.fixed(i, j);
         for (int c = 0; c < 2; ++c) {
-            unsigned int h = (unsigned int)(2 * n + c) * 2654435761u;
+            unsigned int h = (unsigned int)(2 * (n + (size_t)g.j_off * g.Lx) + c) * 2654435761u;
             h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
             v[2 * n + c] = f ? T(0) : (T)(0.5 + (double)(h & 0xffffu) / 65536.0);
         }

@@ -15,7 +15,17 @@ struct P1Geom {
     double hx, hy;
     double Ke[2][3][3];    // |T| grad(lambda_i).grad(lambda_j), T_A then T_B
     double Me[3][3];       // |T|/12 (1 + delta_ij)
+    // assembled interior rows of K1 and M1: centre, E, W, N, S, NE, SW (the "right" diagonal
+    // couples NE/SW only); boundary vertices go through the element loop
+    double sK[7], sM[7];
+    // row-strip sharding: local vertex row 0 is global row iy_off; only rows in
+    // [own_iy0, own_iy1) are written / summed by this rank (one GPU: 0, ny_global = ny, all rows)
+    int iy_off, ny_global, own_iy0, own_iy1;
+    __host__ __device__ bool owns_row(int iy) const { return iy >= own_iy0 && iy < own_iy1; }
 };
+
+// fills sK/sM by assembling the row of the centre vertex of a 2x2-cell patch
+inline void p1_fill_interior_stencil(P1Geom& g);
 
 // triangle-local vertex (0..2) of cell corner (ax,ay) in {0,1}^2, or -1
 __host__ __device__ __forceinline__ int corner_to_tri_local(int type, int ax, int ay) {
@@ -31,6 +41,60 @@ __host__ __device__ __forceinline__ size_t tri_vertex(int type, int k, int cx, i
     return (size_t)(cy + ay) * (nx + 1) + (cx + ax);
 }
 
+// row (ix,iy) of alpha K1 + beta M1 applied to the field f(vertex index)
+template <class F>
+__device__ __forceinline__ double p1_row_apply(const P1Geom& g, double alpha, double beta, int ix,
+                                               int iy, F&& f) {
+    if (ix > 0 && ix < g.nx && iy > 0 && iy < g.ny) {
+        const size_t v = (size_t)iy * (g.nx + 1) + ix;
+        const size_t W1 = g.nx + 1;
+        double acc = (alpha * g.sK[0] + beta * g.sM[0]) * f(v);
+        acc += (alpha * g.sK[1] + beta * g.sM[1]) * f(v + 1);
+        acc += (alpha * g.sK[2] + beta * g.sM[2]) * f(v - 1);
+        acc += (alpha * g.sK[3] + beta * g.sM[3]) * f(v + W1);
+        acc += (alpha * g.sK[4] + beta * g.sM[4]) * f(v - W1);
+        acc += (alpha * g.sK[5] + beta * g.sM[5]) * f(v + W1 + 1);
+        acc += (alpha * g.sK[6] + beta * g.sM[6]) * f(v - W1 - 1);
+        return acc;
+    }
+    double acc = 0.0;
+    for (int cy = max(iy - 1, 0); cy <= min(iy, g.ny - 1); ++cy)
+        for (int cx = max(ix - 1, 0); cx <= min(ix, g.nx - 1); ++cx) {
+#pragma unroll
+            for (int type = 0; type < 2; ++type) {
+                const int kl = corner_to_tri_local(type, ix - cx, iy - cy);
+                if (kl < 0) continue;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    acc += (alpha * g.Ke[type][kl][k] + beta * g.Me[kl][k]) *
+                           f(tri_vertex(type, k, cx, cy, g.nx));
+            }
+        }
+    return acc;
+}
+
+inline void p1_fill_interior_stencil(P1Geom& g) {
+    for (int k = 0; k < 7; ++k) g.sK[k] = g.sM[k] = 0.0;
+    const int off[7][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {-1, -1}};
+    // centre vertex (1,1) of a 2x2-cell patch
+    for (int cy = 0; cy < 2; ++cy)
+        for (int cx = 0; cx < 2; ++cx)
+            for (int type = 0; type < 2; ++type) {
+                const int kl = corner_to_tri_local(type, 1 - cx, 1 - cy);
+                if (kl < 0) continue;
+                for (int k = 0; k < 3; ++k) {
+                    const int ax = (k == 2) ? 1 : ((k == 1 && type == 0) ? 1 : 0);
+                    const int ay = (k == 2) ? 1 : ((k == 1 && type == 1) ? 1 : 0);
+                    const int dx = cx + ax - 1, dy = cy + ay - 1;
+                    for (int o = 0; o < 7; ++o)
+                        if (off[o][0] == dx && off[o][1] == dy) {
+                            g.sK[o] += g.Ke[type][kl][k];
+                            g.sM[o] += g.Me[kl][k];
+                        }
+                }
+            }
+}
+
 // y = (alpha K1 + beta M1) x    [optionally the grid-wide x . y]
 // Filter operator A_f = eps^2 K1 + M1 (reference: FEM_src/filter.py:27-33); alpha=0, beta=1
 // gives the consistent-mass product M1 rho of the filter's right-hand side (:35-36).
@@ -40,21 +104,8 @@ __global__ void p1_apply_kernel(const P1Geom g, double alpha, double beta, const
     const int ix = blockIdx.x * blockDim.x + threadIdx.x;
     const int iy = blockIdx.y * blockDim.y + threadIdx.y;
     double dot = 0.0;
-    if (ix <= g.nx && iy <= g.ny) {
-        double acc = 0.0;
-        for (int cy = max(iy - 1, 0); cy <= min(iy, g.ny - 1); ++cy)
-            for (int cx = max(ix - 1, 0); cx <= min(ix, g.nx - 1); ++cx) {
-#pragma unroll
-                for (int type = 0; type < 2; ++type) {
-                    const int kl = corner_to_tri_local(type, ix - cx, iy - cy);
-                    if (kl < 0) continue;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const double xv = (double)x[tri_vertex(type, k, cx, cy, g.nx)];
-                        acc += (alpha * g.Ke[type][kl][k] + beta * g.Me[kl][k]) * xv;
-                    }
-                }
-            }
+    if (ix <= g.nx && iy <= g.ny && g.owns_row(iy)) {
+        const double acc = p1_row_apply(g, alpha, beta, ix, iy, [&](size_t j) { return (double)x[j]; });
         const size_t v = (size_t)iy * (g.nx + 1) + ix;
         y[v] = (T)acc;
         if (DOT) dot = (double)x[v] * acc;
@@ -85,9 +136,10 @@ __global__ void p1_diag_kernel(const P1Geom g, double alpha, double beta, T* __r
 
 // nodal quadrature weight w_i = (M1 . 1)_i = |T|/3 * (#incident triangles)
 // (reference: FEM_src/solver.py:81-84, integrate = assemble(f*dx) of the P1 interpolant)
-__device__ __forceinline__ double p1_weight(const P1Geom& g, int ix, int iy) {
+__device__ __forceinline__ double p1_weight(const P1Geom& g, int ix, int iy_local) {
     int cnt = 0;
-    for (int cy = max(iy - 1, 0); cy <= min(iy, g.ny - 1); ++cy)
+    const int iy = iy_local + g.iy_off;  // global vertex row decides the boundary weights
+    for (int cy = max(iy - 1, 0); cy <= min(iy, g.ny_global - 1); ++cy)
         for (int cx = max(ix - 1, 0); cx <= min(ix, g.nx - 1); ++cx)
             for (int type = 0; type < 2; ++type)
                 if (corner_to_tri_local(type, ix - cx, iy - cy) >= 0) ++cnt;
@@ -106,6 +158,7 @@ __global__ void md_volume_kernel(const P1Geom g, const T* __restrict__ half, dou
     for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n1;
          v += (size_t)gridDim.x * blockDim.x) {
         const int iy = (int)(v / (g.nx + 1)), ix = (int)(v - (size_t)iy * (g.nx + 1));
+        if (!g.owns_row(iy)) continue;
         const double w = p1_weight(g, ix, iy);
         const double s = expit_d((double)half[v] + c);
         val[0] += w * s;
@@ -126,6 +179,7 @@ __global__ void md_apply_kernel(const P1Geom g, const T* __restrict__ half, doub
     for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n1;
          v += (size_t)gridDim.x * blockDim.x) {
         const int iy = (int)(v / (g.nx + 1)), ix = (int)(v - (size_t)iy * (g.nx + 1));
+        if (!g.owns_row(iy)) continue;
         const double w = p1_weight(g, ix, iy);
         const double prev = expit_d((double)psi_prev[v]);
         const double p = (double)half[v] + c;
@@ -148,6 +202,7 @@ __global__ void p1_integrate_kernel(const P1Geom g, const T* __restrict__ values
     for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n1;
          v += (size_t)gridDim.x * blockDim.x) {
         const int iy = (int)(v / (g.nx + 1)), ix = (int)(v - (size_t)iy * (g.nx + 1));
+        if (!g.owns_row(iy)) continue;
         val[0] += p1_weight(g, ix, iy) * (double)values[v];
     }
     double* const outs[1] = {out};
@@ -159,10 +214,11 @@ __global__ void p1_integrate_kernel(const P1Geom g, const T* __restrict__ values
 // (reference: FEM_src/elasisity_problem.py:146-150), gathered per vertex
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void sens_rhs_kernel(const LevelGeom<T> g, const T* __restrict__ u, T* __restrict__ out) {
+__global__ void sens_rhs_kernel(const LevelGeom<T> g, int own_iy0, int own_iy1,
+                                const T* __restrict__ u, T* __restrict__ out) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x;
     const int iy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ix > g.nx || iy > g.ny) return;
+    if (ix > g.nx || iy > g.ny || iy < own_iy0 || iy >= own_iy1) return;
     double acc = 0.0;
     for (int cy = max(iy - 1, 0); cy <= min(iy, g.ny - 1); ++cy)
         for (int cx = max(ix - 1, 0); cx <= min(ix, g.nx - 1); ++cx) {
@@ -203,7 +259,8 @@ __global__ void sens_rhs_kernel(const LevelGeom<T> g, const T* __restrict__ u, T
 // (round-to-nearest ops, no FMA contraction): which nodes are "inside" decides the load.
 // ---------------------------------------------------------------------------------------
 struct LoadSpec {
-    int nx, ny;
+    int nx, ny;        // global cell counts
+    int j_off, Ly_loc; // local lattice rows [j_off, j_off + Ly_loc) are produced
     double W, H;
     int has_force;
     double fcx, fcy, frad, fx, fy;
@@ -249,8 +306,9 @@ template <typename T>
 __global__ void load_vector_kernel(const LoadSpec s, T* __restrict__ b) {
     const int Lx = 2 * s.nx + 1, Ly = 2 * s.ny + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= Lx || j >= Ly) return;
+    const int jl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= Lx || jl >= s.Ly_loc) return;
+    const int j = jl + s.j_off;  // global lattice row
     double b0 = 0.0, b1 = 0.0;
     if (s.has_force) {
         double acc = 0.0;
@@ -307,7 +365,7 @@ __global__ void load_vector_kernel(const LoadSpec s, T* __restrict__ b) {
         b0 += a0;
         b1 += a1;
     }
-    const size_t n = (size_t)j * Lx + i;
+    const size_t n = (size_t)jl * Lx + i;
     b[2 * n] = (T)b0;
     b[2 * n + 1] = (T)b1;
 }

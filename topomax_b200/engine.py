@@ -42,7 +42,8 @@ class Engine:
 
     def __init__(self, nx: int, ny: int, width: float, height: float, *, lame_lambda: float = 1.0,
                  lame_mu: float = 1.0, simp_min: float = 1e-6, filter_radius: float = 0.0,
-                 fixed_sides=(), dtype: str = "float64", device=None):
+                 fixed_sides=(), dtype: str = "float64", device=None, rank: int = 0, nranks: int = 1,
+                 dist_levels: int = 0):
         self.lib = _lib.load_library()
         self.device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0) \
             if device is None else torch.device(device)
@@ -53,9 +54,7 @@ class Engine:
         self.dtype = _TORCH_DTYPE[dtype]
         self.nx, self.ny = int(nx), int(ny)
         self.width, self.height = float(width), float(height)
-        self.n1 = (self.nx + 1) * (self.ny + 1)
-        self.n2 = (2 * self.nx + 1) * (2 * self.ny + 1)
-        self.nu = 2 * self.n2
+        self.rank, self.nranks = int(rank), int(nranks)
         bits = 0
         for side in fixed_sides:
             if side not in _SIDE_BITS:
@@ -65,12 +64,48 @@ class Engine:
             nx=self.nx, ny=self.ny, width=self.width, height=self.height,
             lame_lambda=lame_lambda, lame_mu=lame_mu, simp_min=simp_min,
             filter_radius=filter_radius, fixed_sides=bits, dtype=_TM_DTYPE[dtype],
-            device=self.device.index or 0,
+            device=self.device.index or 0, rank=self.rank, nranks=self.nranks, mg_dist_levels=int(dist_levels),
         )
         handle = c_void_p()
         _lib.check(self.lib.tm_create(byref(cfg), byref(handle)))
         self._h = handle
+        # rank-local storage: cell rows [cl0, cl1) are stored (owned [c0, c1) + halo rows)
+        lay = (c_int * 10)()
+        _lib.check(self.lib.tm_local_layout(self._h, lay, 10))
+        (_, _, _, _, self.cl0, self.cl1, self.c0, self.c1, owns_top, self.dist_levels) = tuple(lay)
+        self.owns_top = bool(owns_top)
+        self.ny_local = self.cl1 - self.cl0
+        self.n1 = (self.nx + 1) * (self.ny_local + 1)
+        self.n2 = (2 * self.nx + 1) * (2 * self.ny_local + 1)
+        self.nu = 2 * self.n2
         self._sync_stream()
+
+    # ---------------------------------------------------------------- sharding
+    def init_comm(self, group=None):
+        """Create the engine's NCCL communicator; the unique id travels over torch.distributed."""
+        if self.nranks == 1:
+            return
+        import torch.distributed as dist
+        buf = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(self.lib.tm_comm_unique_id(buf))
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=self.device if on_gpu else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        self._sync_stream()
+        _lib.check(self.lib.tm_comm_init(self._h, raw))
+
+    def owned_p1_rows(self):
+        """(first, last+1) local vertex rows this rank owns, and their global offset."""
+        lo = self.c0 - self.cl0
+        hi = self.c1 - self.cl0 + (1 if self.owns_top else 0)
+        return lo, hi, self.c0
+
+    def owned_p2_rows(self):
+        lo = 2 * (self.c0 - self.cl0)
+        hi = 2 * (self.c1 - self.cl0) + (1 if self.owns_top else 0)
+        return lo, hi, 2 * self.c0
 
     def __del__(self):
         h = getattr(self, "_h", None)
