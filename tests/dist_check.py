@@ -86,7 +86,25 @@ def main():
         report[tag + "_volume"] = max(abs(v - v_ref) / abs(v_ref), abs(dv - dv_ref) / abs(dv_ref))
         report[tag + "_integrate"] = abs(eng.integrate(half) - ref.integrate(t(rhs_g))) / abs(ref.integrate(t(rhs_g)))
         del eng, ref
+    # the whole optimiser, sharded vs unsharded (device loop and the numpy-hook loop)
+    from topomax_b200.fem_solver import FEMSolver
+    design = os.path.join(ROOT, "designs", "cantilever.json")
+    sharded = FEMSolver(40, design, data_path=f"/tmp/tm_dist_{rank}", verbose=False, distributed=True, dist_levels=2)
+    rs = sharded.solve(fixed_iterations=4)
+    rho_s = sharded.to_array(sharded.rho)
+    single = FEMSolver(40, design, data_path=f"/tmp/tm_single_{rank}", verbose=False)
+    r1 = single.solve(fixed_iterations=4)
+    report["solver_objectives"] = float(max(abs(a - b) / abs(b) for a, b in zip(rs["objectives"], r1["objectives"])))
+    report["solver_rho"] = float(np.abs(rho_s - single.to_array(single.rho)).max())
+    hooks = FEMSolver(40, design, data_path=f"/tmp/tm_hooks_{rank}", skip_multiple=999, verbose=False, distributed=True,
+                      dist_levels=2)
+    hooks.solve_generic()
+    full = FEMSolver(40, design, data_path=f"/tmp/tm_full_{rank}", skip_multiple=999, verbose=False)
+    full.solve()
+    report["hooks_k"] = [hooks.last_result["k_final"], full.last_result["k_final"]]
+    report["hooks_rho"] = float(np.abs(hooks.to_array(hooks.rho) - full.to_array(full.rho)).max())
     if rank == 0:
+        report["files"] = sorted(os.listdir(f"/tmp/tm_hooks_0/FEM/cantilever/data"))[:3]
         print("DIST_REPORT " + json.dumps(report))
     dist.barrier()
     dist.destroy_process_group()

@@ -61,9 +61,10 @@ template <typename T, int EP>
 __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, bool fixed, T v0, T v1,
                                                T x0, T x1, double& dot) {
     using V2 = typename Vec2<T>::type;
-    if (fixed) {  // identity row
-        v0 = x0;
-        v1 = x1;
+    if (fixed) {  // identity row: the registers hold the masked input (0), fetch the raw value
+        const V2 xr = reinterpret_cast<const V2*>(a.x)[n];
+        x0 = v0 = xr.x;
+        x1 = v1 = xr.y;
     }
     V2 out;
     if (EP == EP_PLAIN || EP == EP_DOT) {
@@ -119,7 +120,6 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 
     if (warp_active) {
         const V2* __restrict__ xv = reinterpret_cast<const V2*>(a.x);
-        V2* __restrict__ yv = reinterpret_cast<V2*>(a.y);
         const int Lx = g.Lx;
         const int i0 = 2 * ix;
         bool colok[3], colfix[3];
@@ -129,7 +129,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             colfix[c] = (i0 + c) <= g.dl || (i0 + c) >= g.dr;
         }
 
-        T X[9][2];  // raw input of the cell's 3x3 lattice block
+        T X[9][2];  // input on the cell's 3x3 lattice block, zeroed on Dirichlet nodes
 #pragma unroll
         for (int q = 0; q < 9; ++q) X[q][0] = X[q][1] = T(0);
         T xiv[4] = {T(0), T(0), T(0), T(0)};  // density at v0 v1 v2 v3 (level 0)
@@ -140,11 +140,13 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
         {
             const size_t row = (size_t)(2 * iy_start) * Lx;
 #pragma unroll
+            const bool rowfix = g.row_fixed(2 * iy_start);
             for (int c = 0; c < 3; ++c)
                 if (colok[c]) {
                     const V2 v = xv[row + i0 + c];
-                    X[6 + c][0] = v.x;
-                    X[6 + c][1] = v.y;
+                    const bool f = rowfix || colfix[c];
+                    X[6 + c][0] = f ? T(0) : v.x;
+                    X[6 + c][1] = f ? T(0) : v.y;
                 }
             if (!STORED_W && cell_ok) {
                 xiv[2] = g.xi[(size_t)iy_start * (g.nx + 1) + ix];
@@ -183,12 +185,14 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
             for (int r = 1; r < 3; ++r) {
                 const size_t row = (size_t)(j0 + r) * Lx;
+                const bool rowfix = g.row_fixed(j0 + r);
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                     if (colok[c]) {
                         const V2 v = xv[row + i0 + c];
-                        X[3 * r + c][0] = v.x;
-                        X[3 * r + c][1] = v.y;
+                        const bool f = rowfix || colfix[c];
+                        X[3 * r + c][0] = f ? T(0) : v.x;
+                        X[3 * r + c][1] = f ? T(0) : v.y;
                     }
             }
             T acc[9][2];
@@ -210,18 +214,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                     moments_from_xi<T>(xiv[0], xiv[1], xiv[3], g.simp_min, wA);
                     moments_from_xi<T>(xiv[0], xiv[2], xiv[3], g.simp_min, wB);
                 }
-                T Xm[9][2];  // Dirichlet columns of the operator: masked input
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const bool rowfix = g.row_fixed(j0 + r);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const bool f = rowfix || colfix[c];
-                        Xm[3 * r + c][0] = f ? T(0) : X[3 * r + c][0];
-                        Xm[3 * r + c][1] = f ? T(0) : X[3 * r + c][1];
-                    }
-                }
-                cell_apply<T>(Xm, wA, wB, g.mat, acc);
+                cell_apply<T>(X, wA, wB, g.mat, acc);
             }
             // right lattice column of the cell -> owner of that column (lane + 1)
 #pragma unroll

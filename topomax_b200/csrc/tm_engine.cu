@@ -177,7 +177,7 @@ class Engine : public EngineBase {
             case 102: blocks_per_sm_target_ = std::max(1, (int)value); break;
             case 103: min_rows_per_strip_ = std::max(1, (int)value); break;
             case 104: filter_persistent_ = value != 0.0; break;
-            case 105: apply_minb_ = (int)value == 3 ? 3 : 2; break;
+            case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
             case 106: apply_prefetch_ = value != 0.0; break;
             case 107:
                 filter_blocks_per_sm_ = std::max(1, (int)value);
@@ -800,6 +800,10 @@ class Engine : public EngineBase {
             TM_LAUNCH_APPLY_EP(true, 2, false)
         } else if (apply_minb_ == 3) {
             if (apply_prefetch_) { TM_LAUNCH_APPLY_EP(false, 3, true) } else { TM_LAUNCH_APPLY_EP(false, 3, false) }
+        } else if (apply_minb_ == 4) {
+            TM_LAUNCH_APPLY_EP(false, 4, true)
+        } else if (apply_minb_ == 5) {
+            TM_LAUNCH_APPLY_EP(false, 5, true)
         } else {
             if (apply_prefetch_) { TM_LAUNCH_APPLY_EP(false, 2, true) } else { TM_LAUNCH_APPLY_EP(false, 2, false) }
         }

@@ -22,8 +22,8 @@ class ElasticityProblem(Problem):
     def __init__(self, mesh: RectangleMesh, control_space: FunctionSpace,
                  domain_parameters: DomainParameters, elasticity_parameters: ElasticityParameters,
                  *, state_rtol: float = 1e-10, state_max_iterations: int = 200000,
-                 filter_rtol: float = 1e-13, preconditioner: str = "multigrid",
-                 warm_start: bool = True):
+                 filter_rtol: float = 1e-11, preconditioner: str = "multigrid",
+                 warm_start: bool = True, engine: Engine | None = None):
         self.parameters = elasticity_parameters
         self.domain_size = (domain_parameters.width, domain_parameters.height)
         self.mesh = mesh
@@ -36,7 +36,8 @@ class ElasticityProblem(Problem):
         self.lamé_mu = self.Young_modulus / (2 * (1 + self.Poisson_ratio))
         self.lamé_lda = self.lamé_mu * self.Poisson_ratio / (0.5 - self.Poisson_ratio)
 
-        self.engine = Engine(
+        # a sharded FEMSolver builds the engine first (it needs the partition to size its arrays)
+        self.engine = engine if engine is not None else Engine(
             mesh.nx, mesh.ny, mesh.width, mesh.height,
             lame_lambda=self.lamé_lda, lame_mu=self.lamé_mu, simp_min=self.penalizer.minimum,
             filter_radius=self.parameters.filter_radius, fixed_sides=self.parameters.fixed_sides,
@@ -51,7 +52,7 @@ class ElasticityProblem(Problem):
         self.warm_start = warm_start
 
         self.solution_space = FunctionSpace(mesh, "CG", 2, dtype=control_space.dtype_name,
-                                            device=self.engine.device)
+                                            device=self.engine.device, local_rows=control_space.local_rows)
         self.body_force = self.parameters.body_force
         self.traction_term = self.parameters.tractions or []
         # load vector, assembled once like SmartMumpsSolver(l_has_no_args=True)

@@ -57,12 +57,24 @@ def load_function(filename: str, *, dtype: str = "float64", device=None):
 class FEMSolver(Solver):
     def __init__(self, N: int, design_file: str, data_path: str = "output", skip_multiple: int = 1,
                  *, dtype: str = "float64", device=None, problem_options: dict | None = None,
-                 verbose: bool = True):
+                 verbose: bool = True, distributed: bool = False, dist_levels: int = 0):
+        """``distributed=True``: one process per GPU under torch.distributed; the mesh is cut into
+        strips of cell rows, every rank holds its strip + halo rows and the same
+        optimisation runs collectively.  Rank 0 prints and writes the output files."""
         self.dtype_name = dtype
         self.device = torch.device(device) if device is not None else None
         self.problem_options = dict(problem_options or {})
+        self.distributed = distributed
+        self.dist_levels = dist_levels
+        self.rank, self.world = 0, 1
+        if distributed:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._engine = None
         super().__init__(N, design_file, data_path, skip_multiple)
-        self.verbose = verbose
+        self.verbose = verbose and self.rank == 0
         self.problem: ElasticityProblem = self.problem
 
     # ------------------------------------------------------------------ hooks
@@ -79,7 +91,24 @@ class FEMSolver(Solver):
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.mesh = RectangleMesh(self.width, self.height,
                                   int(self.width * self.N), int(self.height * self.N))
-        self.control_space = FunctionSpace(self.mesh, "CG", 1, dtype=self.dtype_name, device=self.device)
+        local_rows = None
+        if self.world > 1:
+            # the partition comes from the library, so the engine is built before the spaces
+            from .designs.design_parser import parse_design
+            from .engine import Engine
+            from .penalizers import ElasticPenalizer
+            _, prm = parse_design(self.design_file)
+            mu = prm.young_modulus / (2 * (1 + prm.poisson_ratio))
+            lda = mu * prm.poisson_ratio / (0.5 - prm.poisson_ratio)
+            self._engine = Engine(self.mesh.nx, self.mesh.ny, self.width, self.height, lame_lambda=lda,
+                                  lame_mu=mu, simp_min=ElasticPenalizer().minimum,
+                                  filter_radius=prm.filter_radius, fixed_sides=prm.fixed_sides,
+                                  dtype=self.dtype_name, device=self.device, rank=self.rank,
+                                  nranks=self.world, dist_levels=self.dist_levels)
+            self._engine.init_comm()
+            local_rows = (self._engine.cl0, self._engine.cl1)
+        self.control_space = FunctionSpace(self.mesh, "CG", 1, dtype=self.dtype_name, device=self.device,
+                                           local_rows=local_rows)
 
     def create_rho(self, volume_fraction: float):
         rho = Function(self.control_space)
@@ -89,7 +118,7 @@ class FEMSolver(Solver):
     def create_problem(self, problem_parameters):
         if isinstance(problem_parameters, ElasticityParameters):
             return ElasticityProblem(self.mesh, self.control_space, self.parameters,
-                                     problem_parameters, **self.problem_options)
+                                     problem_parameters, engine=self._engine, **self.problem_options)
         if isinstance(problem_parameters, FluidParameters):
             raise NotImplementedError(
                 "the fluid problem is outside the accelerated path (SURVEY.md section 8f)")
@@ -98,20 +127,51 @@ class FEMSolver(Solver):
             f"with problem parameters of type '{type(problem_parameters)}'"
         )
 
+    # The numpy hooks always speak GLOBAL arrays (row-major vertex grid); on a sharded solver they
+    # gather / slice the rank-local strips.
     def to_array(self, rho: Function) -> np.ndarray:
+        if self.world > 1:
+            from . import sharding
+            return sharding.gather_p1(self.problem.engine, rho.tensor)
         return rho.vector()[:]
 
     def set_from_array(self, rho: Function, values: np.ndarray):
-        rho.vector()[:] = values
+        if self.world > 1:
+            from . import sharding
+            rho.tensor.copy_(sharding.local_p1(self.problem.engine, values))
+        else:
+            rho.vector()[:] = values
 
     def integrate(self, values: np.ndarray) -> float:
+        if self.world > 1:
+            from . import sharding
+            return self.problem.engine.integrate(sharding.local_p1(self.problem.engine, values))
         t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.rho.tensor.dtype).to(self.device)
         return self.problem.engine.integrate(t)
 
     def save_rho(self, rho: Function, file_root: str):
         rho_file = file_root + "_rho.dat"
-        save_function(rho, rho_file, "design")
+        if self.world > 1:
+            values = self.to_array(rho)  # collective
+            if self.rank == 0:
+                mesh = self.mesh
+                data = {"N": int(round(1 / (mesh.hmin() / np.sqrt(2)))), "domain_size": mesh.domain_size,
+                        "problem": "design", "vector": values.astype(np.float64)}
+                with open(rho_file, "wb") as fh:
+                    pickle.dump(data, fh)
+        else:
+            save_function(rho, rho_file, "design")
         return os.path.basename(rho_file)
+
+    def save_iteration(self, rho, objective, k, penalty):
+        if self.world > 1 and self.rank != 0:
+            self.save_rho(rho, "")  # take part in the gather, write nothing
+            return
+        super().save_iteration(rho, objective, k, penalty)
+
+    def save_result(self, objectives, times, penalty, exit_condition):
+        if self.rank == 0:
+            super().save_result(objectives, times, penalty, exit_condition)
 
     # ------------------------------------------------------------------ device-resident step
     def step_device(self, previous_psi: torch.Tensor, step_size: float, psi_out: torch.Tensor,

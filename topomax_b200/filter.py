@@ -20,7 +20,7 @@ class AssembledP1Form:
 
 class HelmholtzFilter:
     def __init__(self, epsilon: float, function_space: FunctionSpace, *, engine: Engine | None = None,
-                 rtol: float = 1e-13, max_iterations: int = 50000):
+                 rtol: float = 1e-11, max_iterations: int = 50000):
         if function_space.degree != 1:
             raise ValueError("the filter acts on the P1 control space")
         self.epsilon = float(epsilon)

@@ -36,7 +36,7 @@ class FunctionSpace:
     """"CG" degree 1 (scalar, vertex grid) or vector "CG" degree 2 (half-step lattice)."""
 
     def __init__(self, mesh: RectangleMesh, family: str = "CG", degree: int = 1, *,
-                 dtype: str = "float64", device=None):
+                 dtype: str = "float64", device=None, local_rows: tuple[int, int] | None = None):
         if family not in ("CG", "Lagrange", "P"):
             raise ValueError(f"unsupported element family {family!r}")
         if degree not in (1, 2):
@@ -45,10 +45,13 @@ class FunctionSpace:
         self.degree = degree
         self.dtype_name = dtype
         self.device = device
+        # row-strip sharding: this rank stores cell rows [cl0, cl1) only (owned + halo rows)
+        self.local_rows = local_rows
+        ny_stored = mesh.ny if local_rows is None else local_rows[1] - local_rows[0]
         if degree == 1:
-            self.shape = (mesh.ny + 1, mesh.nx + 1)
+            self.shape = (ny_stored + 1, mesh.nx + 1)
         else:
-            self.shape = (2 * mesh.ny + 1, 2 * mesh.nx + 1, 2)
+            self.shape = (2 * ny_stored + 1, 2 * mesh.nx + 1, 2)
 
     def mesh(self):
         return self._mesh
