@@ -37,7 +37,7 @@ enum { TM_PRECOND_JACOBI = 0, TM_PRECOND_MULTIGRID = 1 };
 /* integer / real options for tm_set_option */
 enum {
     TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
-    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps  (default 3)           */
+    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 2; coarse levels 3) */
     TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
     TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (default 2)     */
     TM_OPT_PROFILE = 5       /* 1: time every fine-level operator launch with CUDA events */

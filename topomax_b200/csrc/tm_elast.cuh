@@ -154,46 +154,71 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             }
         }
 
-        for (int iy = iy_start; iy < iy1; ++iy) {
-            const int j0 = 2 * iy;
-            if (PF && colok[0]) {
-                if (iy + 1 < iy1) {  // rows j0+3, j0+4 feed the next step (even columns touch every line)
-                    prefetch_l1(&xv[(size_t)(j0 + 3) * Lx + i0]);
-                    prefetch_l1(&xv[(size_t)(j0 + 4) * Lx + i0]);
-                    if (!STORED_W && cell_ok) prefetch_l1(&g.xi[(size_t)(iy + 2) * (g.nx + 1) + ix]);
-                }
-                if ((EP == EP_RESID || EP == EP_CHEB) && iy >= iy0) {
+        // software pipeline: the two new lattice rows (and densities) of step iy+1 are loaded
+        // into registers while step iy computes; epilogue operands are prefetched into L1 one
+        // step ahead.  Xn/xin hold the rows 2iy+1, 2iy+2 / vertex row iy+1 of the coming step.
+        T Xn[6][2];
+        T xin[2] = {T(0), T(0)};
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const size_t n = (size_t)(j0 + r) * Lx + i0;
-                        prefetch_l1(reinterpret_cast<const V2*>(a.b) + n);
-                        if (EP == EP_CHEB) {
-                            prefetch_l1(reinterpret_cast<const V2*>(a.dinv) + n);
-                            if (a.c1 != T(0)) prefetch_l1(reinterpret_cast<const V2*>(a.d) + n);
-                        }
+        for (int q = 0; q < 6; ++q) Xn[q][0] = Xn[q][1] = T(0);
+        auto load_next = [&](int iy_next) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int j = 2 * iy_next + 1 + r;
+                const size_t row = (size_t)j * Lx;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (colok[c]) {  // raw values: nothing may consume them before the next step
+                        const V2 v = xv[row + i0 + c];
+                        Xn[3 * r + c][0] = v.x;
+                        Xn[3 * r + c][1] = v.y;
                     }
+            }
+            if (!STORED_W && cell_ok) {
+                xin[0] = g.xi[(size_t)(iy_next + 1) * (g.nx + 1) + ix];
+                xin[1] = g.xi[(size_t)(iy_next + 1) * (g.nx + 1) + ix + 1];
+            }
+        };
+        auto prefetch_epilogue = [&](int iy_e) {
+            if (!(PF && colok[0] && (EP == EP_RESID || EP == EP_CHEB)) || iy_e < iy0) return;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const size_t n = (size_t)(2 * iy_e + r) * Lx + i0;
+                prefetch_l1(reinterpret_cast<const V2*>(a.b) + n);
+                if (EP == EP_CHEB) {
+                    prefetch_l1(reinterpret_cast<const V2*>(a.dinv) + n);
+                    if (a.c1 != T(0)) prefetch_l1(reinterpret_cast<const V2*>(a.d) + n);
                 }
             }
-            // shift: previous top row becomes the bottom row
+        };
+        load_next(iy_start);
+        prefetch_epilogue(iy_start);
+
+        for (int iy = iy_start; iy < iy1; ++iy) {
+            const int j0 = 2 * iy;
+            // shift: previous top row becomes the bottom row, the preloaded rows come in
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 X[c][0] = X[6 + c][0];
                 X[c][1] = X[6 + c][1];
             }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {  // Dirichlet nodes enter the operator as zeros
+                const bool rowfix = g.row_fixed(j0 + 1 + r);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const bool f = rowfix || colfix[c];
+                    X[3 + 3 * r + c][0] = f ? T(0) : Xn[3 * r + c][0];
+                    X[3 + 3 * r + c][1] = f ? T(0) : Xn[3 * r + c][1];
+                }
+            }
             xiv[0] = xiv[2];
             xiv[1] = xiv[3];
-#pragma unroll
-            for (int r = 1; r < 3; ++r) {
-                const size_t row = (size_t)(j0 + r) * Lx;
-                const bool rowfix = g.row_fixed(j0 + r);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if (colok[c]) {
-                        const V2 v = xv[row + i0 + c];
-                        const bool f = rowfix || colfix[c];
-                        X[3 * r + c][0] = f ? T(0) : v.x;
-                        X[3 * r + c][1] = f ? T(0) : v.y;
-                    }
+            xiv[2] = xin[0];
+            xiv[3] = xin[1];
+            if (iy + 1 < iy1) {
+                load_next(iy + 1);
+                prefetch_epilogue(iy + 1);
             }
             T acc[9][2];
 #pragma unroll
@@ -209,8 +234,6 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                         wB[k] = g.W[(6 + k) * plane + cidx];
                     }
                 } else {
-                    xiv[2] = g.xi[(size_t)(iy + 1) * (g.nx + 1) + ix];
-                    xiv[3] = g.xi[(size_t)(iy + 1) * (g.nx + 1) + ix + 1];
                     moments_from_xi<T>(xiv[0], xiv[1], xiv[3], g.simp_min, wA);
                     moments_from_xi<T>(xiv[0], xiv[2], xiv[3], g.simp_min, wB);
                 }

@@ -139,6 +139,8 @@ class Engine : public EngineBase {
         TM_CUDA(cudaMemset(sc_, 0, sizeof(double) * SC_COUNT));
         TM_CUDA(cudaMalloc(&eig_sc_, sizeof(double) * 64));
         TM_CUDA(cudaMallocHost(&h_sc_, sizeof(double) * 128));
+        TM_CUDA(cudaStreamCreate(&own_stream_));
+        stream_ = own_stream_;
     }
 
     ~Engine() override {
@@ -149,6 +151,8 @@ class Engine : public EngineBase {
         cudaFree(sc_);
         cudaFree(eig_sc_);
         cudaFree(filter_part_);
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if (own_stream_) cudaStreamDestroy(own_stream_);
         cudaFreeHost(h_sc_);
         for (auto& p : prof_pending_) prof_free_.push_back(p.second);
         for (auto& e : prof_free_) {
@@ -157,7 +161,10 @@ class Engine : public EngineBase {
         }
     }
 
-    void set_stream(cudaStream_t s) override { stream_ = s; }
+    // The legacy default stream cannot be captured into a CUDA graph, so work addressed to it is
+    // issued on an engine-owned BLOCKING stream instead: blocking streams order implicitly with
+    // the legacy stream, so torch work on stream 0 before/after a call is still sequenced.
+    void set_stream(cudaStream_t s) override { stream_ = s ? s : own_stream_; }
 
     void set_option(int opt, double value) override {
         switch (opt) {
@@ -173,10 +180,13 @@ class Engine : public EngineBase {
                 break;
             case 100: cheb_ratio_ = value; break;
             case 101: eig_safety_ = value; break;
-            case TM_OPT_PROFILE: profile_ = value != 0.0; break;
+            case TM_OPT_PROFILE: profile_ = (int)value; break;  // 1: level-0 kernel, 2: every level
             case 102: blocks_per_sm_target_ = std::max(1, (int)value); break;
             case 103: min_rows_per_strip_ = std::max(1, (int)value); break;
             case 104: filter_persistent_ = value != 0.0; break;
+            case 109: coarse_degree_ = std::max(0, (int)value); break;
+            case 110: use_graph_ = value != 0.0; graph_dirty_ = true; break;
+            case 111: filter_cheb_ = value != 0.0; break;
             case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
             case 106: apply_prefetch_ = value != 0.0; break;
             case 107:
@@ -290,23 +300,54 @@ class Engine : public EngineBase {
             }
             const int nb = (int)std::max<size_t>(
                 1, std::min<size_t>(filter_blocks_, (n1_ + kFilterThreads - 1) / kFilterThreads));
-            FilterPcgArgs fa;
-            fa.g = p1_; fa.alpha = alpha; fa.beta = beta; fa.rtol = rtol; fa.maxit = maxit;
-            fa.partA = filter_part_;
-            fa.partB = filter_part_ + filter_blocks_;
-            fa.result = filter_part_ + 4 * (size_t)filter_blocks_;
+            double* result = filter_part_ + 4 * (size_t)filter_blocks_;
             const T* dinv_p = f_dinv_.p;
             T *x_p = out, *r_p = f_r_.p, *Ap_p = f_Ap_.p, *p0_p = f_p_.p, *p1_p = f_p2_.p;
-            void* kargs[] = {&fa, &rhs_p, &dinv_p, &x_p, &r_p, &Ap_p, &p0_p, &p1_p};
-            TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_pcg_kernel<T>, dim3(nb), dim3(kFilterThreads),
-                                                kargs, 0, stream_));
-            ++g_launches;
-            TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, fa.result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
-            TM_CUDA(cudaStreamSynchronize(stream_));
             SolveStats st;
-            st.iters = (int)h_sc_[64];
-            st.relres = h_sc_[65];
-            st.converged = h_sc_[66] != 0.0;
+            bool done = false;
+            if (filter_cheb_ && filter_bounds_ready_) {
+                // Chebyshev semi-iteration: one grid barrier per iteration, no dot products
+                FilterChebArgs ca;
+                ca.g = p1_; ca.alpha = alpha; ca.beta = beta;
+                ca.lmin = filter_lmin_; ca.lmax = filter_lmax_; ca.rtol = rtol;
+                ca.maxit = std::min(maxit, 4 * filter_cg_iters_ + 50); ca.check = 8;
+                ca.part = filter_part_; ca.result = result;
+                T* xalt_p = f_Ap_.p;
+                T* d_p = f_p_.p;
+                void* kargs[] = {&ca, &rhs_p, &dinv_p, &x_p, &xalt_p, &d_p};
+                TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_cheb_kernel<T>, dim3(nb), dim3(kFilterThreads),
+                                                    kargs, 0, stream_));
+                ++g_launches;
+                TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
+                TM_CUDA(cudaStreamSynchronize(stream_));
+                st.iters = (int)h_sc_[64];
+                st.relres = h_sc_[65];
+                st.converged = h_sc_[66] != 0.0;
+                done = st.converged;  // otherwise continue with CG from the current iterate,
+                if (!done) filter_bounds_ready_ = false;  // ... and re-estimate the spectral bounds
+            }
+            if (!done) {
+                FilterPcgArgs fa;
+                fa.g = p1_; fa.alpha = alpha; fa.beta = beta; fa.rtol = rtol; fa.maxit = maxit;
+                fa.partA = filter_part_;
+                fa.partB = filter_part_ + filter_blocks_;
+                fa.result = result;
+                const bool record = filter_cheb_ && !filter_bounds_ready_;
+                if (record) filter_coef_.ensure(2 * 4096);
+                fa.coef = record ? filter_coef_.p : nullptr;
+                fa.coef_cap = 4096;
+                void* kargs[] = {&fa, &rhs_p, &dinv_p, &x_p, &r_p, &Ap_p, &p0_p, &p1_p};
+                TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_pcg_kernel<T>, dim3(nb), dim3(kFilterThreads),
+                                                    kargs, 0, stream_));
+                ++g_launches;
+                TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
+                TM_CUDA(cudaStreamSynchronize(stream_));
+                const int cg_its = (int)h_sc_[64];
+                st.iters += cg_its;
+                st.relres = h_sc_[65];
+                st.converged = h_sc_[66] != 0.0;
+                if (record && st.converged && cg_its >= 8) lanczos_bounds(std::min(cg_its, 4096));
+            }
             return st;
         }
         // launch-per-operation PCG (sharded runs: the search direction needs a halo exchange)
@@ -336,6 +377,49 @@ class Engine : public EngineBase {
                             precond, true, rtol, maxit, check);
         exchange_p1(out);
         return st;
+    }
+
+    // Extreme eigenvalues of D^-1 A_f from the Lanczos tridiagonal of one converged CG solve
+    // (diag_k = 1/a_k + b_{k-1}/a_{k-1}, off_k = sqrt(b_k)/a_k), by Sturm bisection.
+    void lanczos_bounds(int m) {
+        std::vector<double> c(2 * m);
+        TM_CUDA(cudaMemcpyAsync(c.data(), filter_coef_.p, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        std::vector<double> d(m), e(m, 0.0);
+        for (int k = 0; k < m; ++k) {
+            const double ak = c[2 * k], bk = c[2 * k + 1];
+            if (!(ak > 0.0)) return;
+            d[k] = 1.0 / ak + (k > 0 ? c[2 * (k - 1) + 1] / c[2 * (k - 1)] : 0.0);
+            e[k] = std::sqrt(std::max(bk, 0.0)) / ak;  // couples k and k+1
+        }
+        auto count_below = [&](double x) {
+            int cnt = 0;
+            double q = d[0] - x;
+            if (q < 0) ++cnt;
+            for (int k = 1; k < m; ++k) {
+                if (q == 0.0) q = 1e-300;
+                q = d[k] - x - e[k - 1] * e[k - 1] / q;
+                if (q < 0) ++cnt;
+            }
+            return cnt;
+        };
+        double lo = 0.0, hi = 0.0;
+        for (int k = 0; k < m; ++k) hi = std::max(hi, d[k] + (k > 0 ? e[k - 1] : 0.0) + e[k]);
+        auto kth = [&](int k) {  // k-th smallest eigenvalue
+            double a = lo, b = hi;
+            for (int it = 0; it < 200; ++it) {
+                const double mid = 0.5 * (a + b);
+                if (count_below(mid) > k) b = mid; else a = mid;
+            }
+            return 0.5 * (a + b);
+        };
+        const double emin = kth(0), emax = kth(m - 1);
+        if (!(emin > 0.0) || !(emax > emin)) return;
+        // Ritz values converge from inside the spectrum; keep the widest interval seen so far
+        filter_lmin_ = filter_lmin_ > 0.0 ? std::min(filter_lmin_, 0.9 * emin) : 0.9 * emin;
+        filter_lmax_ = std::max(filter_lmax_, 1.05 * emax);
+        filter_cg_iters_ = m;
+        filter_bounds_ready_ = true;
     }
 
     // ------------------------------------------------------------------ elasticity operator
@@ -478,27 +562,40 @@ class Engine : public EngineBase {
     }
 
     void last_stats(double* out, int n) override {
-        const double v[5] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
-                             (double)nlevels_, levels_.empty() ? 0.0 : levels_[0].lmax};
-        for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
+        // [5..8]: cumulative level-0 operator launches per epilogue (plain, dot, residual, Chebyshev)
+        const double v[9] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
+                             (double)nlevels_, levels_.empty() ? 0.0 : levels_[0].lmax,
+                             (double)fine_ep_count_[0], (double)fine_ep_count_[1], (double)fine_ep_count_[2],
+                             (double)fine_ep_count_[3]};
+        for (int i = 0; i < n && i < 9; ++i) out[i] = v[i];
     }
 
     // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
+    // out[0..3] ms / out[4..7] launches of the level-0 kernel per epilogue; then for every level
+    // l < 16: out[8+8l .. +3] ms and out[8+8l+4 .. +7] launches of that level's operator kernel
     void profile_read(double* out, int n) override {
-        double ms[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+        std::vector<double> ms(64, 0.0), cnt(64, 0.0);
         TM_CUDA(cudaStreamSynchronize(stream_));
         for (auto& p : prof_pending_) {
             float t = 0.f;
             TM_CUDA(cudaEventElapsedTime(&t, p.second.first, p.second.second));
-            ms[p.first] += t;
-            cnt[p.first] += 1;
+            if (p.first < 64) {
+                ms[p.first] += t;
+                cnt[p.first] += 1;
+            }
             prof_free_.push_back(p.second);
         }
         prof_pending_.clear();
+        for (int i = 0; i < n; ++i) out[i] = 0.0;
         for (int i = 0; i < 4; ++i) {
             if (i < n) out[i] = ms[i];
             if (4 + i < n) out[4 + i] = cnt[i];
         }
+        for (int l = 0; l < 16; ++l)
+            for (int e = 0; e < 4; ++e) {
+                if (8 + 8 * l + e < n) out[8 + 8 * l + e] = ms[4 * l + e];
+                if (8 + 8 * l + 4 + e < n) out[8 + 8 * l + 4 + e] = cnt[4 * l + e];
+            }
     }
 
     // diagnostics (tests): multigrid internals on the hierarchy built for xi (single rank)
@@ -776,8 +873,11 @@ class Engine : public EngineBase {
         dim3 grd(bx, strips), blk(kApplyWarps * 32);
         if ((long)bx * strips > rs_.capacity) throw Invalid{"reduction scratch too small"};
         const bool fine = g.nx == nx_ && g.nyg == nyg_;
+        int level = 0;
+        while (level + 1 < nlevels_ && !(lv_nx_[level] == g.nx && lv_ny_[level] == g.nyg)) ++level;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-        if (fine && profile_) {
+        const bool timed = profile_ == 2 || (profile_ == 1 && fine);
+        if (timed) {
             if (prof_free_.empty()) {
                 TM_CUDA(cudaEventCreate(&ev.first));
                 TM_CUDA(cudaEventCreate(&ev.second));
@@ -810,11 +910,14 @@ class Engine : public EngineBase {
 #undef TM_LAUNCH_APPLY_EP
 #undef TM_LAUNCH_APPLY
         TM_CHECK_LAUNCH();
-        if (fine && profile_) {
+        if (timed) {
             TM_CUDA(cudaEventRecord(ev.second, stream_));
-            prof_pending_.push_back({ep, ev});
+            prof_pending_.push_back({4 * level + ep, ev});
         }
-        if (fine) ++stats_fine_applies_;
+        if (fine) {
+            ++stats_fine_applies_;
+            ++fine_ep_count_[ep & 3];
+        }
     }
 
     void launch_diag(const LevelGeom<T>& g, bool stored, T* dinv) {
@@ -961,6 +1064,8 @@ class Engine : public EngineBase {
 
     void setup_hierarchy(T* xi) {
         const int nl = nlevels_;
+        graph_dirty_ = true;  // coefficients / smoother bounds change: re-capture the V-cycle
+        graph_sampled_ = false;
         levels_[0].g.xi = xi;
         for (int l = 1; l < nl; ++l) {
             Level& F = levels_[l - 1];
@@ -1050,7 +1155,8 @@ class Engine : public EngineBase {
         } else {
             cur = xin;
         }
-        for (int k = k0; k < cheb_degree_; ++k) {
+        const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
+        for (int k = k0; k < degree; ++k) {
             double c1, c2;
             if (k == 0) {
                 c1 = 0.0;
@@ -1072,8 +1178,65 @@ class Engine : public EngineBase {
         return cur;
     }
 
-    // z = V(r): one symmetric V-cycle with zero initial guess
+    // z = V(r).  The ~80 small dependent launches of one V-cycle are captured once per solve
+    // into a CUDA graph and replayed for the remaining PCG iterations (single rank; the sharded
+    // path keeps stream launches because of its NCCL calls).  With TM_OPT_PROFILE on, the first
+    // V-cycle of every solve runs un-captured so its level-0 launches can be event-timed.
     T* vcycle(T* r) {
+        if (!use_graph_ || nranks_ > 1 || profile_ == 2) return vcycle_body(r);
+        if (graph_exec_ && graph_r_ == r && !graph_dirty_) {
+            TM_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+            ++g_launches;
+            ++stats_vcycles_;
+            stats_fine_applies_ += graph_fine_applies_;
+            for (int e = 0; e < 4; ++e) fine_ep_count_[e] += graph_ep_count_[e];
+            return graph_z_;
+        }
+        if (profile_ == 1 && !graph_sampled_) {
+            graph_sampled_ = true;  // event-timed sample, capture on the next call
+            return vcycle_body(r);
+        }
+        if (graph_exec_) {
+            cudaGraphExecDestroy(graph_exec_);
+            graph_exec_ = nullptr;
+        }
+        const int saved_profile = profile_;
+        const long fa0 = stats_fine_applies_, vc0 = stats_vcycles_;
+        long ep0[4];
+        for (int e = 0; e < 4; ++e) ep0[e] = fine_ep_count_[e];
+        const long long l0 = g_launches.load();
+        profile_ = 0;
+        cudaGraph_t graph = nullptr;
+        TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        T* z = nullptr;
+        try {
+            z = vcycle_body(r);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            profile_ = saved_profile;
+            throw;
+        }
+        TM_CUDA(cudaStreamEndCapture(stream_, &graph));
+        profile_ = saved_profile;
+        graph_fine_applies_ = stats_fine_applies_ - fa0;
+        stats_fine_applies_ = fa0;  // capture launched nothing
+        for (int e = 0; e < 4; ++e) {
+            graph_ep_count_[e] = fine_ep_count_[e] - ep0[e];
+            fine_ep_count_[e] = ep0[e];
+        }
+        stats_vcycles_ = vc0;
+        g_launches.store(l0);
+        TM_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+        cudaGraphDestroy(graph);
+        graph_r_ = r;
+        graph_z_ = z;
+        graph_dirty_ = false;
+        graph_kernels_ = 0;
+        return vcycle(r);
+    }
+
+    T* vcycle_body(T* r) {
         const int nl = nlevels_;
         std::vector<T*> xs(nl, nullptr);
         std::vector<const T*> bs(nl, nullptr);
@@ -1116,7 +1279,7 @@ class Engine : public EngineBase {
 
     // ------------------------------------------------------------------ state
     tm_config cfg_;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
     int nx_, nyg_, ny_ = 0, num_sms_ = 148;
     int rank_ = 0, nranks_ = 1, dist_levels_ = 0, nlevels_ = 1;
     NcclComm comm_ = nullptr;
@@ -1134,8 +1297,8 @@ class Engine : public EngineBase {
     double* eig_sc_ = nullptr;
     double* h_sc_ = nullptr;
 
-    int precond_ = TM_PRECOND_MULTIGRID, cheb_degree_ = 3, check_every_ = 0, coarse_cells_ = 2;
-    double cheb_ratio_ = 10.0, eig_safety_ = 1.1;
+    int precond_ = TM_PRECOND_MULTIGRID, cheb_degree_ = 1, check_every_ = 0, coarse_cells_ = 2;
+    double cheb_ratio_ = 30.0, eig_safety_ = 1.1;
 
     DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_, f_p2_;
     bool f_dinv_ready_ = false;
@@ -1144,10 +1307,19 @@ class Engine : public EngineBase {
     DevBuf<double> coarse_A_;
 
     long stats_fine_applies_ = 0, stats_vcycles_ = 0;
-    bool profile_ = false;
-    int blocks_per_sm_target_ = 4, min_rows_per_strip_ = 1;
-    bool filter_persistent_ = true;
+    int profile_ = 0;
+    int blocks_per_sm_target_ = 4, min_rows_per_strip_ = 1, coarse_degree_ = 3;
+    bool filter_persistent_ = true, filter_cheb_ = true, filter_bounds_ready_ = false;
+    double filter_lmin_ = 0.0, filter_lmax_ = 0.0;
+    int filter_cg_iters_ = 0;
+    DevBuf<double> filter_coef_;
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
+    bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
+    cudaGraphExec_t graph_exec_ = nullptr;
+    T* graph_r_ = nullptr;
+    T* graph_z_ = nullptr;
+    long graph_fine_applies_ = 0, graph_kernels_ = 0;
+    long fine_ep_count_[4] = {0, 0, 0, 0}, graph_ep_count_[4] = {0, 0, 0, 0};
     bool apply_prefetch_ = true;
     int filter_blocks_ = 0;
     double* filter_part_ = nullptr;

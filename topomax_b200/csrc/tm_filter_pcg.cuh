@@ -32,6 +32,8 @@ struct FilterPcgArgs {
     double* partA;        // [1][nblocks]
     double* partB;        // [3][nblocks]
     double* result;       // [0] iterations, [1] relres, [2] converged flag
+    double* coef;         // optional [2*maxit]: CG alpha_k, beta_k (Lanczos coefficients)
+    int coef_cap;
 };
 
 // fold nvals per-block partial arrays (stride nblocks) in a fixed order; result to all threads
@@ -166,6 +168,10 @@ filter_pcg_kernel(const FilterPcgArgs a, const T* __restrict__ rhs, const T* __r
         rr = red[0];
         beta_cg = rz != 0.0 ? red[1] / rz : 0.0;
         rz = red[1];
+        if (a.coef && it < a.coef_cap && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.coef[2 * it] = alpha_cg;
+            a.coef[2 * it + 1] = beta_cg;
+        }
         ++it;
         T* t = pold; pold = pnew; pnew = t;
         converged = rr <= target || !(rr == rr);
@@ -174,6 +180,94 @@ filter_pcg_kernel(const FilterPcgArgs a, const T* __restrict__ rhs, const T* __r
         a.result[0] = (double)it;
         a.result[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
         a.result[2] = (rr <= target || !(bb > 0.0)) ? 1.0 : 0.0;
+    }
+}
+
+}  // namespace tmx
+
+namespace tmx {
+
+// Chebyshev-Jacobi semi-iteration for the same system, also one cooperative launch, but with
+// ONE grid barrier per iteration and no dot products on the critical path (the residual norm
+// is folded only every `check` iterations).  The operator is constant, so the spectral bounds
+// [lmin, lmax] of D^-1 A are estimated once per engine.  x ping-pongs between `x` and `xalt`.
+struct FilterChebArgs {
+    P1Geom g;
+    double alpha, beta;
+    double lmin, lmax;
+    double rtol;
+    int maxit, check;
+    double* part;    // [2][nblocks]
+    double* result;  // [0] iterations, [1] relres, [2] converged flag
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kFilterThreads)
+filter_cheb_kernel(const FilterChebArgs a, const T* __restrict__ rhs, const T* __restrict__ dinv,
+                   T* x, T* xalt, T* d) {
+    cg::grid_group grid = cg::this_grid();
+    const P1Geom& g = a.g;
+    const int nb = gridDim.x;
+    const size_t n1 = (size_t)(g.nx + 1) * (g.ny + 1);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const int W1 = g.nx + 1;
+    const double theta = 0.5 * (a.lmax + a.lmin), delta = 0.5 * (a.lmax - a.lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    T* cur = x;
+    T* nxt = xalt;
+    double bb = 0.0, rr = 0.0;
+    bool converged = false;
+    int it = 0;
+    for (; it < a.maxit && !converged; ++it) {
+        double c1, c2;
+        if (it == 0) {
+            c1 = 0.0;
+            c2 = 1.0 / theta;
+        } else {
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            c1 = rho_new * rho;
+            c2 = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+        const bool check = (it % a.check) == 0;
+        double val[2] = {0.0, 0.0};
+        for (size_t v = first; v < n1; v += stride) {
+            const int iy = (int)(v / W1), ix = (int)(v - (size_t)iy * W1);
+            const double ax = p1_row_apply(g, a.alpha, a.beta, ix, iy, [&](size_t j) { return (double)cur[j]; });
+            const double b = (double)rhs[v];
+            const double r = b - ax;
+            const double dn = (it == 0 ? 0.0 : c1 * (double)d[v]) + c2 * (double)dinv[v] * r;
+            d[v] = (T)dn;
+            nxt[v] = (T)((double)cur[v] + dn);
+            if (check) {
+                val[0] += r * r;
+                val[1] += b * b;
+            }
+        }
+        if (check) store_block_partials<2>(val, a.part, nb);
+        grid.sync();
+        if (check) {
+            double red[2];
+            fold_partials<2>(a.part, nb, red);
+            rr = red[0];
+            bb = red[1];
+            // rr is the residual of the iterate we just left; the new one is at least as good
+            converged = !(bb > 0.0) || rr <= a.rtol * a.rtol * bb || !(rr == rr);
+        }
+        T* t = cur; cur = nxt; nxt = t;
+    }
+    // the solution must end in `x`
+    if (cur != x) {
+        for (size_t v = first; v < n1; v += stride) x[v] = cur[v];
+    }
+    if (!(bb > 0.0)) {
+        for (size_t v = first; v < n1; v += stride) x[v] = T(0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.result[0] = (double)it;
+        a.result[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+        a.result[2] = (!(bb > 0.0) || rr <= a.rtol * a.rtol * bb) ? 1.0 : 0.0;
     }
 }
 

@@ -238,18 +238,28 @@ class Engine:
         return out.value
 
     def last_solve_stats(self) -> dict:
-        buf = (c_double * 5)()
-        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 5))
+        buf = (c_double * 9)()
+        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 9))
         return {"iterations": int(buf[0]), "vcycles": int(buf[1]), "fine_applies": int(buf[2]),
-                "levels": int(buf[3]), "lambda_max": buf[4]}
+                "levels": int(buf[3]), "lambda_max": buf[4],
+                "fine_launches_total": {"plain": int(buf[5]), "dot": int(buf[6]), "resid": int(buf[7]),
+                                        "cheb": int(buf[8])}}
 
     def profile_read(self) -> dict:
         """Milliseconds / launch counts of the fine-level operator kernel per epilogue since the
         last read (needs ``set_option(OPT_PROFILE, 1)``)."""
-        buf = (c_double * 8)()
-        _lib.check(self.lib.tm_profile_read(self._h, buf, 8))
+        buf = (c_double * 136)()
+        _lib.check(self.lib.tm_profile_read(self._h, buf, 136))
         names = ("plain", "dot", "resid", "cheb")
-        return {n: {"ms": buf[i], "launches": int(buf[4 + i])} for i, n in enumerate(names)}
+        out = {n: {"ms": buf[i], "launches": int(buf[4 + i])} for i, n in enumerate(names)}
+        levels = []
+        for lvl in range(16):
+            base = 8 + 8 * lvl
+            ms, cnt = sum(buf[base:base + 4]), int(sum(buf[base + 4:base + 8]))
+            if cnt:
+                levels.append({"level": lvl, "ms": ms, "launches": cnt})
+        self.last_level_profile = levels
+        return out
 
     def launch_count(self) -> int:
         return int(self.lib.tm_launch_count())
