@@ -203,7 +203,7 @@ def run_cuda_arm(args):
     tmp = tempfile.mkdtemp(prefix="tm_bench_")
     # weak scaling: the same design at N * sqrt(world), i.e. ~world x the cells, cut into one
     # strip of cell rows per GPU (NCCL halo exchange per operator application, all-reduced dots)
-    run_n = args.N if world == 1 else int(round(args.N * world ** 0.5))
+    run_n = args.N if (world == 1 or args.exact_N) else int(round(args.N * world ** 0.5))
     base_nx, base_ny = mesh_of(design_path, args.N)
     solver = FEMSolver(run_n, design_path, data_path=tmp, verbose=False, dtype=args.dtype,
                        distributed=world > 1, dist_levels=args.dist_levels,
@@ -312,7 +312,7 @@ def run_cuda_arm(args):
     traffic["d2h"] = 0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(0 if args.no_e2e else args.steps):
         psi_host = solver.step(psi_host.copy(), solver.step_size_at_iter(k))
         solver.set_from_array(solver.rho, expit(psi_host))
         objectives.append(problem.calculate_objective(solver.rho))
@@ -322,7 +322,7 @@ def run_cuda_arm(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = size_factor * args.steps / float(t.item())
+    e2e_value = None if args.no_e2e else size_factor * args.steps / float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -419,6 +419,8 @@ def main():
     ap.add_argument("--sample_n", type=int, default=0, help="resolution of the CPU baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--dist_levels", type=int, default=0, help="sharded multigrid levels (0 = automatic)")
+    ap.add_argument("--exact_N", action="store_true", help="multi-GPU: run exactly --N (strong scaling of a named config)")
+    ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large meshes)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

@@ -335,3 +335,23 @@ def test_float32_accuracy_is_stated_separately(repo_root):
     print(f"fp32 engine: PCG its={info.iterations} relres={info.relative_residual:.1e} "
           f"displacement err={err_u:.2e} compliance err={err_c:.2e}")
     assert err_u < 2e-2 and err_c < 5e-3
+
+
+@pytest.mark.parametrize("nx,ny,eps", [(40, 24, 0.07), (45, 27, 0.3), (129, 65, 0.02), (16, 16, 1.5)])
+def test_filter_multigrid_matches_oracle(nx, ny, eps):
+    """The P1 multigrid-preconditioned filter solve (used on large meshes and sharded runs),
+    forced on here, against the direct solve; odd cell counts exercise the ceil coarsening."""
+    W, H = 0.05 * nx, 0.05 * ny
+    mesh = StructuredMesh(W, H, nx, ny)
+    K1, M1 = mesh.p1_matrices()
+    rng = np.random.default_rng(nx)
+    rho, rhs = rng.random(mesh.n1), rng.standard_normal(mesh.n1)
+    eng = _engine(nx, ny, W, H, filter_radius=eps)
+    eng.set_option(112, 1)  # filter multigrid on
+    xi, info0 = eng.filter_apply(_t(rho), assembled=False, rtol=1e-13)
+    g, info1 = eng.filter_apply(_t(rhs), assembled=True, rtol=1e-13)
+    print(f"filter MG {nx}x{ny} eps={eps}: PCG iterations {info0.iterations}, {info1.iterations}")
+    A = eps * eps * K1 + M1
+    assert _rel(xi.cpu().numpy(), solve_spd(A, M1 @ rho)) < 1e-10
+    assert _rel(g.cpu().numpy(), solve_spd(A, rhs)) < 1e-10
+    assert info1.iterations <= 25

@@ -22,6 +22,7 @@
 #include "tm_filter_pcg.cuh"
 #include "tm_mg.cuh"
 #include "tm_p1.cuh"
+#include "tm_p1mg.cuh"
 #include "tm_vec.cuh"
 
 namespace tmx {
@@ -152,6 +153,7 @@ class Engine : public EngineBase {
         cudaFree(eig_sc_);
         cudaFree(filter_part_);
         if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if (fgraph_exec_) cudaGraphExecDestroy(fgraph_exec_);
         if (own_stream_) cudaStreamDestroy(own_stream_);
         cudaFreeHost(h_sc_);
         for (auto& p : prof_pending_) prof_free_.push_back(p.second);
@@ -187,6 +189,10 @@ class Engine : public EngineBase {
             case 109: coarse_degree_ = std::max(0, (int)value); break;
             case 110: use_graph_ = value != 0.0; graph_dirty_ = true; break;
             case 111: filter_cheb_ = value != 0.0; break;
+            case 112: filter_mg_mode_ = (int)value; break;
+            case 115: eig_first_its_ = std::max(1, (int)value); break;
+            case 113: filter_mg_degree_ = std::max(1, (int)value); break;
+            case 114: filter_mg_ratio_ = value; break;
             case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
             case 106: apply_prefetch_ = value != 0.0; break;
             case 107:
@@ -278,6 +284,9 @@ class Engine : public EngineBase {
             TM_CHECK_LAUNCH();
             f_dinv_ready_ = true;
         }
+        const bool use_fmg = filter_mg_mode_ == 1 ||
+                             (filter_mg_mode_ == 0 && nlevels_ >= 2 && (nranks_ > 1 || n1_ > (size_t)2000000));
+        if (use_fmg && nlevels_ >= 2) return filter_apply_mg(kind, in, out, alpha, beta, rtol, maxit);
         if (filter_persistent_ && nranks_ == 1) {
             // whole solve in one cooperative launch (tm_filter_pcg.cuh)
             const T* rhs_p = in;
@@ -375,6 +384,302 @@ class Engine : public EngineBase {
         const int check = check_every_ > 0 ? check_every_ : 10;
         SolveStats st = pcg(p1_off_, p1_cnt_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, f_dinv_.p, apply_dot,
                             precond, true, rtol, maxit, check);
+        exchange_p1(out);
+        return st;
+    }
+
+    // ------------------------------------------------------------------ filter multigrid
+    struct FLevel {
+        P1Level<T> L;      // local geometry + stencils
+        P1Geom gpiece;     // first replicated level: full geometry, own rows = my piece
+        size_t n = 0, off = 0, cnt = 0;
+        bool sharded = false;
+        DevBuf<T> S, dinv, x, xalt, b, d, tmp, eig;
+        double lmax = 0.0;
+    };
+
+    P1Geom p1_level_geom(int l, bool replicated) const {
+        const RowRange r = row_range(l, rank_, replicated);
+        P1Geom g = p1_;
+        g.nx = lv_nx_[l];
+        g.ny = r.ny();
+        g.hx = hx_ * (1 << l);
+        g.hy = hy_ * (1 << l);
+        g.iy_off = r.cl0;
+        g.ny_global = r.nyg;
+        g.own_iy0 = r.c0 - r.cl0;
+        g.own_iy1 = r.c1 - r.cl0 + (r.last ? 1 : 0);
+        return g;
+    }
+    // halo exchange of a P1 array of sharded level l (2 vertex rows each way)
+    void exchange_p1_level(int l, T* v) {
+        if (nranks_ == 1 || l >= dist_levels_) return;
+        const RowRange& r = ranges_[l];
+        exchange_rows(v, (size_t)lv_nx_[l] + 1, r.c0 - r.cl0, r.c1 - r.cl0, 2, 2, r.last);
+    }
+    // gather of a FULL P1 array of level l from the owned vertex rows of every rank
+    void gather_p1_rows(int l, T* full) {
+        if (nranks_ == 1) return;
+        need_comm();
+        const int dtype = sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32;
+        const size_t row_elems = (size_t)lv_nx_[l] + 1;
+        nccl_check(nccl().GroupStart(), "ncclGroupStart");
+        for (int q = 0; q < nranks_; ++q) {
+            const int j0 = starts_[q] >> l;
+            const int j1 = q == nranks_ - 1 ? lv_ny_[l] + 1 : (starts_[q + 1] >> l);
+            if (j1 <= j0) continue;
+            T* ptr = full + (size_t)j0 * row_elems;
+            nccl().Broadcast(ptr, ptr, (size_t)(j1 - j0) * row_elems, dtype, q, comm_, stream_);
+        }
+        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+    }
+
+    void fmg_apply(int l, int ep, const T* x, T* y, const T* b, double c1, double c2, double* dot_out) {
+        FLevel& F = flevels_[l];
+        dim3 blk(32, 8), grd(ceil_div(F.L.g.nx + 1, 32), ceil_div(F.L.g.ny + 1, 8));
+        if ((long)grd.x * grd.y > rs_.capacity) throw Invalid{"reduction scratch too small"};
+        switch (ep) {
+            case P1EP_PLAIN:
+                p1mg_apply_kernel<T, P1EP_PLAIN><<<grd, blk, 0, stream_>>>(F.L, x, y, b, F.dinv.p, F.d.p, c1, c2, rs_, dot_out);
+                break;
+            case P1EP_DOT:
+                p1mg_apply_kernel<T, P1EP_DOT><<<grd, blk, 0, stream_>>>(F.L, x, y, b, F.dinv.p, F.d.p, c1, c2, rs_, dot_out);
+                break;
+            case P1EP_RESID:
+                p1mg_apply_kernel<T, P1EP_RESID><<<grd, blk, 0, stream_>>>(F.L, x, y, b, F.dinv.p, F.d.p, c1, c2, rs_, dot_out);
+                break;
+            default:
+                p1mg_apply_kernel<T, P1EP_CHEB><<<grd, blk, 0, stream_>>>(F.L, x, y, b, F.dinv.p, F.d.p, c1, c2, rs_, dot_out);
+                break;
+        }
+        TM_CHECK_LAUNCH();
+    }
+
+    // one-off: Galerkin stencils, diagonals, smoother bounds, coarse factor (operator is constant)
+    void build_filter_mg(double alpha, double beta) {
+        flevels_.clear();
+        flevels_.resize(nlevels_);
+        for (int l = 0; l < nlevels_; ++l) {
+            FLevel& F = flevels_[l];
+            F.sharded = l < dist_levels_;
+            F.L.g = p1_level_geom(l, !F.sharded);
+            F.L.alpha = alpha;
+            F.L.beta = beta;
+            F.L.S = nullptr;
+            F.gpiece = F.L.g;
+            const size_t W1 = (size_t)F.L.g.nx + 1;
+            F.n = W1 * (F.L.g.ny + 1);
+            F.off = (size_t)F.L.g.own_iy0 * W1;
+            F.cnt = (size_t)(F.L.g.own_iy1 - F.L.g.own_iy0) * W1;
+            if (nranks_ > 1 && l == dist_levels_) {
+                F.gpiece.own_iy0 = starts_[rank_] >> l;
+                F.gpiece.own_iy1 = rank_ == nranks_ - 1 ? lv_ny_[l] + 1 : (starts_[rank_ + 1] >> l);
+            }
+            const bool coarsest = l + 1 == nlevels_;
+            F.x.ensure(F.n);
+            if (l > 0) {
+                F.S.ensure(7 * F.n);
+                F.b.ensure(F.n);
+            }
+            if (!coarsest) {
+                F.dinv.ensure(F.n); F.xalt.ensure(F.n); F.d.ensure(F.n); F.tmp.ensure(F.n); F.eig.ensure(F.n);
+            }
+            if (F.n > (size_t)kP1CoarseMax && coarsest) throw Invalid{"coarsest filter level too large"};
+        }
+        dim3 blk(32, 8);
+        for (int l = 1; l < nlevels_; ++l) {
+            FLevel& Ff = flevels_[l - 1];
+            FLevel& Fc = flevels_[l];
+            const bool gather = nranks_ > 1 && l == dist_levels_;
+            const int c_off = Fc.sharded ? ranges_[l].cl0 : 0;
+            int own0 = 0, own1 = Fc.L.g.ny + 1;
+            if (Fc.sharded || gather) {
+                const RowRange rc = row_range(l, rank_, false);
+                own0 = rc.c0 - c_off;
+                own1 = rc.c1 - c_off + (rc.last ? 1 : 0);
+            }
+            dim3 grd(ceil_div(Fc.L.g.nx + 1, 32), ceil_div(Fc.L.g.ny + 1, 8));
+            p1mg_coarsen_kernel<T><<<grd, blk, 0, stream_>>>(Ff.L, lv_ny_[l - 1], Ff.L.g.iy_off, Fc.L.g.nx, Fc.L.g.ny,
+                                                            c_off, own0, own1, Fc.S.p);
+            TM_CHECK_LAUNCH();
+            for (int k = 0; k < 7; ++k) {
+                if (Fc.sharded) exchange_p1_level(l, Fc.S.p + k * Fc.n);
+                if (gather) gather_p1_rows(l, Fc.S.p + k * Fc.n);
+            }
+            Fc.L.S = Fc.S.p;
+        }
+        for (int l = 0; l + 1 < nlevels_; ++l) {
+            FLevel& F = flevels_[l];
+            dim3 grd(ceil_div(F.L.g.nx + 1, 32), ceil_div(F.L.g.ny + 1, 8));
+            p1mg_diag_kernel<T><<<grd, blk, 0, stream_>>>(F.L, F.dinv.p);
+            TM_CHECK_LAUNCH();
+            // lambda_max(D^-1 A) by power iteration from a constant+ramp start
+            const int g1 = grid1d(F.cnt);
+            waxpby_kernel<T><<<grid1d(F.n), kVecThreads, 0, stream_>>>(F.n, 0.0, F.dinv.p, 0.0, F.dinv.p, F.eig.p);
+            TM_CHECK_LAUNCH();
+            fill_alternating_kernel<T><<<grid1d(F.n), kVecThreads, 0, stream_>>>(F.n, F.eig.p);
+            TM_CHECK_LAUNCH();
+            double* slot = eig_sc_ + 32 + l;
+            dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(F.cnt, F.eig.p + F.off, F.eig.p + F.off, rs_, slot);
+            TM_CHECK_LAUNCH();
+            if (F.sharded) sum_ranks(slot, 1);
+            for (int it = 0; it < 15; ++it) {
+                exchange_p1_level(l, F.eig.p);
+                fmg_apply(l, P1EP_PLAIN, F.eig.p, F.tmp.p, nullptr, 0, 0, nullptr);
+                normalize_scale_kernel<T><<<g1, kVecThreads, 0, stream_>>>(F.cnt, F.dinv.p + F.off, F.tmp.p + F.off,
+                                                                          F.eig.p + F.off, slot);
+                TM_CHECK_LAUNCH();
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(F.cnt, F.eig.p + F.off, F.eig.p + F.off, rs_, slot);
+                TM_CHECK_LAUNCH();
+                if (F.sharded) sum_ranks(slot, 1);
+            }
+        }
+        {
+            FLevel& C = flevels_[nlevels_ - 1];
+            fcoarse_A_.ensure(C.n * C.n);
+            p1mg_coarse_factor_kernel<T><<<1, 64, 0, stream_>>>(C.L, fcoarse_A_.p);
+            TM_CHECK_LAUNCH();
+        }
+        TM_CUDA(cudaMemcpyAsync(h_sc_ + 80, eig_sc_ + 32, sizeof(double) * 32, cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (int l = 0; l + 1 < nlevels_; ++l) {
+            const double lam = std::sqrt(h_sc_[80 + l]);
+            if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"filter multigrid: eigenvalue estimate failed"};
+            flevels_[l].lmax = lam;
+        }
+        fmg_ready_ = true;
+    }
+
+    T* fsmooth(int l, const T* b, T* xin) {
+        FLevel& F = flevels_[l];
+        const double hi = 1.1 * F.lmax, lo = hi / filter_mg_ratio_;
+        const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+        double rho = 1.0 / sigma;
+        T* cur;
+        int k0 = 0;
+        if (!xin) {
+            cheb_first_kernel<T><<<grid1d(F.cnt), kVecThreads, 0, stream_>>>(
+                F.cnt, 1.0 / theta, F.dinv.p + F.off, b + F.off, F.d.p + F.off, F.x.p + F.off);
+            TM_CHECK_LAUNCH();
+            cur = F.x.p;
+            k0 = 1;
+        } else {
+            cur = xin;
+        }
+        for (int k = k0; k < filter_mg_degree_; ++k) {
+            double c1, c2;
+            if (k == 0) {
+                c1 = 0.0;
+                c2 = 1.0 / theta;
+            } else {
+                const double rho_new = 1.0 / (2.0 * sigma - rho);
+                c1 = rho_new * rho;
+                c2 = 2.0 * rho_new / delta;
+                rho = rho_new;
+            }
+            T* other = (cur == F.x.p) ? F.xalt.p : F.x.p;
+            exchange_p1_level(l, cur);
+            fmg_apply(l, P1EP_CHEB, cur, other, b, c1, c2, nullptr);
+            cur = other;
+        }
+        return cur;
+    }
+
+    T* fvcycle_body(T* r) {
+        const int nl = nlevels_;
+        std::vector<T*> xs(nl, nullptr);
+        std::vector<const T*> bs(nl, nullptr);
+        bs[0] = r;
+        dim3 blk(32, 8);
+        for (int l = 0; l + 1 < nl; ++l) {
+            FLevel& F = flevels_[l];
+            FLevel& C = flevels_[l + 1];
+            xs[l] = fsmooth(l, bs[l], nullptr);
+            exchange_p1_level(l, xs[l]);
+            fmg_apply(l, P1EP_RESID, xs[l], F.tmp.p, bs[l], 0, 0, nullptr);
+            exchange_p1_level(l, F.tmp.p);
+            const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
+            dim3 grd(ceil_div(C.L.g.nx + 1, 32), ceil_div(C.L.g.ny + 1, 8));
+            p1mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(F.L.g, lv_ny_[l], gather ? C.gpiece : C.L.g, F.tmp.p, C.b.p);
+            TM_CHECK_LAUNCH();
+            if (gather) gather_p1_rows(l + 1, C.b.p);
+            bs[l + 1] = C.b.p;
+        }
+        {
+            FLevel& C = flevels_[nl - 1];
+            p1mg_coarse_solve_kernel<T><<<1, 32, 0, stream_>>>((int)C.n, fcoarse_A_.p, bs[nl - 1], C.x.p);
+            TM_CHECK_LAUNCH();
+            xs[nl - 1] = C.x.p;
+        }
+        for (int l = nl - 1; l-- > 0;) {
+            FLevel& F = flevels_[l];
+            FLevel& C = flevels_[l + 1];
+            exchange_p1_level(l + 1, xs[l + 1]);
+            dim3 grd(ceil_div(F.L.g.nx + 1, 32), ceil_div(F.L.g.ny + 1, 8));
+            p1mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(F.L.g, C.L.g, xs[l + 1], xs[l]);
+            TM_CHECK_LAUNCH();
+            xs[l] = fsmooth(l, bs[l], xs[l]);
+        }
+        return xs[0];
+    }
+
+    // graph replay of the filter V-cycle (the operator never changes: captured once per engine)
+    T* fvcycle(T* r) {
+        if (!use_graph_ || nranks_ > 1) return fvcycle_body(r);
+        if (fgraph_exec_ && fgraph_r_ == r) {
+            TM_CUDA(cudaGraphLaunch(fgraph_exec_, stream_));
+            ++g_launches;
+            return fgraph_z_;
+        }
+        if (fgraph_exec_) {
+            cudaGraphExecDestroy(fgraph_exec_);
+            fgraph_exec_ = nullptr;
+        }
+        const long long l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        T* z = nullptr;
+        try {
+            z = fvcycle_body(r);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        TM_CUDA(cudaStreamEndCapture(stream_, &graph));
+        g_launches.store(l0);
+        TM_CUDA(cudaGraphInstantiate(&fgraph_exec_, graph, 0));
+        cudaGraphDestroy(graph);
+        fgraph_r_ = r;
+        fgraph_z_ = z;
+        return fvcycle(r);
+    }
+
+    SolveStats filter_apply_mg(int kind, T* in, T* out, double alpha, double beta, double rtol, int maxit) {
+        if (!fmg_ready_) build_filter_mg(alpha, beta);
+        const T* rhs;
+        if (kind == 0) {
+            exchange_p1(in);
+            p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
+            rhs = f_rhs_.p;
+            if (out != in) TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            p1_apply(alpha, beta, out, f_Ap_.p, nullptr);
+            waxpby_kernel<T><<<grid1d(p1_cnt_), kVecThreads, 0, stream_>>>(
+                p1_cnt_, 1.0, rhs + p1_off_, -1.0, f_Ap_.p + p1_off_, f_r_.p + p1_off_);
+            TM_CHECK_LAUNCH();
+        } else {
+            rhs = in;
+            TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
+            TM_CUDA(cudaMemcpyAsync(f_r_.p, rhs, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        }
+        auto apply_dot = [&](T* p, T* Ap) {
+            exchange_p1(p);
+            p1_apply(alpha, beta, p, Ap, sc_ + SC_PAP);
+            sum_ranks(sc_ + SC_PAP, 1);
+        };
+        auto precond = [&](T* r) -> T* { return fvcycle(r); };
+        SolveStats st = pcg(p1_off_, p1_cnt_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, nullptr, apply_dot, precond, false,
+                            rtol, maxit, 1);
         exchange_p1(out);
         return st;
     }
@@ -1101,7 +1406,7 @@ class Engine : public EngineBase {
             if (!L.eig_ready) {
                 mg_seed_vector_kernel<T><<<grid1d(L.nu / 2), kVecThreads, 0, stream_>>>(L.g, L.eig.p);
                 TM_CHECK_LAUNCH();
-                its = 10;
+                its = eig_first_its_;  // the top of the spectrum is clustered: the power method is slow
                 L.eig_ready = true;
             }
             double* slot = eig_sc_ + 2 * l + 1;
@@ -1310,6 +1615,15 @@ class Engine : public EngineBase {
     int profile_ = 0;
     int blocks_per_sm_target_ = 4, min_rows_per_strip_ = 1, coarse_degree_ = 3;
     bool filter_persistent_ = true, filter_cheb_ = true, filter_bounds_ready_ = false;
+    std::vector<FLevel> flevels_;
+    DevBuf<double> fcoarse_A_;
+    bool fmg_ready_ = false;
+    int eig_first_its_ = 30;
+    int filter_mg_mode_ = 0, filter_mg_degree_ = 2;  // 0 auto, 1 multigrid, 2 never
+    double filter_mg_ratio_ = 10.0;
+    cudaGraphExec_t fgraph_exec_ = nullptr;
+    T* fgraph_r_ = nullptr;
+    T* fgraph_z_ = nullptr;
     double filter_lmin_ = 0.0, filter_lmax_ = 0.0;
     int filter_cg_iters_ = 0;
     DevBuf<double> filter_coef_;

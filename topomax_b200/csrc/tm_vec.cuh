@@ -138,6 +138,16 @@ __global__ void cheb_first_kernel(size_t n, double s, const T* __restrict__ dinv
     }
 }
 
+// deterministic start vector for the filter power iteration: mixes smooth and oscillatory parts
+template <typename T>
+__global__ void fill_alternating_kernel(size_t n, T* __restrict__ v) {
+    TM_GRID_STRIDE(i, n) {
+        unsigned int h = (unsigned int)i * 2654435761u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        v[i] = (T)(0.25 + (double)(h & 0xffffu) / 65536.0);
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void convert_kernel(size_t n, const TI* __restrict__ in, TO* __restrict__ out) {
     TM_GRID_STRIDE(i, n) out[i] = (TO)in[i];
