@@ -189,6 +189,8 @@ def run_cuda_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: keep NCCL's version banner off it
+    os.environ["NCCL_DEBUG"] = os.environ.get("TM_NCCL_DEBUG", "WARN")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (CUDA arm) needs a GPU; use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -209,6 +211,9 @@ def run_cuda_arm(args):
                        distributed=world > 1, dist_levels=args.dist_levels,
                        problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol})
     problem, engine = solver.problem, solver.problem.engine
+    for kv in args.engine_option:
+        key, val = kv.split("=")
+        engine.set_option(int(key), float(val))
     nx, ny = solver.mesh.nx, solver.mesh.ny
     n1, nu = engine.n1, engine.nu  # rank-local sizes (owned + halo rows)
     nu_global = 2 * (2 * nx + 1) * (2 * ny + 1)
@@ -419,6 +424,7 @@ def main():
     ap.add_argument("--sample_n", type=int, default=0, help="resolution of the CPU baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--dist_levels", type=int, default=0, help="sharded multigrid levels (0 = automatic)")
+    ap.add_argument("--engine_option", action="append", default=[], help="KEY=VALUE passed to tm_set_option (tuning studies)")
     ap.add_argument("--exact_N", action="store_true", help="multi-GPU: run exactly --N (strong scaling of a named config)")
     ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large meshes)")
     args = ap.parse_args()

@@ -191,6 +191,7 @@ class Engine : public EngineBase {
             case 111: filter_cheb_ = value != 0.0; break;
             case 112: filter_mg_mode_ = (int)value; break;
             case 115: eig_first_its_ = std::max(1, (int)value); break;
+            case 116: graph_sharded_ = value != 0.0; graph_dirty_ = true; break;
             case 113: filter_mg_degree_ = std::max(1, (int)value); break;
             case 114: filter_mg_ratio_ = value; break;
             case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
@@ -625,7 +626,7 @@ class Engine : public EngineBase {
 
     // graph replay of the filter V-cycle (the operator never changes: captured once per engine)
     T* fvcycle(T* r) {
-        if (!use_graph_ || nranks_ > 1) return fvcycle_body(r);
+        if (!use_graph_ || (nranks_ > 1 && !graph_sharded_)) return fvcycle_body(r);
         if (fgraph_exec_ && fgraph_r_ == r) {
             TM_CUDA(cudaGraphLaunch(fgraph_exec_, stream_));
             ++g_launches;
@@ -1488,7 +1489,7 @@ class Engine : public EngineBase {
     // path keeps stream launches because of its NCCL calls).  With TM_OPT_PROFILE on, the first
     // V-cycle of every solve runs un-captured so its level-0 launches can be event-timed.
     T* vcycle(T* r) {
-        if (!use_graph_ || nranks_ > 1 || profile_ == 2) return vcycle_body(r);
+        if (!use_graph_ || (nranks_ > 1 && !graph_sharded_) || profile_ == 2) return vcycle_body(r);
         if (graph_exec_ && graph_r_ == r && !graph_dirty_) {
             TM_CUDA(cudaGraphLaunch(graph_exec_, stream_));
             ++g_launches;
@@ -1629,6 +1630,7 @@ class Engine : public EngineBase {
     DevBuf<double> filter_coef_;
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
+    bool graph_sharded_ = false;  // NCCL calls inside captured V-cycles (all ranks capture alike)
     cudaGraphExec_t graph_exec_ = nullptr;
     T* graph_r_ = nullptr;
     T* graph_z_ = nullptr;
