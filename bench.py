@@ -209,7 +209,8 @@ def run_cuda_arm(args):
     base_nx, base_ny = mesh_of(design_path, args.N)
     solver = FEMSolver(run_n, design_path, data_path=tmp, verbose=False, dtype=args.dtype,
                        distributed=world > 1, dist_levels=args.dist_levels,
-                       problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol})
+                       problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
+                                        "mixed_precision": args.mixed})
     problem, engine = solver.problem, solver.problem.engine
     for kv in args.engine_option:
         key, val = kv.split("=")
@@ -337,9 +338,10 @@ def run_cuda_arm(args):
     # ---- roofline of the dominant kernel: the fine-level operator with the fused
     # Chebyshev-Jacobi epilogue (reads x, b, D^-1, d and xi; writes d, x_new)
     peak, peak_src = measured_peak_hbm()
+    es_mg = 4 if (args.mixed and esize == 8) else esize  # multigrid-side launches run in fp32 when mixed
     alg_bytes = {
-        "cheb": (6 * nu + n1) * esize, "resid": (3 * nu + n1) * esize,
-        "dot": (2 * nu + n1) * esize, "plain": (2 * nu + n1) * esize,
+        "cheb": (6 * nu + n1) * es_mg, "resid": (3 * nu + n1) * es_mg,
+        "dot": (2 * nu + n1) * esize, "plain": (2 * nu + n1) * es_mg,
     }
     # Event-timed launches are a sample (V-cycles replayed from a CUDA graph are not individually
     # timed): time per epilogue = sampled mean x true launch count in the timed region
@@ -389,7 +391,8 @@ def run_cuda_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if esize == 8 else "f32",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": ("f64 (fp32 multigrid preconditioner)" if args.mixed else "f64") if esize == 8 else "f32",
         "data": "synthetic", "config": cfg, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": traffic["h2d"] // args.steps,
@@ -424,6 +427,7 @@ def main():
     ap.add_argument("--sample_n", type=int, default=0, help="resolution of the CPU baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--dist_levels", type=int, default=0, help="sharded multigrid levels (0 = automatic)")
+    ap.add_argument("--mixed", action="store_true", help="fp32 multigrid preconditioner inside the fp64 PCG (reported separately)")
     ap.add_argument("--engine_option", action="append", default=[], help="KEY=VALUE passed to tm_set_option (tuning studies)")
     ap.add_argument("--exact_N", action="store_true", help="multi-GPU: run exactly --N (strong scaling of a named config)")
     ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large meshes)")

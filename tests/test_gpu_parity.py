@@ -355,3 +355,26 @@ def test_filter_multigrid_matches_oracle(nx, ny, eps):
     assert _rel(xi.cpu().numpy(), solve_spd(A, M1 @ rho)) < 1e-10
     assert _rel(g.cpu().numpy(), solve_spd(A, rhs)) < 1e-10
     assert info1.iterations <= 25
+
+
+def test_mixed_precision_preconditioner_keeps_fp64_accuracy(repo_root):
+    """fp32 multigrid preconditioner inside the fp64 PCG: the converged displacement meets the
+    same fp64 parity bar (the preconditioner's precision does not enter the solution)."""
+    d, prm, mesh, lam, mu = _state_case("short_cantilever", 35, repo_root)
+    rng = np.random.default_rng(13)
+    xi = 0.02 + 0.95 * rng.random(mesh.n1)
+    b = mesh.load_vector(d["body_force"], d["tractions"])
+    fix = mesh.dirichlet_mask(d["fixed_sides"])
+    u_ref = solve_spd(mesh.elasticity_matrix(xi, lam, mu), np.where(fix, 0.0, b), free=~fix)
+    its = {}
+    for mixed in (0, 1):
+        eng = _engine(mesh.nx, mesh.ny, mesh.W, mesh.H, lame_lambda=lam, lame_mu=mu, fixed_sides=prm.fixed_sides)
+        eng.set_option(117, mixed)
+        bt = eng.load_vector(prm.body_force, prm.tractions)
+        u, info = eng.state_solve(_t(xi), bt, rtol=1e-11, maxit=500)
+        u = u.cpu().numpy()
+        its[mixed] = info.iterations
+        assert np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref) < 1e-6
+        assert abs(u @ b - u_ref @ b) / abs(u_ref @ b) < 1e-6
+    print("PCG iterations fp64 / mixed:", its)
+    assert its[1] <= its[0] + 6

@@ -108,6 +108,9 @@ struct RowRange {
 
 template <typename T>
 class Engine : public EngineBase {
+    template <typename U>
+    friend class Engine;
+
    public:
     explicit Engine(const tm_config& cfg) : cfg_(cfg) {
         device = cfg.device;
@@ -146,7 +149,8 @@ class Engine : public EngineBase {
 
     ~Engine() override {
         cudaSetDevice(device);
-        if (comm_) nccl().CommDestroy(comm_);
+        inner_.reset();
+        if (comm_ && owns_comm_) nccl().CommDestroy(comm_);
         cudaFree(rs_.partials);
         cudaFree(rs_.counter);
         cudaFree(sc_);
@@ -192,6 +196,7 @@ class Engine : public EngineBase {
             case 112: filter_mg_mode_ = (int)value; break;
             case 115: eig_first_its_ = std::max(1, (int)value); break;
             case 116: graph_sharded_ = value != 0.0; graph_dirty_ = true; break;
+            case 117: mixed_ = value != 0.0; break;
             case 113: filter_mg_degree_ = std::max(1, (int)value); break;
             case 114: filter_mg_ratio_ = value; break;
             case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
@@ -773,9 +778,14 @@ class Engine : public EngineBase {
         TM_CHECK_LAUNCH();
 
         bool use_mg = precond_ == TM_PRECOND_MULTIGRID && nlevels_ >= 2;
-        if (use_mg && levels_.empty()) build_levels();
+        // mixed precision: the multigrid preconditioner runs in fp32 inside the fp64 PCG (the
+        // converged solution and its residual test stay fp64)
+        const bool mixed = use_mg && mixed_ && sizeof(T) == 8;
         const T* dinv = nullptr;
-        if (use_mg) {
+        if (use_mg && mixed) {
+            prepare_inner(xi);
+        } else if (use_mg) {
+            if (levels_.empty()) build_levels();
             setup_hierarchy(xi);
         } else {
             s_dinv_.ensure(nu_);
@@ -802,13 +812,17 @@ class Engine : public EngineBase {
             launch_apply(g, false, EP_DOT, a);
             sum_ranks(sc_ + SC_PAP, 1);
         };
-        auto precond = [&](T* r) -> T* { return use_mg ? vcycle(r) : nullptr; };
+        auto precond = [&](T* r) -> T* { return !use_mg ? nullptr : (mixed ? mixed_vcycle(r) : vcycle(r)); };
         int check = check_every_;
         if (check <= 0) check = use_mg ? 1 : 25;
         SolveStats st = pcg(p2_off_, p2_cnt_, s_b_.p, u, s_r_.p, s_p_.p, s_Ap_.p, dinv, apply_dot, precond,
                             !use_mg, rtol, maxit, check);
         exchange_p2(0, u);
         stats_iters_ = st.iters;
+        if (mixed) {
+            stats_fine_applies_ += inner_->stats_fine_applies_;
+            stats_vcycles_ = inner_->stats_vcycles_;
+        }
         return st;
     }
 
@@ -869,10 +883,13 @@ class Engine : public EngineBase {
 
     void last_stats(double* out, int n) override {
         // [5..8]: cumulative level-0 operator launches per epilogue (plain, dot, residual, Chebyshev)
+        long epc[4];
+        for (int e = 0; e < 4; ++e) epc[e] = fine_ep_count_[e] + (inner_ ? inner_->fine_ep_count_[e] : 0);
+        const double lmax0 = inner_ && !inner_->levels_.empty() ? inner_->levels_[0].lmax
+                                                                : (levels_.empty() ? 0.0 : levels_[0].lmax);
         const double v[9] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
-                             (double)nlevels_, levels_.empty() ? 0.0 : levels_[0].lmax,
-                             (double)fine_ep_count_[0], (double)fine_ep_count_[1], (double)fine_ep_count_[2],
-                             (double)fine_ep_count_[3]};
+                             (double)nlevels_, lmax0, (double)epc[0], (double)epc[1], (double)epc[2],
+                             (double)epc[3]};
         for (int i = 0; i < n && i < 9; ++i) out[i] = v[i];
     }
 
@@ -902,6 +919,11 @@ class Engine : public EngineBase {
                 if (8 + 8 * l + e < n) out[8 + 8 * l + e] = ms[4 * l + e];
                 if (8 + 8 * l + 4 + e < n) out[8 + 8 * l + 4 + e] = cnt[4 * l + e];
             }
+        if (inner_) {  // the fp32 twin's launches (mixed precision) count as well
+            std::vector<double> t(n, 0.0);
+            inner_->profile_read(t.data(), n);
+            for (int i = 0; i < n; ++i) out[i] += t[i];
+        }
     }
 
     // diagnostics (tests): multigrid internals on the hierarchy built for xi (single rank)
@@ -1432,6 +1454,9 @@ class Engine : public EngineBase {
             Level& C = levels_[nl - 1];
             mg_coarse_factor_kernel<T><<<1, 256, 0, stream_>>>(C.g, coarse_A_.p);
             TM_CHECK_LAUNCH();
+            coarse_Ainv_.ensure(C.nu * C.nu);
+            mg_coarse_invert_kernel<<<1, 192, 0, stream_>>>((int)C.nu, coarse_A_.p, coarse_Ainv_.p);
+            TM_CHECK_LAUNCH();
         }
         TM_CUDA(cudaMemcpyAsync(h_sc_ + SC_COUNT, eig_sc_, sizeof(double) * 2 * (nl - 1),
                                 cudaMemcpyDeviceToHost, stream_));
@@ -1442,6 +1467,42 @@ class Engine : public EngineBase {
             if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"multigrid: eigenvalue estimate failed"};
             levels_[l].lmax = lam;
         }
+    }
+
+    // ---- mixed precision: an fp32 twin engine owns the multigrid hierarchy
+    void prepare_inner(const T* xi) {
+        if (!inner_) {
+            tm_config c = cfg_;
+            c.dtype = TM_F32;
+            inner_.reset(new Engine<float>(c));
+            inner_->comm_ = comm_;
+            inner_->owns_comm_ = false;
+        }
+        Engine<float>& in = *inner_;
+        in.stream_ = stream_;
+        in.cheb_degree_ = cheb_degree_; in.coarse_degree_ = coarse_degree_; in.cheb_ratio_ = cheb_ratio_;
+        in.eig_safety_ = eig_safety_; in.apply_minb_ = apply_minb_; in.apply_prefetch_ = apply_prefetch_;
+        in.blocks_per_sm_target_ = blocks_per_sm_target_; in.min_rows_per_strip_ = min_rows_per_strip_;
+        in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
+        in.stats_fine_applies_ = 0;
+        in.stats_vcycles_ = 0;
+        xi32_.ensure(n1_);
+        convert_kernel<T, float><<<grid1d(n1_), kVecThreads, 0, stream_>>>(n1_, xi, xi32_.p);
+        TM_CHECK_LAUNCH();
+        if (in.levels_.empty()) in.build_levels();
+        in.setup_hierarchy(xi32_.p);
+        in.s_r_.ensure(nu_);
+        s_z_.ensure(nu_);
+    }
+    T* mixed_vcycle(T* r) {
+        Engine<float>& in = *inner_;
+        const int g1 = grid1d(p2_cnt_);
+        convert_kernel<T, float><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, r + p2_off_, in.s_r_.p + p2_off_);
+        TM_CHECK_LAUNCH();
+        float* z = in.vcycle(in.s_r_.p);
+        convert_kernel<float, T><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, z + p2_off_, s_z_.p + p2_off_);
+        TM_CHECK_LAUNCH();
+        return s_z_.p;
     }
 
     // Chebyshev-Jacobi smoothing of A x = b on level l; xin == nullptr means zero initial guess
@@ -1566,7 +1627,7 @@ class Engine : public EngineBase {
         }
         {
             Level& C = levels_[nl - 1];
-            mg_coarse_solve_kernel<T><<<1, 128, 0, stream_>>>((int)C.nu, coarse_A_.p, bs[nl - 1], C.x.p);
+            mg_coarse_apply_inverse_kernel<T><<<1, 192, 0, stream_>>>((int)C.nu, coarse_Ainv_.p, bs[nl - 1], C.x.p);
             TM_CHECK_LAUNCH();
             xs[nl - 1] = C.x.p;
         }
@@ -1610,7 +1671,7 @@ class Engine : public EngineBase {
     bool f_dinv_ready_ = false;
     DevBuf<T> s_r_, s_p_, s_Ap_, s_b_, s_dinv_;
     std::vector<Level> levels_;
-    DevBuf<double> coarse_A_;
+    DevBuf<double> coarse_A_, coarse_Ainv_;
 
     long stats_fine_applies_ = 0, stats_vcycles_ = 0;
     int profile_ = 0;
@@ -1620,6 +1681,10 @@ class Engine : public EngineBase {
     DevBuf<double> fcoarse_A_;
     bool fmg_ready_ = false;
     int eig_first_its_ = 30;
+    bool mixed_ = false, owns_comm_ = true;
+    std::unique_ptr<Engine<float>> inner_;
+    DevBuf<float> xi32_;
+    DevBuf<T> s_z_;
     int filter_mg_mode_ = 0, filter_mg_degree_ = 2;  // 0 auto, 1 multigrid, 2 never
     double filter_mg_ratio_ = 10.0;
     cudaGraphExec_t fgraph_exec_ = nullptr;

@@ -112,15 +112,16 @@ __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
     double a0 = 0.0, a1 = 0.0;
     if (!c.fixed(I, J)) {
         const int Jg = J + c.j_off;  // global coarse lattice row
+        const double* rw = tab.Rw[(I & 1) + 2 * (Jg & 1)];
         for (int dj = -3; dj <= 3; ++dj) {
             const int jg = 2 * Jg + dj;  // global fine lattice row
             const int j = jg - f.j_off;
             if (jg < 0 || jg > 2 * f.nyg || j < 0 || j >= f.Ly) continue;
+#pragma unroll
             for (int di = -3; di <= 3; ++di) {
                 const int i = 2 * I + di;
-                if (i < 0 || i >= f.Lx) continue;
-                const double w = transfer_weight(tab, c.nx, c.nyg, i, jg, I, Jg);
-                if (w == 0.0) continue;
+                const double w = rw[7 * (dj + 3) + (di + 3)];
+                if (w == 0.0 || i < 0 || i >= f.Lx) continue;
                 const size_t n = (size_t)j * f.Lx + i;
                 a0 += w * (double)r[2 * n];
                 a1 += w * (double)r[2 * n + 1];
@@ -212,6 +213,39 @@ __global__ void mg_coarse_factor_kernel(const LevelGeom<T> g, double* __restrict
             if (j <= i) A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
         }
         __syncthreads();
+    }
+}
+
+// Ainv (n x n) from the Cholesky factor L (lower, in A): column c of the inverse by one thread
+__global__ void mg_coarse_invert_kernel(int n, const double* __restrict__ L, double* __restrict__ Ainv) {
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double* y = Ainv + (size_t)c * n;  // column c, stored contiguously (the inverse is symmetric)
+        for (int i = 0; i < n; ++i) y[i] = i == c ? 1.0 : 0.0;
+        for (int k = 0; k < n; ++k) {
+            y[k] /= L[(size_t)k * n + k];
+            const double yk = y[k];
+            for (int i = k + 1; i < n; ++i) y[i] -= L[(size_t)i * n + k] * yk;
+        }
+        for (int k = n - 1; k >= 0; --k) {
+            y[k] /= L[(size_t)k * n + k];
+            const double yk = y[k];
+            for (int i = 0; i < k; ++i) y[i] -= L[(size_t)k * n + i] * yk;
+        }
+    }
+}
+
+// x = Ainv b: one thread per row (the coarsest level has <= 162 dofs)
+template <typename T>
+__global__ void mg_coarse_apply_inverse_kernel(int n, const double* __restrict__ Ainv,
+                                               const T* __restrict__ b, T* __restrict__ x) {
+    __shared__ double sb[kCoarseMaxDofs];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sb[i] = (double)b[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double* row = Ainv + (size_t)i * n;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += row[k] * sb[k];
+        x[i] = (T)acc;
     }
 }
 

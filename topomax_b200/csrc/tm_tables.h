@@ -35,6 +35,9 @@ inline DiagTable make_diag_table(const Material<double>& mat) {
 // node at local position (a,b) in 0..4 takes  sum_q Pw[5b+a][q] * coarse cell-local node q.
 struct TransferTable {
     double Pw[25][9];
+    // restriction as a gather: weight of the coarse node of parity type (I&1) + 2*(J&1) at the
+    // fine node offset (di, dj) in -3..3 from it (dense 7x7, mostly zeros)
+    double Rw[4][49];
 };
 
 inline void coarse_barycentrics(int type, double x, double y, double lam[3]) {
@@ -55,6 +58,19 @@ inline TransferTable make_transfer_table() {
                                    4 * l[0] * l[1], 4 * l[1] * l[2], 4 * l[0] * l[2]};
             for (int k = 0; k < 6; ++k) t.Pw[5 * b + a][tri_local_to_cell(type, k)] += phi[k];
         }
+    // translation invariant: evaluate around a coarse node well inside a large mesh
+    for (int type = 0; type < 4; ++type) {
+        const int I = 8 + (type & 1), J = 8 + (type >> 1);
+        for (int dj = -3; dj <= 3; ++dj)
+            for (int di = -3; di <= 3; ++di) {
+                const int i = 2 * I + di, j = 2 * J + dj;
+                const int cx = i >> 2, cy = j >> 2;
+                const int qx = I - 2 * cx, qy = J - 2 * cy;
+                double w = 0.0;
+                if (qx >= 0 && qx <= 2 && qy >= 0 && qy <= 2) w = t.Pw[5 * (j - 4 * cy) + (i - 4 * cx)][3 * qy + qx];
+                t.Rw[type][7 * (dj + 3) + (di + 3)] = w;
+            }
+    }
     return t;
 }
 

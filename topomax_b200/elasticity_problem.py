@@ -23,7 +23,7 @@ class ElasticityProblem(Problem):
                  domain_parameters: DomainParameters, elasticity_parameters: ElasticityParameters,
                  *, state_rtol: float = 1e-10, state_max_iterations: int = 200000,
                  filter_rtol: float = 1e-11, preconditioner: str = "multigrid",
-                 warm_start: bool = True, engine: Engine | None = None):
+                 warm_start: bool = True, engine: Engine | None = None, mixed_precision: bool = False):
         self.parameters = elasticity_parameters
         self.domain_size = (domain_parameters.width, domain_parameters.height)
         self.mesh = mesh
@@ -47,6 +47,10 @@ class ElasticityProblem(Problem):
         self.engine.set_option(_lib.OPT_PRECOND, _lib.PRECOND_MULTIGRID if preconditioner == "multigrid"
                                else _lib.PRECOND_JACOBI)
         self.preconditioner = preconditioner
+        # optional: fp32 multigrid preconditioner inside the fp64 PCG (solution accuracy unchanged)
+        self.mixed_precision = mixed_precision
+        if mixed_precision:
+            self.engine.set_option(117, 1)
         self.state_rtol = state_rtol
         self.state_max_iterations = state_max_iterations
         self.warm_start = warm_start
