@@ -201,7 +201,7 @@ def run_cuda_arm(args):
     from topomax_b200.fem_solver import FEMSolver
     from topomax_b200.solver import expit, logit
 
-    design_path = os.path.join(ROOT, "designs", f"{args.design}.json")
+    design_path = args.design if os.path.isfile(args.design) else os.path.join(ROOT, "designs", f"{args.design}.json")
     tmp = tempfile.mkdtemp(prefix="tm_bench_")
     # weak scaling: the same design at N * sqrt(world), i.e. ~world x the cells, cut into one
     # strip of cell rows per GPU (NCCL halo exchange per operator application, all-reduced dots)
@@ -314,7 +314,7 @@ def run_cuda_arm(args):
     solver.integrate = lambda values: engine.integrate(to_device(values))
     solver.to_array = lambda f: to_host(f.tensor)
     solver.set_from_array = lambda f, values: f.tensor.copy_(to_device(values))
-    psi_host = to_host(psi).copy()
+    psi_host = None if args.no_e2e else to_host(psi).copy()
     traffic["d2h"] = 0
     barrier()
     t0 = time.perf_counter()
