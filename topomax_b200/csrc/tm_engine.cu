@@ -149,6 +149,12 @@ class Engine : public EngineBase {
 
     ~Engine() override {
         cudaSetDevice(device);
+        cudaStreamSynchronize(stream_);
+        // graphs that captured NCCL operations must go before the communicator does
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if (fgraph_exec_) cudaGraphExecDestroy(fgraph_exec_);
+        graph_exec_ = nullptr;
+        fgraph_exec_ = nullptr;
         inner_.reset();
         if (comm_ && owns_comm_) nccl().CommDestroy(comm_);
         cudaFree(rs_.partials);
@@ -156,15 +162,13 @@ class Engine : public EngineBase {
         cudaFree(sc_);
         cudaFree(eig_sc_);
         cudaFree(filter_part_);
-        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
-        if (fgraph_exec_) cudaGraphExecDestroy(fgraph_exec_);
-        if (own_stream_) cudaStreamDestroy(own_stream_);
         cudaFreeHost(h_sc_);
         for (auto& p : prof_pending_) prof_free_.push_back(p.second);
         for (auto& e : prof_free_) {
             cudaEventDestroy(e.first);
             cudaEventDestroy(e.second);
         }
+        if (own_stream_) cudaStreamDestroy(own_stream_);
     }
 
     // The legacy default stream cannot be captured into a CUDA graph, so work addressed to it is
@@ -1695,7 +1699,7 @@ class Engine : public EngineBase {
     DevBuf<double> filter_coef_;
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
-    bool graph_sharded_ = false;  // NCCL calls inside captured V-cycles (all ranks capture alike)
+    bool graph_sharded_ = true;  // NCCL calls inside captured V-cycles (all ranks capture alike)
     cudaGraphExec_t graph_exec_ = nullptr;
     T* graph_r_ = nullptr;
     T* graph_z_ = nullptr;
