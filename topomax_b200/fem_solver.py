@@ -127,27 +127,53 @@ class FEMSolver(Solver):
             f"with problem parameters of type '{type(problem_parameters)}'"
         )
 
-    # The numpy hooks always speak GLOBAL arrays (row-major vertex grid); on a sharded solver they
-    # gather / slice the rank-local strips.
-    def to_array(self, rho: Function) -> np.ndarray:
+    # The numpy hooks always speak GLOBAL host arrays (row-major vertex grid).  Every host<->device
+    # crossing goes through _h2d / _d2h (pinned staging, byte counters for bench.py's e2e leg); on a
+    # sharded solver they slice / gather the rank-local strips.
+    h2d_bytes = 0
+    d2h_bytes = 0
+
+    def _h2d(self, values: np.ndarray) -> torch.Tensor:
         if self.world > 1:
             from . import sharding
-            return sharding.gather_p1(self.problem.engine, rho.tensor)
-        return rho.vector()[:]
+            t = sharding.local_p1(self.problem.engine, values)
+        else:
+            dtype = torch.float64 if self.dtype_name == "float64" else torch.float32
+            n = int(np.size(values))
+            if getattr(self, "_pinned", None) is None or self._pinned.numel() != n:
+                self._pinned = torch.empty(n, dtype=dtype).pin_memory()
+            self._pinned.copy_(torch.from_numpy(np.ascontiguousarray(values).reshape(-1)))
+            t = self._pinned.to(self.device, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()  # the staging buffer is reused
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t
+
+    def _d2h(self, tensor: torch.Tensor) -> np.ndarray:
+        self.d2h_bytes += tensor.numel() * tensor.element_size()
+        if self.world > 1:
+            from . import sharding
+            return sharding.gather_p1(self.problem.engine, tensor)
+        return tensor.detach().cpu().numpy()
+
+    def to_array(self, rho: Function) -> np.ndarray:
+        return self._d2h(rho.tensor)
 
     def set_from_array(self, rho: Function, values: np.ndarray):
-        if self.world > 1:
-            from . import sharding
-            rho.tensor.copy_(sharding.local_p1(self.problem.engine, values))
-        else:
-            rho.vector()[:] = values
+        rho.tensor.copy_(self._h2d(values))
 
     def integrate(self, values: np.ndarray) -> float:
-        if self.world > 1:
-            from . import sharding
-            return self.problem.engine.integrate(sharding.local_p1(self.problem.engine, values))
-        t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.rho.tensor.dtype).to(self.device)
-        return self.problem.engine.integrate(t)
+        return self.problem.engine.integrate(self._h2d(values))
+
+    def step(self, previous_psi: np.ndarray, step_size: float) -> np.ndarray:
+        """``Solver.step`` (reference: src/solver.py:188-194) with host arrays in and out: the latent
+        variable crosses PCIe once each way; filtered sensitivity, half step and the Newton/Brent
+        volume projection run on the device (``step_device``).  ``Solver.project`` through the
+        ``integrate`` hook stays available for callers that drive the projection themselves."""
+        prev = self._h2d(previous_psi)
+        psi = torch.empty_like(prev)
+        rho = torch.empty_like(prev)
+        self.step_device(prev, step_size, psi, rho)
+        return self._d2h(psi)
 
     def save_rho(self, rho: Function, file_root: str):
         rho_file = file_root + "_rho.dat"
