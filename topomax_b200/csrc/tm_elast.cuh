@@ -19,6 +19,8 @@
 //   EP_DOT    y = A x, and the grid-wide  x . A x   (PCG)
 //   EP_RESID  y = b - A x
 //   EP_CHEB   r = b - A x;  d = c1 d + c2 D^-1 r;  y = x + d   (one Chebyshev-Jacobi step)
+//   EP_RESID0 x = c2 D^-1 b evaluated on the fly at the 9 nodes (the first smoothing step from a
+//             zero guess, never materialised before the operator); y = b - A x, x stored to d
 // Dirichlet nodes are identity rows/columns (symmetric elimination; same solution as the
 // reference's bc.apply because the prescribed value is zero).
 #pragma once
@@ -28,7 +30,7 @@
 
 namespace tmx {
 
-enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3 };
+enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3, EP_RESID0 = 4 };
 
 template <typename T>
 struct Vec2;
@@ -48,7 +50,8 @@ struct ApplyArgs {
     const T* b;     // EP_RESID / EP_CHEB
     const T* dinv;  // EP_CHEB: inverse diagonal
     T* d;           // EP_CHEB: Chebyshev direction, updated in place
-    T c1, c2;       // EP_CHEB coefficients
+    T c1, c2;       // EP_CHEB coefficients; EP_RESID0: c2 scales D^-1 b
+    int store_d;    // EP_CHEB: 0 = the updated direction is not needed any more (last step)
     ReduceScratch rs;
     double* dot_out;  // EP_DOT
     int rows_per_strip;
@@ -61,7 +64,9 @@ template <typename T, int EP>
 __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, bool fixed, T v0, T v1,
                                                T x0, T x1, double& dot) {
     using V2 = typename Vec2<T>::type;
-    if (fixed) {  // identity row: the registers hold the masked input (0), fetch the raw value
+    if (fixed && EP == EP_RESID0) {  // x = c2 D^-1 b vanishes on Dirichlet nodes (b_D = 0)
+        x0 = x1 = v0 = v1 = T(0);
+    } else if (fixed) {  // identity row: the registers hold the masked input (0), fetch the raw value
         const V2 xr = reinterpret_cast<const V2*>(a.x)[n];
         x0 = v0 = xr.x;
         x1 = v1 = xr.y;
@@ -74,9 +79,15 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
     } else {
         const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
         const T r0 = bb.x - v0, r1 = bb.y - v1;
-        if (EP == EP_RESID) {
+        if (EP == EP_RESID || EP == EP_RESID0) {
             out.x = r0;
             out.y = r1;
+            if (EP == EP_RESID0) {
+                V2 xo;
+                xo.x = x0;
+                xo.y = x1;
+                reinterpret_cast<V2*>(a.d)[n] = xo;
+            }
         } else {
             const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
             V2 dd;
@@ -87,7 +98,7 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
                 dd.x += a.c1 * dold.x;
                 dd.y += a.c1 * dold.y;
             }
-            reinterpret_cast<V2*>(a.d)[n] = dd;
+            if (a.store_d) reinterpret_cast<V2*>(a.d)[n] = dd;
             out.x = x0 + dd.x;
             out.y = x1 + dd.y;
         }
@@ -139,11 +150,19 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
         // lattice row 2*iy_start enters as the "top row of the previous step"
         {
             const size_t row = (size_t)(2 * iy_start) * Lx;
-#pragma unroll
             const bool rowfix = g.row_fixed(2 * iy_start);
+#pragma unroll
             for (int c = 0; c < 3; ++c)
                 if (colok[c]) {
-                    const V2 v = xv[row + i0 + c];
+                    V2 v;
+                    if (EP == EP_RESID0) {
+                        const V2 bv = reinterpret_cast<const V2*>(a.b)[row + i0 + c];
+                        const V2 dv = reinterpret_cast<const V2*>(a.dinv)[row + i0 + c];
+                        v.x = a.c2 * dv.x * bv.x;
+                        v.y = a.c2 * dv.y * bv.y;
+                    } else {
+                        v = xv[row + i0 + c];
+                    }
                     const bool f = rowfix || colfix[c];
                     X[6 + c][0] = f ? T(0) : v.x;
                     X[6 + c][1] = f ? T(0) : v.y;
@@ -158,9 +177,10 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
         // into registers while step iy computes; epilogue operands are prefetched into L1 one
         // step ahead.  Xn/xin hold the rows 2iy+1, 2iy+2 / vertex row iy+1 of the coming step.
         T Xn[6][2];
+        T Dn[6][2];  // EP_RESID0 only: raw D^-1 next to raw b (in Xn); multiplied when consumed
         T xin[2] = {T(0), T(0)};
 #pragma unroll
-        for (int q = 0; q < 6; ++q) Xn[q][0] = Xn[q][1] = T(0);
+        for (int q = 0; q < 6; ++q) Xn[q][0] = Xn[q][1] = Dn[q][0] = Dn[q][1] = T(0);
         auto load_next = [&](int iy_next) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -169,9 +189,18 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                     if (colok[c]) {  // raw values: nothing may consume them before the next step
-                        const V2 v = xv[row + i0 + c];
-                        Xn[3 * r + c][0] = v.x;
-                        Xn[3 * r + c][1] = v.y;
+                        if (EP == EP_RESID0) {
+                            const V2 bv = reinterpret_cast<const V2*>(a.b)[row + i0 + c];
+                            const V2 dv = reinterpret_cast<const V2*>(a.dinv)[row + i0 + c];
+                            Xn[3 * r + c][0] = bv.x;
+                            Xn[3 * r + c][1] = bv.y;
+                            Dn[3 * r + c][0] = dv.x;
+                            Dn[3 * r + c][1] = dv.y;
+                        } else {
+                            const V2 v = xv[row + i0 + c];
+                            Xn[3 * r + c][0] = v.x;
+                            Xn[3 * r + c][1] = v.y;
+                        }
                     }
             }
             if (!STORED_W && cell_ok) {
@@ -188,6 +217,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                 if (EP == EP_CHEB) {
                     prefetch_l1(reinterpret_cast<const V2*>(a.dinv) + n);
                     if (a.c1 != T(0)) prefetch_l1(reinterpret_cast<const V2*>(a.d) + n);
+                    // (EP_RESID0 needs no epilogue prefetch: b was just read for the on-the-fly x)
                 }
             }
         };
@@ -208,8 +238,13 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const bool f = rowfix || colfix[c];
-                    X[3 + 3 * r + c][0] = f ? T(0) : Xn[3 * r + c][0];
-                    X[3 + 3 * r + c][1] = f ? T(0) : Xn[3 * r + c][1];
+                    if (EP == EP_RESID0) {
+                        X[3 + 3 * r + c][0] = f ? T(0) : a.c2 * Dn[3 * r + c][0] * Xn[3 * r + c][0];
+                        X[3 + 3 * r + c][1] = f ? T(0) : a.c2 * Dn[3 * r + c][1] * Xn[3 * r + c][1];
+                    } else {
+                        X[3 + 3 * r + c][0] = f ? T(0) : Xn[3 * r + c][0];
+                        X[3 + 3 * r + c][1] = f ? T(0) : Xn[3 * r + c][1];
+                    }
                 }
             }
             xiv[0] = xiv[2];

@@ -201,6 +201,7 @@ class Engine : public EngineBase {
             case 115: eig_first_its_ = std::max(1, (int)value); break;
             case 116: graph_sharded_ = value != 0.0; graph_dirty_ = true; break;
             case 117: mixed_ = value != 0.0; break;
+            case 118: fuse_first_ = value != 0.0; graph_dirty_ = true; break;
             case 113: filter_mg_degree_ = std::max(1, (int)value); break;
             case 114: filter_mg_ratio_ = value; break;
             case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
@@ -1188,6 +1189,7 @@ class Engine : public EngineBase {
         ApplyArgs<T> a;
         std::memset(&a, 0, sizeof(a));
         a.rs = rs_;
+        a.store_d = 1;
         return a;
     }
 
@@ -1221,34 +1223,31 @@ class Engine : public EngineBase {
         }
 #define TM_LAUNCH_APPLY(ST, EPV, MB, PFV) \
     elast_apply_kernel<T, ST, EPV, MB, PFV><<<grd, blk, 0, stream_>>>(g, a)
-#define TM_LAUNCH_APPLY_EP(ST, MB, PFV)                             \
-    switch (ep) {                                                   \
-        case EP_PLAIN: TM_LAUNCH_APPLY(ST, EP_PLAIN, MB, PFV); break; \
-        case EP_DOT: TM_LAUNCH_APPLY(ST, EP_DOT, MB, PFV); break;     \
-        case EP_RESID: TM_LAUNCH_APPLY(ST, EP_RESID, MB, PFV); break; \
-        default: TM_LAUNCH_APPLY(ST, EP_CHEB, MB, PFV); break;        \
+#define TM_LAUNCH_APPLY_EP(ST, MB, PFV)                               \
+    switch (ep) {                                                     \
+        case EP_PLAIN: TM_LAUNCH_APPLY(ST, EP_PLAIN, MB, PFV); break;   \
+        case EP_DOT: TM_LAUNCH_APPLY(ST, EP_DOT, MB, PFV); break;       \
+        case EP_RESID: TM_LAUNCH_APPLY(ST, EP_RESID, MB, PFV); break;   \
+        case EP_RESID0: TM_LAUNCH_APPLY(ST, EP_RESID0, MB, PFV); break; \
+        default: TM_LAUNCH_APPLY(ST, EP_CHEB, MB, PFV); break;          \
     }
         if (stored) {
             TM_LAUNCH_APPLY_EP(true, 2, false)
-        } else if (apply_minb_ == 3) {
-            if (apply_prefetch_) { TM_LAUNCH_APPLY_EP(false, 3, true) } else { TM_LAUNCH_APPLY_EP(false, 3, false) }
-        } else if (apply_minb_ == 4) {
+        } else if (apply_minb_ >= 4) {
             TM_LAUNCH_APPLY_EP(false, 4, true)
-        } else if (apply_minb_ == 5) {
-            TM_LAUNCH_APPLY_EP(false, 5, true)
         } else {
-            if (apply_prefetch_) { TM_LAUNCH_APPLY_EP(false, 2, true) } else { TM_LAUNCH_APPLY_EP(false, 2, false) }
+            TM_LAUNCH_APPLY_EP(false, 2, true)
         }
 #undef TM_LAUNCH_APPLY_EP
 #undef TM_LAUNCH_APPLY
         TM_CHECK_LAUNCH();
         if (timed) {
             TM_CUDA(cudaEventRecord(ev.second, stream_));
-            prof_pending_.push_back({4 * level + ep, ev});
+            prof_pending_.push_back({4 * level + (ep == EP_RESID0 ? (int)EP_RESID : (int)ep), ev});
         }
         if (fine) {
             ++stats_fine_applies_;
-            ++fine_ep_count_[ep & 3];
+            ++fine_ep_count_[ep == EP_RESID0 ? (int)EP_RESID : (int)ep];
         }
     }
 
@@ -1427,6 +1426,7 @@ class Engine : public EngineBase {
         for (int l = 0; l + 1 < nl; ++l) {
             Level& L = levels_[l];
             launch_diag(L.g, l > 0, L.dinv.p);
+            exchange_p2(l, L.dinv.p);  // the fused first smoothing step reads D^-1 on halo rows
             // lambda_max(D^-1 A) by power iteration, warm-started across solves
             const int g1 = grid1d(L.cnt);
             int its = 4;
@@ -1488,6 +1488,7 @@ class Engine : public EngineBase {
         in.eig_safety_ = eig_safety_; in.apply_minb_ = apply_minb_; in.apply_prefetch_ = apply_prefetch_;
         in.blocks_per_sm_target_ = blocks_per_sm_target_; in.min_rows_per_strip_ = min_rows_per_strip_;
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
+        in.fuse_first_ = fuse_first_;
         in.stats_fine_applies_ = 0;
         in.stats_vcycles_ = 0;
         xi32_.ensure(n1_);
@@ -1543,6 +1544,7 @@ class Engine : public EngineBase {
             ApplyArgs<T> a = apply_args();
             a.x = cur; a.y = other; a.b = b; a.dinv = L.dinv.p; a.d = L.d.p;
             a.c1 = (T)c1; a.c2 = (T)c2;
+            a.store_d = (k + 1 < degree) ? 1 : 0;
             launch_apply(L.g, l > 0, EP_CHEB, a);
             cur = other;
         }
@@ -1615,11 +1617,24 @@ class Engine : public EngineBase {
         for (int l = 0; l + 1 < nl; ++l) {
             Level& L = levels_[l];
             Level& C = levels_[l + 1];
-            xs[l] = smooth(l, bs[l], nullptr);
-            exchange_p2(l, xs[l]);
-            ApplyArgs<T> a = apply_args();
-            a.x = xs[l]; a.y = L.tmp.p; a.b = bs[l];
-            launch_apply(L.g, l > 0, EP_RESID, a);
+            const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
+            if (degree == 1 && fuse_first_) {
+                // x = (1/theta) D^-1 b and r = b - A x in ONE pass: x is formed on the fly from b and
+                // D^-1 at the nodes the operator touches (saves the separate first-step kernel)
+                const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
+                exchange_p2(l, const_cast<T*>(bs[l]));
+                ApplyArgs<T> a = apply_args();
+                a.y = L.tmp.p; a.b = bs[l]; a.dinv = L.dinv.p; a.d = L.x.p;
+                a.c2 = (T)(1.0 / (0.5 * (hi + lo)));
+                launch_apply(L.g, l > 0, EP_RESID0, a);
+                xs[l] = L.x.p;
+            } else {
+                xs[l] = smooth(l, bs[l], nullptr);
+                exchange_p2(l, xs[l]);
+                ApplyArgs<T> a = apply_args();
+                a.x = xs[l]; a.y = L.tmp.p; a.b = bs[l];
+                launch_apply(L.g, l > 0, EP_RESID, a);
+            }
             exchange_p2(l, L.tmp.p);
             const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
             dim3 blk(32, 8), grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
@@ -1699,6 +1714,7 @@ class Engine : public EngineBase {
     DevBuf<double> filter_coef_;
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
+    bool fuse_first_ = true;
     bool graph_sharded_ = true;  // NCCL calls inside captured V-cycles (all ranks capture alike)
     cudaGraphExec_t graph_exec_ = nullptr;
     T* graph_r_ = nullptr;
