@@ -378,3 +378,29 @@ def test_mixed_precision_preconditioner_keeps_fp64_accuracy(repo_root):
         assert abs(u @ b - u_ref @ b) / abs(u_ref @ b) < 1e-6
     print("PCG iterations fp64 / mixed:", its)
     assert its[1] <= its[0] + 6
+
+
+@pytest.mark.parametrize("design,N,degree", [("short_cantilever", 70, 3), ("bridge", 30, 3), ("cantilever", 48, 1),
+                                             ("short_cantilever", 35, 2)])
+def test_cluster_tail_equals_launch_per_phase_vcycle(repo_root, design, N, degree):
+    """The coarse tail of the V-cycle as one cluster kernel on assembled stencils (tm_tail.cuh) is the
+    same preconditioner as the launch-per-phase path: same PCG iteration count (round-off may move
+    it by one) and the same displacement."""
+    d, prm, mesh, lam, mu = _state_case(design, N, repo_root)
+    rng = np.random.default_rng(17)
+    xi = 0.02 + 0.95 * rng.random(mesh.n1)
+    out = {}
+    for tail in (0, 1):
+        eng = _engine(mesh.nx, mesh.ny, mesh.W, mesh.H, lame_lambda=lam, lame_mu=mu, fixed_sides=prm.fixed_sides)
+        eng.set_option(109, degree)
+        if not tail:
+            eng.set_option(119, 0)
+        bt = eng.load_vector(prm.body_force, prm.tractions)
+        u, info = eng.state_solve(_t(xi), bt, rtol=1e-11, maxit=500)
+        stats = eng.last_solve_stats()
+        out[tail] = (u.cpu().numpy(), info.iterations, stats)
+    print("iterations without / with tail:", out[0][1], out[1][1], "tail from level", out[1][2]["tail_first_level"],
+          "of", out[1][2]["levels"], "cluster", out[1][2]["tail_cluster"])
+    assert out[0][2]["tail_first_level"] == -1 and out[1][2]["tail_first_level"] >= 1
+    assert abs(out[0][1] - out[1][1]) <= 1
+    assert np.linalg.norm(out[0][0] - out[1][0]) / np.linalg.norm(out[0][0]) < 1e-9

@@ -23,6 +23,7 @@
 #include "tm_mg.cuh"
 #include "tm_p1.cuh"
 #include "tm_p1mg.cuh"
+#include "tm_tail.cuh"
 #include "tm_vec.cuh"
 
 namespace tmx {
@@ -202,6 +203,9 @@ class Engine : public EngineBase {
             case 116: graph_sharded_ = value != 0.0; graph_dirty_ = true; break;
             case 117: mixed_ = value != 0.0; break;
             case 118: fuse_first_ = value != 0.0; graph_dirty_ = true; break;
+            case 119: tail_max_nodes_ = (int)value; levels_.clear(); graph_dirty_ = true; break;
+            case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
+            case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
             case 113: filter_mg_degree_ = std::max(1, (int)value); break;
             case 114: filter_mg_ratio_ = value; break;
             case 105: apply_minb_ = std::min(5, std::max(2, (int)value)); break;
@@ -892,10 +896,13 @@ class Engine : public EngineBase {
         for (int e = 0; e < 4; ++e) epc[e] = fine_ep_count_[e] + (inner_ ? inner_->fine_ep_count_[e] : 0);
         const double lmax0 = inner_ && !inner_->levels_.empty() ? inner_->levels_[0].lmax
                                                                 : (levels_.empty() ? 0.0 : levels_[0].lmax);
-        const double v[9] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
-                             (double)nlevels_, lmax0, (double)epc[0], (double)epc[1], (double)epc[2],
-                             (double)epc[3]};
-        for (int i = 0; i < n && i < 9; ++i) out[i] = v[i];
+        // [9]: first level of the cluster tail (-1: none), [10]: its cluster size
+        const int tf = inner_ ? inner_->tail_first_ : tail_first_;
+        const int tc = inner_ ? inner_->tail_cluster_used_ : tail_cluster_used_;
+        const double v[11] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
+                              (double)nlevels_, lmax0, (double)epc[0], (double)epc[1], (double)epc[2],
+                              (double)epc[3], (double)tf, (double)(tf >= 0 ? tc : 0)};
+        for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
     }
 
     // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
@@ -973,6 +980,28 @@ class Engine : public EngineBase {
         } else if (op == 5) {
             if (level == nl - 1) throw Invalid{"coarsest level has no diagonal"};
             TM_CUDA(cudaMemcpyAsync(out, L.dinv.p, L.nu * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        } else if (op == 6) {
+            // study: out[0] = mean ms of one V-cycle (graph replay when enabled, as in a solve),
+            // out[1] = mean ms of one hierarchy set-up
+            s_r_.ensure(nu_);
+            TM_CUDA(cudaMemcpyAsync(s_r_.p, in, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            cudaEvent_t e0, e1, e2;
+            TM_CUDA(cudaEventCreate(&e0)); TM_CUDA(cudaEventCreate(&e1)); TM_CUDA(cudaEventCreate(&e2));
+            for (int k = 0; k < 3; ++k) vcycle(s_r_.p);
+            const int reps = 40, sreps = 5;
+            TM_CUDA(cudaEventRecord(e0, stream_));
+            for (int k = 0; k < reps; ++k) vcycle(s_r_.p);
+            TM_CUDA(cudaEventRecord(e1, stream_));
+            for (int k = 0; k < sreps; ++k) setup_hierarchy((T*)xi);
+            TM_CUDA(cudaEventRecord(e2, stream_));
+            TM_CUDA(cudaStreamSynchronize(stream_));
+            float ms_v = 0.f, ms_s = 0.f;
+            TM_CUDA(cudaEventElapsedTime(&ms_v, e0, e1));
+            TM_CUDA(cudaEventElapsedTime(&ms_s, e1, e2));
+            const T res[2] = {(T)(ms_v / reps), (T)(ms_s / sreps)};
+            TM_CUDA(cudaMemcpyAsync(out, res, sizeof(res), cudaMemcpyHostToDevice, stream_));
+            TM_CUDA(cudaStreamSynchronize(stream_));
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         } else {
             throw Invalid{"unknown mg_debug op"};
         }
@@ -1355,6 +1384,7 @@ class Engine : public EngineBase {
         size_t nu = 0, off = 0, cnt = 0;  // local size; owned flat range
         bool sharded = false;
         DevBuf<T> W, dinv, x, xalt, b, d, tmp, eig;
+        DevBuf<T> S;  // tail levels only: assembled node stencils (tm_tail.cuh)
         bool eig_ready = false;
         double lmax = 0.0;
     };
@@ -1391,6 +1421,124 @@ class Engine : public EngineBase {
         }
         const size_t nc = levels_.back().nu;
         coarse_A_.ensure(nc * nc);
+        plan_tail();
+    }
+
+    // The levels from tail_first_ down run as one cluster kernel per V-cycle (tm_tail.cuh):
+    // replicated levels with stored moments whose lattice has at most tail_max_nodes_ nodes.
+    void plan_tail() {
+        tail_first_ = -1;
+        const int degree = coarse_degree_ > 0 ? coarse_degree_ : cheb_degree_;
+        if (tail_max_nodes_ <= 0 || degree > kTailMaxDegree) return;
+        int first = -1;
+        for (int l = std::max(1, nranks_ > 1 ? dist_levels_ : 1); l < nlevels_; ++l)
+            if ((long)levels_[l].g.Lx * levels_[l].g.Ly <= (long)tail_max_nodes_) {
+                first = l;
+                break;
+            }
+        if (first < 0 || nlevels_ - first < 2) return;
+        first = std::max(first, nlevels_ - kTailMaxLevels);
+        int csize = tail_cluster_;
+        for (; csize >= 1; csize /= 2) {
+            if (csize > 8 &&
+                cudaFuncSetAttribute(tail_vcycle_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                    cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(csize);
+            cfg.blockDim = dim3(kTailThreads);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = csize;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, tail_vcycle_kernel<T>, &cfg) == cudaSuccess &&
+                nclusters >= 1)
+                break;
+            cudaGetLastError();
+        }
+        if (csize < 1) return;
+        tail_cluster_used_ = csize;
+        tail_first_ = first;
+        for (int l = first; l + 1 < nlevels_; ++l)
+            levels_[l].S.ensure(100 * (size_t)levels_[l].g.Lx * levels_[l].g.Ly);
+        tail_dev_.ensure(sizeof(TailArgs<T>));
+    }
+
+    // stencils of the tail levels (after the moments were coarsened) ...
+    void assemble_tail() {
+        if (tail_first_ < 0) return;
+        for (int l = tail_first_; l + 1 < nlevels_; ++l) {
+            Level& L = levels_[l];
+            const int n2 = 2 * L.g.Lx * L.g.Ly;
+            tail_assemble_kernel<T><<<ceil_div(n2, 128), 128, 0, stream_>>>(L.g, L.S.p);
+            TM_CHECK_LAUNCH();
+        }
+    }
+    // ... and the argument block (needs the smoother bounds, i.e. the host copy of lambda_max)
+    void upload_tail() {
+        if (tail_first_ < 0) return;
+        TailArgs<T>& A = tail_host_;
+        std::memset(&A, 0, sizeof(A));
+        const int nl = nlevels_;
+        A.nt = nl - tail_first_;
+        A.degree = coarse_degree_ > 0 ? coarse_degree_ : cheb_degree_;
+        A.nc = (int)levels_[nl - 1].nu;
+        A.Ainv = coarse_Ainv_.p;
+        A.tab = tr_tab_;
+        for (int t = 0; t < A.nt; ++t) {
+            Level& L = levels_[tail_first_ + t];
+            TailLevel<T>& V = A.lv[t];
+            V.g = L.g;
+            V.n = L.g.Lx * L.g.Ly;
+            V.S = L.S.p;
+            V.dinv = L.dinv.p;
+            V.b = L.b.p;
+            V.xa = L.x.p;
+            V.xb = L.xalt.p;
+            V.d = L.d.p;
+            V.r = L.tmp.p;
+            if (t + 1 == A.nt) break;
+            const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
+            const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+            double rho = 1.0 / sigma;
+            V.c1[0] = T(0);
+            V.c2[0] = (T)(1.0 / theta);
+            for (int k = 1; k < A.degree; ++k) {
+                const double rho_new = 1.0 / (2.0 * sigma - rho);
+                V.c1[k] = (T)(rho_new * rho);
+                V.c2[k] = (T)(2.0 * rho_new / delta);
+                rho = rho_new;
+            }
+        }
+        TM_CUDA(cudaMemcpyAsync(tail_dev_.p, &A, sizeof(A), cudaMemcpyHostToDevice, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+    }
+    // x of level tail_first_ after the kernel: the ping-pong buffer the last step wrote
+    T* launch_tail() {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(tail_cluster_used_);
+        cfg.blockDim = dim3(kTailThreads);
+        cfg.stream = stream_;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = tail_cluster_used_;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        TM_CUDA(cudaLaunchKernelEx(&cfg, tail_vcycle_kernel<T>,
+                                   reinterpret_cast<const TailArgs<T>*>(tail_dev_.p)));
+        TM_CHECK_LAUNCH();
+        const int D = tail_host_.degree;
+        const int flips = std::max(D - 2, 0) + D;
+        Level& L = levels_[tail_first_];
+        return (flips & 1) ? L.xalt.p : L.x.p;
     }
 
     void setup_hierarchy(T* xi) {
@@ -1423,6 +1571,7 @@ class Engine : public EngineBase {
                 for (int k = 0; k < 12; ++k) gather_rows(l, C.W.p + k * plane, (size_t)C.g.nx, true);
             }
         }
+        assemble_tail();
         for (int l = 0; l + 1 < nl; ++l) {
             Level& L = levels_[l];
             launch_diag(L.g, l > 0, L.dinv.p);
@@ -1471,6 +1620,7 @@ class Engine : public EngineBase {
             if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"multigrid: eigenvalue estimate failed"};
             levels_[l].lmax = lam;
         }
+        upload_tail();
     }
 
     // ---- mixed precision: an fp32 twin engine owns the multigrid hierarchy
@@ -1489,6 +1639,8 @@ class Engine : public EngineBase {
         in.blocks_per_sm_target_ = blocks_per_sm_target_; in.min_rows_per_strip_ = min_rows_per_strip_;
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
         in.fuse_first_ = fuse_first_;
+        if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
+        in.tail_max_nodes_ = tail_max_nodes_; in.tail_cluster_ = tail_cluster_;
         in.stats_fine_applies_ = 0;
         in.stats_vcycles_ = 0;
         xi32_.ensure(n1_);
@@ -1614,7 +1766,10 @@ class Engine : public EngineBase {
         std::vector<T*> xs(nl, nullptr);
         std::vector<const T*> bs(nl, nullptr);
         bs[0] = r;
-        for (int l = 0; l + 1 < nl; ++l) {
+        int lbot = tail_first_ >= 0 ? tail_first_ : nl - 1;  // first level the loops do not visit
+        const bool truncated = depth_limit_ > 0 && depth_limit_ < lbot;  // timing studies only
+        if (truncated) lbot = depth_limit_;
+        for (int l = 0; l < lbot; ++l) {
             Level& L = levels_[l];
             Level& C = levels_[l + 1];
             const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
@@ -1644,13 +1799,17 @@ class Engine : public EngineBase {
             if (gather) gather_rows(l + 1, C.b.p, (size_t)C.g.Lx * 2, false);
             bs[l + 1] = C.b.p;
         }
-        {
+        if (truncated) {
+            xs[lbot] = smooth(lbot, bs[lbot], nullptr);
+        } else if (tail_first_ >= 0) {
+            xs[lbot] = launch_tail();
+        } else {
             Level& C = levels_[nl - 1];
             mg_coarse_apply_inverse_kernel<T><<<1, 192, 0, stream_>>>((int)C.nu, coarse_Ainv_.p, bs[nl - 1], C.x.p);
             TM_CHECK_LAUNCH();
             xs[nl - 1] = C.x.p;
         }
-        for (int l = nl - 1; l-- > 0;) {
+        for (int l = lbot; l-- > 0;) {
             Level& L = levels_[l];
             Level& C = levels_[l + 1];
             exchange_p2(l + 1, xs[l + 1]);
@@ -1715,6 +1874,10 @@ class Engine : public EngineBase {
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
     bool fuse_first_ = true;
+    int depth_limit_ = 0;
+    int tail_max_nodes_ = 2304, tail_cluster_ = 16, tail_cluster_used_ = 0, tail_first_ = -1;
+    TailArgs<T> tail_host_;
+    DevBuf<unsigned char> tail_dev_;
     bool graph_sharded_ = true;  // NCCL calls inside captured V-cycles (all ranks capture alike)
     cudaGraphExec_t graph_exec_ = nullptr;
     T* graph_r_ = nullptr;

@@ -101,6 +101,88 @@ __device__ __forceinline__ double transfer_weight(const TransferTable& tab, int 
     return tab.Pw[5 * (j - 4 * cy) + (i - 4 * cx)][3 * qy + qx];
 }
 
+// CG: read through L2 only (ld.global.cg) - for the cluster tail kernel, whose inputs were
+// written by other CTAs of the same launch.
+template <typename T>
+struct MgVec2;
+template <>
+struct MgVec2<double> {
+    using type = double2;
+};
+template <>
+struct MgVec2<float> {
+    using type = float2;
+};
+template <typename T, bool CG>
+__device__ __forceinline__ typename MgVec2<T>::type mg_ld2(const T* p, size_t node) {
+    using V2 = typename MgVec2<T>::type;
+    const V2* q = reinterpret_cast<const V2*>(p) + node;
+    return CG ? __ldcg(q) : *q;
+}
+
+// (P^T r)(I, J) on the coarse lattice: zero on coarse Dirichlet nodes.  The 7x7 gather is
+// unrolled with predicated loads so that all of them are in flight together.
+template <typename T, bool CG>
+__device__ __forceinline__ void restrict_node(const LevelGeom<T>& f, const LevelGeom<T>& c,
+                                              const TransferTable& tab, const T* __restrict__ r, int I,
+                                              int J, double& a0, double& a1) {
+    a0 = 0.0;
+    a1 = 0.0;
+    if (c.fixed(I, J)) return;
+    const int Jg = J + c.j_off;  // global coarse lattice row
+    const double* rw = tab.Rw[(I & 1) + 2 * (Jg & 1)];
+    double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int dj = -3; dj <= 3; ++dj) {
+        const int jg = 2 * Jg + dj;  // global fine lattice row
+        const int j = jg - f.j_off;
+        const bool rowok = jg >= 0 && jg <= 2 * f.nyg && j >= 0 && j < f.Ly;
+        const int jc = min(max(j, 0), f.Ly - 1);
+#pragma unroll
+        for (int di = -3; di <= 3; ++di) {
+            const int i = 2 * I + di;
+            const bool ok = rowok && i >= 0 && i < f.Lx;
+            const int ic = min(max(i, 0), f.Lx - 1);
+            const double w = ok ? rw[7 * (dj + 3) + (di + 3)] : 0.0;
+            const size_t n = (size_t)jc * f.Lx + ic;
+            typename MgVec2<T>::type v;
+            v.x = v.y = T(0);
+            if (w != 0.0) v = mg_ld2<T, CG>(r, n);  // predicated: never touches unrelated memory
+            if ((dj + di) & 1) {
+                e0 += w * (double)v.x;
+                e1 += w * (double)v.y;
+            } else {
+                a0 += w * (double)v.x;
+                a1 += w * (double)v.y;
+            }
+        }
+    }
+    a0 += e0;
+    a1 += e1;
+}
+
+// (P xc)(i, j) on the fine lattice (the caller skips fine Dirichlet nodes)
+template <typename T, bool CG>
+__device__ __forceinline__ void prolong_node(const LevelGeom<T>& f, const LevelGeom<T>& c,
+                                             const TransferTable& tab, const T* __restrict__ xc, int i,
+                                             int j, double& a0, double& a1) {
+    const int jg = j + f.j_off;  // global fine lattice row
+    const int cx = min(i >> 2, c.nx - 1), cy = min(jg >> 2, c.nyg - 1);
+    const double* pw = tab.Pw[5 * (jg - 4 * cy) + (i - 4 * cx)];
+    a0 = 0.0;
+    a1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const double w = pw[q];
+        const size_t N = (size_t)(2 * cy + q / 3 - c.j_off) * c.Lx + (2 * cx + q % 3);
+        typename MgVec2<T>::type v;
+        v.x = v.y = T(0);
+        if (w != 0.0) v = mg_ld2<T, CG>(xc, N);
+        a0 += w * (double)v.x;
+        a1 += w * (double)v.y;
+    }
+}
+
 // bc = P^T r  (zero on coarse Dirichlet nodes)
 template <typename T>
 __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
@@ -109,25 +191,8 @@ __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= c.Lx || J >= c.Ly || !c.owns_row(J)) return;
-    double a0 = 0.0, a1 = 0.0;
-    if (!c.fixed(I, J)) {
-        const int Jg = J + c.j_off;  // global coarse lattice row
-        const double* rw = tab.Rw[(I & 1) + 2 * (Jg & 1)];
-        for (int dj = -3; dj <= 3; ++dj) {
-            const int jg = 2 * Jg + dj;  // global fine lattice row
-            const int j = jg - f.j_off;
-            if (jg < 0 || jg > 2 * f.nyg || j < 0 || j >= f.Ly) continue;
-#pragma unroll
-            for (int di = -3; di <= 3; ++di) {
-                const int i = 2 * I + di;
-                const double w = rw[7 * (dj + 3) + (di + 3)];
-                if (w == 0.0 || i < 0 || i >= f.Lx) continue;
-                const size_t n = (size_t)j * f.Lx + i;
-                a0 += w * (double)r[2 * n];
-                a1 += w * (double)r[2 * n + 1];
-            }
-        }
-    }
+    double a0, a1;
+    restrict_node<T, false>(f, c, tab, r, I, J, a0, a1);
     const size_t N = (size_t)J * c.Lx + I;
     bc[2 * N] = (T)a0;
     bc[2 * N + 1] = (T)a1;
@@ -142,18 +207,8 @@ __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= f.Lx || j >= f.Ly || !f.owns_row(j)) return;
     if (f.fixed(i, j)) return;
-    const int jg = j + f.j_off;  // global fine lattice row
-    const int cx = min(i >> 2, c.nx - 1), cy = min(jg >> 2, c.nyg - 1);
-    const double* pw = tab.Pw[5 * (jg - 4 * cy) + (i - 4 * cx)];
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < 9; ++q) {
-        const double w = pw[q];
-        if (w == 0.0) continue;
-        const size_t N = (size_t)(2 * cy + q / 3 - c.j_off) * c.Lx + (2 * cx + q % 3);
-        a0 += w * (double)xc[2 * N];
-        a1 += w * (double)xc[2 * N + 1];
-    }
+    double a0, a1;
+    prolong_node<T, false>(f, c, tab, xc, i, j, a0, a1);
     const size_t n = (size_t)j * f.Lx + i;
     x[2 * n] = (T)((double)x[2 * n] + a0);
     x[2 * n + 1] = (T)((double)x[2 * n + 1] + a1);
