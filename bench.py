@@ -321,12 +321,15 @@ def run_cuda_arm(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the fine-level operator with the fused
-    # Chebyshev-Jacobi epilogue (reads x, b, D^-1, d and xi; writes d, x_new)
+    # ---- roofline of the dominant kernel: the fine-level operator with a fused epilogue.
+    # Algorithmic bytes per launch (every lattice vector once), with the
+    # default fine smoother degree 1: Chebyshev step  reads x, b, D^-1, xi, writes x_new (the
+    # direction d is neither read, c1 = 0, nor stored, last step); residual with the fused first
+    # step  reads b, D^-1, xi, writes x, r;  p.Ap  reads p, xi, writes Ap.
     peak, peak_src = measured_peak_hbm()
     es_mg = 4 if (args.mixed and esize == 8) else esize  # multigrid-side launches run in fp32 when mixed
     alg_bytes = {
-        "cheb": (6 * nu + n1) * es_mg, "resid": (3 * nu + n1) * es_mg,
+        "cheb": (4 * nu + n1) * es_mg, "resid": (4 * nu + n1) * es_mg,
         "dot": (2 * nu + n1) * esize, "plain": (2 * nu + n1) * es_mg,
     }
     # Event-timed launches are a sample (V-cycles replayed from a CUDA graph are not individually

@@ -204,6 +204,7 @@ class Engine : public EngineBase {
             case 117: mixed_ = value != 0.0; break;
             case 118: fuse_first_ = value != 0.0; graph_dirty_ = true; break;
             case 119: tail_max_nodes_ = (int)value; levels_.clear(); graph_dirty_ = true; break;
+            case 122: tail_dry_ = (int)value; break;
             case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
             case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
             case 113: filter_mg_degree_ = std::max(1, (int)value); break;
@@ -1438,17 +1439,31 @@ class Engine : public EngineBase {
             }
         if (first < 0 || nlevels_ - first < 2) return;
         first = std::max(first, nlevels_ - kTailMaxLevels);
-        int csize = tail_cluster_;
-        for (; csize >= 1; csize /= 2) {
-            if (csize > 8 &&
-                cudaFuncSetAttribute(tail_vcycle_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
-                    cudaSuccess) {
+        int smem_max = 0;
+        TM_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        const size_t arg_bytes = (sizeof(TailArgs<T>) + 15) / 16 * 16;
+        for (int csize = tail_cluster_; csize >= 1; csize /= 2) {
+            // stencil images of the smoothed tail levels for this cluster size
+            std::memset(&tail_host_, 0, sizeof(tail_host_));
+            int img_len = 0;
+            for (int l = first; l + 1 < nlevels_; ++l) {
+                TailLevel<T>& V = tail_host_.lv[l - first];
+                V.g = levels_[l].g;
+                img_len += tail_plan_level(V, csize, img_len);
+            }
+            const size_t smem = arg_bytes + (size_t)img_len * sizeof(T);
+            if (smem > (size_t)smem_max) continue;
+            if (cudaFuncSetAttribute(tail_vcycle_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem) != cudaSuccess ||
+                (csize > 8 && cudaFuncSetAttribute(tail_vcycle_kernel<T>,
+                                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
                 cudaGetLastError();
                 continue;
             }
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(csize);
             cfg.blockDim = dim3(kTailThreads);
+            cfg.dynamicSmemBytes = smem;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = csize;
@@ -1457,26 +1472,29 @@ class Engine : public EngineBase {
             cfg.attrs = at;
             cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, tail_vcycle_kernel<T>, &cfg) == cudaSuccess &&
-                nclusters >= 1)
-                break;
-            cudaGetLastError();
+            if (cudaOccupancyMaxActiveClusters(&nclusters, tail_vcycle_kernel<T>, &cfg) != cudaSuccess ||
+                nclusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            tail_cluster_used_ = csize;
+            tail_first_ = first;
+            tail_smem_ = smem;
+            tail_host_.img_len = img_len;
+            tail_img_.ensure((size_t)csize * img_len);
+            tail_dev_.ensure(sizeof(TailArgs<T>));
+            return;
         }
-        if (csize < 1) return;
-        tail_cluster_used_ = csize;
-        tail_first_ = first;
-        for (int l = first; l + 1 < nlevels_; ++l)
-            levels_[l].S.ensure(100 * (size_t)levels_[l].g.Lx * levels_[l].g.Ly);
-        tail_dev_.ensure(sizeof(TailArgs<T>));
     }
 
     // stencils of the tail levels (after the moments were coarsened) ...
     void assemble_tail() {
         if (tail_first_ < 0) return;
         for (int l = tail_first_; l + 1 < nlevels_; ++l) {
-            Level& L = levels_[l];
-            const int n2 = 2 * L.g.Lx * L.g.Ly;
-            tail_assemble_kernel<T><<<ceil_div(n2, 128), 128, 0, stream_>>>(L.g, L.S.p);
+            TailLevel<T>& V = tail_host_.lv[l - tail_first_];
+            V.g = levels_[l].g;  // W pointer is current
+            tail_assemble_kernel<T><<<ceil_div(V.toff[4] * V.npt * 2, 128), 128, 0, stream_>>>(
+                V, tail_cluster_used_, tail_host_.img_len, tail_img_.p);
             TM_CHECK_LAUNCH();
         }
     }
@@ -1484,11 +1502,12 @@ class Engine : public EngineBase {
     void upload_tail() {
         if (tail_first_ < 0) return;
         TailArgs<T>& A = tail_host_;
-        std::memset(&A, 0, sizeof(A));
         const int nl = nlevels_;
         A.nt = nl - tail_first_;
         A.degree = coarse_degree_ > 0 ? coarse_degree_ : cheb_degree_;
         A.nc = (int)levels_[nl - 1].nu;
+        A.dry = tail_dry_;
+        A.img = tail_img_.p;
         A.Ainv = coarse_Ainv_.p;
         A.tab = tr_tab_;
         for (int t = 0; t < A.nt; ++t) {
@@ -1496,14 +1515,16 @@ class Engine : public EngineBase {
             TailLevel<T>& V = A.lv[t];
             V.g = L.g;
             V.n = L.g.Lx * L.g.Ly;
-            V.S = L.S.p;
             V.dinv = L.dinv.p;
             V.b = L.b.p;
             V.xa = L.x.p;
             V.xb = L.xalt.p;
             V.d = L.d.p;
             V.r = L.tmp.p;
-            if (t + 1 == A.nt) break;
+            if (t + 1 == A.nt) {  // coarsest level: only its lattice and the transfer split are used
+                if (V.G == 0) tail_plan_level(V, tail_cluster_used_, 0);
+                break;
+            }
             const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
             const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
             double rho = 1.0 / sigma;
@@ -1524,6 +1545,7 @@ class Engine : public EngineBase {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(tail_cluster_used_);
         cfg.blockDim = dim3(kTailThreads);
+        cfg.dynamicSmemBytes = tail_smem_;
         cfg.stream = stream_;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1874,10 +1896,12 @@ class Engine : public EngineBase {
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
     bool fuse_first_ = true;
-    int depth_limit_ = 0;
+    int depth_limit_ = 0, tail_dry_ = 0;
     int tail_max_nodes_ = 2304, tail_cluster_ = 16, tail_cluster_used_ = 0, tail_first_ = -1;
     TailArgs<T> tail_host_;
     DevBuf<unsigned char> tail_dev_;
+    DevBuf<T> tail_img_;
+    size_t tail_smem_ = 0;
     bool graph_sharded_ = true;  // NCCL calls inside captured V-cycles (all ranks capture alike)
     cudaGraphExec_t graph_exec_ = nullptr;
     T* graph_r_ = nullptr;
