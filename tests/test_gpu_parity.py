@@ -404,3 +404,33 @@ def test_cluster_tail_equals_launch_per_phase_vcycle(repo_root, design, N, degre
     assert out[0][2]["tail_first_level"] == -1 and out[1][2]["tail_first_level"] >= 1
     assert abs(out[0][1] - out[1][1]) <= 1
     assert np.linalg.norm(out[0][0] - out[1][0]) / np.linalg.norm(out[0][0]) < 1e-9
+
+
+@pytest.mark.parametrize("nx,ny,eps,steps", [(40, 24, 0.07, 4), (129, 65, 0.02, 4), (200, 90, 0.015, 6),
+                                             (7, 5, 0.3, 3), (333, 1, 0.05, 2)])
+def test_filter_temporal_blocking_matches_oracle(nx, ny, eps, steps):
+    """The Chebyshev filter solve with several iterations per grid barrier (shared-memory tiles with
+    halo recomputation) against the direct solve and against the un-blocked kernel.  The first
+    solve of an engine runs CG (it estimates the spectral bounds), the following ones Chebyshev."""
+    W, H = 0.05 * nx, 0.05 * ny
+    mesh = StructuredMesh(W, H, nx, ny)
+    K1, M1 = mesh.p1_matrices()
+    A = eps * eps * K1 + M1
+    rng = np.random.default_rng(nx + ny)
+    rho, rhs = rng.random(mesh.n1), rng.standard_normal(mesh.n1)
+    res = {}
+    for tb in (1, 0):
+        eng = _engine(nx, ny, W, H, filter_radius=eps)
+        eng.set_option(112, 2)  # never the multigrid filter
+        eng.set_option(123, tb)
+        eng.set_option(124, steps)
+        eng.filter_apply(_t(rho), assembled=False, rtol=1e-13)  # CG + Lanczos bounds
+        xi, info0 = eng.filter_apply(_t(rho), assembled=False, rtol=1e-13)
+        g, info1 = eng.filter_apply(_t(rhs), assembled=True, rtol=1e-13)
+        res[tb] = (xi.cpu().numpy(), g.cpu().numpy(), info0.iterations, info1.iterations)
+        assert _rel(res[tb][0], solve_spd(A, M1 @ rho)) < 1e-10
+        assert _rel(res[tb][1], solve_spd(A, rhs)) < 1e-10
+    print(f"filter {nx}x{ny}: iterations blocked {res[1][2:]}, un-blocked {res[0][2:]}")
+    assert _rel(res[1][0], res[0][0]) < 1e-11 and _rel(res[1][1], res[0][1]) < 1e-11
+    # blocked solves test convergence every `steps` iterations: never much later than un-blocked
+    assert res[1][3] <= 1.25 * res[0][3] + 8 + 2 * steps

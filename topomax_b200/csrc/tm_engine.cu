@@ -205,6 +205,8 @@ class Engine : public EngineBase {
             case 118: fuse_first_ = value != 0.0; graph_dirty_ = true; break;
             case 119: tail_max_nodes_ = (int)value; levels_.clear(); graph_dirty_ = true; break;
             case 122: tail_dry_ = (int)value; break;
+            case 123: filter_tb_ = value != 0.0; break;
+            case 124: filter_tb_steps_ = std::max(1, (int)value); filter_tb_state_ = 0; break;
             case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
             case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
             case 113: filter_mg_degree_ = std::max(1, (int)value); break;
@@ -339,9 +341,24 @@ class Engine : public EngineBase {
                 ca.part = filter_part_; ca.result = result;
                 T* xalt_p = f_Ap_.p;
                 T* d_p = f_p_.p;
-                void* kargs[] = {&ca, &rhs_p, &dinv_p, &x_p, &xalt_p, &d_p};
-                TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_cheb_kernel<T>, dim3(nb), dim3(kFilterThreads),
-                                                    kargs, 0, stream_));
+                FilterTbArgs ta;
+                if (filter_tb_ && plan_filter_tb(ta)) {
+                    // temporally blocked: filter_tb_steps_ iterations per grid barrier
+                    ta.lmin = filter_lmin_; ta.lmax = filter_lmax_; ta.rtol = rtol;
+                    ta.maxit = ca.maxit; ta.part = filter_part_; ta.result = result;
+                    for (int cy = 0; cy < 3; ++cy)
+                        for (int cx = 0; cx < 3; ++cx) p1_class_stencil(p1_, alpha, beta, cx, cy, ta.coef[3 * cy + cx]);
+                    T* dalt_p = f_r_.p;
+                    const double* c12_p = filter_c12(ta.maxit + ta.S + 1);
+                    void* kargs[] = {&ta, &rhs_p, &c12_p, &x_p, &xalt_p, &d_p, &dalt_p};
+                    TM_CUDA(cudaLaunchCooperativeKernel(filter_tb_entry(ta.rows_per_thread),
+                                                        dim3(ta.tiles_x * ta.tiles_y), dim3(kFilterTbThreads), kargs,
+                                                        filter_tb_smem_, stream_));
+                } else {
+                    void* kargs[] = {&ca, &rhs_p, &dinv_p, &x_p, &xalt_p, &d_p};
+                    TM_CUDA(cudaLaunchCooperativeKernel((void*)filter_cheb_kernel<T>, dim3(nb),
+                                                        dim3(kFilterThreads), kargs, 0, stream_));
+                }
                 ++g_launches;
                 TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
                 TM_CUDA(cudaStreamSynchronize(stream_));
@@ -1425,6 +1442,97 @@ class Engine : public EngineBase {
         plan_tail();
     }
 
+    static const void* filter_tb_entry(int rows) {
+        switch (rows) {
+            case 2: return (const void*)filter_cheb_tb_kernel<T, 2>;
+            case 4: return (const void*)filter_cheb_tb_kernel<T, 4>;
+            case 6: return (const void*)filter_cheb_tb_kernel<T, 6>;
+            case 8: return (const void*)filter_cheb_tb_kernel<T, 8>;
+            case 10: return (const void*)filter_cheb_tb_kernel<T, 10>;
+            case 12: return (const void*)filter_cheb_tb_kernel<T, 12>;
+            default: return (const void*)filter_cheb_tb_kernel<T, 14>;
+        }
+    }
+    // Chebyshev coefficients (c1, c2) of iterations 0 .. len-1 for the current spectral bounds
+    const double* filter_c12(int len) {
+        if ((int)filter_c12_host_.size() < 2 * len || filter_c12_lmin_ != filter_lmin_ ||
+            filter_c12_lmax_ != filter_lmax_) {
+            len = std::max(len, 2048);
+            filter_c12_host_.resize(2 * (size_t)len);
+            const double theta = 0.5 * (filter_lmax_ + filter_lmin_), delta = 0.5 * (filter_lmax_ - filter_lmin_);
+            const double sigma = theta / delta;
+            double rho = 1.0 / sigma;
+            filter_c12_host_[0] = 0.0;
+            filter_c12_host_[1] = 1.0 / theta;
+            for (int k = 1; k < len; ++k) {
+                const double rho_new = 1.0 / (2.0 * sigma - rho);
+                filter_c12_host_[2 * k] = rho_new * rho;
+                filter_c12_host_[2 * k + 1] = 2.0 * rho_new / delta;
+                rho = rho_new;
+            }
+            filter_c12_.ensure(2 * (size_t)len);
+            TM_CUDA(cudaMemcpyAsync(filter_c12_.p, filter_c12_host_.data(), sizeof(double) * 2 * len,
+                                    cudaMemcpyHostToDevice, stream_));
+            TM_CUDA(cudaStreamSynchronize(stream_));
+            filter_c12_lmin_ = filter_lmin_;
+            filter_c12_lmax_ = filter_lmax_;
+        }
+        return filter_c12_.p;
+    }
+
+    // Tiling of the vertex grid for the temporally blocked Chebyshev filter (tm_filter_pcg.cuh):
+    // at most one tile per SM; the two padded x arrays of the extended tile must fit shared
+    // memory and a thread's column segment its register arrays.  Among those, the tiling with
+    // the shortest per-thread march (the critical path of a step), then the smallest tile.
+    bool plan_filter_tb(FilterTbArgs& a) {
+        if (filter_tb_state_ < 0) return false;
+        const int S = std::max(1, filter_tb_steps_);
+        if (filter_tb_state_ == 0) {
+            filter_tb_state_ = -1;
+            int smem_max = 0;
+            TM_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            const long budget = ((long)smem_max - 4096) / (2 * (long)sizeof(double));  // doubles per array
+            const int W1 = p1_.nx + 1, H1 = p1_.ny + 1;
+            long best = -1;
+            for (int tx = 1; tx <= num_sms_; ++tx)
+                for (int ty = 1; tx * ty <= num_sms_; ++ty) {
+                    const int tw = ceil_div(W1, tx), th = ceil_div(H1, ty);
+                    if (ceil_div(W1, tw) != tx || ceil_div(H1, th) != ty) continue;  // no empty tiles
+                    const int EW = tw + 2 * S, EH = th + 2 * S;
+                    if (EW > kFilterTbThreads) continue;
+                    const int nseg = kFilterTbThreads / EW;
+                    const int rows = 2 * ceil_div(ceil_div(EH, nseg), 2);  // instantiated: 2, 4, .. 14
+                    if (rows > kFilterTbMaxRows || (long)(EW + 2) * (nseg * rows + 2) > budget) continue;
+                    const long cost = (long)rows * 1000000 + (long)EW * EH;
+                    if (best < 0 || cost < best) {
+                        best = cost;
+                        filter_tb_tx_ = tx; filter_tb_ty_ = ty; filter_tb_tw_ = tw; filter_tb_th_ = th;
+                        filter_tb_rows_ = rows;
+                        filter_tb_smem_ = (size_t)(EW + 2) * (nseg * rows + 2) * 2 * sizeof(double);
+                    }
+                }
+            if (best < 0) return false;
+            const void* entry = filter_tb_entry(filter_tb_rows_);
+            if (cudaFuncSetAttribute(entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_tb_smem_) !=
+                cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entry, kFilterTbThreads, filter_tb_smem_) !=
+                    cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                return false;
+            }
+            filter_tb_state_ = 1;
+        }
+        a.g = p1_;
+        a.S = S;
+        a.tiles_x = filter_tb_tx_; a.tiles_y = filter_tb_ty_; a.tw = filter_tb_tw_; a.th = filter_tb_th_;
+        a.rows_per_thread = filter_tb_rows_;
+        return true;
+    }
+
     // The levels from tail_first_ down run as one cluster kernel per V-cycle (tm_tail.cuh):
     // replicated levels with stored moments whose lattice has at most tail_max_nodes_ nodes.
     void plan_tail() {
@@ -1897,6 +2005,13 @@ class Engine : public EngineBase {
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
     bool fuse_first_ = true;
     int depth_limit_ = 0, tail_dry_ = 0;
+    bool filter_tb_ = true;
+    int filter_tb_steps_ = 8, filter_tb_state_ = 0;  // state: 0 unplanned, 1 ready, -1 not usable
+    int filter_tb_tx_ = 0, filter_tb_ty_ = 0, filter_tb_tw_ = 0, filter_tb_th_ = 0, filter_tb_rows_ = 0;
+    size_t filter_tb_smem_ = 0;
+    std::vector<double> filter_c12_host_;
+    DevBuf<double> filter_c12_;
+    double filter_c12_lmin_ = -1.0, filter_c12_lmax_ = -1.0;
     int tail_max_nodes_ = 2304, tail_cluster_ = 16, tail_cluster_used_ = 0, tail_first_ = -1;
     TailArgs<T> tail_host_;
     DevBuf<unsigned char> tail_dev_;
