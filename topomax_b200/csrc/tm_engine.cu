@@ -154,6 +154,8 @@ class Engine : public EngineBase {
         // graphs that captured NCCL operations must go before the communicator does
         if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
         if (fgraph_exec_) cudaGraphExecDestroy(fgraph_exec_);
+        if (setup_graph_exec_) cudaGraphExecDestroy(setup_graph_exec_);
+        setup_graph_exec_ = nullptr;
         graph_exec_ = nullptr;
         fgraph_exec_ = nullptr;
         inner_.reset();
@@ -799,6 +801,11 @@ class Engine : public EngineBase {
         stats_vcycles_ = 0;
 
         exchange_p1(xi);
+        // engine-owned copy: the captured set-up / V-cycle graphs stay valid whatever buffer the
+        // caller's allocator hands over from one solve to the next
+        s_xi_.ensure(n1_);
+        TM_CUDA(cudaMemcpyAsync(s_xi_.p, xi, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        xi = s_xi_.p;
         LevelGeom<T> g = g0_;
         g.xi = xi;
         mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, b, s_b_.p);
@@ -1408,6 +1415,10 @@ class Engine : public EngineBase {
     };
 
     void build_levels() {
+        if (setup_graph_exec_) {
+            cudaGraphExecDestroy(setup_graph_exec_);
+            setup_graph_exec_ = nullptr;
+        }
         levels_.clear();
         levels_.resize(nlevels_);
         for (int l = 0; l < nlevels_; ++l) {
@@ -1671,10 +1682,61 @@ class Engine : public EngineBase {
         return (flips & 1) ? L.xalt.p : L.x.p;
     }
 
+    // Coefficients of every level, smoother bounds, coarsest factorisation, tail stencils.  The
+    // ~150 small launches of the device part are captured into a CUDA graph once the warm-started
+    // eigenvector iteration has its steady shape, and replayed while `xi` is the same buffer.
     void setup_hierarchy(T* xi) {
         const int nl = nlevels_;
         graph_dirty_ = true;  // coefficients / smoother bounds change: re-capture the V-cycle
         graph_sampled_ = false;
+        bool steady = use_graph_ && nranks_ == 1 && profile_ != 2;
+        for (int l = 0; steady && l + 1 < nl; ++l) steady = levels_[l].eig_ready;
+        if (!steady) {
+            setup_device_part(xi);
+        } else if (setup_graph_exec_ && setup_graph_xi_ == xi) {
+            TM_CUDA(cudaGraphLaunch(setup_graph_exec_, stream_));
+            ++g_launches;
+        } else {
+            if (setup_graph_exec_) {
+                cudaGraphExecDestroy(setup_graph_exec_);
+                setup_graph_exec_ = nullptr;
+            }
+            const long long l0 = g_launches.load();
+            const int saved_profile = profile_;
+            profile_ = 0;  // no event records inside a capture
+            cudaGraph_t graph = nullptr;
+            TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+            try {
+                setup_device_part(xi);
+            } catch (...) {
+                cudaStreamEndCapture(stream_, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                profile_ = saved_profile;
+                throw;
+            }
+            TM_CUDA(cudaStreamEndCapture(stream_, &graph));
+            profile_ = saved_profile;
+            g_launches.store(l0);
+            TM_CUDA(cudaGraphInstantiate(&setup_graph_exec_, graph, 0));
+            cudaGraphDestroy(graph);
+            setup_graph_xi_ = xi;
+            TM_CUDA(cudaGraphLaunch(setup_graph_exec_, stream_));
+            ++g_launches;
+        }
+        TM_CUDA(cudaMemcpyAsync(h_sc_ + SC_COUNT, eig_sc_, sizeof(double) * 2 * (nl - 1),
+                                cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (int l = 0; l + 1 < nl; ++l) {
+            // after normalising by the previous norm, ||eig||^2 -> lambda^2
+            const double lam = std::sqrt(h_sc_[SC_COUNT + 2 * l + 1]);
+            if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"multigrid: eigenvalue estimate failed"};
+            levels_[l].lmax = lam;
+        }
+        upload_tail();
+    }
+
+    void setup_device_part(T* xi) {
+        const int nl = nlevels_;
         levels_[0].g.xi = xi;
         for (int l = 1; l < nl; ++l) {
             Level& F = levels_[l - 1];
@@ -1741,16 +1803,6 @@ class Engine : public EngineBase {
             mg_coarse_invert_kernel<<<1, 192, 0, stream_>>>((int)C.nu, coarse_A_.p, coarse_Ainv_.p);
             TM_CHECK_LAUNCH();
         }
-        TM_CUDA(cudaMemcpyAsync(h_sc_ + SC_COUNT, eig_sc_, sizeof(double) * 2 * (nl - 1),
-                                cudaMemcpyDeviceToHost, stream_));
-        TM_CUDA(cudaStreamSynchronize(stream_));
-        for (int l = 0; l + 1 < nl; ++l) {
-            // after normalising by the previous norm, ||eig||^2 -> lambda^2
-            const double lam = std::sqrt(h_sc_[SC_COUNT + 2 * l + 1]);
-            if (!(lam > 0.0) || !(lam == lam)) throw Invalid{"multigrid: eigenvalue estimate failed"};
-            levels_[l].lmax = lam;
-        }
-        upload_tail();
     }
 
     // ---- mixed precision: an fp32 twin engine owns the multigrid hierarchy
@@ -1977,7 +2029,7 @@ class Engine : public EngineBase {
 
     DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_, f_p2_;
     bool f_dinv_ready_ = false;
-    DevBuf<T> s_r_, s_p_, s_Ap_, s_b_, s_dinv_;
+    DevBuf<T> s_r_, s_p_, s_Ap_, s_b_, s_dinv_, s_xi_;
     std::vector<Level> levels_;
     DevBuf<double> coarse_A_, coarse_Ainv_;
 
@@ -2005,6 +2057,8 @@ class Engine : public EngineBase {
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
     bool fuse_first_ = true;
     int depth_limit_ = 0, tail_dry_ = 0;
+    cudaGraphExec_t setup_graph_exec_ = nullptr;
+    T* setup_graph_xi_ = nullptr;
     bool filter_tb_ = true;
     int filter_tb_steps_ = 8, filter_tb_state_ = 0;  // state: 0 unplanned, 1 ready, -1 not usable
     int filter_tb_tx_ = 0, filter_tb_ty_ = 0, filter_tb_tw_ = 0, filter_tb_th_ = 0, filter_tb_rows_ = 0;

@@ -153,7 +153,13 @@ class FEMSolver(Solver):
         if self.world > 1:
             from . import sharding
             return sharding.gather_p1(self.problem.engine, tensor)
-        return tensor.detach().cpu().numpy()
+        n = tensor.numel()
+        if getattr(self, "_pinned_out", None) is None or self._pinned_out.numel() != n \
+                or self._pinned_out.dtype != tensor.dtype:
+            self._pinned_out = torch.empty(n, dtype=tensor.dtype).pin_memory()
+        self._pinned_out.copy_(tensor.detach().reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pinned_out.numpy().copy()  # the staging buffer is reused
 
     def to_array(self, rho: Function) -> np.ndarray:
         return self._d2h(rho.tensor)
@@ -168,11 +174,13 @@ class FEMSolver(Solver):
         """``Solver.step`` (reference: src/solver.py:188-194) with host arrays in and out: the latent
         variable crosses PCIe once each way; filtered sensitivity, half step and the Newton/Brent
         volume projection run on the device (``step_device``).  ``Solver.project`` through the
-        ``integrate`` hook stays available for callers that drive the projection themselves."""
+        ``integrate`` hook stays available for callers that drive the projection themselves.
+        Side effect: ``self.rho`` already holds expit(psi_new) on the device when this returns, so
+        a caller that only needs the next objective can skip the host-side expit + upload the
+        reference loop does next (doing it anyway, as ``Solver.solve`` does, is harmless)."""
         prev = self._h2d(previous_psi)
         psi = torch.empty_like(prev)
-        rho = torch.empty_like(prev)
-        self.step_device(prev, step_size, psi, rho)
+        self.step_device(prev, step_size, psi, self.rho.tensor)
         return self._d2h(psi)
 
     def save_rho(self, rho: Function, file_root: str):
