@@ -59,10 +59,29 @@ struct ApplyArgs {
 
 constexpr int kApplyWarps = 4;  // warps (column groups) per block
 
+// Epilogue operands of one owned node, loaded into registers BEFORE the element arithmetic of the
+// march step so that their HBM latency hides behind it (an ncu source view of the first version
+// showed 44 % of all stall samples on the instructions consuming b and D^-1 right after loading
+// them; prefetch.global.L1 did not remove that).
+template <typename T>
+struct EpiOps {
+    typename Vec2<T>::type b, dinv, d;
+};
+
+template <typename T, int EP>
+__device__ __forceinline__ void load_epi_ops(const ApplyArgs<T>& a, size_t n, EpiOps<T>& o) {
+    using V2 = typename Vec2<T>::type;
+    if (EP == EP_RESID || EP == EP_RESID0 || EP == EP_CHEB) o.b = reinterpret_cast<const V2*>(a.b)[n];
+    if (EP == EP_CHEB) {
+        o.dinv = reinterpret_cast<const V2*>(a.dinv)[n];
+        if (a.c1 != T(0)) o.d = reinterpret_cast<const V2*>(a.d)[n];
+    }
+}
+
 // what happens to one owned node once its row of K x is complete (v), x being the input there
 template <typename T, int EP>
 __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, bool fixed, T v0, T v1,
-                                               T x0, T x1, double& dot) {
+                                               T x0, T x1, double& dot, const EpiOps<T>& ops) {
     using V2 = typename Vec2<T>::type;
     if (fixed && EP == EP_RESID0) {  // x = c2 D^-1 b vanishes on Dirichlet nodes (b_D = 0)
         x0 = x1 = v0 = v1 = T(0);
@@ -77,7 +96,7 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
         out.y = v1;
         if (EP == EP_DOT) dot += (double)x0 * (double)v0 + (double)x1 * (double)v1;
     } else {
-        const V2 bb = reinterpret_cast<const V2*>(a.b)[n];
+        const V2 bb = ops.b;
         const T r0 = bb.x - v0, r1 = bb.y - v1;
         if (EP == EP_RESID || EP == EP_RESID0) {
             out.x = r0;
@@ -89,14 +108,13 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
                 reinterpret_cast<V2*>(a.d)[n] = xo;
             }
         } else {
-            const V2 di = reinterpret_cast<const V2*>(a.dinv)[n];
+            const V2 di = ops.dinv;
             V2 dd;
             dd.x = a.c2 * di.x * r0;
             dd.y = a.c2 * di.y * r1;
             if (a.c1 != T(0)) {
-                const V2 dold = reinterpret_cast<const V2*>(a.d)[n];
-                dd.x += a.c1 * dold.x;
-                dd.y += a.c1 * dold.y;
+                dd.x += a.c1 * ops.d.x;
+                dd.y += a.c1 * ops.d.y;
             }
             if (a.store_d) reinterpret_cast<V2*>(a.d)[n] = dd;
             out.x = x0 + dd.x;
@@ -255,6 +273,23 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                 load_next(iy + 1);
                 prefetch_epilogue(iy + 1);
             }
+            // epilogue operands of this step's four owned nodes: in flight during the arithmetic
+            // (fine level only: the stored-moment kernels of the coarse levels are better off with
+            // the registers, i.e. a third resident block per SM, and load them where they are used)
+            EpiOps<T> eo[2][2];
+            if (!STORED_W && (EP == EP_RESID || EP == EP_RESID0 || EP == EP_CHEB)) {
+                if (iy >= iy0 && owner) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (!g.owns_row(j0 + r)) continue;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (c == 1 && !own_c1) continue;
+                            load_epi_ops<T, EP>(a, (size_t)(j0 + r) * Lx + i0 + c, eo[r][c]);
+                        }
+                    }
+                }
+            }
             T acc[9][2];
 #pragma unroll
             for (int q = 0; q < 9; ++q) acc[q][0] = acc[q][1] = T(0);
@@ -298,8 +333,9 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
                             v0 += carry[c][0];
                             v1 += carry[c][1];
                         }
+                        if (STORED_W) load_epi_ops<T, EP>(a, (size_t)j * Lx + i0 + c, eo[r][c]);
                         apply_epilogue<T, EP>(a, (size_t)j * Lx + i0 + c, rowfix || colfix[c], v0, v1,
-                                              X[3 * r + c][0], X[3 * r + c][1], dot);
+                                              X[3 * r + c][0], X[3 * r + c][1], dot, eo[r][c]);
                     }
                 }
             }
@@ -316,8 +352,10 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 if (c == 1 && !own_c1) continue;
+                EpiOps<T> et;
+                load_epi_ops<T, EP>(a, (size_t)j * Lx + i0 + c, et);
                 apply_epilogue<T, EP>(a, (size_t)j * Lx + i0 + c, rowfix || colfix[c], carry[c][0],
-                                      carry[c][1], X[6 + c][0], X[6 + c][1], dot);
+                                      carry[c][1], X[6 + c][0], X[6 + c][1], dot, et);
             }
         }
     }
