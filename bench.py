@@ -144,6 +144,33 @@ def oracle_iteration_seconds(design_path, sample_n, steps, warmup):
     return times, s
 
 
+def omp_kernel_baseline(design_path, full_n, max_iterations=60):
+    """Like-for-like CPU *kernel* figure: the C + OpenMP matrix-free operator with
+    Jacobi-PCG (oracle/c/elast_omp.c) on all host cores, at the FULL resolution of the GPU
+    workload, for a bounded number of PCG iterations on the initial (uniform) design."""
+    import numpy as np
+    from oracle.fem_oracle import StructuredMesh, lame
+    from oracle.md_oracle import read_design
+    from oracle.omp_kernels import OmpElasticity
+
+    d = read_design(design_path)
+    n = int(full_n / min(d["width"], d["height"]))
+    nx, ny = int(d["width"] * n), int(d["height"] * n)
+    lda, mu = lame(d["E"], d["nu"])
+    op = OmpElasticity(d["width"], d["height"], nx, ny, lda, mu, d["fixed_sides"], p=d["penalties"][0])
+    xi = np.full(op.n1, d["volume_fraction"])
+    if d["body_force"] is None:
+        b = StructuredMesh(d["width"], d["height"], nx, ny).load_vector(None, d["tractions"])
+    else:  # the P2 mass matrix of the body-force load is not worth assembling for a timing
+        b = np.zeros(op.nu)
+        b[1::2] = -1.0
+    _, its, rel, sec = op.jacobi_pcg(xi, b, rtol=1e-10, maxit=max_iterations)
+    return {"what": "C + OpenMP matrix-free P2 elasticity operator (quadrature) + Jacobi-PCG, fp64",
+            "dof_iters_per_sec": op.nu * its / sec if sec > 0 else None, "cores": op.threads,
+            "sample": f"{its} PCG iterations at the full workload resolution (nx={nx}, ny={ny}, {op.nu} dofs)",
+            "seconds": sec}
+
+
 def pick_sample_n(full_n, steps_total, budget_s):
     # sparse LU with nested dissection on a 2-D mesh: ~17 s at N=256 here, flops ~ N^3
     for n in (full_n, 384, 256, 192, 128, 96, 64):
@@ -182,6 +209,10 @@ def run_reference_arm(args):
                          "split_seconds": {k: round(v, 3) for k, v in s.problem.timings.items()}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    try:
+        line["cpu_baseline"]["state_solve_kernel"] = omp_kernel_baseline(design_path, args.N)
+    except Exception as exc:  # the direct-solver figure above is the arm's value either way
+        line["cpu_baseline"]["state_solve_kernel"] = {"unavailable": repr(exc)}
     print(json.dumps(line))
 
 
@@ -379,6 +410,10 @@ def run_cuda_arm(args):
                        f"{(nx * ny) / (s.mesh.nx * s.mesh.ny):.1f}x fewer cells than the GPU workload"),
             "split_seconds": {k2: round(v, 3) for k2, v in s.problem.timings.items()},
         }
+        try:
+            cpu_baseline["state_solve_kernel"] = omp_kernel_baseline(design_path, args.N)
+        except Exception as exc:
+            cpu_baseline["state_solve_kernel"] = {"unavailable": repr(exc)}
 
     cfg = workload_description(args.design, run_n, nx, ny)
     cfg.update({
