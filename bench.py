@@ -248,7 +248,7 @@ def run_cuda_arm(args):
     solver = FEMSolver(run_n, design_path, data_path=tmp, verbose=False, dtype=args.dtype,
                        distributed=world > 1, dist_levels=args.dist_levels,
                        problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
-                                        "mixed_precision": args.mixed})
+                                        "mixed_precision": args.mixed, "warm_start": not args.no_warm_start})
     problem, engine = solver.problem, solver.problem.engine
     for kv in args.engine_option:
         key, val = kv.split("=")
@@ -441,6 +441,8 @@ def run_cuda_arm(args):
                 "dof_iters_per_sec": pcg_iters * nu_global / (elapsed_ms * 1e-3),
                 "fine_operator_applies_per_step": fine_applies / args.steps,
                 "state_solves": len(solves),
+                "warm_starts_kept": sum(1 for s in solves if s.get("warm_start_used")),
+                "iterations_by_solve": [s["iterations"] for s in solves],
                 "last_relative_residual": solves[-1]["relative_residual"] if solves else None},
         "objective_trace": objectives[: args.warmup + args.steps + 1],
     }
@@ -466,6 +468,7 @@ def main():
     ap.add_argument("--mixed", action="store_true", help="fp32 multigrid preconditioner inside the fp64 PCG (reported separately)")
     ap.add_argument("--engine_option", action="append", default=[], help="KEY=VALUE passed to tm_set_option (tuning studies)")
     ap.add_argument("--exact_N", action="store_true", help="multi-GPU: run exactly --N (strong scaling of a named config)")
+    ap.add_argument("--no_warm_start", action="store_true", help="state solves start from zero (study)")
     ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large meshes)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":

@@ -138,7 +138,10 @@ int tm_md_apply(tm_handle h, const void* half, double c, const void* psi_prev, v
 int tm_integrate(tm_handle h, const void* values, double* out);
 
 /* statistics of the last tm_state_solve: out[0] iterations, [1] V-cycles, [2] fine-level
- * operator applications, [3] levels, [4] lambda_max estimate of level 0 */
+ * operator applications, [3] levels, [4] lambda_max estimate of level 0, [5..8] cumulative
+ * level-0 operator launches per epilogue, [9] first level of the cluster tail (-1: none), [10] its
+ * cluster size, [11] 1 if the caller's initial guess was kept (a warm start whose residual
+ * exceeds that of the zero guess is dropped) */
 int tm_last_solve_stats(tm_handle h, double* out, int n);
 
 /* Measurement support (bench.py): with TM_OPT_PROFILE on, out[0..3] = milliseconds spent in the

@@ -41,6 +41,16 @@ struct CudaFailure {
         TM_CUDA(cudaGetLastError()); \
     } while (0)
 
+// Programmatic dependent launch (the V-cycle's chain of small dependent kernels): a kernel first
+// lets its programmatic dependents be scheduled, then waits for the grids it depends on to
+// complete and flush.  Every global access of the kernel comes after the wait, so dependents
+// only overlap their launch latency and prologue with the tail of their predecessor.  Both
+// instructions are no-ops in launches without a programmatic edge.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // lattice description of one multigrid level
 // ---------------------------------------------------------------------------------------

@@ -135,6 +135,7 @@ template <typename T, bool STORED_W, int EP, int MINB = 2, bool PF = false>
 __global__ void __launch_bounds__(kApplyWarps * 32, MINB)
 elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
     using V2 = typename Vec2<T>::type;
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int cgroup = blockIdx.x * kApplyWarps + (threadIdx.x >> 5);
     const int ix = cgroup * 31 + lane - 1;  // cell column of this thread

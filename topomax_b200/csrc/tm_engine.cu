@@ -208,6 +208,8 @@ class Engine : public EngineBase {
             case 119: tail_max_nodes_ = (int)value; levels_.clear(); graph_dirty_ = true; break;
             case 122: tail_dry_ = (int)value; break;
             case 123: filter_tb_ = value != 0.0; break;
+            case 125: warm_guard_ = value != 0.0; break;
+            case 126: pdl_ = value != 0.0; graph_dirty_ = true; break;
             case 124: filter_tb_steps_ = std::max(1, (int)value); filter_tb_state_ = 0; break;
             case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
             case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
@@ -827,14 +829,32 @@ class Engine : public EngineBase {
             dinv = s_dinv_.p;
         }
 
-        if (flags & 1) {
+        bool warm = (flags & 1) != 0;
+        stats_warm_used_ = 0;
+        if (warm) {
             mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, u, u);
             TM_CHECK_LAUNCH();
             exchange_p2(0, u);
             ApplyArgs<T> a = apply_args();
             a.x = u; a.y = s_r_.p; a.b = s_b_.p;
             launch_apply(g, false, EP_RESID, a);
-        } else {
+            if (warm_guard_) {
+                // The previous displacement is only a good guess once the design settles: while the
+                // SIMP stiffness of whole regions still moves by orders of magnitude its residual can
+                // exceed ||b|| (the residual of the zero guess) by far.  Keep whichever is smaller.
+                const int g1 = grid1d(p2_cnt_);
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, s_r_.p + p2_off_, s_r_.p + p2_off_, rs_,
+                                                              sc_ + SC_TMP);
+                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, s_b_.p + p2_off_, s_b_.p + p2_off_, rs_,
+                                                              sc_ + SC_TMP + 1);
+                TM_CHECK_LAUNCH();
+                sum_ranks(sc_ + SC_TMP, 2);
+                read_scalars();
+                if (!(h_sc_[SC_TMP] < h_sc_[SC_TMP + 1])) warm = false;
+            }
+            stats_warm_used_ = warm ? 1 : 0;
+        }
+        if (!warm) {
             TM_CUDA(cudaMemsetAsync(u, 0, nu_ * sizeof(T), stream_));
             TM_CUDA(cudaMemcpyAsync(s_r_.p, s_b_.p, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
         }
@@ -924,10 +944,10 @@ class Engine : public EngineBase {
         // [9]: first level of the cluster tail (-1: none), [10]: its cluster size
         const int tf = inner_ ? inner_->tail_first_ : tail_first_;
         const int tc = inner_ ? inner_->tail_cluster_used_ : tail_cluster_used_;
-        const double v[11] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
+        const double v[12] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
                               (double)nlevels_, lmax0, (double)epc[0], (double)epc[1], (double)epc[2],
-                              (double)epc[3], (double)tf, (double)(tf >= 0 ? tc : 0)};
-        for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+                              (double)epc[3], (double)tf, (double)(tf >= 0 ? tc : 0), (double)stats_warm_used_};
+        for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
     }
 
     // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
@@ -1247,6 +1267,24 @@ class Engine : public EngineBase {
         return a;
     }
 
+    // Launch of a kernel that starts with pdl_prologue(): inside a V-cycle (pdl_active_) it carries
+    // the programmatic-stream-serialization attribute, so that under stream capture the graph gets
+    // programmatic edges and each kernel's launch overlaps the tail of its predecessor.
+    template <class... P, class... A>
+    void launch_chain(void (*kernel)(P...), dim3 grd, dim3 blk, A&&... args) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grd;
+        cfg.blockDim = blk;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream_;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = pdl_active_ ? 1 : 0;
+        TM_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...));
+    }
+
     void launch_apply(const LevelGeom<T>& g, bool stored, int ep, ApplyArgs<T> a) {
         const int ncg = ceil_div(g.nx + 1, 31);
         const int bx = ceil_div(ncg, kApplyWarps);
@@ -1275,8 +1313,7 @@ class Engine : public EngineBase {
             }
             TM_CUDA(cudaEventRecord(ev.first, stream_));
         }
-#define TM_LAUNCH_APPLY(ST, EPV, MB, PFV) \
-    elast_apply_kernel<T, ST, EPV, MB, PFV><<<grd, blk, 0, stream_>>>(g, a)
+#define TM_LAUNCH_APPLY(ST, EPV, MB, PFV) launch_chain(elast_apply_kernel<T, ST, EPV, MB, PFV>, grd, blk, g, a)
 #define TM_LAUNCH_APPLY_EP(ST, MB, PFV)                               \
     switch (ep) {                                                     \
         case EP_PLAIN: TM_LAUNCH_APPLY(ST, EP_PLAIN, MB, PFV); break;   \
@@ -1853,8 +1890,8 @@ class Engine : public EngineBase {
         T* cur;
         int k0 = 0;
         if (!xin) {
-            cheb_first_kernel<T><<<grid1d(L.cnt), kVecThreads, 0, stream_>>>(
-                L.cnt, 1.0 / theta, L.dinv.p + L.off, b + L.off, L.d.p + L.off, L.x.p + L.off);
+            launch_chain(cheb_first_kernel<T>, dim3(grid1d(L.cnt)), dim3(kVecThreads), L.cnt, 1.0 / theta,
+                         (const T*)(L.dinv.p + L.off), b + L.off, L.d.p + L.off, L.x.p + L.off);
             TM_CHECK_LAUNCH();
             cur = L.x.p;
             k0 = 1;
@@ -1944,6 +1981,11 @@ class Engine : public EngineBase {
     }
 
     T* vcycle_body(T* r) {
+        struct PdlScope {  // programmatic dependent launches for the kernels of this V-cycle
+            bool& flag;
+            PdlScope(bool& f, bool on) : flag(f) { flag = on; }
+            ~PdlScope() { flag = false; }
+        } pdl_scope(pdl_active_, pdl_ && nranks_ == 1);
         const int nl = nlevels_;
         std::vector<T*> xs(nl, nullptr);
         std::vector<const T*> bs(nl, nullptr);
@@ -1975,8 +2017,8 @@ class Engine : public EngineBase {
             exchange_p2(l, L.tmp.p);
             const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
             dim3 blk(32, 8), grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
-            mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, gather ? C.gpiece : C.g, tr_tab_, L.tmp.p,
-                                                           C.b.p);
+            launch_chain(mg_restrict_kernel<T>, grd, blk, L.g, gather ? C.gpiece : C.g, tr_tab_,
+                         (const T*)L.tmp.p, C.b.p);
             TM_CHECK_LAUNCH();
             if (gather) gather_rows(l + 1, C.b.p, (size_t)C.g.Lx * 2, false);
             bs[l + 1] = C.b.p;
@@ -1996,7 +2038,7 @@ class Engine : public EngineBase {
             Level& C = levels_[l + 1];
             exchange_p2(l + 1, xs[l + 1]);
             dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
-            mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, xs[l + 1], xs[l]);
+            launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
             xs[l] = smooth(l, bs[l], xs[l]);
         }
@@ -2060,6 +2102,9 @@ class Engine : public EngineBase {
     cudaGraphExec_t setup_graph_exec_ = nullptr;
     T* setup_graph_xi_ = nullptr;
     bool filter_tb_ = true;
+    bool pdl_ = true, pdl_active_ = false;  // option 126: programmatic dependent launch in V-cycles
+    bool warm_guard_ = true;   // option 125: drop a warm start whose residual exceeds the zero guess's
+    int stats_warm_used_ = 0;  // last state solve: 1 if the caller's initial guess was kept
     int filter_tb_steps_ = 8, filter_tb_state_ = 0;  // state: 0 unplanned, 1 ready, -1 not usable
     int filter_tb_tx_ = 0, filter_tb_ty_ = 0, filter_tb_tw_ = 0, filter_tb_th_ = 0, filter_tb_rows_ = 0;
     size_t filter_tb_smem_ = 0;

@@ -188,6 +188,7 @@ template <typename T>
 __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
                                    const TransferTable tab, const T* __restrict__ r,
                                    T* __restrict__ bc) {
+    pdl_prologue();
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= c.Lx || J >= c.Ly || !c.owns_row(J)) return;
@@ -203,6 +204,7 @@ template <typename T>
 __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
                                       const TransferTable tab, const T* __restrict__ xc,
                                       T* __restrict__ x) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= f.Lx || j >= f.Ly || !f.owns_row(j)) return;

@@ -131,6 +131,7 @@ __global__ void normalize_scale_kernel(size_t n, const T* __restrict__ dinv, con
 template <typename T>
 __global__ void cheb_first_kernel(size_t n, double s, const T* __restrict__ dinv,
                                   const T* __restrict__ b, T* __restrict__ d, T* __restrict__ x) {
+    pdl_prologue();
     TM_GRID_STRIDE(i, n) {
         const T v = (T)(s * (double)dinv[i] * (double)b[i]);
         d[i] = v;

@@ -238,13 +238,14 @@ class Engine:
         return out.value
 
     def last_solve_stats(self) -> dict:
-        buf = (c_double * 11)()
-        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 11))
+        buf = (c_double * 12)()
+        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 12))
         return {"iterations": int(buf[0]), "vcycles": int(buf[1]), "fine_applies": int(buf[2]),
                 "levels": int(buf[3]), "lambda_max": buf[4],
                 "fine_launches_total": {"plain": int(buf[5]), "dot": int(buf[6]), "resid": int(buf[7]),
                                         "cheb": int(buf[8])},
-                "tail_first_level": int(buf[9]), "tail_cluster": int(buf[10])}
+                "tail_first_level": int(buf[9]), "tail_cluster": int(buf[10]),
+                "warm_start_used": bool(buf[11])}
 
     def profile_read(self) -> dict:
         """Milliseconds / launch counts of the fine-level operator kernel per epilogue since the
