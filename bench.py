@@ -112,6 +112,16 @@ class Function_like:
         self.tensor = tensor
 
 
+def measured_traffic(design, full_n, dtype, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            entry = json.load(fh).get(f"{design}:{full_n}:{dtype}:{kernel}")
+        return (entry["bytes_per_launch"], entry["source"]) if entry else (None, None)
+    except Exception:
+        return None, None
+
+
 def measured_peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -383,9 +393,13 @@ def run_cuda_arm(args):
     avg_ms = d["ms"] / max(d["launches"], 1)
     achieved = alg_bytes[dominant] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     kernel_ms = sum(est_ms.values())
+    traffic_bytes, traffic_src = (None, None)
+    if world == 1 and not args.mixed:
+        traffic_bytes, traffic_src = measured_traffic(os.path.splitext(os.path.basename(design_path))[0], run_n,
+                                                      args.dtype, dominant)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic_bytes, "traffic_source": traffic_src, "peak_source": peak_src,
         "kernel": f"elast_apply_kernel<{'double' if esize == 8 else 'float'},xi,EP_{dominant.upper()}>",
         "algorithmic_bytes_per_launch": alg_bytes[dominant], "avg_launch_ms": avg_ms,
         "launches_in_timed_region": true_counts[dominant], "launches_event_timed": d["launches"],

@@ -137,6 +137,15 @@ int tm_md_apply(tm_handle h, const void* half, double c, const void* psi_prev, v
 /* *out = int values dx (nodal quadrature)   reference: FEM_src/solver.py:81-84 */
 int tm_integrate(tm_handle h, const void* values, double* out);
 
+/* out[sy][sx][c] = field(x0 + sx dx, y0 + sy dy): point evaluation of a P1 (degree 1, one
+ * component) or vector-P2 (degree 2, two components) field on a regular grid of nsx x nsy sample
+ * points inside the rectangle; `out` is a device array of nsx*nsy*degree values of the engine's
+ * dtype.  Unsharded engines only.
+ * reference: the  f(x, y)  evaluations of sample_function, FEM_src/utils.py:112-162 (consumed
+ * by plot.py:54-69) */
+int tm_sample_field(tm_handle h, int degree, const void* field, int nsx, int nsy, double x0, double dx,
+                    double y0, double dy, void* out);
+
 /* statistics of the last tm_state_solve: out[0] iterations, [1] V-cycles, [2] fine-level
  * operator applications, [3] levels, [4] lambda_max estimate of level 0, [5..8] cumulative
  * level-0 operator launches per epilogue, [9] first level of the cluster tail (-1: none), [10] its

@@ -419,3 +419,66 @@ def l2_error_p1(mesh, xi, exact, nq=6):
             xq, yq, fq = X[v] @ q, Y[v] @ q, xi[v] @ q
             err += w * area * np.sum((fq - exact(xq, yq)) ** 2)
     return np.sqrt(err)
+
+
+# --------------------------------------------------------------------------------------
+# point evaluation (the role of dolfin's ``f(x, y)`` in sample_function, FEM_src/utils.py:112-162)
+# --------------------------------------------------------------------------------------
+def evaluate_field(mesh: StructuredMesh, values, degree: int, xs, ys):
+    """Values of a P1 (degree 1, returns (n,1)) or vector-P2 (degree 2, returns (n,2)) field at
+    the points (xs[k], ys[k]).  Geometric, as dolfin does it: find a triangle that contains the
+    point (barycentric coordinates from the triangle's actual vertex coordinates, all >= -1e-12),
+    then sum basis function x dof.  Points on shared edges give the same value from either side
+    because the spaces are continuous."""
+    xs, ys = np.atleast_1d(np.asarray(xs, float)), np.atleast_1d(np.asarray(ys, float))
+    values = np.asarray(values, float)
+    X, Y = np.meshgrid(mesh.xv, mesh.yv, indexing="xy")
+    X, Y = X.ravel(), Y.ravel()
+    # candidate cell by bisection on the vertex coordinates (the bounding-box tree's job)
+    cx = np.clip(np.searchsorted(mesh.xv, xs, side="right") - 1, 0, mesh.nx - 1)
+    cy = np.clip(np.searchsorted(mesh.yv, ys, side="right") - 1, 0, mesh.ny - 1)
+    cell = cy * mesh.nx + cx
+    out = np.full((xs.size, degree), np.nan)
+    done = np.zeros(xs.size, bool)
+    for t in ("A", "B"):
+        v = mesh.tri_v[t][cell]  # (n, 3) vertex ids
+        p0 = np.stack([X[v[:, 0]], Y[v[:, 0]]], 1)
+        e1 = np.stack([X[v[:, 1]], Y[v[:, 1]]], 1) - p0
+        e2 = np.stack([X[v[:, 2]], Y[v[:, 2]]], 1) - p0
+        d = np.stack([xs, ys], 1) - p0
+        det = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+        l1 = (d[:, 0] * e2[:, 1] - d[:, 1] * e2[:, 0]) / det
+        l2 = (e1[:, 0] * d[:, 1] - e1[:, 1] * d[:, 0]) / det
+        lam = np.stack([1.0 - l1 - l2, l1, l2], 1)
+        inside = np.all(lam >= -1e-12, axis=1) & ~done
+        if degree == 1:
+            out[inside, 0] = np.sum(lam[inside] * values[v[inside]], axis=1)
+        else:
+            nodes = mesh.tri_n[t][cell[inside]]  # (m, 6) lattice node ids
+            phi = p2_basis(lam[inside].T).T  # (m, 6)
+            for c in range(2):
+                out[inside, c] = np.sum(phi * values[2 * nodes + c], axis=1)
+        done |= inside
+    if not done.all():
+        raise ValueError("evaluate_field: a point lies outside the mesh")
+    return out
+
+
+def sample_function(mesh: StructuredMesh, values, degree: int, points: int, sample_type: str, N: int):
+    """Restatement of FEM_src/utils.py:112-162 on the oracle mesh: returns (domain_rays,
+    output_grid[nsy, nsx, degree])."""
+    domain_size = (mesh.W, mesh.H)
+    multiplier = int(np.ceil(points / N))
+    domain_samples = [int(s * N * multiplier) for s in domain_size]
+    if sample_type == "edges":
+        domain_samples = [ns + 1 for ns in domain_samples]
+    domain_rays = [np.linspace(0, s, ns) for s, ns in zip(domain_size, domain_samples)]
+    xi, yi = np.meshgrid(np.arange(domain_samples[0]), np.arange(domain_samples[1]), indexing="xy")
+    if sample_type == "center":
+        x, y = (0.5 + xi) / (multiplier * N), (0.5 + yi) / (multiplier * N)
+    elif sample_type == "edges":
+        x, y = xi / (multiplier * N), yi / (multiplier * N)
+    else:
+        raise ValueError(f"Unknown sample_type: {sample_type}. sample_type must be either 'center' or 'edges'")
+    grid = evaluate_field(mesh, values, degree, x.ravel(), y.ravel())
+    return domain_rays, grid.reshape(domain_samples[1], domain_samples[0], degree)

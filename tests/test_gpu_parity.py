@@ -434,3 +434,68 @@ def test_filter_temporal_blocking_matches_oracle(nx, ny, eps, steps):
     assert _rel(res[1][0], res[0][0]) < 1e-11 and _rel(res[1][1], res[0][1]) < 1e-11
     # blocked solves test convergence every `steps` iterations: never much later than un-blocked
     assert res[1][3] <= 1.25 * res[0][3] + 8 + 2 * steps
+
+
+@pytest.mark.parametrize("sample_type", ["center", "edges"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_sample_function_matches_oracle(sample_type, dtype):
+    """sample_function (reference FEM_src/utils.py:112-162) on the device == the oracle's geometric
+    point evaluation, for a random P1 field and a random vector-P2 field; a linear / quadratic
+    field is reproduced exactly; sample counts follow the reference."""
+    from oracle.fem_oracle import sample_function as oracle_sample
+    from FEM_src.utils import sample_function
+    from topomax_b200.mesh import Function, FunctionSpace, RectangleMesh
+    W, H, N = 3.0, 2.0, 7
+    nx, ny = int(W * N), int(H * N)
+    mesh = StructuredMesh(W, H, nx, ny)
+    rmesh = RectangleMesh(W, H, nx, ny)
+    rng = np.random.default_rng(11)
+    tol = 1e-13 if dtype == "float64" else 2e-6
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    for degree, n in ((1, mesh.n1), (2, mesh.nu)):
+        values = rng.standard_normal(n)
+        f = Function(FunctionSpace(rmesh, "CG", degree, dtype=dtype, device="cuda"), _t(values, tdt))
+        for points in (3, 7, 20):
+            rays, grid = sample_function(f, points, sample_type)
+            orays, ogrid = oracle_sample(mesh, values, degree, points, sample_type, N)
+            assert grid.shape == ogrid.shape and grid.dtype == np.float64
+            assert all(np.array_equal(a, b) for a, b in zip(rays, orays))
+            assert np.abs(grid - ogrid).max() < tol * max(1.0, np.abs(ogrid).max())
+    # exactness: P2 interpolant of a quadratic, sampled anywhere
+    XL, YL = np.meshgrid(mesh.xl, mesh.yl, indexing="xy")
+    quad = np.stack([(XL ** 2 - XL * YL + 2).ravel(), (YL ** 2 + 3 * XL).ravel()], 1).ravel()
+    f = Function(FunctionSpace(rmesh, "CG", 2, dtype=dtype, device="cuda"), _t(quad, tdt))
+    rays, grid = sample_function(f, 30, "edges")
+    xs, ys = np.meshgrid(rays[0], rays[1], indexing="xy")
+    assert np.abs(grid[:, :, 0] - (xs ** 2 - xs * ys + 2)).max() < 100 * tol
+    assert np.abs(grid[:, :, 1] - (ys ** 2 + 3 * xs)).max() < 100 * tol
+    with pytest.raises(ValueError):
+        sample_function(f, 3, "corner")
+
+
+def test_save_load_round_trip_and_plot_sampling(tmp_path):
+    """reference tests/test_save_load.py:15-43 (design and elasticity vectors instead of the
+    Taylor-Hood one), followed by what plot.py:54-69 does with a saved design."""
+    from FEM_src.utils import load_function, sample_function, save_function
+    from topomax_b200.mesh import Function, FunctionSpace, RectangleMesh
+    N = 20
+    rmesh = RectangleMesh(1.0, 1.0, N, N)
+    rng = np.random.default_rng(198)
+    for degree, problem in ((1, "design"), (2, "elasticity")):
+        space = FunctionSpace(rmesh, "CG", degree, device="cuda")
+        f = Function(space)
+        f.vector()[:] = rng.random(space.dim())
+        path = str(tmp_path / f"temp_{problem}.dat")
+        save_function(f, path, problem)
+        g, mesh2, space2 = load_function(path)
+        assert (mesh2.nx, mesh2.ny, space2.degree) == (N, N, degree)
+        assert np.array_equal(f.vector()[:], g.vector()[:])
+    rho, *_ = load_function(str(tmp_path / "temp_design.dat"))
+    _, design_data = sample_function(rho, int(200 / 1.0), "center")
+    assert design_data[:, :, 0].shape == (200, 200)
+    assert 0.0 <= design_data.min() and design_data.max() <= 1.0
+    with pytest.raises(ValueError):
+        with open(tmp_path / "bad.dat", "wb") as fh:
+            import pickle
+            pickle.dump({"N": 2, "domain_size": (1.0, 1.0), "problem": "nope", "vector": np.zeros(9)}, fh)
+        load_function(str(tmp_path / "bad.dat"))

@@ -160,3 +160,40 @@ def test_projection_falls_back_to_brent():
     assert abs(find_volume_shift(f, df) - 1.5) < 1e-9
     with pytest.raises(ValueError):
         find_volume_shift(lambda c: 1.0, lambda c: 0.0)
+
+
+def test_sample_grid_matches_reference_sample_positions():
+    """sample counts / positions of sample_function (reference FEM_src/utils.py:136-158)."""
+    from topomax_b200.sampling import sample_grid
+    for points, kind, N, size in [(5, "edges", 2, (3.0, 1.0)), (7, "center", 2, (3.0, 1.0)),
+                                  (40, "center", 102, (10.0, 5.0)), (200, "center", 40, (3.0, 1.0))]:
+        nsx, nsy, x0, dx, y0, dy, mult = sample_grid(points, kind, N, size)
+        assert mult == int(np.ceil(points / N))
+        extra = 1 if kind == "edges" else 0
+        assert (nsx, nsy) == (int(size[0] * N * mult) + extra, int(size[1] * N * mult) + extra)
+        i = np.arange(nsx)
+        ref = (0.5 + i) / (mult * N) if kind == "center" else i / (mult * N)
+        assert np.abs(x0 + i * dx - ref).max() < 1e-13
+        assert dx == dy
+    with pytest.raises(ValueError):
+        sample_grid(5, "corner", 2, (1.0, 1.0))
+
+
+def test_output_tree_round_trip(tmp_path):
+    """get_solver_data reads back what save_iteration / save_result wrote (reference:
+    src/utils.py:99-121 on the tree of src/solver.py:304-349); records unpickle as src.utils.*"""
+    from src.utils import IterationData, SolverResult, get_solver_data
+    folder = tmp_path / "FEM" / "bridge" / "data"
+    folder.mkdir(parents=True)
+    it = IterationData((12.0, 2.0), 3.5, 4, "N=20_p=3.0_k=4_rho.dat", 3.0)
+    res = SolverResult("Convergence treshold reached", 3.5, [9.0, 3.5], 4, 1, [0.1, 0.2])
+    with open(folder / "N=20_p=3.0_k=4.dat", "wb") as fh:
+        pickle.dump(it, fh)
+    with open(folder / "N=20_p=3.0_k=4_rho.dat", "wb") as fh:
+        pickle.dump({"N": 10, "domain_size": (12.0, 2.0), "problem": "design", "vector": np.zeros(3)}, fh)
+    with open(folder / "N=20_p=3.0_result.dat", "wb") as fh:
+        pickle.dump(res, fh)
+    results, data_list = get_solver_data("FEM", "bridge", str(tmp_path))
+    assert results == [(20, "3.0", res)]
+    assert data_list == [(20, "3.0", 4, it)]
+    assert type(data_list[0][3]).__module__ == "src.utils"

@@ -107,3 +107,33 @@ def test_elasticity_matrix_symmetric_and_rigid_body_nullspace():
     for mode in (np.stack([np.ones_like(X), 0 * X], 1), np.stack([0 * X, np.ones_like(X)], 1),
                  np.stack([-Y, X], 1)):
         assert np.abs(K @ mode.ravel()).max() < 1e-12
+
+
+def test_oracle_point_evaluation_reproduces_polynomials():
+    """evaluate_field / sample_function (FEM_src/utils.py:112-162): P1 reproduces linear, vector P2
+    quadratic fields exactly at arbitrary points, including on cell edges, diagonals and corners."""
+    from oracle.fem_oracle import evaluate_field, sample_function
+    mesh = StructuredMesh(3.0, 1.0, 6, 2)
+    X, Y = np.meshgrid(mesh.xv, mesh.yv, indexing="xy")
+    p1 = (2 * X - 3 * Y + 1).ravel()
+    XL, YL = np.meshgrid(mesh.xl, mesh.yl, indexing="xy")
+    p2 = np.stack([(XL ** 2 - XL * YL + 2).ravel(), (YL ** 2 + 3 * XL).ravel()], 1).ravel()
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.random(50) * 3.0, [0.0, 3.0, 0.5, 1.25, 3.0]])
+    ys = np.concatenate([rng.random(50), [0.0, 1.0, 0.5, 0.25, 0.0]])
+    assert np.abs(evaluate_field(mesh, p1, 1, xs, ys)[:, 0] - (2 * xs - 3 * ys + 1)).max() < 1e-14
+    got = evaluate_field(mesh, p2, 2, xs, ys)
+    assert np.abs(got[:, 0] - (xs ** 2 - xs * ys + 2)).max() < 1e-13
+    assert np.abs(got[:, 1] - (ys ** 2 + 3 * xs)).max() < 1e-13
+    with pytest.raises(ValueError):
+        evaluate_field(mesh, p1, 1, [3.5], [0.5])
+    # sample counts of the reference: multiple of N with >= points per unit length, +1 for "edges"
+    rays, grid = sample_function(mesh, p1, 1, 5, "edges", 2)
+    assert grid.shape == (7, 19, 1) and len(rays[0]) == 19 and len(rays[1]) == 7
+    rays, grid = sample_function(mesh, p2, 2, 7, "center", 2)
+    assert grid.shape == (8, 24, 2)
+    # values at the vertices are the nodal values
+    _, grid = sample_function(mesh, p1, 1, 2, "edges", 2)
+    assert np.abs(grid[:, :, 0].ravel() - p1).max() < 1e-14
+    with pytest.raises(ValueError):
+        sample_function(mesh, p1, 1, 2, "corner", 2)

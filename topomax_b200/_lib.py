@@ -25,7 +25,7 @@ ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOT_CONVERGED = -1, -2, -3, -4
 EXPORTED_SYMBOLS = (
     "tm_create", "tm_destroy", "tm_set_stream", "tm_set_option", "tm_last_error", "tm_version",
     "tm_load_vector", "tm_filter_apply", "tm_elast_matvec", "tm_elast_diag", "tm_state_solve",
-    "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate",
+    "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate", "tm_sample_field",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
     "tm_comm_unique_id", "tm_comm_init", "tm_local_layout",
 )
@@ -97,6 +97,7 @@ def load_library() -> ctypes.CDLL:
         "tm_md_volume": ([V, V, D, POINTER(D), POINTER(D)], I),
         "tm_md_apply": ([V, V, D, V, V, V, POINTER(D), POINTER(D)], I),
         "tm_integrate": ([V, V, POINTER(D)], I),
+        "tm_sample_field": ([V, I, V, I, I, D, D, D, D, V], I),
         "tm_last_solve_stats": ([V, POINTER(D), I], I),
         "tm_comm_unique_id": ([ctypes.c_char_p], I),
         "tm_comm_init": ([V, ctypes.c_char_p], I),

@@ -89,6 +89,8 @@ class EngineBase {
     virtual void md_apply(const void* half, double c, const void* psi_prev, void* psi, void* rho,
                           double* delta_sq, double* vol) = 0;
     virtual double integrate(const void* values) = 0;
+    virtual void sample_field(int degree, const void* field, int nsx, int nsy, double x0, double dx, double y0,
+                              double dy, void* out) = 0;
     virtual void last_stats(double* out, int n) = 0;
     virtual void mg_debug(void* xi, int op, int level, const void* in, void* out) = 0;
     virtual int mg_level_info(int level, int* info) = 0;
@@ -933,6 +935,22 @@ class Engine : public EngineBase {
         sum_ranks(sc_ + SC_TMP, 1);
         read_scalars();
         return h_sc_[SC_TMP];
+    }
+
+    void sample_field(int degree, const void* field, int nsx, int nsy, double x0, double dx, double y0,
+                      double dy, void* out) override {
+        if (nranks_ > 1) throw Unsupported{"tm_sample_field works on an unsharded engine (gather the field first)"};
+        if (degree != 1 && degree != 2) throw Invalid{"tm_sample_field: degree must be 1 (P1) or 2 (vector P2)"};
+        if (nsx < 0 || nsy < 0) throw Invalid{"tm_sample_field: negative sample count"};
+        if (nsx == 0 || nsy == 0) return;
+        dim3 blk(32, 8), grd(ceil_div(nsx, 32), ceil_div(nsy, 8));
+        if (degree == 1)
+            sample_field_kernel<T, 1><<<grd, blk, 0, stream_>>>(nx_, nyg_, hx_, hy_, (const T*)field, nsx, nsy, x0,
+                                                               dx, y0, dy, (T*)out);
+        else
+            sample_field_kernel<T, 2><<<grd, blk, 0, stream_>>>(nx_, nyg_, hx_, hy_, (const T*)field, nsx, nsy, x0,
+                                                               dx, y0, dy, (T*)out);
+        TM_CHECK_LAUNCH();
     }
 
     void last_stats(double* out, int n) override {
@@ -2305,6 +2323,12 @@ int tm_md_apply(tm_handle h, const void* half, double c, const void* psi_prev, v
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->md_apply(half, c, psi_prev, psi, rho, delta_sq, vol); });
 }
+int tm_sample_field(tm_handle h, int degree, const void* field, int nsx, int nsy, double x0, double dx, double y0,
+                    double dy, void* out) {
+    TM_REQUIRE_HANDLE(h);
+    return guarded(h, [&] { h->impl->sample_field(degree, field, nsx, nsy, x0, dx, y0, dy, out); });
+}
+
 int tm_integrate(tm_handle h, const void* values, double* out) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { *out = h->impl->integrate(values); });

@@ -370,4 +370,55 @@ __global__ void load_vector_kernel(const LoadSpec s, T* __restrict__ b) {
     b[2 * n + 1] = (T)b1;
 }
 
+// ---------------------------------------------------------------------------------------
+// point evaluation of a P1 (COMP = 1) or vector-P2 (COMP = 2) field on a regular grid of sample
+// points  (x, y) = (x0 + sx dx, y0 + sy dy): the role of  f(x, y)  inside the double loop of the
+// reference's sample_function (FEM_src/utils.py:112-162), which is what plot.py consumes.
+// The containing cell is found by index arithmetic; s >= t selects T_A = (v0, v1, v3), else
+// T_B = (v0, v2, v3) ("right" diagonal); the fields are continuous, so points on cell or
+// triangle boundaries get the same value from either side (to rounding).
+// out[sy][sx][COMP], one thread per sample, coalesced stores.
+// ---------------------------------------------------------------------------------------
+template <typename T, int COMP>
+__global__ void sample_field_kernel(int nx, int ny, double hx, double hy, const T* __restrict__ f, int nsx,
+                                    int nsy, double x0, double dx, double y0, double dy, T* __restrict__ out) {
+    const int sx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (sx >= nsx || sy >= nsy) return;
+    const double x = x0 + sx * dx, y = y0 + sy * dy;
+    int cx = (int)floor(x / hx), cy = (int)floor(y / hy);
+    cx = min(max(cx, 0), nx - 1);
+    cy = min(max(cy, 0), ny - 1);
+    const double s = x / hx - cx, t = y / hy - cy;  // local coordinates in the cell
+    const bool lower = s >= t;                       // T_A below the diagonal v0 -> v3
+    // barycentrics of (v0, vm, v3) with vm = v1 (T_A) or v2 (T_B)
+    const double l0 = lower ? 1.0 - s : 1.0 - t;
+    const double lm = lower ? s - t : t - s;
+    const double l3 = lower ? t : s;
+    const size_t o = ((size_t)sy * nsx + sx) * COMP;
+    if (COMP == 1) {
+        const size_t W1 = nx + 1, v0 = (size_t)cy * W1 + cx;
+        const size_t vm = lower ? v0 + 1 : v0 + W1;
+        out[o] = (T)(l0 * (double)f[v0] + lm * (double)f[vm] + l3 * (double)f[v0 + W1 + 1]);
+    } else {
+        const size_t Lx = 2 * (size_t)nx + 1;
+        const int i0 = 2 * cx, j0 = 2 * cy;
+        // lattice offsets of (v0, vm, v3, mid(v0,vm), mid(vm,v3), mid(v0,v3))
+        const int mi = lower ? 2 : 0, mj = lower ? 0 : 2;
+        const int di[6] = {0, mi, 2, mi / 2, (mi + 2) / 2, 1};
+        const int dj[6] = {0, mj, 2, mj / 2, (mj + 2) / 2, 1};
+        const double phi[6] = {l0 * (2.0 * l0 - 1.0), lm * (2.0 * lm - 1.0), l3 * (2.0 * l3 - 1.0),
+                               4.0 * l0 * lm, 4.0 * lm * l3, 4.0 * l0 * l3};
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const size_t n = (size_t)(j0 + dj[k]) * Lx + (i0 + di[k]);
+            a0 += phi[k] * (double)f[2 * n];
+            a1 += phi[k] * (double)f[2 * n + 1];
+        }
+        out[o] = (T)a0;
+        out[o + 1] = (T)a1;
+    }
+}
+
 }  // namespace tmx

@@ -237,6 +237,18 @@ class Engine:
         _lib.check(self.lib.tm_integrate(self._h, self._p(values, self.n1), byref(out)))
         return out.value
 
+    def sample_field(self, field, degree: int, nsx: int, nsy: int, x0: float, dx: float, y0: float,
+                     dy: float):
+        """(nsy, nsx, degree) tensor of field values at (x0 + sx dx, y0 + sy dy); ``field`` is a
+        P1 (degree 1) or vector-P2 (degree 2) tensor of this engine's mesh."""
+        if degree not in (1, 2):
+            raise ValueError("degree must be 1 (P1) or 2 (vector P2)")
+        out = torch.empty((int(nsy), int(nsx), degree), dtype=self.dtype, device=self.device)
+        _lib.check(self.lib.tm_sample_field(self._h, degree, self._p(field, self.n1 if degree == 1 else self.nu),
+                                            int(nsx), int(nsy), float(x0), float(dx), float(y0), float(dy),
+                                            out.data_ptr()))
+        return out
+
     def last_solve_stats(self) -> dict:
         buf = (c_double * 12)()
         _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 12))

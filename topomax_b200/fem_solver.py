@@ -25,14 +25,17 @@ from .solver import MAX_ITERATIONS, Solver, find_volume_shift
 from .utils import Timer
 
 
-def save_function(f: Function, filename: str, problem: str):
+def save_function(f: Function, filename: str, problem: str, N: int | None = None, domain_size=None):
     """Pickle ``{N, domain_size, problem, vector}`` (reference: FEM_src/utils.py:47-70).
-    ``vector`` is stored in this package's row-major vertex order, not dolfin's dof order."""
+    ``vector`` is stored in this package's row-major node order, not dolfin's dof order."""
     mesh = f.function_space().mesh()
-    n = 1 / (mesh.hmin() / np.sqrt(2))
+    if N is None:
+        N = int(round(1 / (mesh.hmin() / np.sqrt(2))))
+    if domain_size is None:
+        domain_size = mesh.domain_size
     data = {
-        "N": int(round(n)),
-        "domain_size": mesh.domain_size,
+        "N": N,
+        "domain_size": domain_size,
         "problem": problem,
         "vector": f.vector()[:].astype(np.float64),
     }
@@ -41,14 +44,22 @@ def save_function(f: Function, filename: str, problem: str):
 
 
 def load_function(filename: str, *, dtype: str = "float64", device=None):
-    """Inverse of ``save_function`` for ``problem == 'design'`` (reference: FEM_src/utils.py:73-109)."""
+    """Inverse of ``save_function`` (reference: FEM_src/utils.py:73-109): ``problem == 'design'``
+    gives a P1 function, ``'elasticity'`` a vector-P2 function; ``'fluid'`` (Taylor-Hood) is
+    outside this path."""
     with open(filename, "rb") as fh:
         data = pickle.load(fh)
-    if data["problem"] != "design":
-        raise ValueError(f"load_function got unsupported problem: {data['problem']}")
+    if data["problem"] == "design":
+        degree = 1
+    elif data["problem"] == "elasticity":
+        degree = 2
+    elif data["problem"] == "fluid":
+        raise ValueError("load_function: the fluid problem is outside the accelerated path")
+    else:
+        raise ValueError(f"load_function got malformed problem: {data['problem']}")
     w, h = data["domain_size"]
     mesh = RectangleMesh(w, h, int(w * data["N"]), int(h * data["N"]))
-    space = FunctionSpace(mesh, "CG", 1, dtype=dtype, device=device)
+    space = FunctionSpace(mesh, "CG", degree, dtype=dtype, device=device)
     f = Function(space)
     f.vector()[:] = data["vector"]
     return f, mesh, space

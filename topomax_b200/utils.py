@@ -4,6 +4,8 @@ their ``__module__`` is set to the reference's ``src.utils`` so that files writt
 readable by the reference's tools (``plot.py``) and vice versa (see ``src/utils.py`` shim)."""
 from __future__ import annotations
 
+import os
+import pickle
 import time
 from dataclasses import dataclass
 
@@ -74,3 +76,22 @@ def smart_brentq(f, initial_radius: float, max_radius: float):
         except ValueError:
             r *= 2
     raise ValueError("f(-max_radius) and f(max_radius) must have different signs!")
+
+
+def get_solver_data(solver: str, design: str, root_folder="output"):
+    """Read an output tree back: ``(results, data_list)`` with results = [(N, p, SolverResult)]
+    and data_list = [(N, p, k, IterationData)], parsed from the file names
+    ``N=.._p=.._k=...dat`` / ``N=.._p=.._result.dat`` (reference: src/utils.py:99-121)."""
+    data_folder = os.path.join(root_folder, solver, design, "data")
+    results, data_list = [], []
+    for data_file in os.listdir(data_folder):
+        data_path = os.path.join(data_folder, data_file)
+        if "result" in data_file:
+            n_str, p_str = [v.split("=")[1] for v in data_file.split("_")[:2]]
+            with open(data_path, "rb") as fh:
+                results.append((int(n_str), p_str, pickle.load(fh)))
+        elif "rho" not in data_file:
+            n_str, p_str, k_str = [v.split("=")[1] for v in data_file.split("_")[:3]]
+            with open(data_path, "rb") as fh:
+                data_list.append((int(n_str), p_str, int(k_str[:-4]), pickle.load(fh)))
+    return results, data_list
