@@ -104,7 +104,13 @@ int tm_load_vector(tm_handle h, const tm_loads* loads, void* b);
 int tm_filter_apply(tm_handle h, int rhs_kind, void* in, void* out, double rtol, int maxit,
                     int* iters, double* relres);
 
-/* y = K(xi) x with identity rows on the fixed sides; penalty must be 3.
+/* y = K(xi) x with identity rows on the fixed sides, r(xi) = m + (1-m) xi^penalty.
+ * penalty = 3 (every elasticity design of the reference) is the fast path: closed-form SIMP
+ * moments inside the fine-level operator.  Any other penalty > 0 is supported through level-0
+ * moments stored once per call (integer penalty <= 16: exact; otherwise a 16-point degree-6 rule,
+ * parity unpinned); penalty <= 0 -> TM_ERR_INVALID.  The same holds for tm_elast_diag,
+ * tm_state_solve and tm_sens_rhs (reference: src/penalizers.py:36-46, penalties loop
+ * src/solver.py:230-231).
  * reference: a_func, FEM_src/elasisity_problem.py:112-118 assembled in
  * FEM_src/pde_solver.py:117-119, bc.apply :125. */
 int tm_elast_matvec(tm_handle h, void* xi, double penalty, void* x, void* y);

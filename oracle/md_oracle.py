@@ -82,6 +82,7 @@ class OracleElasticityProblem:
         self.lda, self.mu = lame(design["E"], design["nu"])
         self.minimum = 1e-6
         self.penalization = None
+        self.nq = 4
         K1, M1 = mesh.p1_matrices()
         self.M1 = M1
         eps = design["filter_radius"]
@@ -95,6 +96,10 @@ class OracleElasticityProblem:
 
     def set_penalization(self, p):
         self.penalization = p
+        # integer exponent: polynomial integrand of degree p + 2, integrated exactly (as FFC does);
+        # otherwise the 16-point rule (UFL's degree estimate for a non-integer power is a heuristic;
+        # PARITY UNPINNED for p != 3)
+        self.nq = max(4, int(np.ceil((p + 4) / 2))) if float(p).is_integer() else 4
 
     def filter_nodal(self, rho):
         t0 = time.perf_counter()
@@ -112,7 +117,7 @@ class OracleElasticityProblem:
         if self.penalization is None:
             raise ValueError("You must set penalization before calling penalizer")
         t0 = time.perf_counter()
-        K = self.mesh.elasticity_matrix(xi, self.lda, self.mu, self.penalization, self.minimum)
+        K = self.mesh.elasticity_matrix(xi, self.lda, self.mu, self.penalization, self.minimum, nq=self.nq)
         t1 = time.perf_counter()
         u = solve_spd(K, self.b_bc, free=~self.fixed, lattice=(self.mesh.Lx, self.mesh.Ly))
         t2 = time.perf_counter()
@@ -132,7 +137,7 @@ class OracleElasticityProblem:
             )
         t0 = time.perf_counter()
         rhs = self.mesh.sensitivity_rhs(
-            self.u, self.filtered_rho, self.lda, self.mu, self.penalization, self.minimum
+            self.u, self.filtered_rho, self.lda, self.mu, self.penalization, self.minimum, nq=self.nq
         )
         self.timings["sens"] += time.perf_counter() - t0
         return self.filter_rhs(rhs)

@@ -68,3 +68,49 @@ def test_cell_sensitivity_matches_oracle(hc):
     mesh = StructuredMesh(hx, hy, 1, 1)
     ref = mesh.sensitivity_rhs(u, xi4, lam, mu, 3.0, m, nq=5)
     assert np.abs(g4 - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+# ---- general SIMP exponent: integer p exact, other p on the oracle's 16-point rule
+@pytest.mark.parametrize("p", [1.0, 2.0, 3.0, 4.0, 5.0, 8.0, 16.0])
+def test_general_moments_integer_exponent_exact(hc, p):
+    rng = np.random.default_rng(int(p))
+    pts, wts = triangle_rule(12)  # exact to degree 22 >= p + 2
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]
+    for _ in range(4):
+        xi, m, w = rng.random(3), 1e-6, np.zeros(6)
+        hc.hc_moments_general(_ptr(xi), D(m), D(p), _ptr(w))
+        r = m + (1 - m) * (pts @ xi) ** p
+        ref = np.array([0.5 * np.sum(wts * r * pts[:, a] * pts[:, b]) for a, b in pairs])
+        assert np.abs(w - ref).max() < 2e-15
+        if p == 3.0:
+            w3 = np.zeros(6)
+            hc.hc_moments(_ptr(xi), D(m), _ptr(w3))
+            assert np.abs(w - w3).max() < 1e-16
+
+
+@pytest.mark.parametrize("p", [0.5, 1.5, 2.5, 3.7, 17.0])
+def test_general_moments_other_exponents_use_the_oracle_rule(hc, p):
+    rng = np.random.default_rng(11)
+    pts, wts = triangle_rule(4)
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]
+    xi, m, w = rng.random(3), 1e-6, np.zeros(6)
+    hc.hc_moments_general(_ptr(xi), D(m), D(p), _ptr(w))
+    r = m + (1 - m) * (pts @ xi) ** p
+    ref = np.array([0.5 * np.sum(wts * r * pts[:, a] * pts[:, b]) for a, b in pairs])
+    assert np.abs(w - ref).max() < 1e-15
+
+
+@pytest.mark.parametrize("p,nq", [(1.0, 6), (2.0, 6), (4.0, 6), (6.0, 8), (2.5, 4), (0.75, 4)])
+def test_general_cell_matrix_and_sensitivity_match_oracle(hc, p, nq):
+    rng = np.random.default_rng(13)
+    hx, hy, lam, mu, m = 0.5, 0.25, 2.0, 1.5, 1e-6
+    xi4 = 0.05 + 0.95 * rng.random(4)
+    mesh = StructuredMesh(hx, hy, 1, 1)
+    K = np.zeros((18, 18))
+    hc.hc_cell_matrix_general(_ptr(xi4), D(m), D(p), D(lam), D(mu), D(hx), D(hy), _ptr(K))
+    Ko = mesh.elasticity_matrix(xi4, lam, mu, p, m, nq=nq).toarray()
+    assert np.abs(K - Ko).max() < 1e-13 * np.abs(Ko).max()
+    u, g4 = rng.standard_normal(18), np.zeros(4)
+    hc.hc_cell_sensitivity_general(_ptr(u), _ptr(xi4), D(m), D(p), D(lam), D(mu), D(hx), D(hy), _ptr(g4))
+    ref = mesh.sensitivity_rhs(u, xi4, lam, mu, p, m, nq=nq)
+    assert np.abs(g4 - ref).max() < 1e-12 * np.abs(ref).max()

@@ -83,12 +83,99 @@ def test_elast_diag_matches_oracle():
     assert _rel(dinv, ref) < 1e-12
 
 
-def test_unsupported_penalty_is_an_error():
+def test_invalid_penalty_is_an_error():
     from topomax_b200._lib import EngineError
     eng = _engine(4, 4, 1.0, 1.0)
-    with pytest.raises(EngineError):
-        eng.elast_matvec(torch.ones(25, dtype=torch.float64).cuda(),
-                         torch.ones(eng.nu, dtype=torch.float64).cuda(), penalty=2.5)
+    for bad in (0.0, -1.0, float("nan")):
+        with pytest.raises(EngineError):
+            eng.elast_matvec(torch.ones(25, dtype=torch.float64).cuda(),
+                             torch.ones(eng.nu, dtype=torch.float64).cuda(), penalty=bad)
+
+
+def _oracle_nq(p):
+    return max(4, int(np.ceil((p + 4) / 2))) if float(p).is_integer() else 4
+
+
+@pytest.mark.parametrize("p", [1.0, 2.0, 4.0, 7.0, 2.5, 0.5])
+def test_general_penalty_operator_diag_sensitivity_match_oracle(p):
+    """SIMP exponents other than 3: level-0 stored moments.  Integer p exact, other p
+    on the oracle's 16-point rule (parity with the reference unpinned for p != 3)."""
+    nx, ny, W, H = 37, 11, 3.7, 1.1
+    rng = np.random.default_rng(int(10 * p))
+    mesh = StructuredMesh(W, H, nx, ny)
+    xi = 0.02 + 0.98 * rng.random(mesh.n1)
+    x = rng.standard_normal(mesh.nu)
+    lam, mu = 1.3, 0.8
+    K = mesh.elasticity_matrix(xi, lam, mu, p, nq=_oracle_nq(p))
+    fix = mesh.dirichlet_mask(["Left"])
+    eng = _engine(nx, ny, W, H, lame_lambda=lam, lame_mu=mu, fixed_sides=_sides(["Left"]))
+    y = eng.elast_matvec(_t(xi), _t(x), penalty=p).cpu().numpy()
+    ref = np.where(fix, x, K @ np.where(fix, 0.0, x))
+    assert _rel(y, ref) < 1e-12
+    dinv = eng.elast_diag_inverse(_t(xi), penalty=p).cpu().numpy()
+    assert _rel(dinv, np.where(fix, 1.0, 1.0 / K.diagonal())) < 1e-12
+    g = eng.sens_rhs(_t(xi), _t(x), penalty=p).cpu().numpy()
+    assert _rel(g, mesh.sensitivity_rhs(x, xi, lam, mu, p, nq=_oracle_nq(p))) < 1e-12
+    # switching back to p = 3 on the same engine returns to the closed-form path
+    y3 = eng.elast_matvec(_t(xi), _t(x), penalty=3.0).cpu().numpy()
+    K3 = mesh.elasticity_matrix(xi, lam, mu, 3.0)
+    assert _rel(y3, np.where(fix, x, K3 @ np.where(fix, 0.0, x))) < 1e-12
+
+
+@pytest.mark.parametrize("precond", ["multigrid", "jacobi"])
+@pytest.mark.parametrize("p", [2.0, 4.5])
+def test_general_penalty_state_solve_matches_direct_solver(repo_root, precond, p):
+    from topomax_b200 import _lib
+    design = read_design(os.path.join(repo_root, "designs", "cantilever.json"))
+    N = 12
+    W, H = design["width"], design["height"]
+    nx, ny = int(W * N), int(H * N)
+    mesh = StructuredMesh(W, H, nx, ny)
+    rng = np.random.default_rng(3)
+    xi = 0.05 + 0.9 * rng.random(mesh.n1)
+    lda, mu = lame(design["E"], design["nu"])
+    b = mesh.load_vector(design["body_force"], design["tractions"])
+    fix = mesh.dirichlet_mask(design["fixed_sides"])
+    K = mesh.elasticity_matrix(xi, lda, mu, p, nq=_oracle_nq(p))
+    u_ref = solve_spd(K, np.where(fix, 0.0, b), free=~fix, lattice=(mesh.Lx, mesh.Ly))
+    eng = _engine(nx, ny, W, H, lame_lambda=lda, lame_mu=mu, fixed_sides=_sides(design["fixed_sides"]))
+    eng.set_option(_lib.OPT_PRECOND, _lib.PRECOND_MULTIGRID if precond == "multigrid" else _lib.PRECOND_JACOBI)
+    for repeat in range(2):  # the second solve replays the captured set-up graph
+        u, info = eng.state_solve(_t(xi), _t(b), p, rtol=1e-11)
+        u = u.cpu().numpy()
+        assert np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref) < 1e-6
+        assert abs(u @ b - u_ref @ b) < 1e-6 * abs(u_ref @ b)
+    # a different exponent on the same engine (continuation) re-derives everything
+    K3 = mesh.elasticity_matrix(xi, lda, mu, 3.0)
+    u3_ref = solve_spd(K3, np.where(fix, 0.0, b), free=~fix, lattice=(mesh.Lx, mesh.Ly))
+    u3, _ = eng.state_solve(_t(xi), _t(b), 3.0, rtol=1e-11)
+    assert np.linalg.norm(u3.cpu().numpy() - u3_ref) / np.linalg.norm(u3_ref) < 1e-6
+
+
+def test_penalty_continuation_matches_oracle(repo_root, tmp_path):
+    """Multi-penalty continuation (reference: the penalties loop of src/solver.py:230-302 with the
+    capped step size of :201-206): psi carries over from one exponent to the next."""
+    with open(os.path.join(repo_root, "designs", "cantilever.json")) as fh:
+        data = json.load(fh)
+    data["Elasticity"]["domain_parameters"]["penalties"] = [1.0, 2.0, 3.0]
+    path = str(tmp_path / "cantilever_continuation.json")
+    with open(path, "w") as fh:
+        json.dump(data, fh)
+    from topomax_b200.fem_solver import FEMSolver
+    solver = FEMSolver(12, path, data_path=str(tmp_path / "out"), verbose=False)
+    result = solver.solve(fixed_iterations=3)
+    oracle = OracleSolver(12, path)
+    expected = oracle.solve(fixed_iterations=3)
+    assert result["penalty"] == expected["penalty"] == 3.0
+    assert max(abs(a - b) / abs(b) for a, b in zip(result["objectives"], expected["objectives"])) < 1e-6
+    rho = solver.rho.vector()[:]
+    assert float(np.sqrt(oracle.w @ (rho - expected["rho"]) ** 2)) < 1e-4
+    # the stop-rule loop writes one result file per exponent, zero-padded alike
+    solver = FEMSolver(8, path, data_path=str(tmp_path / "out2"), verbose=False)
+    solver.solve()
+    names = sorted(os.listdir(solver.output_folder))
+    assert [n for n in names if n.endswith("_result.dat")] == [
+        f"N={solver.full_N}_p={p}_result.dat" for p in ("1.0", "2.0", "3.0")]
 
 
 @pytest.mark.parametrize("design,N", [("triangle", 10), ("cantilever", 40), ("short_cantilever", 50),

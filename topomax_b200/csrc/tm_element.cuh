@@ -20,6 +20,8 @@
 // from xi.
 #pragma once
 
+#include <cmath>
+
 #ifdef __CUDACC__
 #define TM_HD __host__ __device__ __forceinline__
 #else
@@ -238,6 +240,124 @@ TM_HD void tri_sensitivity(const T e[3][3], const T xi[3], T m, const Material<T
             }
         g[i] = scale * acc;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// General SIMP exponent (reference: src/penalizers.py:36-46, the penalties loop of
+// src/solver.py:230-231).  The p = 3 closed forms above are the fast path of the fine-level
+// operator; any other p goes through the functions below, evaluated ONCE per solve into stored
+// level-0 moments (the operator then runs its stored-moment variant, like the coarse levels).
+//
+//  * integer p in [1, kMaxIntPenalty]: exact.  xi_h^p is a polynomial, and the p-th moment of a
+//    linear form under a Dirichlet distribution with integer parameters is
+//        E[(xi . lambda)^k] = k! / (n (n+1) .. (n+k-1)) * h_k(xs),
+//    h_k the complete homogeneous symmetric polynomial of the n variables xs (vertex densities
+//    repeated alpha_c times), from the power sums by Newton's identities.  (What FFC does for an
+//    integer exponent: exact quadrature of degree p + 2.)
+//  * any other p > 0: 16-point collapsed Gauss rule (degree 6), the same rule the oracle uses.
+//    PARITY UNPINNED: the reference would integrate with FFC's default scheme for UFL's estimated
+//    degree (heuristic degree(xi^p) = degree(xi) + 2); the integrand is not polynomial, so the
+//    two differ at quadrature-error level.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxIntPenalty = 16;
+
+struct PenaltySpec {
+    double p;
+    int ip;  // p when it is an integer in [1, kMaxIntPenalty], else 0 (quadrature)
+};
+
+TM_HD double dirichlet_power_moment(int k, const double* xs, int n) {
+    double pw[6], ps[kMaxIntPenalty + 1], h[kMaxIntPenalty + 1];
+    for (int j = 0; j < n; ++j) pw[j] = 1.0;
+    h[0] = 1.0;
+    double f = 1.0;
+    for (int i = 1; i <= k; ++i) {
+        double sum = 0.0;
+        for (int j = 0; j < n; ++j) {
+            pw[j] *= xs[j];
+            sum += pw[j];
+        }
+        ps[i] = sum;
+        double acc = 0.0;
+        for (int t = 1; t <= i; ++t) acc += ps[t] * h[i - t];
+        h[i] = acc / (double)i;
+        f *= (double)i / (double)(n + i - 1);
+    }
+    return f * h[k];
+}
+
+// barycentric points / weights (sum 1) of the 4 x 4 collapsed Gauss rule: (x, y) = (a, b (1 - a))
+TM_HD void collapsed_gauss16(int q, double lam[3], double& wt) {
+    const double g[4] = {0.06943184420297371, 0.33000947820757187, 0.66999052179242813, 0.93056815579702629};
+    const double w[4] = {0.17392742256872693, 0.32607257743127307, 0.32607257743127307, 0.17392742256872693};
+    const double a = g[q >> 2], b = g[q & 3];
+    const double x = a, y = b * (1.0 - a);
+    lam[0] = 1.0 - x - y;
+    lam[1] = x;
+    lam[2] = y;
+    wt = w[q >> 2] * w[q & 3] * (1.0 - a) * 2.0;
+}
+
+// w_ab = (2|T|)^-1 int r(xi_h) lambda_a lambda_b,  r = m + (1 - m) xi^p  (slots as moments_from_xi)
+TM_HD void moments_general(double x0, double x1, double x2, double m, const PenaltySpec& ps, double w[6]) {
+    const double x[3] = {x0, x1, x2};
+    const int sa[6] = {0, 1, 2, 0, 1, 0}, sb[6] = {0, 1, 2, 1, 2, 2};
+    if (ps.ip > 0) {
+        for (int k = 0; k < 6; ++k) {
+            const double xs[5] = {x0, x1, x2, x[sa[k]], x[sb[k]]};
+            const double c = (sa[k] == sb[k]) ? 1.0 / 12.0 : 1.0 / 24.0;
+            w[k] = c * (m + (1.0 - m) * dirichlet_power_moment(ps.ip, xs, 5));
+        }
+        return;
+    }
+    for (int k = 0; k < 6; ++k) w[k] = 0.0;
+    for (int q = 0; q < 16; ++q) {
+        double lam[3], wt;
+        collapsed_gauss16(q, lam, wt);
+        const double xq = lam[0] * x0 + lam[1] * x1 + lam[2] * x2;
+        const double r = 0.5 * wt * (m + (1.0 - m) * pow(xq, ps.p));
+        for (int k = 0; k < 6; ++k) w[k] += r * lam[sa[k]] * lam[sb[k]];
+    }
+}
+
+// tri_sensitivity for a general exponent:  r' = p (1 - m) xi^(p-1)
+template <typename T>
+TM_HD void tri_sensitivity_general(const T e[3][3], const T xi[3], T m, const Material<T>& mat,
+                                   const PenaltySpec& ps, T g[3]) {
+    double E[3][3];
+    for (int c = 0; c < 3; ++c)
+        for (int d = c; d < 3; ++d) {
+            E[c][d] = (double)(mat.A11 * e[c][0] * e[d][0] + mat.A22 * e[c][1] * e[d][1] +
+                               mat.A12 * (e[c][0] * e[d][1] + e[c][1] * e[d][0]) + mat.A33 * e[c][2] * e[d][2]);
+            E[d][c] = E[c][d];
+        }
+    const double x[3] = {(double)xi[0], (double)xi[1], (double)xi[2]};
+    const double scale = -ps.p * (1.0 - (double)m);
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (ps.ip > 0) {
+        const double fact[4] = {1.0, 1.0, 2.0, 6.0};
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) {
+                    int cnt[3] = {0, 0, 0};
+                    cnt[c]++; cnt[d]++; cnt[i]++;
+                    const double af = fact[cnt[0]] * fact[cnt[1]] * fact[cnt[2]];
+                    const double xs[6] = {x[0], x[1], x[2], x[c], x[d], x[i]};
+                    acc[i] += E[c][d] * af * (1.0 / 120.0) * dirichlet_power_moment(ps.ip - 1, xs, 6);
+                }
+    } else {
+        for (int q = 0; q < 16; ++q) {
+            double lam[3], wt;
+            collapsed_gauss16(q, lam, wt);
+            const double xq = lam[0] * x[0] + lam[1] * x[1] + lam[2] * x[2];
+            double energy = 0.0;
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) energy += lam[c] * lam[d] * E[c][d];
+            const double f = 0.5 * wt * pow(xq, ps.p - 1.0) * energy;
+            for (int i = 0; i < 3; ++i) acc[i] += f * lam[i];
+        }
+    }
+    for (int i = 0; i < 3; ++i) g[i] = (T)(scale * acc[i]);
 }
 
 }  // namespace tmx

@@ -767,19 +767,53 @@ class Engine : public EngineBase {
     }
 
     // ------------------------------------------------------------------ elasticity operator
-    void check_penalty(double p) {
-        if (p != 3.0)
-            throw Unsupported{"penalty p=" + std::to_string(p) +
-                              ": the closed-form SIMP moments are implemented for p = 3 only"};
+    // SIMP exponent of the current call.  p = 3 (every elasticity design of the reference) keeps
+    // the closed-form moments inside the fine-level operator; any other p > 0 evaluates level-0
+    // moments once per call into w0_ (mg_fine_moments_kernel) and level 0 runs the stored-moment
+    // kernels, like the coarse levels (reference: src/penalizers.py:36-46, the penalties loop of
+    // src/solver.py:230-231).
+    void set_penalty(double p) {
+        if (!(p > 0.0) || !(p < 1e6)) throw Invalid{"penalty p=" + std::to_string(p) + ": p must be positive"};
+        if (p == spec_.p) return;
+        spec_.p = p;
+        const int ip = (int)p;
+        spec_.ip = ((double)ip == p && ip >= 1 && ip <= kMaxIntPenalty) ? ip : 0;
+        general_ = p != 3.0;
+        // captured kernels carry the coefficient source by value; smoother bounds restart
+        if (setup_graph_exec_) {
+            cudaGraphExecDestroy(setup_graph_exec_);
+            setup_graph_exec_ = nullptr;
+        }
+        graph_dirty_ = true;
+        for (auto& L : levels_) L.eig_ready = false;
+    }
+    void compute_w0(const T* xi) {
+        if (!general_) return;
+        w0_.ensure((size_t)12 * g0_.nx * g0_.ny);
+        LevelGeom<T> g = g0_;
+        g.xi = xi;
+        dim3 blk(32, 8), grd(ceil_div(g.nx, 32), ceil_div(g.ny, 8));
+        mg_fine_moments_kernel<T><<<grd, blk, 0, stream_>>>(g, spec_, w0_.p);
+        TM_CHECK_LAUNCH();
+    }
+    // level-0 geometry bound to a density (its halo rows already exchanged)
+    LevelGeom<T> fine_geom(const T* xi, bool compute) {
+        LevelGeom<T> g = g0_;
+        g.xi = xi;
+        if (general_) {
+            w0_.ensure((size_t)12 * g0_.nx * g0_.ny);
+            if (compute) compute_w0(xi);
+            g.W = w0_.p;
+        }
+        return g;
     }
 
     void elast_matvec(void* xi, double p, void* x, void* y) override {
-        check_penalty(p);
+        set_penalty(p);
         if (x == y) throw Invalid{"tm_elast_matvec: x and y must not alias"};
         exchange_p1((T*)xi);
         exchange_p2(0, (T*)x);
-        LevelGeom<T> g = g0_;
-        g.xi = (const T*)xi;
+        const LevelGeom<T> g = fine_geom((const T*)xi, true);
         ApplyArgs<T> a = apply_args();
         a.x = (const T*)x;
         a.y = (T*)y;
@@ -787,16 +821,15 @@ class Engine : public EngineBase {
     }
 
     void elast_diag(void* xi, double p, void* dinv) override {
-        check_penalty(p);
+        set_penalty(p);
         exchange_p1((T*)xi);
-        LevelGeom<T> g = g0_;
-        g.xi = (const T*)xi;
+        const LevelGeom<T> g = fine_geom((const T*)xi, true);
         launch_diag(g, false, (T*)dinv);
     }
 
     SolveStats state_solve(void* xi_, double p, const void* b_, void* u_, double rtol, int maxit,
                            int flags) override {
-        check_penalty(p);
+        set_penalty(p);
         T* xi = (T*)xi_;
         const T* b = (const T*)b_;
         T* u = (T*)u_;
@@ -820,6 +853,9 @@ class Engine : public EngineBase {
         // converged solution and its residual test stay fp64)
         const bool mixed = use_mg && mixed_ && sizeof(T) == 8;
         const T* dinv = nullptr;
+        // general exponent: the level-0 moments come from setup_device_part when this engine owns
+        // the hierarchy, else from here
+        g = fine_geom(xi, !(use_mg && !mixed));
         if (use_mg && mixed) {
             prepare_inner(xi);
         } else if (use_mg) {
@@ -892,11 +928,15 @@ class Engine : public EngineBase {
     }
 
     void sens_rhs(const void* xi, double p, const void* u, void* out) override {
-        check_penalty(p);
+        set_penalty(p);
         LevelGeom<T> g = g0_;
         g.xi = (const T*)xi;
-        sens_rhs_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, p1_.own_iy0, p1_.own_iy1,
-                                                                    (const T*)u, (T*)out);
+        if (general_)
+            sens_rhs_kernel<T, true><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, spec_, p1_.own_iy0, p1_.own_iy1,
+                                                                              (const T*)u, (T*)out);
+        else
+            sens_rhs_kernel<T, false><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, spec_, p1_.own_iy0,
+                                                                               p1_.own_iy1, (const T*)u, (T*)out);
         TM_CHECK_LAUNCH();
     }
 
@@ -1304,6 +1344,7 @@ class Engine : public EngineBase {
     }
 
     void launch_apply(const LevelGeom<T>& g, bool stored, int ep, ApplyArgs<T> a) {
+        stored = stored || g.W != nullptr;  // level 0 with a general SIMP exponent carries stored moments
         const int ncg = ceil_div(g.nx + 1, 31);
         const int bx = ceil_div(ncg, kApplyWarps);
         // A strip re-evaluates the cell row below it ((H+1)/H flops) and marches H rows
@@ -1361,6 +1402,7 @@ class Engine : public EngineBase {
     }
 
     void launch_diag(const LevelGeom<T>& g, bool stored, T* dinv) {
+        stored = stored || g.W != nullptr;
         dim3 blk(32, 8), grd(ceil_div(g.Lx, 32), ceil_div(g.Ly, 8));
         if (stored)
             elast_diag_kernel<T, true><<<grd, blk, 0, stream_>>>(g, diag_tab_, dinv);
@@ -1792,7 +1834,9 @@ class Engine : public EngineBase {
 
     void setup_device_part(T* xi) {
         const int nl = nlevels_;
+        compute_w0(xi);
         levels_[0].g.xi = xi;
+        levels_[0].g.W = general_ ? w0_.p : nullptr;
         for (int l = 1; l < nl; ++l) {
             Level& F = levels_[l - 1];
             Level& C = levels_[l];
@@ -1805,7 +1849,7 @@ class Engine : public EngineBase {
                 own1 = rc.c1 - cell_off;
             }
             dim3 blk(32, 8), grd(ceil_div(C.g.nx, 32), ceil_div(C.g.ny, 8));
-            if (l == 1)
+            if (F.g.W == nullptr)
                 mg_coarsen_moments_kernel<T, false><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, cell_off, own0,
                                                                              own1, co_tab_, C.W.p);
             else
@@ -1876,6 +1920,7 @@ class Engine : public EngineBase {
         in.blocks_per_sm_target_ = blocks_per_sm_target_; in.min_rows_per_strip_ = min_rows_per_strip_;
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
         in.fuse_first_ = fuse_first_;
+        in.set_penalty(spec_.p);
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
         in.tail_max_nodes_ = tail_max_nodes_; in.tail_cluster_ = tail_cluster_;
         in.stats_fine_applies_ = 0;
@@ -2090,6 +2135,9 @@ class Engine : public EngineBase {
     DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_, f_p2_;
     bool f_dinv_ready_ = false;
     DevBuf<T> s_r_, s_p_, s_Ap_, s_b_, s_dinv_, s_xi_;
+    PenaltySpec spec_{3.0, 3};
+    bool general_ = false;  // spec_.p != 3: level 0 runs on the stored moments w0_
+    DevBuf<T> w0_;
     std::vector<Level> levels_;
     DevBuf<double> coarse_A_, coarse_Ainv_;
 

@@ -45,6 +45,27 @@ __device__ __forceinline__ void fine_moments(const LevelGeom<T>& f, int type, in
     }
 }
 
+// Level-0 moments for a general SIMP exponent (p != 3; tm_element.cuh, "General SIMP exponent"):
+// W0 (SoA, 12 planes of nx*ny local cells) from the P1 density, one thread per cell.  The
+// fine-level operator, diagonal and coarsening then run their stored-moment variants on it.
+template <typename T>
+__global__ void mg_fine_moments_kernel(const LevelGeom<T> g, const PenaltySpec ps, T* __restrict__ W0) {
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= g.nx || cy >= g.ny) return;
+    const size_t plane = (size_t)g.nx * g.ny, cidx = (size_t)cy * g.nx + cx;
+    const size_t v0 = (size_t)cy * (g.nx + 1) + cx;
+    const double x0 = (double)g.xi[v0], x1 = (double)g.xi[v0 + 1];
+    const double x2 = (double)g.xi[v0 + g.nx + 1], x3 = (double)g.xi[v0 + g.nx + 2];
+    double w[6];
+    moments_general(x0, x1, x3, (double)g.simp_min, ps, w);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) W0[k * plane + cidx] = (T)w[k];
+    moments_general(x0, x2, x3, (double)g.simp_min, ps, w);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) W0[(6 + k) * plane + cidx] = (T)w[k];
+}
+
 // W_c (SoA, 12 planes of nxc*nyc) from the fine level
 template <typename T, bool FINE_STORED>
 __global__ void mg_coarsen_moments_kernel(const LevelGeom<T> f, int nxc, int nyc, int c_cell_off,

@@ -213,8 +213,9 @@ __global__ void p1_integrate_kernel(const P1Geom g, const T* __restrict__ values
 // sensitivity right-hand side  b^g_i = int -r'(xi_h) (lambda (div u)^2 + 2 mu eps:eps) phi_i
 // (reference: FEM_src/elasisity_problem.py:146-150), gathered per vertex
 // ---------------------------------------------------------------------------------------
-template <typename T>
-__global__ void sens_rhs_kernel(const LevelGeom<T> g, int own_iy0, int own_iy1,
+// GENERAL = false: p = 3 closed form; true: any exponent (tri_sensitivity_general)
+template <typename T, bool GENERAL>
+__global__ void sens_rhs_kernel(const LevelGeom<T> g, const PenaltySpec ps, int own_iy0, int own_iy1,
                                 const T* __restrict__ u, T* __restrict__ out) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x;
     const int iy = blockIdx.y * blockDim.y + threadIdx.y;
@@ -244,7 +245,10 @@ __global__ void sens_rhs_kernel(const LevelGeom<T> g, int own_iy0, int own_iy1,
                     tri_vertex_strains<T, false>(U, M, g.mat.kappa, e);
                 else
                     tri_vertex_strains<T, true>(U, M, g.mat.kappa, e);
-                tri_sensitivity<T>(e, xi, g.simp_min, g.mat, gl);
+                if (GENERAL)
+                    tri_sensitivity_general<T>(e, xi, g.simp_min, g.mat, ps, gl);
+                else
+                    tri_sensitivity<T>(e, xi, g.simp_min, g.mat, gl);
                 acc += (double)gl[kl];
             }
         }
