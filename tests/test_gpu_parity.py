@@ -586,3 +586,32 @@ def test_save_load_round_trip_and_plot_sampling(tmp_path):
             import pickle
             pickle.dump({"N": 2, "domain_size": (1.0, 1.0), "problem": "nope", "vector": np.zeros(9)}, fh)
         load_function(str(tmp_path / "bad.dat"))
+
+
+@pytest.mark.parametrize("p", [3.0, 2.0])
+def test_fused_rz_dot_equals_separate_dot_kernel(repo_root, p):
+    """r . z of the PCG taken inside the V-cycle's last smoothing step (EP_CHEBDOT, option 127) against
+    the separate dot kernel: same iteration count, same displacement to round-off, replayed graphs
+    included (several solves on one engine)."""
+    design = read_design(os.path.join(repo_root, "designs", "cantilever.json"))
+    N = 24
+    W, H = design["width"], design["height"]
+    nx, ny = int(W * N), int(H * N)
+    mesh = StructuredMesh(W, H, nx, ny)
+    rng = np.random.default_rng(4)
+    lda, mu = lame(design["E"], design["nu"])
+    b = mesh.load_vector(design["body_force"], design["tractions"])
+    out = {}
+    for fused in (1, 0):
+        eng = _engine(nx, ny, W, H, lame_lambda=lda, lame_mu=mu, fixed_sides=_sides(design["fixed_sides"]))
+        eng.set_option(127, fused)
+        rng = np.random.default_rng(4)
+        res = []
+        for _ in range(3):
+            xi = 0.05 + 0.9 * rng.random(mesh.n1)
+            u, info = eng.state_solve(_t(xi), _t(b), p, rtol=1e-11)
+            res.append((info.iterations, u.cpu().numpy()))
+        out[fused] = res
+    for (it1, u1), (it0, u0) in zip(out[1], out[0]):
+        assert abs(it1 - it0) <= 1
+        assert np.linalg.norm(u1 - u0) / np.linalg.norm(u0) < 1e-9

@@ -19,6 +19,7 @@
 //   EP_DOT    y = A x, and the grid-wide  x . A x   (PCG)
 //   EP_RESID  y = b - A x
 //   EP_CHEB   r = b - A x;  d = c1 d + c2 D^-1 r;  y = x + d   (one Chebyshev-Jacobi step)
+//   EP_CHEBDOT  EP_CHEB + the dot product b . y of the owned nodes (r . z of the PCG)
 //   EP_RESID0 x = c2 D^-1 b evaluated on the fly at the 9 nodes (the first smoothing step from a
 //             zero guess, never materialised before the operator); y = b - A x, x stored to d
 // Dirichlet nodes are identity rows/columns (symmetric elimination; same solution as the
@@ -30,7 +31,10 @@
 
 namespace tmx {
 
-enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3, EP_RESID0 = 4 };
+enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3, EP_RESID0 = 4, EP_CHEBDOT = 5 };
+// EP_CHEBDOT: EP_CHEB that also accumulates  b . y  -- on the last smoothing step of a V-cycle b is
+// the PCG residual r and y the preconditioned residual z, so r.z costs no extra pass over r and z
+__host__ __device__ constexpr bool ep_is_cheb(int ep) { return ep == EP_CHEB || ep == EP_CHEBDOT; }
 
 template <typename T>
 struct Vec2;
@@ -53,7 +57,7 @@ struct ApplyArgs {
     T c1, c2;       // EP_CHEB coefficients; EP_RESID0: c2 scales D^-1 b
     int store_d;    // EP_CHEB: 0 = the updated direction is not needed any more (last step)
     ReduceScratch rs;
-    double* dot_out;  // EP_DOT
+    double* dot_out;  // EP_DOT, EP_CHEBDOT
     int rows_per_strip;
 };
 
@@ -71,8 +75,8 @@ struct EpiOps {
 template <typename T, int EP>
 __device__ __forceinline__ void load_epi_ops(const ApplyArgs<T>& a, size_t n, EpiOps<T>& o) {
     using V2 = typename Vec2<T>::type;
-    if (EP == EP_RESID || EP == EP_RESID0 || EP == EP_CHEB) o.b = reinterpret_cast<const V2*>(a.b)[n];
-    if (EP == EP_CHEB) {
+    if (EP == EP_RESID || EP == EP_RESID0 || ep_is_cheb(EP)) o.b = reinterpret_cast<const V2*>(a.b)[n];
+    if (ep_is_cheb(EP)) {
         o.dinv = reinterpret_cast<const V2*>(a.dinv)[n];
         if (a.c1 != T(0)) o.d = reinterpret_cast<const V2*>(a.d)[n];
     }
@@ -119,6 +123,7 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
             if (a.store_d) reinterpret_cast<V2*>(a.d)[n] = dd;
             out.x = x0 + dd.x;
             out.y = x1 + dd.y;
+            if (EP == EP_CHEBDOT) dot += (double)bb.x * (double)out.x + (double)bb.y * (double)out.y;
         }
     }
     reinterpret_cast<V2*>(a.y)[n] = out;
@@ -228,12 +233,12 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             }
         };
         auto prefetch_epilogue = [&](int iy_e) {
-            if (!(PF && colok[0] && (EP == EP_RESID || EP == EP_CHEB)) || iy_e < iy0) return;
+            if (!(PF && colok[0] && (EP == EP_RESID || ep_is_cheb(EP))) || iy_e < iy0) return;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t n = (size_t)(2 * iy_e + r) * Lx + i0;
                 prefetch_l1(reinterpret_cast<const V2*>(a.b) + n);
-                if (EP == EP_CHEB) {
+                if (ep_is_cheb(EP)) {
                     prefetch_l1(reinterpret_cast<const V2*>(a.dinv) + n);
                     if (a.c1 != T(0)) prefetch_l1(reinterpret_cast<const V2*>(a.d) + n);
                     // (EP_RESID0 needs no epilogue prefetch: b was just read for the on-the-fly x)
@@ -278,7 +283,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             // (fine level only: the stored-moment kernels of the coarse levels are better off with
             // the registers, i.e. a third resident block per SM, and load them where they are used)
             EpiOps<T> eo[2][2];
-            if (!STORED_W && (EP == EP_RESID || EP == EP_RESID0 || EP == EP_CHEB)) {
+            if (!STORED_W && (EP == EP_RESID || EP == EP_RESID0 || ep_is_cheb(EP))) {
                 if (iy >= iy0 && owner) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
@@ -360,7 +365,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             }
         }
     }
-    if (EP == EP_DOT) {
+    if (EP == EP_DOT || EP == EP_CHEBDOT) {
         double v[1] = {dot};
         double* const outs[1] = {a.dot_out};
         grid_reduce<1>(v, a.rs, outs);

@@ -212,6 +212,7 @@ class Engine : public EngineBase {
             case 123: filter_tb_ = value != 0.0; break;
             case 125: warm_guard_ = value != 0.0; break;
             case 126: pdl_ = value != 0.0; graph_dirty_ = true; break;
+            case 127: fuse_rz_ = value != 0.0; graph_dirty_ = true; break;
             case 124: filter_tb_steps_ = std::max(1, (int)value); filter_tb_state_ = 0; break;
             case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
             case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
@@ -626,6 +627,7 @@ class Engine : public EngineBase {
 
     T* fvcycle_body(T* r) {
         const int nl = nlevels_;
+        vcycle_rz_ = false;
         std::vector<T*> xs(nl, nullptr);
         std::vector<const T*> bs(nl, nullptr);
         bs[0] = r;
@@ -1362,6 +1364,8 @@ class Engine : public EngineBase {
         while (level + 1 < nlevels_ && !(lv_nx_[level] == g.nx && lv_ny_[level] == g.nyg)) ++level;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         const bool timed = profile_ == 2 || (profile_ == 1 && fine);
+        // statistics file the fused variants under their base epilogue
+        const int ep_slot = ep == EP_RESID0 ? (int)EP_RESID : (ep == EP_CHEBDOT ? (int)EP_CHEB : ep);
         if (timed) {
             if (prof_free_.empty()) {
                 TM_CUDA(cudaEventCreate(&ev.first));
@@ -1379,6 +1383,7 @@ class Engine : public EngineBase {
         case EP_DOT: TM_LAUNCH_APPLY(ST, EP_DOT, MB, PFV); break;       \
         case EP_RESID: TM_LAUNCH_APPLY(ST, EP_RESID, MB, PFV); break;   \
         case EP_RESID0: TM_LAUNCH_APPLY(ST, EP_RESID0, MB, PFV); break; \
+        case EP_CHEBDOT: TM_LAUNCH_APPLY(ST, EP_CHEBDOT, MB, PFV); break; \
         default: TM_LAUNCH_APPLY(ST, EP_CHEB, MB, PFV); break;          \
     }
         if (stored) {
@@ -1393,11 +1398,11 @@ class Engine : public EngineBase {
         TM_CHECK_LAUNCH();
         if (timed) {
             TM_CUDA(cudaEventRecord(ev.second, stream_));
-            prof_pending_.push_back({4 * level + (ep == EP_RESID0 ? (int)EP_RESID : (int)ep), ev});
+            prof_pending_.push_back({4 * level + ep_slot, ev});
         }
         if (fine) {
             ++stats_fine_applies_;
-            ++fine_ep_count_[ep == EP_RESID0 ? (int)EP_RESID : (int)ep];
+            ++fine_ep_count_[ep_slot];
         }
     }
 
@@ -1483,15 +1488,22 @@ class Engine : public EngineBase {
                 }
             }
             if (jacobi) {
-                pcg_direction_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p + off,
+                pcg_direction_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, -1, p + off,
                                                                               r + off, dv);
             } else {
+                vcycle_rz_ = false;
                 const T* z = precond(r);
-                dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, r + off, z + off, rs_, sc_ + (cur ^ 1));
-                TM_CHECK_LAUNCH();
-                sum_ranks(sc_ + (cur ^ 1), 1);
-                pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, p + off,
-                                                                               r + off, z + off);
+                if (vcycle_rz_) {  // r . z came out of the V-cycle's last smoothing step
+                    sum_ranks(sc_ + SC_RZV, 1);
+                    pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, SC_RZV, cur ^ 1,
+                                                                                   p + off, r + off, z + off);
+                } else {
+                    dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, r + off, z + off, rs_, sc_ + (cur ^ 1));
+                    TM_CHECK_LAUNCH();
+                    sum_ranks(sc_ + (cur ^ 1), 1);
+                    pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, -1,
+                                                                                   p + off, r + off, z + off);
+                }
             }
             TM_CHECK_LAUNCH();
             cur ^= 1;
@@ -1921,6 +1933,7 @@ class Engine : public EngineBase {
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
         in.fuse_first_ = fuse_first_;
         in.set_penalty(spec_.p);
+        in.fuse_rz_ = false;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
         in.tail_max_nodes_ = tail_max_nodes_; in.tail_cluster_ = tail_cluster_;
         in.stats_fine_applies_ = 0;
@@ -1945,7 +1958,8 @@ class Engine : public EngineBase {
     }
 
     // Chebyshev-Jacobi smoothing of A x = b on level l; xin == nullptr means zero initial guess
-    T* smooth(int l, const T* b, T* xin) {
+    // rz_out != nullptr: the last step also delivers b . x_out there (EP_CHEBDOT)
+    T* smooth(int l, const T* b, T* xin, double* rz_out = nullptr) {
         Level& L = levels_[l];
         const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
         const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
@@ -1979,7 +1993,10 @@ class Engine : public EngineBase {
             a.x = cur; a.y = other; a.b = b; a.dinv = L.dinv.p; a.d = L.d.p;
             a.c1 = (T)c1; a.c2 = (T)c2;
             a.store_d = (k + 1 < degree) ? 1 : 0;
-            launch_apply(L.g, l > 0, EP_CHEB, a);
+            const bool with_dot = rz_out != nullptr && k + 1 == degree;
+            a.dot_out = rz_out;
+            launch_apply(L.g, l > 0, with_dot ? EP_CHEBDOT : EP_CHEB, a);
+            if (with_dot) vcycle_rz_ = true;
             cur = other;
         }
         return cur;
@@ -1997,6 +2014,7 @@ class Engine : public EngineBase {
             ++stats_vcycles_;
             stats_fine_applies_ += graph_fine_applies_;
             for (int e = 0; e < 4; ++e) fine_ep_count_[e] += graph_ep_count_[e];
+            vcycle_rz_ = graph_rz_;
             return graph_z_;
         }
         if (profile_ == 1 && !graph_sampled_) {
@@ -2038,6 +2056,7 @@ class Engine : public EngineBase {
         cudaGraphDestroy(graph);
         graph_r_ = r;
         graph_z_ = z;
+        graph_rz_ = vcycle_rz_;
         graph_dirty_ = false;
         graph_kernels_ = 0;
         return vcycle(r);
@@ -2050,6 +2069,7 @@ class Engine : public EngineBase {
             ~PdlScope() { flag = false; }
         } pdl_scope(pdl_active_, pdl_ && nranks_ == 1);
         const int nl = nlevels_;
+        vcycle_rz_ = false;
         std::vector<T*> xs(nl, nullptr);
         std::vector<const T*> bs(nl, nullptr);
         bs[0] = r;
@@ -2103,7 +2123,8 @@ class Engine : public EngineBase {
             dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
             launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
-            xs[l] = smooth(l, bs[l], xs[l]);
+            // the V-cycle ends with the level-0 post-smoothing: its last step also returns r . z
+            xs[l] = smooth(l, bs[l], xs[l], (l == 0 && fuse_rz_) ? sc_ + SC_RZV : nullptr);
         }
         ++stats_vcycles_;
         return xs[0];
@@ -2164,6 +2185,9 @@ class Engine : public EngineBase {
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
     bool fuse_first_ = true;
+    bool fuse_rz_ = true;      // option 127: r . z of the PCG from the V-cycle's last smoothing step
+    bool vcycle_rz_ = false;   // the V-cycle just run (or replayed) left r . z in sc_[SC_RZV]
+    bool graph_rz_ = false;    // ... as captured in graph_exec_
     int depth_limit_ = 0, tail_dry_ = 0;
     cudaGraphExec_t setup_graph_exec_ = nullptr;
     T* setup_graph_xi_ = nullptr;

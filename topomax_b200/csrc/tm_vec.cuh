@@ -12,7 +12,9 @@
 
 namespace tmx {
 
-enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RR = 3, SC_BB = 4, SC_TMP = 5, SC_COUNT = 16 };
+// SC_RZV: r . z delivered by the V-cycle's last smoothing step (EP_CHEBDOT); a fixed slot, so that
+// the captured V-cycle graph can be replayed whichever of SC_RZ0/1 is current
+enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RR = 3, SC_BB = 4, SC_TMP = 5, SC_RZV = 8, SC_COUNT = 16 };
 
 constexpr int kVecThreads = 256;
 
@@ -47,13 +49,16 @@ __global__ void pcg_update_kernel(size_t n, double* sc, int rz_old, int rz_new, 
     }
 }
 
-// p = z + beta p,  beta = sc[rz_new] / sc[rz_old];  JACOBI: z = dinv r on the fly
+// p = z + beta p,  beta = sc[rz_new] / sc[rz_old];  JACOBI: z = dinv r on the fly.
+// rz_store >= 0: sc[rz_new] is also filed under sc[rz_store] for the next iteration (no thread of
+// this kernel reads that slot)
 template <typename T, bool JACOBI>
-__global__ void pcg_direction_kernel(size_t n, const double* sc, int rz_old, int rz_new,
+__global__ void pcg_direction_kernel(size_t n, double* sc, int rz_old, int rz_new, int rz_store,
                                      T* __restrict__ p, const T* __restrict__ r,
                                      const T* __restrict__ z_or_dinv) {
     const double den = sc[rz_old];
     const double beta = den != 0.0 ? sc[rz_new] / den : 0.0;
+    if (rz_store >= 0 && blockIdx.x == 0 && threadIdx.x == 0) sc[rz_store] = sc[rz_new];
     TM_GRID_STRIDE(i, n) {
         const double z = JACOBI ? (double)z_or_dinv[i] * (double)r[i] : (double)z_or_dinv[i];
         p[i] = (T)(z + beta * (double)p[i]);
