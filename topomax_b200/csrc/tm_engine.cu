@@ -212,7 +212,7 @@ class Engine : public EngineBase {
             case 123: filter_tb_ = value != 0.0; break;
             case 125: warm_guard_ = value != 0.0; break;
             case 126: pdl_ = value != 0.0; graph_dirty_ = true; break;
-            case 127: fuse_rz_ = value != 0.0; graph_dirty_ = true; break;
+            case 127: fuse_rz_ = (int)value; graph_dirty_ = true; break;
             case 124: filter_tb_steps_ = std::max(1, (int)value); filter_tb_state_ = 0; break;
             case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
             case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
@@ -1933,7 +1933,7 @@ class Engine : public EngineBase {
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
         in.fuse_first_ = fuse_first_;
         in.set_penalty(spec_.p);
-        in.fuse_rz_ = false;  // r . z is taken in fp64 on the converted vectors
+        in.fuse_rz_ = 0;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
         in.tail_max_nodes_ = tail_max_nodes_; in.tail_cluster_ = tail_cluster_;
         in.stats_fine_applies_ = 0;
@@ -2124,7 +2124,8 @@ class Engine : public EngineBase {
             launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
             // the V-cycle ends with the level-0 post-smoothing: its last step also returns r . z
-            xs[l] = smooth(l, bs[l], xs[l], (l == 0 && fuse_rz_) ? sc_ + SC_RZV : nullptr);
+            xs[l] = smooth(l, bs[l], xs[l], (l == 0 && (fuse_rz_ > 0 || (fuse_rz_ < 0 && p2_cnt_ >= ((size_t)1 << 24)))) ? sc_ + SC_RZV
+                                                                                                 : nullptr);
         }
         ++stats_vcycles_;
         return xs[0];
@@ -2185,7 +2186,10 @@ class Engine : public EngineBase {
     int apply_minb_ = 2, filter_blocks_per_sm_ = 2;
     bool use_graph_ = true, graph_dirty_ = true, graph_sampled_ = false;
     bool fuse_first_ = true;
-    bool fuse_rz_ = true;      // option 127: r . z of the PCG from the V-cycle's last smoothing step
+    // option 127: r . z of the PCG from the V-cycle's last smoothing step.  -1 = automatic: on
+    // bandwidth-bound meshes only (it saves two vector passes, but its grid reduction adds ~5 us to
+    // the kernel, more than the separate dot costs on a latency-bound mesh: measured at N=512)
+    int fuse_rz_ = -1;
     bool vcycle_rz_ = false;   // the V-cycle just run (or replayed) left r . z in sc_[SC_RZV]
     bool graph_rz_ = false;    // ... as captured in graph_exec_
     int depth_limit_ = 0, tail_dry_ = 0;
