@@ -1353,6 +1353,11 @@ class Engine : public EngineBase {
         // serially: large meshes get H up to 64, small (latency-bound) levels H down to 1 so
         // that there are always ~4 blocks per SM to overlap the march latencies.
         int strips = ceil_div((long)blocks_per_sm_target_ * num_sms_, bx);
+        // The density-driven fine-level kernel holds apply_minb_ blocks per SM (250 registers): size
+        // its grid to ONE full wave when the mesh allows, never slightly more (A/B on N=512: 288
+        // blocks of 16 rows against 576 of 8: 3 % faster, less pre-roll; the stored-moment levels
+        // are better off with ~4 blocks per SM)
+        if (!stored) strips = std::max(1, (int)((long)apply_minb_ * num_sms_ / bx));
         strips = std::min(strips, g.ny);
         strips = std::max(strips, ceil_div(g.ny, 64));
         a.rows_per_strip = std::max(min_rows_per_strip_, ceil_div(g.ny, strips));
