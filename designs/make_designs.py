@@ -1,4 +1,5 @@
-"""Writes the elasticity design files of the hot path into ``designs/``.
+"""Writes the design files into ``designs/``: the four elasticity designs of the hot path and the
+three fluid designs of the reference (the latter are consumed by ``oracle/fluid_oracle.py`` only).
 
 The reference generates its JSONs with a small Rust program
 (reference: designs/design_creator/src/main.rs:11-28); there is no cargo in this
@@ -40,6 +41,26 @@ def elasticity(width, height, fem_step, dem_step, vf, fixed, force, tractions, r
     }
 
 
+def fluid(width, height, fem_step, dem_step, penalties, vf, flows, viscosity=1.0):
+    """Fluid branch of the schema (reference: designs/definitions.py, Flow / FluidParameters)."""
+    return {
+        "Fluid": {
+            "domain_parameters": {
+                "width": width,
+                "height": height,
+                "fem_step_size": fem_step,
+                "dem_step_size": dem_step,
+                "penalties": penalties,
+                "volume_fraction": vf,
+            },
+            "problem_parameters": {
+                "flows": [{"side": s, "center": c, "length": l, "rate": r} for s, c, l, r in flows],
+                "viscosity": viscosity,
+            },
+        }
+    }
+
+
 def disc_force(cx, cy, r, fx, fy):
     return {"region": {"center": [cx, cy], "radius": r}, "value": [fx, fy]}
 
@@ -62,6 +83,14 @@ DESIGNS = {
     "bridge": elasticity(12.0, 2.0, 0.001, 0.2, 0.4, ["Left", "Right"], None,
                          [traction("Top", 6.0, 0.5, 0.0, -2000.0)],
                          STEEL_RADIUS, 200000.0, 0.3),
+    # values of the reference's designs/{diffuser,pipe_bend,twin_pipe}.json
+    "diffuser": fluid(1.0, 1.0, 0.0011, 0.0002, [0.1], 0.5,
+                      [("Left", 0.5, 1.0, 1.0), ("Right", 0.5, 1.0 / 3.0, -3.0)]),
+    "pipe_bend": fluid(1.0, 1.0, 0.0015, 0.0001, [0.1], 0.251,
+                       [("Left", 0.8, 0.2, 1.0), ("Bottom", 0.8, 0.2, -1.0)]),
+    "twin_pipe": fluid(1.5, 1.0, 0.0015, 0.0004, [0.01, 0.1], 1.0 / 3.0,
+                       [("Left", 0.25, 1.0 / 6.0, 1.0), ("Left", 0.75, 1.0 / 6.0, 1.0),
+                        ("Right", 0.25, 1.0 / 6.0, -1.0), ("Right", 0.75, 1.0 / 6.0, -1.0)]),
 }
 
 

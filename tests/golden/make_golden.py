@@ -10,6 +10,9 @@ GPU box):   python tests/golden/make_golden.py
    array reconstruction.  ``rho_dolfin_order`` is the vector as stored; ``rho_lex`` is the
    same data re-ordered to the row-major vertex grid through the dolfin P1 dof permutation
    (dofs sorted by (ix-iy, ix)).
+   ``diffuser_N20_reference.json`` -- the same for the fluid fixture
+   (tests/test_data/FEM/diffuser/data/correct_{data,rho}.dat, tests/test_fluid_solver.py:33-60);
+   its data file pickles a ``src.utils.IterationData`` dataclass, admitted as an inert stub.
 2. ``oracle_anchors.json`` -- outputs of ``oracle/`` (NOT of the reference) at a few
    configurations, used as regression anchors for oracle and CUDA path alike.  The traction
    designs are parity-unpinned by the reference; that is recorded in the file.
@@ -30,6 +33,10 @@ REF = "/root/reference"
 sys.path.insert(0, ROOT)
 
 
+class IterationDataStub:
+    """Inert stand-in for src/utils.py:12-19 ``IterationData`` (plain attribute bag)."""
+
+
 class NumpyOnlyUnpickler(pickle.Unpickler):
     ALLOWED = {
         ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
@@ -38,6 +45,8 @@ class NumpyOnlyUnpickler(pickle.Unpickler):
     }
 
     def find_class(self, module, name):
+        if (module, name) == ("src.utils", "IterationData"):
+            return IterationDataStub
         if (module, name) not in self.ALLOWED:
             raise pickle.UnpicklingError(f"refusing to load {module}.{name}")
         return getattr(importlib.import_module(module), name)
@@ -76,6 +85,29 @@ def reference_fixture():
     return out
 
 
+def reference_fluid_fixture():
+    base = os.path.join(REF, "tests", "test_data", "FEM", "diffuser", "data")
+    data = load(os.path.join(base, "correct_data.dat")).__dict__
+    rho = load(os.path.join(base, "correct_rho.dat"))
+    n = int(rho["N"])
+    vec = np.asarray(rho["vector"], dtype=np.float64)
+    perm = dolfin_p1_permutation(n, n)
+    lex = np.empty_like(vec)
+    lex[perm] = vec
+    out = {
+        "source": "reference tests/test_data/FEM/diffuser/data/correct_{data,rho}.dat",
+        "design": "designs/diffuser.json", "N": n,
+        "objective": float(data["objective"]), "iteration": int(data["iteration"]),
+        "penalty": float(data["penalty"]),
+        "domain_size": [float(x) for x in data["domain_size"]],
+        "rho_dolfin_order": [float(x) for x in vec],
+        "rho_lex": [float(x) for x in lex],
+    }
+    with open(os.path.join(HERE, "diffuser_N20_reference.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    return out
+
+
 def oracle_anchors(ref):
     from oracle.md_oracle import OracleSolver
 
@@ -108,5 +140,6 @@ def oracle_anchors(ref):
 
 if __name__ == "__main__":
     ref = reference_fixture()
+    reference_fluid_fixture()
     oracle_anchors(ref)
     print("golden fixtures written to", HERE)
