@@ -470,7 +470,10 @@ def run_cuda_arm(args):
     cfg.update({
         "preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
         "parallelism": "1 GPU" if world == 1 else
-        f"{world} GPUs, row strips of cells, NCCL halo exchange + all-reduce, {engine.dist_levels} sharded multigrid levels",
+        f"{world} GPUs, row strips of cells, " + (
+            "halo rows and scalar sums by the library's own kernels over peer-mapped NVLink windows (TM_OPT_P2P)"
+            if engine.peer_memory_active else "NCCL halo exchange + all-reduce") +
+        f", {engine.dist_levels} sharded multigrid levels",
         "weak_scaling_N": run_n, "value_normalisation": f"iter/s x (global dofs / dofs of the N={args.N} mesh) = x{size_factor:.3f}",
         "l2": f"working set of a state solve ~{10 * nu * esize / 1e6:.0f} MB of lattice vectors, larger than the 126 MB L2",
         "md_iterations_timed": [args.warmup, args.warmup + args.steps],

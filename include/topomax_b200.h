@@ -40,7 +40,10 @@ enum {
     TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 2; coarse levels 3) */
     TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
     TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (default 2)     */
-    TM_OPT_PROFILE = 5       /* 1: time every fine-level operator launch with CUDA events */
+    TM_OPT_PROFILE = 5,      /* 1: time every fine-level operator launch with CUDA events */
+    TM_OPT_P2P = 130         /* sharded runs: halo exchange and scalar all-reduce by our own kernels over
+                                peer-mapped memory (NVLink) instead of NCCL calls; collective, set alike
+                                on every rank (default: env TM_P2P, else 0)                        */
 };
 
 /* Mesh, material and filter of one problem.
@@ -85,8 +88,11 @@ const char* tm_version(void);
  * broadcasts it (torch.distributed), every rank calls tm_comm_init: the engine then owns an
  * NCCL communicator for halo rows (ncclSend/Recv), dot products (ncclAllReduce) and the gather
  * of the first replicated multigrid level (ncclBroadcast).
- * tm_local_layout: out = {rank, nranks, nx, ny_global, cl0, cl1, c0, c1, owns_top, dist_levels}:
- * this rank stores cell rows [cl0, cl1) and owns [c0, c1); local P1 arrays are
+ * With TM_OPT_P2P (or env TM_P2P=1) the halo rows and the scalar sums travel instead through
+ * peer-mapped windows (cudaIpc) written and polled by the library's own kernels over NVLink
+ * (csrc/tm_p2p.cuh); NCCL then only carries the window handles and the coarse-level gather.
+ * tm_local_layout: out = {rank, nranks, nx, ny_global, cl0, cl1, c0, c1, owns_top, dist_levels,
+ * peer_memory_active}: this rank stores cell rows [cl0, cl1) and owns [c0, c1); local P1 arrays are
  * (cl1-cl0+1) x (nx+1), local P2 arrays (2(cl1-cl0)+1) x (2nx+1) x 2. */
 int tm_comm_unique_id(char* id128);
 int tm_comm_init(tm_handle h, const char* id128);

@@ -28,12 +28,15 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl")
     report = {}
+    want_p2p = os.environ.get("TM_P2P") == "1"
+    p2p_seen = []
     for case, (nx, ny, fixed, ld) in enumerate([(40, 32, [Side.LEFT], 2), (70, 52, [Side.BOTTOM, Side.TOP], 1),
                                                 (96, 64, [Side.LEFT, Side.RIGHT], 3)]):
         W, H = 0.25 * nx, 0.25 * ny
         kw = dict(lame_lambda=1.3, lame_mu=0.8, filter_radius=0.3, fixed_sides=fixed)
         eng = Engine(nx, ny, W, H, rank=rank, nranks=world, dist_levels=ld, **kw)
         eng.init_comm()
+        p2p_seen.append(eng.peer_memory_active)
         ref = Engine(nx, ny, W, H, **kw)
         rng = np.random.default_rng(100 + case)
         n1, nu = (nx + 1) * (ny + 1), 2 * (2 * nx + 1) * (2 * ny + 1)
@@ -120,6 +123,10 @@ def main():
     full.solve()
     report["hooks_k"] = [hooks.last_result["k_final"], full.last_result["k_final"]]
     report["hooks_rho"] = float(np.abs(hooks.to_array(hooks.rho) - full.to_array(full.rho)).max())
+    if want_p2p:  # the peer-memory path must really have been the one that ran
+        assert all(p2p_seen), p2p_seen
+    else:
+        assert not any(p2p_seen), p2p_seen
     if rank == 0:
         report["files"] = sorted(os.listdir(f"/tmp/tm_hooks_0/FEM/cantilever/data"))[:3]
         print("DIST_REPORT " + json.dumps(report))

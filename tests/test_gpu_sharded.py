@@ -15,13 +15,17 @@ def report_k(report):
     return 36  # cantilever N=40 converges at iteration 36 (oracle anchor)
 
 
-def test_sharded_matches_single_gpu(repo_root):
+@pytest.mark.parametrize("peer_memory", [False, True], ids=["nccl", "peer_memory"])
+def test_sharded_matches_single_gpu(repo_root, peer_memory):
+    """peer_memory: halo rows and scalar sums through the library's own kernels over peer-mapped
+    windows (csrc/tm_p2p.cuh, TM_P2P=1) instead of NCCL calls; same checks, same tolerances."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           "--master-addr", "127.0.0.1", "--master-port", "29534" if peer_memory else "29533",
            os.path.join(repo_root, "tests", "dist_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=repo_root)
+    env = dict(os.environ, TM_P2P="1" if peer_memory else "0")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=repo_root, env=env)
     line = [l for l in out.stdout.splitlines() if l.startswith("DIST_REPORT ")]
     assert line, out.stdout[-2000:] + out.stderr[-4000:]
     report = json.loads(line[0][len("DIST_REPORT "):])

@@ -17,6 +17,7 @@ SIDE_LEFT, SIDE_RIGHT, SIDE_TOP, SIDE_BOTTOM = 1, 2, 4, 8
 PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
 OPT_PRECOND, OPT_CHEB_DEGREE, OPT_CHECK_EVERY, OPT_MG_COARSE_CELLS = 1, 2, 3, 4
 OPT_PROFILE = 5
+OPT_P2P = 130
 OPT_CHEB_RATIO, OPT_EIG_SAFETY = 100, 101
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOT_CONVERGED = -1, -2, -3, -4

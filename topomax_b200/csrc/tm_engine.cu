@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -23,6 +24,7 @@
 #include "tm_mg.cuh"
 #include "tm_p1.cuh"
 #include "tm_p1mg.cuh"
+#include "tm_p2p.cuh"
 #include "tm_tail.cuh"
 #include "tm_vec.cuh"
 
@@ -32,6 +34,12 @@ static thread_local std::string g_error;
 std::atomic<long long> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 const char* last_error() { return g_error.c_str(); }
+
+// peer-memory collectives are opt-in this round (TM_P2P=1 or TM_OPT_P2P): not yet run on hardware
+static bool p2p_default() {
+    const char* e = std::getenv("TM_P2P");
+    return e && e[0] == '1';
+}
 
 struct Unsupported {
     std::string what;
@@ -60,6 +68,18 @@ struct DevBuf {
         TM_CUDA(cudaMalloc(&p, count * sizeof(T)));
         TM_CUDA(cudaMemset(p, 0, count * sizeof(T)));
         n = count;
+    }
+};
+
+// peer-mapped windows of all ranks of the node (tm_p2p.cuh); shared with the fp32 twin engine
+struct P2PState {
+    char* win[P2P_MAX_RANKS] = {};
+    size_t slot_bytes = 0;
+    int rank = 0, nranks = 1;
+    ~P2PState() {
+        for (int q = 0; q < nranks; ++q)
+            if (q != rank && win[q]) cudaIpcCloseMemHandle(win[q]);
+        if (win[rank]) cudaFree(win[rank]);
     }
 };
 
@@ -161,6 +181,7 @@ class Engine : public EngineBase {
         graph_exec_ = nullptr;
         fgraph_exec_ = nullptr;
         inner_.reset();
+        p2p_.reset();
         if (comm_ && owns_comm_) nccl().CommDestroy(comm_);
         cudaFree(rs_.partials);
         cudaFree(rs_.counter);
@@ -213,6 +234,12 @@ class Engine : public EngineBase {
             case 125: warm_guard_ = value != 0.0; break;
             case 126: pdl_ = value != 0.0; graph_dirty_ = true; break;
             case 127: fuse_rz_ = (int)value; graph_dirty_ = true; break;
+            case TM_OPT_P2P:  // collective: every rank must set it alike
+                p2p_want_ = value != 0.0;
+                graph_dirty_ = true;
+                if (!p2p_want_) p2p_.reset();
+                else if (comm_ && !p2p_) p2p_setup();
+                break;
             case 124: filter_tb_steps_ = std::max(1, (int)value); filter_tb_state_ = 0; break;
             case 121: depth_limit_ = (int)value; graph_dirty_ = true; break;
             case 120: tail_cluster_ = std::max(1, (int)value); levels_.clear(); graph_dirty_ = true; break;
@@ -238,12 +265,77 @@ class Engine : public EngineBase {
         std::memcpy(id.internal, id128, 128);
         const int rc = nccl().CommInitRank(&comm_, nranks_, id, rank_);
         if (rc != 0) throw Invalid{std::string("ncclCommInitRank: ") + nccl().GetErrorString(rc)};
+        if (p2p_want_) p2p_setup();
     }
+
+    // Peer windows (tm_p2p.cuh): allocate mine, all-gather the IPC handles through NCCL, map the
+    // others.  Collective; if ANY rank fails to map a peer, every rank stays on the NCCL path.
+    void p2p_setup() {
+        need_comm();
+        if (nranks_ > P2P_MAX_RANKS) return;
+        auto st = std::make_shared<P2PState>();
+        st->rank = rank_;
+        st->nranks = nranks_;
+        // largest halo message: 4 lattice rows of a level-0 displacement vector
+        st->slot_bytes = (((size_t)4 * (2 * (size_t)nx_ + 1) * 2 * sizeof(double)) + 255) & ~(size_t)255;
+        // whole 2 MiB pages: an IPC handle exports the allocation's pages, and two windows of one
+        // process (two engines alive at once) must never share a page
+        const size_t page = (size_t)2 << 20;
+        const size_t bytes = std::max(2 * page, (P2P_HEADER_BYTES + 4 * st->slot_bytes + page - 1) / page * page);
+        int ok = 1;
+        char* self = nullptr;
+        cudaIpcMemHandle_t mine;
+        std::memset(&mine, 0, sizeof(mine));
+        if (cudaMalloc(&self, bytes) != cudaSuccess) {
+            ok = 0;
+        } else {
+            st->win[rank_] = self;
+            TM_CUDA(cudaMemsetAsync(self, 0, bytes, stream_));
+            if (cudaIpcGetMemHandle(&mine, self) != cudaSuccess) ok = 0;
+        }
+        cudaGetLastError();
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        DevBuf<char> hb;
+        hb.ensure((size_t)64 * nranks_);
+        TM_CUDA(cudaMemcpyAsync(hb.p + 64 * rank_, &mine, 64, cudaMemcpyHostToDevice, stream_));
+        nccl_check(nccl().GroupStart(), "ncclGroupStart");
+        for (int q = 0; q < nranks_; ++q)
+            nccl().Broadcast(hb.p + 64 * q, hb.p + 64 * q, 64, kNcclInt8, q, comm_, stream_);
+        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+        std::vector<cudaIpcMemHandle_t> all(nranks_);
+        TM_CUDA(cudaMemcpyAsync(all.data(), hb.p, (size_t)64 * nranks_, cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (int q = 0; q < nranks_ && ok; ++q) {
+            if (q == rank_) continue;
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = 0;
+                cudaGetLastError();
+            } else {
+                st->win[q] = static_cast<char*>(ptr);
+            }
+        }
+        // agree: sum of the failure counts over ranks must be zero
+        double* flag = sc_ + SC_TMP;
+        const double bad = ok ? 0.0 : 1.0;
+        TM_CUDA(cudaMemcpyAsync(flag, &bad, sizeof(double), cudaMemcpyHostToDevice, stream_));
+        nccl_check(nccl().AllReduce(flag, flag, 1, kNcclFloat64, kNcclSum, comm_, stream_), "ncclAllReduce");
+        double total = 1.0;
+        TM_CUDA(cudaMemcpyAsync(&total, flag, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        if (total == 0.0) {
+            p2p_ = st;
+            if (inner_) inner_->p2p_ = p2p_;
+        }
+        graph_dirty_ = true;
+    }
+    bool p2p_active() const { return static_cast<bool>(p2p_); }
 
     void layout(int* out, int n) override {
         const RowRange& r = ranges_[0];
-        const int v[10] = {rank_, nranks_, nx_, nyg_, r.cl0, r.cl1, r.c0, r.c1, r.last ? 1 : 0, dist_levels_};
-        for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+        const int v[11] = {rank_, nranks_, nx_, nyg_, r.cl0, r.cl1, r.c0, r.c1, r.last ? 1 : 0, dist_levels_,
+                           p2p_active() ? 1 : 0};
+        for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
     }
 
     // ------------------------------------------------------------------ loads
@@ -1244,7 +1336,16 @@ class Engine : public EngineBase {
 
     void read_scalars() {
         TM_CUDA(cudaMemcpyAsync(h_sc_, sc_, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, stream_));
+        unsigned int* err = reinterpret_cast<unsigned int*>(h_sc_ + 120);
+        *err = 0;
+        if (p2p_) {  // a timed-out peer poll surfaces with the same synchronisation
+            const P2PHeader* h = reinterpret_cast<const P2PHeader*>(p2p_->win[rank_]);
+            TM_CUDA(cudaMemcpyAsync(err, &h->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+        }
         TM_CUDA(cudaStreamSynchronize(stream_));
+        if (*err)
+            throw Invalid{"peer-memory exchange timed out waiting for another rank (code " +
+                          std::to_string(*err) + ")"};
     }
 
     void nccl_check(int rc, const char* what) {
@@ -1258,6 +1359,17 @@ class Engine : public EngineBase {
     void sum_ranks(double* p, int n) {
         if (nranks_ == 1) return;
         need_comm();
+        if (p2p_ && n <= P2P_RED_MAX) {
+            P2PReduceArgs a;
+            for (int q = 0; q < P2P_MAX_RANKS; ++q) a.win[q] = q < nranks_ ? p2p_->win[q] : nullptr;
+            a.rank = rank_;
+            a.nranks = nranks_;
+            a.p = p;
+            a.n = n;
+            p2p_allreduce_kernel<<<1, 64, 0, stream_>>>(a);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         nccl_check(nccl().AllReduce(p, p, (size_t)n, kNcclFloat64, kNcclSum, comm_, stream_), "ncclAllReduce");
     }
 
@@ -1266,6 +1378,31 @@ class Engine : public EngineBase {
     void exchange_rows(T* v, size_t row_elems, int own0, int own1, int up, int down, bool last) {
         if (nranks_ == 1) return;
         need_comm();
+        if (p2p_ && (size_t)std::max(up, down) * row_elems * sizeof(T) <= p2p_->slot_bytes) {
+            P2PHaloArgs a;
+            const size_t rb = row_elems * sizeof(T);
+            a.self = p2p_->win[rank_];
+            a.below = rank_ > 0 ? p2p_->win[rank_ - 1] : nullptr;
+            a.above = !last ? p2p_->win[rank_ + 1] : nullptr;
+            a.slot_bytes = p2p_->slot_bytes;
+            a.v = reinterpret_cast<char*>(v);
+            a.up_src = (size_t)(own1 - up) * rb;
+            a.up_bytes = (size_t)up * rb;
+            a.down_src = (size_t)own0 * rb;
+            a.down_bytes = (size_t)down * rb;
+            a.from_below_dst = (size_t)(own0 - up) * rb;
+            a.from_above_dst = (size_t)own1 * rb;
+            const size_t big = std::max(a.up_bytes, a.down_bytes);
+            const uintptr_t align = reinterpret_cast<uintptr_t>(v) | a.up_src | a.up_bytes | a.down_src |
+                                    a.down_bytes | a.from_below_dst | a.from_above_dst;
+            const int granule = (align % 16 == 0) ? 16 : (align % 8 == 0) ? 8 : 4;
+            const int blocks = (int)std::min<size_t>((size_t)num_sms_, (big / granule + 1023) / 1024 + 1);
+            if (granule == 16) p2p_halo_kernel<uint4><<<blocks, 256, 0, stream_>>>(a);
+            else if (granule == 8) p2p_halo_kernel<uint2><<<blocks, 256, 0, stream_>>>(a);
+            else p2p_halo_kernel<unsigned int><<<blocks, 256, 0, stream_>>>(a);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         const int dtype = sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32;
         nccl_check(nccl().GroupStart(), "ncclGroupStart");
         if (!last) {
@@ -1929,6 +2066,7 @@ class Engine : public EngineBase {
             inner_.reset(new Engine<float>(c));
             inner_->comm_ = comm_;
             inner_->owns_comm_ = false;
+            inner_->p2p_ = p2p_;
         }
         Engine<float>& in = *inner_;
         in.stream_ = stream_;
@@ -2142,6 +2280,8 @@ class Engine : public EngineBase {
     int nx_, nyg_, ny_ = 0, num_sms_ = 148;
     int rank_ = 0, nranks_ = 1, dist_levels_ = 0, nlevels_ = 1;
     NcclComm comm_ = nullptr;
+    std::shared_ptr<P2PState> p2p_;  // peer windows; null = NCCL send/recv/all-reduce
+    bool p2p_want_ = p2p_default();
     std::vector<int> starts_, lv_nx_, lv_ny_, lv_dr_, lv_dt_;
     std::vector<RowRange> ranges_;
     double hx_, hy_;

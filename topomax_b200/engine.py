@@ -96,6 +96,14 @@ class Engine:
         self._sync_stream()
         _lib.check(self.lib.tm_comm_init(self._h, raw))
 
+    @property
+    def peer_memory_active(self) -> bool:
+        """True when halo rows / scalar sums go through the library's peer-memory kernels
+        (``TM_OPT_P2P`` or ``TM_P2P=1``) rather than NCCL calls."""
+        lay = (c_int * 11)()
+        _lib.check(self.lib.tm_local_layout(self._h, lay, 11))
+        return bool(lay[10])
+
     def owned_p1_rows(self):
         """(first, last+1) local vertex rows this rank owns, and their global offset."""
         lo = self.c0 - self.cl0
