@@ -15,8 +15,9 @@
 // No acknowledgement is needed: exchanges are bidirectional between neighbours, so a neighbour can
 // reach epoch e+2 (the next use of the same-parity mailbox) only after it unpacked my push of epoch
 // e+1, which I issue after my unpack of epoch e (stream order).  Two mailboxes per direction suffice.
-// The push phase never waits, the unpack phase waits only on another GPU: no intra-grid dependency,
-// hence no co-residency requirement and no deadlock.
+// The push phase never waits and the unpack phase waits only on another GPU.  A neighbour's flag
+// rises once ALL its blocks have pushed, so the grid is kept <= the SM count (every block resident:
+// a block polling in its unpack phase never keeps a block that still has to push off the machine).
 //
 // All-reduce of <= P2P_RED_MAX doubles = one single-block kernel: every rank writes its values into
 // slot [parity][rank] of EVERY window, raises the flags, waits for all peers, and sums the slots in
