@@ -179,6 +179,21 @@ long long tm_launch_count(void);
 int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* out);
 int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels);
 
+/* the Q1 strain-energy evaluator of the reference's deep-energy back-end, float32 as
+ * there (replaces StrainEnergy.calculate_objective_and_gradient / the internal part of
+ * calculate_energy, reference: DEM_src/elasisity_problem.py:82-129 over
+ * DEM_src/objective_calculator.py:51-143).  Device pointers; layouts are the reference's:
+ * u[(ix*(ny+1)+iy)*2 + c], density / cell_energy / grad_density [iy][ix], grad_u like u.
+ *   cell_energy  = det J * sum over the 2x2 Gauss points of sigma:eps        (may be NULL)
+ *   grad_density = -r'(rho) * cell_energy,  r = m + rho^p (1-m)              (may be NULL)
+ *   *objective   = sum r(rho) * cell_energy  (host double; internal energy = objective / 2)
+ *   grad_u       = d(objective / 2)/du, what the reference obtains by autograd (may be NULL)
+ * Synchronises `stream` before returning. */
+int tm_dem_strain_energy(int nx, int ny, double width, double height, double lame_lambda, double lame_mu,
+                         double simp_min, double penalty, const float* u, const float* density,
+                         float* cell_energy, float* grad_density, float* grad_u, double* objective,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,12 @@ GPU box):   python tests/golden/make_golden.py
    ``diffuser_N20_reference.json`` -- the same for the fluid fixture
    (tests/test_data/FEM/diffuser/data/correct_{data,rho}.dat, tests/test_fluid_solver.py:33-60);
    its data file pickles a ``src.utils.IterationData`` dataclass, admitted as an inert stub.
+   ``dem_strain_energy_reference.json`` -- SURVEY 8f-4: (a) the reference's fixtures
+   tests/test_data/DEM/{short_cantilever,bridge}/problem_data.dat (tests/test_DEM_problem.py:16-47),
+   (b) outputs of the REFERENCE CODE ITSELF (DEM_src/elasisity_problem.py ``StrainEnergy``, imported
+   from /root/reference with the absent ``rff`` package stubbed -- it is only needed by the network,
+   not by the evaluator) on small random fields: objective, density gradient, internal energy and
+   its autograd derivative with respect to the displacement.
 2. ``oracle_anchors.json`` -- outputs of ``oracle/`` (NOT of the reference) at a few
    configurations, used as regression anchors for oracle and CUDA path alike.  The traction
    designs are parity-unpinned by the reference; that is recorded in the file.
@@ -108,6 +114,67 @@ def reference_fluid_fixture():
     return out
 
 
+def dem_reference_vectors():
+    import types
+
+    import torch
+
+    sys.path.insert(0, REF)
+    stub = types.ModuleType("rff")
+    stub.layers = types.ModuleType("rff.layers")
+    sys.modules.setdefault("rff", stub)
+    sys.modules.setdefault("rff.layers", stub.layers)
+    from DEM_src.elasisity_problem import StrainEnergy
+    from DEM_src.utils import Mesh
+
+    out = {"source": "reference DEM_src/elasisity_problem.py StrainEnergy (torch float32) and its fixtures",
+           "fixtures": [], "random_cases": []}
+    for design, N in (("short_cantilever", 45), ("bridge", 30)):
+        with open(os.path.join(REF, "designs", f"{design}.json")) as fh:
+            d = json.load(fh)["Elasticity"]
+        W, H = d["domain_parameters"]["width"], d["domain_parameters"]["height"]
+        n = int(N / min(W, H))
+        mesh = Mesh(int(W * n), int(H * n), W, H)
+        E, nu = d["problem_parameters"]["young_modulus"], d["problem_parameters"]["poisson_ratio"]
+        fx = load(os.path.join(REF, "tests", "test_data", "DEM", design, "problem_data.dat"))
+        # the reference code run here must reproduce its own fixture bit for bit
+        se = StrainEnergy(mesh, None, E, nu, None)
+        se.set_penalization(3.0)
+        x = torch.from_numpy(np.array([mesh.x_grid.T.flat, mesh.y_grid.T.flat]).T).float()
+        rho = torch.full(mesh.intervals, d["domain_parameters"]["volume_fraction"]).float()
+        obj, grad = se.calculate_objective_and_gradient(x, mesh.shape, rho)
+        assert float(obj) == float(fx["objective"]) and np.array_equal(grad.numpy(), fx["gradient"])
+        out["fixtures"].append({
+            "design": design, "N": N, "Nx": mesh.Nx, "Ny": mesh.Ny, "width": W, "height": H,
+            "young_modulus": E, "poisson_ratio": nu, "volume_fraction": d["domain_parameters"]["volume_fraction"],
+            "penalty": 3.0, "objective": float(fx["objective"]),
+            "gradient": [[float(v) for v in row] for row in np.asarray(fx["gradient"])],
+        })
+    rng = np.random.default_rng(5)
+    for (nx, ny, W, H, E, nu, p) in ((7, 5, 1.4, 1.0, 2.5, 0.25, 3.0), (12, 9, 2.0, 3.0, 200000.0, 0.3, 3.0),
+                                     (5, 8, 1.0, 1.0, 1.0, 0.4, 2.0)):
+        mesh = Mesh(nx, ny, W, H)
+        se = StrainEnergy(mesh, None, E, nu, None)
+        se.set_penalization(p)
+        u = torch.from_numpy(rng.standard_normal(((nx + 1) * (ny + 1), 2))).float().requires_grad_(True)
+        rho = torch.from_numpy(0.1 + 0.8 * rng.random((ny, nx))).float()
+        obj, grad = se.calculate_objective_and_gradient(u, mesh.shape, rho)
+        energy = se.calculate_energy(u, mesh.shape, rho)
+        energy.backward()
+        out["random_cases"].append({
+            "Nx": nx, "Ny": ny, "width": W, "height": H, "young_modulus": E, "poisson_ratio": nu, "penalty": p,
+            "u": [[float(a), float(b)] for a, b in u.detach().numpy()],
+            "density": [[float(v) for v in row] for row in rho.numpy()],
+            "objective": float(obj.detach()),
+            "gradient": [[float(v) for v in row] for row in grad.detach().numpy()],
+            "energy": float(energy.detach()),
+            "energy_gradient_u": [[float(a), float(b)] for a, b in u.grad.numpy()],
+        })
+    with open(os.path.join(HERE, "dem_strain_energy_reference.json"), "w") as fh:
+        json.dump(out, fh)
+    return out
+
+
 def oracle_anchors(ref):
     from oracle.md_oracle import OracleSolver
 
@@ -141,5 +208,7 @@ def oracle_anchors(ref):
 if __name__ == "__main__":
     ref = reference_fixture()
     reference_fluid_fixture()
-    oracle_anchors(ref)
+    dem_reference_vectors()
+    if "--anchors" in sys.argv:  # re-running drifts the unpinned anchors at the 1e-11 level: opt-in
+        oracle_anchors(ref)
     print("golden fixtures written to", HERE)

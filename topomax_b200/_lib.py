@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "tm_load_vector", "tm_filter_apply", "tm_elast_matvec", "tm_elast_diag", "tm_state_solve",
     "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate", "tm_sample_field",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
-    "tm_comm_unique_id", "tm_comm_init", "tm_local_layout",
+    "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
 )
 
 
@@ -107,6 +107,7 @@ def load_library() -> ctypes.CDLL:
         "tm_launch_count": ([], ctypes.c_longlong),
         "tm_mg_debug": ([V, V, I, I, V, V], I),
         "tm_mg_level_info": ([V, I, POINTER(I), POINTER(I)], I),
+        "tm_dem_strain_energy": ([I, I, D, D, D, D, D, D, V, V, V, V, V, POINTER(D), V], I),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

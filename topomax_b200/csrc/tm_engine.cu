@@ -19,6 +19,7 @@
 
 #include "../../include/topomax_b200.h"
 #include "tm_comm.h"
+#include "tm_dem.cuh"
 #include "tm_elast.cuh"
 #include "tm_filter_pcg.cuh"
 #include "tm_mg.cuh"
@@ -2570,6 +2571,45 @@ int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* 
 int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { *nlevels = h->impl->mg_level_info(level, info6); });
+}
+
+// Stateless: the evaluator belongs to no mesh hierarchy.  Scratch for the deterministic
+// reduction is allocated per call (the arrays of this path are small).
+int tm_dem_strain_energy(int nx, int ny, double width, double height, double lame_lambda, double lame_mu,
+                         double simp_min, double penalty, const float* u, const float* density,
+                         float* cell_energy, float* grad_density, float* grad_u, double* objective,
+                         void* stream) {
+    return guarded(nullptr, [&] {
+        if (nx < 1 || ny < 1 || !(width > 0) || !(height > 0)) throw tmx::Invalid{"tm_dem_strain_energy: bad mesh"};
+        if (!u || !density || !objective) throw tmx::Invalid{"tm_dem_strain_energy: null argument"};
+        const tmx::DemGeom g = tmx::dem_make_geom(nx, ny, width, height, lame_lambda, lame_mu, simp_min, penalty);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const size_t cells = (size_t)nx * ny, nodes = (size_t)(nx + 1) * (ny + 1);
+        int sms = 148;
+        cudaPointerAttributes attr;
+        TM_CUDA(cudaPointerGetAttributes(&attr, u));
+        if (attr.type != cudaMemoryTypeDevice) throw tmx::Invalid{"tm_dem_strain_energy: u is not device memory"};
+        const int dev = attr.device;
+        TM_CUDA(cudaSetDevice(dev));
+        TM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int blocks = (int)std::min<size_t>((cells + 255) / 256, (size_t)sms * 8);
+        tmx::DevBuf<double> scratch;  // [0] objective, [1..] block partials; counter behind them
+        scratch.ensure((size_t)blocks + 4);
+        tmx::ReduceScratch rs;
+        rs.partials = scratch.p + 2;
+        rs.capacity = blocks;
+        rs.counter = reinterpret_cast<unsigned int*>(scratch.p + 1);
+        TM_CUDA(cudaMemsetAsync(scratch.p, 0, 2 * sizeof(double), st));  // ordered on the caller's stream
+        tmx::dem_cell_kernel<<<blocks, 256, 0, st>>>(g, u, density, cell_energy, grad_density, rs, scratch.p);
+        TM_CHECK_LAUNCH();
+        if (grad_u) {
+            const int nb = (int)std::min<size_t>((nodes + 255) / 256, (size_t)sms * 8);
+            tmx::dem_grad_u_kernel<<<nb, 256, 0, st>>>(g, u, density, grad_u);
+            TM_CHECK_LAUNCH();
+        }
+        TM_CUDA(cudaMemcpyAsync(objective, scratch.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        TM_CUDA(cudaStreamSynchronize(st));
+    });
 }
 
 }  // extern "C"
