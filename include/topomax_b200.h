@@ -179,6 +179,38 @@ long long tm_launch_count(void);
 int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* out);
 int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels);
 
+/* the reference's FEM fluid problem (FEM_src/fluid_problem.py) on the same mesh:
+ * Taylor-Hood (vector-P2 velocity on the half-step lattice, P1 pressure on the vertices)
+ * Stokes-Brinkman state equation with velocities prescribed on the whole boundary.  fp64, one GPU.
+ * Vectors: velocity [Ly][Lx][2] like the elasticity displacement; "up" = [velocity | pressure],
+ * 2*Lx*Ly + (nx+1)(ny+1) doubles.  All pointers are device pointers.
+ *   tm_fluid_create       FluidProblem.__init__ / create_solution_space (:50-66,150-153);
+ *                         r_min, r_max: FluidPenalizer (src/penalizers.py:52-55)
+ *   tm_fluid_set_density  set_penalization(q) + the rho-dependent part of a_func (:76-86): weighted
+ *                         mass matrices (FIAT 12-point rule) and the MINRES preconditioner
+ *   tm_fluid_state_solve  forward(rho) = SmartMumpsSolver.solve(a_arg=rho) (:124-125):
+ *                         boundary_velocity holds the Dirichlet values on boundary nodes (zero
+ *                         inside); preconditioned MINRES on the symmetric saddle-point system to
+ *                         rtol on the preconditioned residual; the pressure comes out with an
+ *                         arbitrary constant (the reference's matrix is singular)
+ *   tm_fluid_objective    calculate_objective's assemble(0.5*(r u^2 + mu grad(u)^2)*dx) (:114-122)
+ *   tm_fluid_sens_rhs     right-hand side of df.project(0.5 r'(rho) u^2, V) (:101-112), 16-point
+ *                         rule; the P1 mass solve that finishes the projection is tm_filter_apply
+ *                         (kind 1) of an engine created with filter_radius = 0
+ *   tm_fluid_apply        the operator itself (mode 0) / the lifting of boundary values (mode 1),
+ *                         for the parity tests */
+typedef struct tm_fluid_s* tm_fluid_handle;
+int tm_fluid_create(int nx, int ny, double width, double height, double viscosity, double r_min, double r_max,
+                    int device, tm_fluid_handle* out);
+int tm_fluid_destroy(tm_fluid_handle h);
+int tm_fluid_set_stream(tm_fluid_handle h, void* stream);
+int tm_fluid_set_density(tm_fluid_handle h, const double* rho, double q);
+int tm_fluid_state_solve(tm_fluid_handle h, const double* boundary_velocity, double rtol, int maxit, double* up,
+                         int* iters, double* relres);
+int tm_fluid_objective(tm_fluid_handle h, const double* u, double* out);
+int tm_fluid_sens_rhs(tm_fluid_handle h, const double* rho, const double* u, double* out);
+int tm_fluid_apply(tm_fluid_handle h, const double* x, double* y, int mode);
+
 /* the Q1 strain-energy evaluator of the reference's deep-energy back-end, float32 as
  * there (replaces StrainEnergy.calculate_objective_and_gradient / the internal part of
  * calculate_energy, reference: DEM_src/elasisity_problem.py:82-129 over

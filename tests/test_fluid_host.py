@@ -101,3 +101,30 @@ def test_state_solve_objective_and_sensitivity_match_the_oracle(hc, repo_root, N
     hc.hc_fluid_sens(*args, ptr(rho), ptr(np.ascontiguousarray(pr.u)), ptr(rhs))
     grad_o = pr.calculate_objective_gradient()   # = M1^-1 rhs
     assert np.abs(rhs - pr.M1 @ grad_o).max() < 1e-12 * np.abs(rhs).max()
+
+
+@pytest.mark.parametrize("design,N", [("diffuser", 20), ("pipe_bend", 10), ("twin_pipe", 12)])
+def test_product_boundary_values_and_penalizer_match_the_oracle(repo_root, design, N):
+    """Host logic of topomax_b200/fluid_problem.py (no GPU needed): the Dirichlet values of
+    BoundaryFlows + the two DirichletBC objects, and FluidPenalizer."""
+    from topomax_b200.designs.design_parser import parse_design
+    from topomax_b200.fluid_problem import BoundaryFlows, FluidPenalizer
+    from topomax_b200.mesh import RectangleMesh
+
+    path = os.path.join(repo_root, "designs", f"{design}.json")
+    s = OracleFluidSolver(N, path)
+    dom, prm = parse_design(path)
+    mesh = RectangleMesh(dom.width, dom.height, s.mesh.nx, s.mesh.ny)
+    g = BoundaryFlows((dom.width, dom.height), prm.flows, mesh).nodal_values().reshape(-1)
+    ref = np.zeros(s.mesh.nu)
+    ref[s.problem.bc_dofs] = s.problem.bc_vals
+    assert np.array_equal(g, ref)
+    assert np.abs(ref).max() > 0
+    pen = FluidPenalizer()
+    with pytest.raises(ValueError):
+        pen(0.5)
+    pen.set_penalization(0.1)
+    s.problem.set_penalization(0.1)
+    rho = np.linspace(0, 1, 11)
+    assert np.array_equal(pen(rho), s.problem.r(rho))
+    assert np.array_equal(pen.derivative(rho), s.problem.r_prime(rho))

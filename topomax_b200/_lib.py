@@ -29,6 +29,8 @@ EXPORTED_SYMBOLS = (
     "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate", "tm_sample_field",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
     "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
+    "tm_fluid_create", "tm_fluid_destroy", "tm_fluid_set_stream", "tm_fluid_set_density", "tm_fluid_state_solve",
+    "tm_fluid_objective", "tm_fluid_sens_rhs", "tm_fluid_apply",
 )
 
 
@@ -108,6 +110,14 @@ def load_library() -> ctypes.CDLL:
         "tm_mg_debug": ([V, V, I, I, V, V], I),
         "tm_mg_level_info": ([V, I, POINTER(I), POINTER(I)], I),
         "tm_dem_strain_energy": ([I, I, D, D, D, D, D, D, V, V, V, V, V, POINTER(D), V], I),
+        "tm_fluid_create": ([I, I, D, D, D, D, D, I, POINTER(c_void_p)], I),
+        "tm_fluid_destroy": ([V], I),
+        "tm_fluid_set_stream": ([V, V], I),
+        "tm_fluid_set_density": ([V, V, D], I),
+        "tm_fluid_state_solve": ([V, V, D, I, V, POINTER(I), POINTER(D)], I),
+        "tm_fluid_objective": ([V, V, POINTER(D)], I),
+        "tm_fluid_sens_rhs": ([V, V, V, V], I),
+        "tm_fluid_apply": ([V, V, V, I], I),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

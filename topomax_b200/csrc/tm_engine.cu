@@ -22,6 +22,7 @@
 #include "tm_dem.cuh"
 #include "tm_elast.cuh"
 #include "tm_filter_pcg.cuh"
+#include "tm_fluid_cuda.cuh"
 #include "tm_mg.cuh"
 #include "tm_p1.cuh"
 #include "tm_p1mg.cuh"
@@ -2413,6 +2414,23 @@ int guarded(tm_handle h, F&& f) {
     }
 }  // namespace
 
+// fluid problem: its own small driver object, see tm_fluid_cuda.cuh
+struct tm_fluid_s {
+    std::unique_ptr<tmx::FluidSolver> impl;
+};
+
+template <typename F>
+static int fluid_guarded(tm_fluid_s* h, F&& f) {
+    if (!h || !h->impl) {
+        tmx::set_error("null fluid handle");
+        return TM_ERR_INVALID;
+    }
+    return guarded(nullptr, [&] {
+        TM_CUDA(cudaSetDevice(h->impl->device()));
+        f();
+    });
+}
+
 extern "C" {
 
 const char* tm_last_error(void) { return tmx::last_error(); }
@@ -2571,6 +2589,78 @@ int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* 
 int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { *nlevels = h->impl->mg_level_info(level, info6); });
+}
+
+// ---- fluid problem: see tm_fluid_cuda.cuh
+int tm_fluid_create(int nx, int ny, double width, double height, double viscosity, double r_min, double r_max,
+                    int device, tm_fluid_handle* out) {
+    if (!out) {
+        tmx::set_error("tm_fluid_create: null argument");
+        return TM_ERR_INVALID;
+    }
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw tmx::CudaFailure{std::string("no CUDA device available: ") + cudaGetErrorString(e)};
+        if (device < 0 || device >= ndev) throw tmx::Invalid{"bad device ordinal"};
+        auto* h = new tm_fluid_s;
+        try {
+            h->impl.reset(new tmx::FluidSolver(nx, ny, width, height, viscosity, r_min, r_max, device));
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+int tm_fluid_destroy(tm_fluid_handle h) {
+    delete h;
+    return TM_OK;
+}
+int tm_fluid_set_stream(tm_fluid_handle h, void* stream) {
+    return fluid_guarded(h, [&] { h->impl->set_stream(static_cast<cudaStream_t>(stream)); });
+}
+int tm_fluid_set_density(tm_fluid_handle h, const double* rho, double q) {
+    return fluid_guarded(h, [&] {
+        if (!rho) throw tmx::Invalid{"tm_fluid_set_density: null argument"};
+        h->impl->set_density(rho, q);
+    });
+}
+int tm_fluid_state_solve(tm_fluid_handle h, const double* boundary_velocity, double rtol, int maxit, double* up,
+                         int* iters, double* relres) {
+    int rc_extra = TM_OK;
+    const int rc = fluid_guarded(h, [&] {
+        if (!boundary_velocity || !up) throw tmx::Invalid{"tm_fluid_state_solve: null argument"};
+        const tmx::MinresResult r = h->impl->solve(boundary_velocity, rtol, maxit, up);
+        if (iters) *iters = r.iterations;
+        if (relres) *relres = r.relres;
+        if (!r.converged) {
+            tmx::set_error("tm_fluid_state_solve: MINRES did not reach the tolerance (relative residual " +
+                           std::to_string(r.relres) + " after " + std::to_string(r.iterations) + " iterations)");
+            rc_extra = TM_ERR_NOT_CONVERGED;
+        }
+    });
+    return rc != TM_OK ? rc : rc_extra;
+}
+int tm_fluid_objective(tm_fluid_handle h, const double* u, double* out) {
+    return fluid_guarded(h, [&] {
+        if (!u || !out) throw tmx::Invalid{"tm_fluid_objective: null argument"};
+        *out = h->impl->objective(u);
+    });
+}
+int tm_fluid_sens_rhs(tm_fluid_handle h, const double* rho, const double* u, double* out) {
+    return fluid_guarded(h, [&] {
+        if (!rho || !u || !out) throw tmx::Invalid{"tm_fluid_sens_rhs: null argument"};
+        h->impl->sens_rhs(rho, u, out);
+    });
+}
+int tm_fluid_apply(tm_fluid_handle h, const double* x, double* y, int mode) {
+    return fluid_guarded(h, [&] {
+        if (!x || !y || (mode != 0 && mode != 1)) throw tmx::Invalid{"tm_fluid_apply: bad argument"};
+        h->impl->apply_mode(x, y, mode);
+    });
 }
 
 // Stateless: the evaluator belongs to no mesh hierarchy.  Scratch for the deterministic

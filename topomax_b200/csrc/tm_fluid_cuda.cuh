@@ -1,0 +1,292 @@
+// CUDA back-end of the fluid path: launches around the host/device work items of tm_fluid.cuh and
+// the driver object behind the tm_fluid_* entries of the C ABI.  (First correct version: see the
+// header of tm_fluid.cuh for what is deliberately simple here.)
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tm_common.cuh"
+#include "tm_fluid.cuh"
+#include "tm_vec.cuh"
+
+namespace tmx {
+
+struct FluidAtomicAdd {
+    __host__ __device__ __forceinline__ void operator()(double* p, double v) const {
+#ifdef __CUDA_ARCH__
+        atomicAdd(p, v);
+#else
+        *p += v;
+#endif
+    }
+};
+
+#define TM_FLUID_TRI_LOOP(tid, ntri) \
+    for (size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tid < (ntri); tid += (size_t)gridDim.x * blockDim.x)
+
+__global__ void __launch_bounds__(128) fluid_mass_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                         const double* __restrict__ rho, double* __restrict__ Me,
+                                                         size_t ntri) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_mass(*T, g, rho, Me, ntri, tid);
+}
+
+__global__ void __launch_bounds__(128) fluid_apply_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                          const double* __restrict__ Me, size_t ntri,
+                                                          const double* __restrict__ x, double* y, int mode) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_apply(*T, g, Me, ntri, x, y, tid, mode, FluidAtomicAdd{});
+}
+
+__global__ void __launch_bounds__(128) fluid_diag_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                         const double* __restrict__ Me, size_t ntri, double* diag) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_diag(*T, g, Me, ntri, diag, tid, FluidAtomicAdd{});
+}
+
+__global__ void __launch_bounds__(128) fluid_schur_kernel(const FluidTables* __restrict__ T, FluidGeom g, double* diag,
+                                                          size_t ntri) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_schur(*T, g, diag, tid, FluidAtomicAdd{});
+}
+
+// diag = 1 on boundary velocity nodes, 0 elsewhere (before the scatter kernels)
+__global__ void fluid_diag_init_kernel(FluidGeom g, double* diag, size_t n) {
+    const size_t n2 = (size_t)g.Lx * g.Ly;
+    TM_GRID_STRIDE(k, n) {
+        double v = 0.0;
+        if (k < 2 * n2) {
+            const size_t node = k >> 1;
+            const int j = (int)(node / g.Lx), i = (int)(node - (size_t)j * g.Lx);
+            if (i == 0 || j == 0 || i == g.Lx - 1 || j == g.Ly - 1) v = 1.0;
+        }
+        diag[k] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128) fluid_objective_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                              const double* __restrict__ Me, size_t ntri,
+                                                              const double* __restrict__ u, ReduceScratch rs,
+                                                              double* out) {
+    double val[1] = {0.0};
+    TM_FLUID_TRI_LOOP(tid, ntri) val[0] += fluid_body_objective(*T, g, Me, ntri, u, tid);
+    double* const outs[1] = {out};
+    grid_reduce<1>(val, rs, outs);
+}
+
+__global__ void __launch_bounds__(128) fluid_sens_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                         const double* __restrict__ rho, const double* __restrict__ u,
+                                                         double* out, size_t ntri) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_sens(*T, g, rho, u, out, tid, FluidAtomicAdd{});
+}
+
+// ---- vector kernels of the MINRES loop (combined vector [u | p])
+__global__ void fluid_precond_kernel(size_t n, const double* __restrict__ diag, const double* __restrict__ r,
+                                     double* __restrict__ z) {
+    TM_GRID_STRIDE(i, n) z[i] = r[i] / diag[i];
+}
+__global__ void fluid_scale_kernel(size_t n, double* x, double s) { TM_GRID_STRIDE(i, n) x[i] *= s; }
+__global__ void fluid_axpy2_kernel(size_t n, double* y, double a, const double* __restrict__ p, double b,
+                                   const double* __restrict__ q) {
+    TM_GRID_STRIDE(i, n) y[i] += a * p[i] + b * q[i];
+}
+__global__ void fluid_direction_kernel(size_t n, double* __restrict__ wn, const double* __restrict__ z, double a3,
+                                       const double* __restrict__ wo, double a2, const double* __restrict__ w,
+                                       double inv_a1, double* __restrict__ x, double step) {
+    TM_GRID_STRIDE(i, n) {
+        const double v = (z[i] - a3 * wo[i] - a2 * w[i]) * inv_a1;
+        wn[i] = v;
+        x[i] += step * v;
+    }
+}
+// sum of the continuity part of b (for the projection onto the range)
+__global__ void fluid_sum_kernel(size_t n, const double* __restrict__ v, ReduceScratch rs, double* out) {
+    double val[1] = {0.0};
+    TM_GRID_STRIDE(i, n) val[0] += v[i];
+    double* const outs[1] = {out};
+    grid_reduce<1>(val, rs, outs);
+}
+// b = -(lifted - mean on the continuity rows)
+__global__ void fluid_rhs_kernel(size_t n, size_t nu, double* b, const double* sum, double inv_n1) {
+    const double mean = *sum * inv_n1;
+    TM_GRID_STRIDE(i, n) b[i] = -(b[i] - (i >= nu ? mean : 0.0));
+}
+// up = x + [g | 0]
+__global__ void fluid_finish_kernel(size_t n, size_t nu, const double* __restrict__ x, const double* __restrict__ g,
+                                    double* __restrict__ up) {
+    TM_GRID_STRIDE(i, n) up[i] = x[i] + (i < nu ? g[i] : 0.0);
+}
+
+class FluidSolver {
+   public:
+    struct DVec {
+        double* p = nullptr;
+    };
+    using Vec = DVec;
+
+    FluidSolver(int nx, int ny, double width, double height, double viscosity, double rmin, double rmax, int device)
+        : device_(device) {
+        if (nx < 1 || ny < 1 || !(width > 0) || !(height > 0)) throw std::runtime_error("fluid: bad mesh");
+        g_.nx = nx; g_.ny = ny; g_.Lx = 2 * nx + 1; g_.Ly = 2 * ny + 1;
+        g_.rmin = rmin; g_.rmax = rmax; g_.q = 0.0; g_.viscosity = viscosity;
+        ntri_ = (size_t)2 * nx * ny;
+        nu_ = (size_t)2 * g_.Lx * g_.Ly;
+        n1_ = (size_t)(nx + 1) * (ny + 1);
+        n_ = nu_ + n1_;
+        TM_CUDA(cudaSetDevice(device_));
+        int sms = 148;
+        TM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+        max_blocks_ = sms * 16;
+        const FluidTables T = fluid_make_tables(width / nx, height / ny);
+        TM_CUDA(cudaMalloc(&d_tab_, sizeof(FluidTables)));
+        TM_CUDA(cudaMemcpy(d_tab_, &T, sizeof(FluidTables), cudaMemcpyHostToDevice));
+        alloc(Me_, 21 * ntri_);
+        alloc(diag_, n_);
+        alloc(b_, n_);
+        alloc(x_, n_);
+        alloc(xg_, n_);
+        for (auto& w : work_) alloc(w.p, n_);
+        rs_.capacity = max_blocks_;
+        alloc(rs_.partials, (size_t)2 * rs_.capacity);
+        TM_CUDA(cudaMalloc(&rs_.counter, sizeof(unsigned int)));
+        TM_CUDA(cudaMemset(rs_.counter, 0, sizeof(unsigned int)));
+        alloc(sc_, 8);
+        TM_CUDA(cudaMallocHost(&h_sc_, sizeof(double) * 8));
+        TM_CUDA(cudaStreamCreate(&own_stream_));
+        stream_ = own_stream_;
+    }
+    ~FluidSolver() {
+        cudaSetDevice(device_);
+        cudaStreamSynchronize(stream_);
+        for (double* p : owned_) cudaFree(p);
+        cudaFree(d_tab_);
+        cudaFree(rs_.counter);
+        cudaFreeHost(h_sc_);
+        if (own_stream_) cudaStreamDestroy(own_stream_);
+    }
+    FluidSolver(const FluidSolver&) = delete;
+    FluidSolver& operator=(const FluidSolver&) = delete;
+
+    int device() const { return device_; }
+    void set_stream(cudaStream_t s) { stream_ = s ? s : own_stream_; }
+
+    // weighted mass matrices and the diagonal preconditioner for a density field and penaliser q
+    void set_density(const double* rho, double q) {
+        if (!(q > 0.0)) throw std::runtime_error("fluid: the penalisation q must be > 0");
+        g_.q = q;
+        fluid_mass_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, rho, Me_, ntri_);
+        TM_CHECK_LAUNCH();
+        fluid_diag_init_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(g_, diag_, n_);
+        TM_CHECK_LAUNCH();
+        fluid_diag_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, Me_, ntri_, diag_);
+        TM_CHECK_LAUNCH();
+        fluid_schur_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, diag_, ntri_);
+        TM_CHECK_LAUNCH();
+        have_density_ = true;
+    }
+
+    // up = [u | p]: u = boundary values + MINRES solution of the homogeneous-boundary system
+    MinresResult solve(const double* boundary_velocity, double rtol, int maxit, double* up) {
+        need_density();
+        TM_CUDA(cudaMemsetAsync(xg_, 0, n_ * sizeof(double), stream_));
+        TM_CUDA(cudaMemcpyAsync(xg_, boundary_velocity, nu_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        apply_mode(xg_, b_, 1);
+        fluid_sum_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n1_, b_ + nu_, rs_, sc_);
+        TM_CHECK_LAUNCH();
+        fluid_rhs_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, nu_, b_, sc_, 1.0 / (double)n1_);
+        TM_CHECK_LAUNCH();
+        DVec b{b_}, x{x_};
+        const MinresResult r = fluid_minres(*this, b, x, rtol, maxit);
+        fluid_finish_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, nu_, x_, xg_, up);
+        TM_CHECK_LAUNCH();
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        return r;
+    }
+
+    double objective(const double* u) {
+        need_density();
+        fluid_objective_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, Me_, ntri_, u, rs_, sc_);
+        TM_CHECK_LAUNCH();
+        return read_scalar();
+    }
+
+    void sens_rhs(const double* rho, const double* u, double* out) {
+        if (!(g_.q > 0.0)) throw std::runtime_error("fluid: set the density / penalisation first");
+        TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(double), stream_));
+        fluid_sens_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, rho, u, out, ntri_);
+        TM_CHECK_LAUNCH();
+    }
+
+    // y = Op x (mode 0) or the lifting of boundary values (mode 1); exposed for the parity tests
+    void apply_mode(const double* x, double* y, int mode) {
+        need_density();
+        TM_CUDA(cudaMemsetAsync(y, 0, n_ * sizeof(double), stream_));
+        fluid_apply_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, Me_, ntri_, x, y, mode);
+        TM_CHECK_LAUNCH();
+    }
+    const double* diagonal() const { return diag_; }
+    size_t n() const { return n_; }
+
+    // ---- back-end interface of fluid_minres
+    DVec& work(int i) { return work_[i]; }
+    void zero(DVec& a) { TM_CUDA(cudaMemsetAsync(a.p, 0, n_ * sizeof(double), stream_)); }
+    void copy(const DVec& a, DVec& b) {
+        TM_CUDA(cudaMemcpyAsync(b.p, a.p, n_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    }
+    void scale(DVec& a, double s) {
+        fluid_scale_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, a.p, s);
+        TM_CHECK_LAUNCH();
+    }
+    void apply(const DVec& x, DVec& y) { apply_mode(x.p, y.p, 0); }
+    void precond(const DVec& r, DVec& z) {
+        fluid_precond_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, diag_, r.p, z.p);
+        TM_CHECK_LAUNCH();
+    }
+    double dot(const DVec& a, const DVec& b) {
+        dot_kernel<double><<<vec_grid(), kVecThreads, 0, stream_>>>(n_, a.p, b.p, rs_, sc_);
+        TM_CHECK_LAUNCH();
+        return read_scalar();
+    }
+    void axpy2(DVec& y, double a, const DVec& p, double b, const DVec& q) {
+        fluid_axpy2_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, y.p, a, p.p, b, q.p);
+        TM_CHECK_LAUNCH();
+    }
+    void direction(DVec& wn, const DVec& z, double a3, const DVec& wo, double a2, const DVec& w, double inv_a1,
+                   DVec& x, double step) {
+        fluid_direction_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, wn.p, z.p, a3, wo.p, a2, w.p, inv_a1,
+                                                                       x.p, step);
+        TM_CHECK_LAUNCH();
+    }
+
+   private:
+    void alloc(double*& p, size_t count) {
+        TM_CUDA(cudaMalloc(&p, count * sizeof(double)));
+        TM_CUDA(cudaMemset(p, 0, count * sizeof(double)));
+        owned_.push_back(p);
+    }
+    void need_density() const {
+        if (!have_density_) throw std::runtime_error("fluid: tm_fluid_set_density must be called first");
+    }
+    int tri_grid() const { return (int)std::min<size_t>((ntri_ + 127) / 128, (size_t)max_blocks_); }
+    int vec_grid() const { return (int)std::min<size_t>((n_ + kVecThreads - 1) / kVecThreads, (size_t)max_blocks_); }
+    double read_scalar() {
+        TM_CUDA(cudaMemcpyAsync(h_sc_, sc_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        return h_sc_[0];
+    }
+
+    int device_, max_blocks_ = 148 * 16;
+    FluidGeom g_;
+    size_t ntri_, nu_, n1_, n_;
+    FluidTables* d_tab_ = nullptr;
+    double *Me_ = nullptr, *diag_ = nullptr, *b_ = nullptr, *x_ = nullptr, *xg_ = nullptr, *sc_ = nullptr;
+    double* h_sc_ = nullptr;
+    DVec work_[8];
+    ReduceScratch rs_{};
+    std::vector<double*> owned_;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    bool have_density_ = false;
+};
+
+}  // namespace tmx

@@ -131,8 +131,13 @@ class FEMSolver(Solver):
             return ElasticityProblem(self.mesh, self.control_space, self.parameters,
                                      problem_parameters, engine=self._engine, **self.problem_options)
         if isinstance(problem_parameters, FluidParameters):
-            raise NotImplementedError(
-                "the fluid problem is outside the accelerated path (SURVEY.md section 8f)")
+            if self.world > 1:
+                raise NotImplementedError("the fluid problem runs on one GPU (SURVEY.md section 8f-3)")
+            from .fluid_problem import FluidProblem
+            options = {k: v for k, v in self.problem_options.items()
+                       if k in ("state_rtol", "state_max_iterations", "projection_rtol")}
+            return FluidProblem(self.mesh, problem_parameters, self.parameters,
+                                control_space=self.control_space, **options)
         raise ValueError(
             f"Got unknown problem '{self.parameters.problem}' "
             f"with problem parameters of type '{type(problem_parameters)}'"
