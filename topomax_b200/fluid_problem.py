@@ -119,12 +119,18 @@ class FluidProblem(Problem):
         self.state_rtol, self.state_max_iterations = state_rtol, state_max_iterations
         self.projection_rtol = projection_rtol
 
+        if device is None and control_space is not None:
+            device = control_space.device
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("FluidProblem needs a CUDA device: topomax_b200 has no CPU fallback")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
         if control_space is None:
-            control_space = FunctionSpace(mesh, "CG", 1, dtype="float64", device=device)
+            control_space = FunctionSpace(mesh, "CG", 1, dtype="float64", device=self.device)
         if control_space.dtype_name != "float64":
             raise ValueError("the fluid path computes in float64")
         self.control_space = control_space
-        self.device = control_space.device
         self.lib = _lib.load_library()
         # P1 services (mass solve of the L2 projection, integrals, the mirror-descent kernels) come
         # from the elasticity engine on the same mesh; its material constants are not used here
