@@ -179,6 +179,13 @@ long long tm_launch_count(void);
 int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* out);
 int tm_mg_level_info(tm_handle h, int level, int* info6, int* nlevels);
 
+/* Loop-back check of the peer-memory kernels on ONE GPU: `nranks` streams of this process play the
+ * ranks (windows = plain allocations of the current device), run `epochs` halo exchanges of
+ * 4 rows up / 3 rows down of `row_elems` doubles without host synchronisation, plus a 2-value
+ * all-reduce every `reduce_every` epochs.  report4 = {data mismatches, ranks with a timed-out poll,
+ * final halo epoch, final reduction epoch}. */
+int tm_p2p_selftest(int nranks, int epochs, int row_elems, int reduce_every, double* report4);
+
 /* the reference's FEM fluid problem (FEM_src/fluid_problem.py) on the same mesh:
  * Taylor-Hood (vector-P2 velocity on the half-step lattice, P1 pressure on the vertices)
  * Stokes-Brinkman state equation with velocities prescribed on the whole boundary.  fp64, one GPU.

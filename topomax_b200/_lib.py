@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
     "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
     "tm_fluid_create", "tm_fluid_destroy", "tm_fluid_set_stream", "tm_fluid_set_density", "tm_fluid_state_solve",
-    "tm_fluid_objective", "tm_fluid_sens_rhs", "tm_fluid_apply",
+    "tm_fluid_objective", "tm_fluid_sens_rhs", "tm_fluid_apply", "tm_p2p_selftest",
 )
 
 
@@ -118,6 +118,7 @@ def load_library() -> ctypes.CDLL:
         "tm_fluid_objective": ([V, V, POINTER(D)], I),
         "tm_fluid_sens_rhs": ([V, V, V, V], I),
         "tm_fluid_apply": ([V, V, V, I], I),
+        "tm_p2p_selftest": ([I, I, I, I, POINTER(D)], I),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

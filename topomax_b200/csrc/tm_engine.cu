@@ -2414,6 +2414,158 @@ int guarded(tm_handle h, F&& f) {
     }
 }  // namespace
 
+
+// ---- single-GPU loop-back check of the peer-memory kernels (tm_p2p.cuh): R "ranks" are R streams
+// of this process whose windows are plain allocations of the same device, so the hand-shake, the
+// epoch bookkeeping and the memory-ordering idioms run on real hardware without a second GPU.
+// The ranks run asynchronously (no host synchronisation between epochs).
+namespace tmx {
+
+// integer-valued, so that fill and check agree whatever the compiler contracts
+__device__ __forceinline__ double p2p_selftest_value(int rank, int epoch, size_t i) {
+    return (double)((long long)rank * 1000003LL + (long long)epoch * 7919LL + (long long)(i % 4099));
+}
+__global__ void p2p_selftest_fill_kernel(double* v, size_t own0_elems, size_t own_elems, int rank, int epoch) {
+    TM_GRID_STRIDE(i, own_elems) v[own0_elems + i] = p2p_selftest_value(rank, epoch, i);
+}
+__global__ void p2p_selftest_check_kernel(const double* v, size_t row_elems, int own_rows, int up, int down, int rank,
+                                          int nranks, int epoch, unsigned int* errors) {
+    const size_t own_elems = (size_t)own_rows * row_elems;
+    // rows from below: the neighbour's last `up` owned rows
+    if (rank > 0) {
+        const size_t n = (size_t)up * row_elems, src0 = own_elems - n;
+        TM_GRID_STRIDE(i, n) {
+            if (v[i] != p2p_selftest_value(rank - 1, epoch, src0 + i)) atomicAdd(errors, 1u);
+        }
+    }
+    if (rank + 1 < nranks) {
+        const size_t n = (size_t)down * row_elems, dst0 = (size_t)(up + own_rows) * row_elems;
+        TM_GRID_STRIDE(i, n) {
+            if (v[dst0 + i] != p2p_selftest_value(rank + 1, epoch, i)) atomicAdd(errors, 1u);
+        }
+    }
+}
+__global__ void p2p_selftest_red_fill_kernel(double* p, int rank, int epoch) {
+    p[0] = (rank + 1) * (double)epoch;
+    p[1] = 0.5 * rank - epoch;
+}
+__global__ void p2p_selftest_red_check_kernel(const double* p, int nranks, int epoch, unsigned int* errors) {
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < nranks; ++q) {
+        a += (q + 1) * (double)epoch;
+        b += 0.5 * q - epoch;
+    }
+    if (p[0] != a || p[1] != b) atomicAdd(errors, 1u);
+}
+
+// report: [0] data mismatches, [1] timed-out polls (header.error != 0 on any rank), [2] final halo
+// epoch of rank 0, [3] final reduction epoch of rank 0
+static void p2p_selftest(int R, int epochs, int row_elems, int reduce_every, double* report) {
+    if (R < 2 || R > 8 || epochs < 1 || row_elems < 1) throw Invalid{"tm_p2p_selftest: bad arguments"};
+    const int up = 4, down = 3, own_rows = 10;
+    const size_t rb = (size_t)row_elems * sizeof(double);
+    const size_t slot = (((size_t)up * rb) + 255) & ~(size_t)255;
+    const size_t wbytes = P2P_HEADER_BYTES + 4 * slot;
+    const size_t vcount = (size_t)(up + own_rows + down) * row_elems;
+    std::vector<char*> win(R, nullptr);
+    std::vector<double*> v(R, nullptr), red(R, nullptr);
+    std::vector<cudaStream_t> st(R, nullptr);
+    unsigned int* d_err = nullptr;
+    auto cleanup = [&] {
+        for (int r = 0; r < R; ++r) {
+            if (st[r]) cudaStreamDestroy(st[r]);
+            cudaFree(win[r]);
+            cudaFree(v[r]);
+            cudaFree(red[r]);
+        }
+        cudaFree(d_err);
+    };
+    try {
+        TM_CUDA(cudaMalloc(&d_err, sizeof(unsigned int)));
+        TM_CUDA(cudaMemset(d_err, 0, sizeof(unsigned int)));
+        for (int r = 0; r < R; ++r) {
+            TM_CUDA(cudaMalloc(&win[r], wbytes));
+            TM_CUDA(cudaMemset(win[r], 0, wbytes));
+            TM_CUDA(cudaMalloc(&v[r], vcount * sizeof(double)));
+            TM_CUDA(cudaMemset(v[r], 0, vcount * sizeof(double)));
+            TM_CUDA(cudaMalloc(&red[r], 2 * sizeof(double)));
+            TM_CUDA(cudaStreamCreateWithFlags(&st[r], cudaStreamNonBlocking));
+        }
+        // load every kernel now: lazily loading one while another stream's kernel polls for a kernel
+        // this thread has yet to launch would stall the launch (single process, single context)
+        cudaFuncAttributes fa;
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_selftest_fill_kernel));
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_selftest_check_kernel));
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_selftest_red_fill_kernel));
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_selftest_red_check_kernel));
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_halo_kernel<uint4>));
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_halo_kernel<uint2>));
+        TM_CUDA(cudaFuncGetAttributes(&fa, p2p_allreduce_kernel));
+        TM_CUDA(cudaDeviceSynchronize());
+        const size_t own_elems = (size_t)own_rows * row_elems;
+        for (int e = 1; e <= epochs; ++e) {
+            // epoch-major launch order: every kernel a poll can wait for is already enqueued
+            for (int r = 0; r < R; ++r) {
+                p2p_selftest_fill_kernel<<<4, 256, 0, st[r]>>>(v[r], (size_t)up * row_elems, own_elems, r, e);
+                TM_CHECK_LAUNCH();
+                P2PHaloArgs a;
+                a.self = win[r];
+                a.below = r > 0 ? win[r - 1] : nullptr;
+                a.above = r + 1 < R ? win[r + 1] : nullptr;
+                a.slot_bytes = slot;
+                a.v = reinterpret_cast<char*>(v[r]);
+                a.up_src = (size_t)(up + own_rows - up) * rb;
+                a.up_bytes = (size_t)up * rb;
+                a.down_src = (size_t)up * rb;
+                a.down_bytes = (size_t)down * rb;
+                a.from_below_dst = 0;
+                a.from_above_dst = (size_t)(up + own_rows) * rb;
+                const int blocks = 1 + (e % 3);  // exercises the last-block bookkeeping
+                if (rb % 16 == 0) p2p_halo_kernel<uint4><<<blocks, 256, 0, st[r]>>>(a);
+                else p2p_halo_kernel<uint2><<<blocks, 256, 0, st[r]>>>(a);
+                TM_CHECK_LAUNCH();
+                p2p_selftest_check_kernel<<<4, 256, 0, st[r]>>>(v[r], (size_t)row_elems, own_rows, up, down, r, R, e,
+                                                               d_err);
+                TM_CHECK_LAUNCH();
+                if (reduce_every > 0 && e % reduce_every == 0) {
+                    p2p_selftest_red_fill_kernel<<<1, 1, 0, st[r]>>>(red[r], r, e);
+                    TM_CHECK_LAUNCH();
+                    P2PReduceArgs ra;
+                    for (int q = 0; q < P2P_MAX_RANKS; ++q) ra.win[q] = q < R ? win[q] : nullptr;
+                    ra.rank = r;
+                    ra.nranks = R;
+                    ra.p = red[r];
+                    ra.n = 2;
+                    p2p_allreduce_kernel<<<1, 64, 0, st[r]>>>(ra);
+                    TM_CHECK_LAUNCH();
+                    p2p_selftest_red_check_kernel<<<1, 1, 0, st[r]>>>(red[r], R, e, d_err);
+                    TM_CHECK_LAUNCH();
+                }
+            }
+        }
+        for (int r = 0; r < R; ++r) TM_CUDA(cudaStreamSynchronize(st[r]));
+        unsigned int err = 0, timeouts = 0;
+        TM_CUDA(cudaMemcpy(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost));
+        P2PHeader h0;
+        for (int r = 0; r < R; ++r) {
+            P2PHeader h;
+            TM_CUDA(cudaMemcpy(&h, win[r], sizeof(h), cudaMemcpyDeviceToHost));
+            if (h.error) ++timeouts;
+            if (r == 0) h0 = h;
+        }
+        report[0] = err;
+        report[1] = timeouts;
+        report[2] = (double)h0.halo_epoch;
+        report[3] = (double)h0.red_epoch;
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+}  // namespace tmx
+
 // fluid problem: its own small driver object, see tm_fluid_cuda.cuh
 struct tm_fluid_s {
     std::unique_ptr<tmx::FluidSolver> impl;
@@ -2660,6 +2812,13 @@ int tm_fluid_apply(tm_fluid_handle h, const double* x, double* y, int mode) {
     return fluid_guarded(h, [&] {
         if (!x || !y || (mode != 0 && mode != 1)) throw tmx::Invalid{"tm_fluid_apply: bad argument"};
         h->impl->apply_mode(x, y, mode);
+    });
+}
+
+int tm_p2p_selftest(int nranks, int epochs, int row_elems, int reduce_every, double* report4) {
+    return guarded(nullptr, [&] {
+        if (!report4) throw tmx::Invalid{"tm_p2p_selftest: null argument"};
+        tmx::p2p_selftest(nranks, epochs, row_elems, reduce_every, report4);
     });
 }
 

@@ -62,8 +62,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// polls a flag of my own window until a peer has raised it to `epoch`
-__device__ __forceinline__ bool p2p_wait(const unsigned long long* flag, unsigned long long epoch) {
+// polls a flag of my own window until a peer has raised it to `epoch`; once a poll has timed out
+// (`*error` set) later polls give up at once, so a broken run drains in seconds, not hours
+__device__ __forceinline__ bool p2p_wait(const unsigned long long* flag, unsigned long long epoch,
+                                         const unsigned int* error) {
+    if (*reinterpret_cast<const volatile unsigned int*>(error) != 0u) return false;
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < epoch) {
         if (clock64() - t0 > P2P_SPIN_LIMIT) return false;
@@ -126,8 +129,8 @@ __global__ void __launch_bounds__(256) p2p_halo_kernel(P2PHaloArgs a) {
     __syncthreads();
     if (threadIdx.x == 0) {
         bool ok = true;
-        if (a.below) ok = p2p_wait(&me->halo_flag[0][par], epoch) && ok;
-        if (a.above) ok = p2p_wait(&me->halo_flag[1][par], epoch) && ok;
+        if (a.below) ok = p2p_wait(&me->halo_flag[0][par], epoch, &me->error) && ok;
+        if (a.above) ok = p2p_wait(&me->halo_flag[1][par], epoch, &me->error) && ok;
         if (!ok) me->error = 1u;
         s_flag = ok;
     }
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(64) p2p_allreduce_kernel(P2PReduceArgs a) {
     __syncthreads();
     if (t < a.nranks && t != a.rank) {
         st_release_sys(&reinterpret_cast<P2PHeader*>(a.win[t])->red_flag[a.rank][par], epoch);
-        if (!p2p_wait(&me->red_flag[t][par], epoch)) {
+        if (!p2p_wait(&me->red_flag[t][par], epoch, &me->error)) {
             me->error = 2u;
             s_ok = 0;
         }
