@@ -111,3 +111,24 @@ def test_gradient_is_the_derivative_of_the_objective(repo_root):
     # fixed boundary values the total derivative equals it (energy minimisation): check to FD accuracy
     # (measured 1.5e-6; the projection's degree-7 rule differs from the objective's degree-6 rule)
     assert abs(fd - d @ (pr.M1 @ g)) < 1e-4 * abs(fd)
+
+
+def test_reference_fluid_gradient_test_on_the_oracle(repo_root):
+    """reference tests/test_fluid_gradient.py:7-40, restated: twin_pipe N=10, q=0.1, constant
+    direction volume/volume_fraction; one-sided differences at t = 1e-3 and 1e-7 against
+    assemble(1/2 r'(rho) d |u|^2 dx); `degree >= 4` in the un-converted coefficient of
+    numpy's Polynomial.fit (scaled domain: a slope of 0.87 in log-log terms)."""
+    s = OracleFluidSolver(10, os.path.join(repo_root, "designs", "twin_pipe.json"))
+    pr = s.problem
+    pr.set_penalization(0.1)
+    rho = s.rho.copy()
+    objective = pr.calculate_objective(rho)
+    direction = s.volume / s.design["volume_fraction"]
+    # sum_i int f lambda_i = int f: the assembled scalar is the sum of the projection's right-hand side
+    gradient = direction * float(np.sum(pr.M1 @ pr.calculate_objective_gradient()))
+    ts, errors = [1e-3, 1e-7], []
+    for t in ts:
+        moved = pr.calculate_objective(rho + t * direction)
+        errors.append(abs((moved - objective) / t - gradient))
+    poly = np.polynomial.Polynomial.fit(np.log(ts), np.log(errors), 1)
+    assert poly.coef[1] >= 4, (errors, poly.coef)
