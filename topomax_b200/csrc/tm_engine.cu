@@ -78,9 +78,15 @@ struct P2PState {
     char* win[P2P_MAX_RANKS] = {};
     size_t slot_bytes = 0;
     int rank = 0, nranks = 1;
-    ~P2PState() {
+    void close_peers() {
         for (int q = 0; q < nranks; ++q)
-            if (q != rank && win[q]) cudaIpcCloseMemHandle(win[q]);
+            if (q != rank && win[q]) {
+                cudaIpcCloseMemHandle(win[q]);
+                win[q] = nullptr;
+            }
+    }
+    ~P2PState() {
+        close_peers();
         if (win[rank]) cudaFree(win[rank]);
     }
 };
@@ -183,7 +189,7 @@ class Engine : public EngineBase {
         graph_exec_ = nullptr;
         fgraph_exec_ = nullptr;
         inner_.reset();
-        p2p_.reset();
+        p2p_release();
         if (comm_ && owns_comm_) nccl().CommDestroy(comm_);
         cudaFree(rs_.partials);
         cudaFree(rs_.counter);
@@ -239,7 +245,7 @@ class Engine : public EngineBase {
             case TM_OPT_P2P:  // collective: every rank must set it alike
                 p2p_want_ = value != 0.0;
                 graph_dirty_ = true;
-                if (!p2p_want_) p2p_.reset();
+                if (!p2p_want_) p2p_release();
                 else if (comm_ && !p2p_) p2p_setup();
                 break;
             case 124: filter_tb_steps_ = std::max(1, (int)value); filter_tb_state_ = 0; break;
@@ -332,6 +338,22 @@ class Engine : public EngineBase {
         graph_dirty_ = true;
     }
     bool p2p_active() const { return static_cast<bool>(p2p_); }
+    // Collective (the owner of the communicator only): every rank unmaps its peers' windows, all
+    // ranks meet, and only then is the own window freed -- an exported allocation must outlive its
+    // importers' mappings.
+    void p2p_release() {
+        if (!p2p_) return;
+        if (owns_comm_ && comm_) {
+            if (inner_) inner_->p2p_.reset();
+            cudaStreamSynchronize(stream_);
+            p2p_->close_peers();
+            double* flag = sc_ + SC_TMP;
+            if (nccl().AllReduce(flag, flag, 1, kNcclFloat64, kNcclSum, comm_, stream_) == 0)
+                cudaStreamSynchronize(stream_);
+        }
+        p2p_.reset();
+        graph_dirty_ = true;
+    }
 
     void layout(int* out, int n) override {
         const RowRange& r = ranges_[0];
