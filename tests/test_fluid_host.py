@@ -128,3 +128,34 @@ def test_product_boundary_values_and_penalizer_match_the_oracle(repo_root, desig
     rho = np.linspace(0, 1, 11)
     assert np.array_equal(pen(rho), s.problem.r(rho))
     assert np.array_equal(pen.derivative(rho), s.problem.r_prime(rho))
+
+
+def test_marker_boundary_values_equal_the_plain_on_boundary_condition():
+    """reference tests/test_marker.py:56-93 in our terms: with flows on Left/Right that vanish at
+    the corners, the two marker-based DirichletBC objects (profile on the flow sides, then no-slip on
+    the others) prescribe the same nodal values as one "on_boundary" condition carrying the
+    BoundaryFlows expression -- so the two solves of that test coincide."""
+    from topomax_b200.designs.definitions import Flow, Side
+    from topomax_b200.fluid_problem import BoundaryFlows
+    from topomax_b200.mesh import RectangleMesh
+
+    domain_size = (1.5, 1.0)
+    mesh = RectangleMesh(domain_size[0], domain_size[1], 30, 20)
+    flows = [Flow(Side.LEFT, 0.25, 1 / 6, 1), Flow(Side.LEFT, 0.75, 1 / 6, 1),
+             Flow(Side.RIGHT, 0.25, 1 / 6, -1), Flow(Side.RIGHT, 0.75, 1 / 6, -1)]
+    bf = BoundaryFlows(domain_size, flows, mesh)
+    marker = bf.nodal_values()
+    # "on_boundary": evaluate the expression (FEM_src/fluid_problem.py:26-42) at every boundary node
+    X, Y = bf.lattice_coordinates()
+    W, H = domain_size
+    ux = np.zeros_like(X)
+    for flow in flows:
+        side, center, length, rate = flow.to_tuple()
+        sign, where = (1.0, X == 0.0) if side == Side.LEFT else (-1.0, X == W)
+        ux += sign * np.where(where, bf.get_flow(Y, center, length, rate), 0.0)
+    on_boundary = (X == 0.0) | (X == W) | (Y == 0) | (Y == H)
+    simple = np.stack([np.where(on_boundary, ux, 0.0), np.zeros_like(X)], axis=-1)
+    assert np.array_equal(marker, simple)
+    assert np.abs(marker).max() == 1.0 or np.abs(marker).max() > 0.9
+    # discrete flux balance of this design: inflow and outflow profiles are mirror images
+    assert abs(marker[:, 0, 0].sum() - marker[:, -1, 0].sum()) < 1e-14
