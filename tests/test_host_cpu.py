@@ -197,3 +197,18 @@ def test_output_tree_round_trip(tmp_path):
     assert results == [(20, "3.0", res)]
     assert data_list == [(20, "3.0", 4, it)]
     assert type(data_list[0][3]).__module__ == "src.utils"
+
+
+def test_weak_scaling_resolution_keeps_equal_strips(repo_root):
+    """bench.py --gpus N: ~N x the cells of the N=512 workload, elements per unit length a multiple
+    of the GPU count (equal strips of cell rows); the 1-GPU workload is the named config itself."""
+    import bench
+
+    design = os.path.join(repo_root, "designs", "short_cantilever.json")
+    base = bench.mesh_of(design, 512)
+    assert base == (1020, 510)
+    for world, mesh in ((2, (1440, 720)), (4, (2040, 1020)), (8, (2880, 1440))):
+        n = bench.weak_scaling_n(design, 512, world)
+        got = bench.mesh_of(design, n)
+        assert got == mesh and got[1] % world == 0
+        assert abs(got[0] * got[1] / (base[0] * base[1]) / world - 1) < 0.01
