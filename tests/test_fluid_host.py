@@ -159,3 +159,132 @@ def test_marker_boundary_values_equal_the_plain_on_boundary_condition():
     assert np.abs(marker).max() == 1.0 or np.abs(marker).max() > 0.9
     # discrete flux balance of this design: inflow and outflow profiles are mirror images
     assert abs(marker[:, 0, 0].sum() - marker[:, -1, 0].sum()) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# multigrid on per-triangle local matrices (csrc/tm_trimg.cuh): Galerkin checks against scipy
+# ---------------------------------------------------------------------------------------------
+def _p2_prolongation(mc, mf):
+    """scalar P2 prolongation by evaluating every coarse basis function at the fine nodes"""
+    from oracle.fem_oracle import evaluate_field
+
+    X, Y = np.meshgrid(mf.xl, mf.yl, indexing="xy")
+    P = sp.lil_matrix((mf.n2, mc.n2))
+    for j in range(mc.n2):
+        vals = np.zeros(mc.nu)
+        vals[2 * j] = 1.0
+        col = np.asarray(evaluate_field(mc, vals, 2, X.ravel(), Y.ravel()))
+        col = col[:, 0] if col.ndim == 2 else col[0::2]
+        nz = np.flatnonzero(np.abs(col) > 1e-14)
+        P[nz, j] = col[nz]
+    return P.tocsr()
+
+
+def _p1_prolongation(mc, mf):
+    from oracle.fem_oracle import evaluate_field
+
+    X, Y = np.meshgrid(mf.xv, mf.yv, indexing="xy")
+    P = sp.lil_matrix((mf.n1, mc.n1))
+    for j in range(mc.n1):
+        vals = np.zeros(mc.n1)
+        vals[j] = 1.0
+        col = np.asarray(evaluate_field(mc, vals, 1, X.ravel(), Y.ravel())).ravel()
+        nz = np.flatnonzero(np.abs(col) > 1e-14)
+        P[nz, j] = col[nz]
+    return P.tocsr()
+
+
+def _boundary_mask(m):
+    I, J = np.meshgrid(np.arange(m.Lx), np.arange(m.Ly), indexing="xy")
+    return ((I == 0) | (I == m.Lx - 1) | (J == 0) | (J == m.Ly - 1)).ravel()
+
+
+@pytest.fixture(scope="module")
+def hc_mg(hc):
+    common = [I, I, D, D, D, D, D, D]
+    hc.hc_trimg_level_apply.argtypes = common + [P, I, I, P, P]
+    hc.hc_trimg_level_apply.restype = I
+    hc.hc_trimg_prolong.argtypes = [I, I, I, P, P]
+    hc.hc_trimg_restrict.argtypes = [I, I, I, P, P]
+    hc.hc_fluid_solve_mg.argtypes = common + [P, P, D, I, P, P]
+    hc.hc_fluid_solve_mg.restype = I
+    return hc
+
+
+def test_multigrid_transfers_and_galerkin_operators(hc_mg, repo_root):
+    from oracle.fem_oracle import StructuredMesh
+
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, 8, "diffuser", seed=5)
+    mc = StructuredMesh(m.W, m.H, m.nx // 2, m.ny // 2)
+    mcc = StructuredMesh(m.W, m.H, m.nx // 4, m.ny // 4)
+    rng = np.random.default_rng(2)
+    # ---- velocity hierarchy: scalar operator M_r + K on both components, Dirichlet boundary
+    P2 = _p2_prolongation(mc, m)
+    bf, bc = _boundary_mask(m), _boundary_mask(mc)
+    P2m = sp.diags((~bf).astype(float)) @ P2 @ sp.diags((~bc).astype(float))
+    xc = rng.standard_normal(2 * mc.n2)
+    xf = np.zeros(2 * m.n2)
+    hc_mg.hc_trimg_prolong(0, m.nx, m.ny, ptr(xc), ptr(xf))
+    ref = np.stack([P2m @ xc[0::2], P2m @ xc[1::2]], 1).ravel()
+    assert np.abs(xf - ref).max() < 1e-13
+    rf = rng.standard_normal(2 * m.n2)
+    rc = np.zeros(2 * mc.n2)
+    hc_mg.hc_trimg_restrict(0, m.nx, m.ny, ptr(rf), ptr(rc))
+    ref = np.stack([P2m.T @ rf[0::2], P2m.T @ rf[1::2]], 1).ravel()
+    assert np.abs(rc - ref).max() < 1e-13
+    full = (pr.A0 + pr._brinkman(rho)).tocsr()
+    As = full[: m.nu, : m.nu][0::2][:, 0::2]                       # the scalar operator on the lattice
+    A0 = sp.diags((~bf).astype(float)) @ As @ sp.diags((~bf).astype(float))
+    A1 = (P2m.T @ A0 @ P2m).tocsr()
+    P2cc = _p2_prolongation(mcc, mc)
+    bcc = _boundary_mask(mcc)
+    P2ccm = sp.diags((~bc).astype(float)) @ P2cc @ sp.diags((~bcc).astype(float))
+    A2 = (P2ccm.T @ A1 @ P2ccm).tocsr()
+    for level, (A, mesh) in enumerate(((A0, m), (A1, mc), (A2, mcc))):
+        x = rng.standard_normal(2 * mesh.n2)
+        y = np.zeros_like(x)
+        nl = hc_mg.hc_trimg_level_apply(*args, ptr(rho), 0, level, ptr(x), ptr(y))
+        assert nl == 4                                              # 8 -> 4 -> 2 -> 1 cells per side
+        ref = np.stack([A @ x[0::2], A @ x[1::2]], 1).ravel()
+        assert np.abs(y - ref).max() < 1e-11 * np.abs(ref).max(), level
+    # ---- pressure hierarchy: P1 Darcy Laplacian int (1/r) grad.grad (+ 1e-8 relative on the diagonal)
+    P1 = _p1_prolongation(mc, m)
+    xc = rng.standard_normal(mc.n1)
+    xf = np.zeros(m.n1)
+    hc_mg.hc_trimg_prolong(1, m.nx, m.ny, ptr(xc), ptr(xf))
+    assert np.abs(xf - P1 @ xc).max() < 1e-13
+    rows, cols, vals = [], [], []
+    for t in ("A", "B"):
+        area, gl = m.geom[t]
+        conn = m.tri_v[t]
+        w = (1.0 / pr.r(rho[conn])).mean(axis=1) * area
+        Ke = gl @ gl.T
+        loc = w[:, None, None] * Ke[None]
+        loc = loc + 1e-8 * np.trace(loc, axis1=1, axis2=2)[:, None, None] / 3.0 * np.eye(3)[None]
+        rows.append(np.repeat(conn, 3, axis=1).ravel())
+        cols.append(np.tile(conn, (1, 3)).ravel())
+        vals.append(loc.reshape(len(conn), 9).ravel())
+    L0 = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(m.n1, m.n1))
+    L1 = (P1.T @ L0 @ P1).tocsr()
+    for level, (A, n) in enumerate(((L0, m.n1), (L1, mc.n1))):
+        x = rng.standard_normal(n)
+        y = np.zeros(n)
+        hc_mg.hc_trimg_level_apply(*args, ptr(rho), 1, level, ptr(x), ptr(y))
+        assert np.abs(y - A @ x).max() < 1e-11 * np.abs(A @ x).max(), level
+
+
+def test_multigrid_preconditioned_solve_matches_oracle_with_few_iterations(hc_mg, repo_root):
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, 16, "diffuser", seed=9)
+    up = np.zeros(m.nu + m.n1)
+    relres = D(0.0)
+    rho_u = np.full(m.n1, 0.5)
+    its_mg = hc_mg.hc_fluid_solve_mg(*args, ptr(rho_u), ptr(g), 1e-10, 2000, ptr(up), ctypes.byref(relres))
+    its_diag = hc_mg.hc_fluid_solve(*args, ptr(rho_u), ptr(g), 1e-10, 20000, ptr(up.copy()), ctypes.byref(relres))
+    assert 0 < its_mg < 100 and its_diag > 2 * its_mg, (its_mg, its_diag)   # numpy prototype: 64 vs ~200
+    pr.calculate_objective(rho_u)
+    assert np.abs(up[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+    # a rough random density
+    its = hc_mg.hc_fluid_solve_mg(*args, ptr(rho), ptr(g), 1e-11, 5000, ptr(up), ctypes.byref(relres))
+    assert its > 0, (its, relres.value)
+    pr.calculate_objective(rho)
+    assert np.abs(up[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()

@@ -347,6 +347,37 @@ TM_HD void fluid_body_schur(const FluidTables& T, const FluidGeom& g, double* di
     }
 }
 
+// local 3x3 matrix of the P1 "Darcy" Laplacian int (1/r) grad lambda_a . grad lambda_b (the pressure
+// Schur complement where the Brinkman term dominates), 1/r averaged over the vertices, plus a
+// relative 1e-8 on the diagonal so that the pure-Neumann operator is definite.  L_all is [6][ntri].
+TM_HD void fluid_body_darcy(const FluidTables& T, const FluidGeom& g, const double* rho, double* L_all,
+                            size_t ntri, size_t tid) {
+    int cx, cy, t, node[6], vert[3];
+    bool interior[6];
+    fluid_tid_to_cell(g, tid, cx, cy, t);
+    fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+    const double w = T.area * (1.0 / fluid_r(g, rho[vert[0]]) + 1.0 / fluid_r(g, rho[vert[1]]) +
+                               1.0 / fluid_r(g, rho[vert[2]])) / 3.0;
+    double L[3][3], tr = 0.0;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            L[a][b] = w * (T.grad_lam[t][a][0] * T.grad_lam[t][b][0] + T.grad_lam[t][a][1] * T.grad_lam[t][b][1]);
+    for (int a = 0; a < 3; ++a) tr += L[a][a];
+    int k = 0;
+    for (int a = 0; a < 3; ++a)
+        for (int b = a; b < 3; ++b, ++k) L_all[(size_t)k * ntri + tid] = L[a][b] + (a == b ? 1e-8 * tr / 3.0 : 0.0);
+}
+
+// diagonal of the P1 mass matrix: |T|/6 per triangle and vertex
+template <class Add>
+TM_HD void fluid_body_pmass_diag(const FluidTables& T, const FluidGeom& g, double* diag, size_t tid, Add add) {
+    int cx, cy, t, node[6], vert[3];
+    bool interior[6];
+    fluid_tid_to_cell(g, tid, cx, cy, t);
+    fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+    for (int c = 0; c < 3; ++c) add(&diag[vert[c]], T.area / 6.0);
+}
+
 TM_HD double fluid_body_objective(const FluidTables& T, const FluidGeom& g, const double* Me_all, size_t ntri,
                                   const double* u, size_t tid) {
     int cx, cy, t, node[6], vert[3];
