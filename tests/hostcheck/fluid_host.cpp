@@ -77,32 +77,6 @@ struct HostBackend {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-inline std::vector<double> dense_inverse(std::vector<double> A, int n) {  // Gauss-Jordan, SPD input
-    std::vector<double> inv((size_t)n * n, 0.0);
-    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
-    for (int c = 0; c < n; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < n; ++r)
-            if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)piv * n + c])) piv = r;
-        for (int k = 0; k < n; ++k) {
-            std::swap(A[(size_t)c * n + k], A[(size_t)piv * n + k]);
-            std::swap(inv[(size_t)c * n + k], inv[(size_t)piv * n + k]);
-        }
-        const double d = 1.0 / A[(size_t)c * n + c];
-        for (int k = 0; k < n; ++k) { A[(size_t)c * n + k] *= d; inv[(size_t)c * n + k] *= d; }
-        for (int r = 0; r < n; ++r) {
-            if (r == c) continue;
-            const double f = A[(size_t)r * n + c];
-            if (f == 0.0) continue;
-            for (int k = 0; k < n; ++k) {
-                A[(size_t)r * n + k] -= f * A[(size_t)c * n + k];
-                inv[(size_t)r * n + k] -= f * inv[(size_t)c * n + k];
-            }
-        }
-    }
-    return inv;
-}
-
 template <int NODES>
 struct HostMG {
     using Vec = double*;
@@ -163,23 +137,8 @@ struct HostMG {
             }
             lmax_[l] = 1.1 * lam;
         }
-        // explicit inverse of the coarsest operator (component 0 block; the operator is block diagonal)
-        const int lc = L - 1;
-        const tmx::TriLevel one{geo[lc].nx, geo[lc].ny, 1, geo[lc].fixed_boundary};
-        ncoarse = (int)tmx::trimg_num_nodes<NODES>(one);
-        std::vector<double> A((size_t)ncoarse * ncoarse, 0.0), e(ncoarse), col(ncoarse);
-        for (int j = 0; j < ncoarse; ++j) {
-            std::fill(e.begin(), e.end(), 0.0);
-            e[j] = 1.0;
-            std::fill(col.begin(), col.end(), 0.0);
-            for (size_t t = 0; t < tmx::trimg_num_tri(one); ++t)
-                tmx::trimg_body_apply<NODES>(one, Lm[lc].data(), tmx::trimg_num_tri(one), e.data(), col.data(), t,
-                                             tmx::FluidSerialAdd{});
-            for (int i = 0; i < ncoarse; ++i) A[(size_t)i * ncoarse + j] = col[i];
-        }
-        for (int i = 0; i < ncoarse; ++i)
-            if (A[(size_t)i * ncoarse + i] == 0.0) A[(size_t)i * ncoarse + i] = 1.0;  // Dirichlet rows
-        inv = dense_inverse(A, ncoarse);
+        // explicit inverse of the coarsest scalar operator (the same for every component)
+        inv = tmx::trimg_coarse_inverse<NODES>(geo[L - 1], Lm[L - 1].data(), ncoarse);
     }
     size_t size(int l) const { return tmx::trimg_num_nodes<NODES>(geo[l]) * geo[l].ncomp; }
     void apply(int l, const double* x, double* y) {

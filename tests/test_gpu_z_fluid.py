@@ -137,3 +137,24 @@ def test_penalty_continuation_and_hook_loop(repo_root, tmp_path):
     assert hooks.last_result["k_final"] == ro["k_final"]
     assert abs(hooks.last_result["objectives"][-1] - ro["objectives"][-1]) < 1e-6 * ro["objectives"][-1]
     assert np.abs(hooks.to_array(hooks.rho) - ro["rho"]).max() < 1e-5
+
+
+@pytest.mark.skipif(os.environ.get("TM_TEST_FLUID_MG") != "1",
+                    reason="multigrid preconditioner of the fluid solver: checked on the CPU "
+                           "(tests/test_fluid_host.py), not yet run on hardware; opt in with TM_TEST_FLUID_MG=1")
+@pytest.mark.parametrize("design,N", [("diffuser", 16), ("diffuser", 32), ("twin_pipe", 16)])
+def test_multigrid_preconditioner_same_solution_fewer_iterations(repo_root, design, N):
+    s, problem, Function = make(repo_root, design, N, state_rtol=1e-11)
+    _, mg, _ = make(repo_root, design, N, state_rtol=1e-11, preconditioner="multigrid")
+    pr, m = s.problem, s.mesh
+    rng = np.random.default_rng(N)
+    rho = 0.05 + 0.9 * rng.random(m.n1)
+    for p in (problem, mg, pr):
+        p.set_penalization(0.1)
+    obj_d = problem.calculate_objective(Function(problem.control_space, _t(rho)))
+    obj_m = mg.calculate_objective(Function(mg.control_space, _t(rho)))
+    obj_o = pr.calculate_objective(rho)
+    assert abs(obj_m - obj_o) < 1e-8 * obj_o and abs(obj_d - obj_o) < 1e-8 * obj_o
+    assert np.abs(mg.u.tensor.cpu().numpy() - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+    its_d, its_m = problem.solve_log[-1]["iterations"], mg.solve_log[-1]["iterations"]
+    assert its_m < 0.6 * its_d, (its_m, its_d)      # host check: 94 vs 243 at N=16, 102 vs 492 at N=32

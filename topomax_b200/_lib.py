@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate", "tm_sample_field",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
     "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
-    "tm_fluid_create", "tm_fluid_destroy", "tm_fluid_set_stream", "tm_fluid_set_density", "tm_fluid_state_solve",
+    "tm_fluid_create", "tm_fluid_destroy", "tm_fluid_set_stream", "tm_fluid_set_option", "tm_fluid_set_density", "tm_fluid_state_solve",
     "tm_fluid_objective", "tm_fluid_sens_rhs", "tm_fluid_apply", "tm_p2p_selftest",
 )
 
@@ -113,6 +113,7 @@ def load_library() -> ctypes.CDLL:
         "tm_fluid_create": ([I, I, D, D, D, D, D, I, POINTER(c_void_p)], I),
         "tm_fluid_destroy": ([V], I),
         "tm_fluid_set_stream": ([V, V], I),
+        "tm_fluid_set_option": ([V, I, D], I),
         "tm_fluid_set_density": ([V, V, D], I),
         "tm_fluid_state_solve": ([V, V, D, I, V, POINTER(I), POINTER(D)], I),
         "tm_fluid_objective": ([V, V, POINTER(D)], I),

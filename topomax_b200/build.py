@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["tm_engine.cu"]
 HEADERS = ["tm_common.cuh", "tm_element.cuh", "tm_elast.cuh", "tm_p1.cuh", "tm_vec.cuh", "tm_mg.cuh",
-           "tm_filter_pcg.cuh", "tm_p1mg.cuh", "tm_tail.cuh", "tm_comm.h", "tm_p2p.cuh", "tm_dem.cuh", "tm_fluid.cuh", "tm_fluid_cuda.cuh",
+           "tm_filter_pcg.cuh", "tm_p1mg.cuh", "tm_tail.cuh", "tm_comm.h", "tm_p2p.cuh", "tm_dem.cuh", "tm_fluid.cuh", "tm_fluid_cuda.cuh", "tm_trimg.cuh", "tm_trimg_cuda.cuh",
            "tm_tables.h", os.path.join("..", "..", "include", "topomax_b200.h")]
 OUTPUT = os.path.join(HERE, "libtopomax_b200.so")
 

@@ -2796,6 +2796,9 @@ int tm_fluid_destroy(tm_fluid_handle h) {
 int tm_fluid_set_stream(tm_fluid_handle h, void* stream) {
     return fluid_guarded(h, [&] { h->impl->set_stream(static_cast<cudaStream_t>(stream)); });
 }
+int tm_fluid_set_option(tm_fluid_handle h, int option, double value) {
+    return fluid_guarded(h, [&] { h->impl->set_option(option, value); });
+}
 int tm_fluid_set_density(tm_fluid_handle h, const double* rho, double q) {
     return fluid_guarded(h, [&] {
         if (!rho) throw tmx::Invalid{"tm_fluid_set_density: null argument"};

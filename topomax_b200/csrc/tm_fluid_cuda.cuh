@@ -12,6 +12,7 @@
 
 #include "tm_common.cuh"
 #include "tm_fluid.cuh"
+#include "tm_trimg_cuda.cuh"
 #include "tm_vec.cuh"
 
 namespace tmx {
@@ -118,6 +119,35 @@ __global__ void fluid_finish_kernel(size_t n, size_t nu, const double* __restric
     TM_GRID_STRIDE(i, n) up[i] = x[i] + (i < nu ? g[i] : 0.0);
 }
 
+// ---- fine-level local matrices of the two multigrid hierarchies (opt-in preconditioner)
+__global__ void __launch_bounds__(128) fluid_vel_local_kernel(const FluidTables* __restrict__ T,
+                                                              const double* __restrict__ Me, double* __restrict__ L,
+                                                              size_t ntri) {
+    TM_FLUID_TRI_LOOP(tid, ntri) {
+        const int t = (int)(tid & 1);
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j, ++k) L[(size_t)k * ntri + tid] = Me[(size_t)k * ntri + tid] + T->Kref[t][i][j];
+    }
+}
+__global__ void __launch_bounds__(128) fluid_darcy_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                          const double* __restrict__ rho, double* __restrict__ L,
+                                                          size_t ntri) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_darcy(*T, g, rho, L, ntri, tid);
+}
+__global__ void __launch_bounds__(128) fluid_pmass_diag_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                               double* diag, size_t ntri) {
+    TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_pmass_diag(*T, g, diag, tid, FluidAtomicAdd{});
+}
+__global__ void fluid_pmass_add_kernel(size_t n, const double* __restrict__ diag, const double* __restrict__ r,
+                                       double* __restrict__ z) {
+    TM_GRID_STRIDE(i, n) z[i] += r[i] / diag[i];
+}
+
+enum { TM_FLUID_OPT_PRECOND = 1, TM_FLUID_OPT_FINE_STEPS = 2, TM_FLUID_OPT_COARSE_STEPS = 3 };
+
 class FluidSolver {
    public:
     struct DVec {
@@ -170,6 +200,19 @@ class FluidSolver {
 
     int device() const { return device_; }
     void set_stream(cudaStream_t s) { stream_ = s ? s : own_stream_; }
+    // TM_FLUID_OPT_PRECOND: 0 = diagonal (default), 1 = multigrid (velocity V-cycle | M_p^-1 + Darcy V-cycle)
+    void set_option(int opt, double value) {
+        switch (opt) {
+            case TM_FLUID_OPT_PRECOND:
+                if (value != 0.0 && value != 1.0) throw std::runtime_error("fluid: preconditioner must be 0 or 1");
+                precond_mode_ = (int)value;
+                have_density_ = false;
+                break;
+            case TM_FLUID_OPT_FINE_STEPS: mg_prm_.fine_steps = std::max(1, (int)value); break;
+            case TM_FLUID_OPT_COARSE_STEPS: mg_prm_.coarse_steps = std::max(1, (int)value); break;
+            default: throw std::runtime_error("fluid: unknown option " + std::to_string(opt));
+        }
+    }
 
     // weighted mass matrices and the diagonal preconditioner for a density field and penaliser q
     void set_density(const double* rho, double q) {
@@ -183,6 +226,21 @@ class FluidSolver {
         TM_CHECK_LAUNCH();
         fluid_schur_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, diag_, ntri_);
         TM_CHECK_LAUNCH();
+        if (precond_mode_ == 1) {
+            if (!mg_vel_.planned()) {
+                mg_vel_.plan(TriLevel{g_.nx, g_.ny, 2, 1}, max_blocks_);
+                mg_prs_.plan(TriLevel{g_.nx, g_.ny, 1, 0}, max_blocks_);
+                alloc(mp_diag_, n1_);
+                fluid_pmass_diag_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, mp_diag_, ntri_);
+                TM_CHECK_LAUNCH();
+            }
+            fluid_vel_local_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, Me_, mg_vel_.level_matrices(0), ntri_);
+            TM_CHECK_LAUNCH();
+            fluid_darcy_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, rho, mg_prs_.level_matrices(0), ntri_);
+            TM_CHECK_LAUNCH();
+            mg_vel_.setup(stream_, rs_, sc_, h_sc_);
+            mg_prs_.setup(stream_, rs_, sc_, h_sc_);
+        }
         have_density_ = true;
     }
 
@@ -240,6 +298,13 @@ class FluidSolver {
     }
     void apply(const DVec& x, DVec& y) { apply_mode(x.p, y.p, 0); }
     void precond(const DVec& r, DVec& z) {
+        if (precond_mode_ == 1) {
+            mg_vel_.precondition(r.p, z.p, mg_prm_);
+            mg_prs_.precondition(r.p + nu_, z.p + nu_, mg_prm_);
+            fluid_pmass_add_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n1_, mp_diag_, r.p + nu_, z.p + nu_);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         fluid_precond_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, diag_, r.p, z.p);
         TM_CHECK_LAUNCH();
     }
@@ -281,6 +346,11 @@ class FluidSolver {
     size_t ntri_, nu_, n1_, n_;
     FluidTables* d_tab_ = nullptr;
     double *Me_ = nullptr, *diag_ = nullptr, *b_ = nullptr, *x_ = nullptr, *xg_ = nullptr, *sc_ = nullptr;
+    double* mp_diag_ = nullptr;
+    int precond_mode_ = 0;
+    TriMGParams mg_prm_;
+    CudaTriMG<6> mg_vel_;
+    CudaTriMG<3> mg_prs_;
     double* h_sc_ = nullptr;
     DVec work_[8];
     ReduceScratch rs_{};

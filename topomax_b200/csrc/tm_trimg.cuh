@@ -17,8 +17,11 @@
 // against scipy Galerkin products (tests/hostcheck/fluid_host.cpp); the CUDA back-end adds launches.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <utility>
+#include <vector>
 
 #include "tm_element.cuh"  // TM_HD
 
@@ -271,6 +274,64 @@ TM_HD void trimg_body_restrict(const TriLevel& gf, const TriLevel& gc, const dou
         for (int k = 0; k < NODES; ++k)
             if (cin[k] && w[k] != 0.0) add(&rc[(size_t)cnode[k] * gf.ncomp + c], w[k] * v);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Coarsest level: explicit inverse of the assembled scalar operator, built on the host from the
+// level's local matrices (both back-ends).  Dirichlet rows (empty after assembly) become identity.
+// ---------------------------------------------------------------------------------------------
+struct TriSerialAdd {
+    TM_HD void operator()(double* p, double v) const { *p += v; }
+};
+
+inline std::vector<double> trimg_dense_inverse(std::vector<double> A, int n) {  // Gauss-Jordan, partial pivoting
+    std::vector<double> inv((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)piv * n + c])) piv = r;
+        if (piv != c)
+            for (int k = 0; k < n; ++k) {
+                std::swap(A[(size_t)c * n + k], A[(size_t)piv * n + k]);
+                std::swap(inv[(size_t)c * n + k], inv[(size_t)piv * n + k]);
+            }
+        const double d = 1.0 / A[(size_t)c * n + c];
+        for (int k = 0; k < n; ++k) {
+            A[(size_t)c * n + k] *= d;
+            inv[(size_t)c * n + k] *= d;
+        }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = A[(size_t)r * n + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < n; ++k) {
+                A[(size_t)r * n + k] -= f * A[(size_t)c * n + k];
+                inv[(size_t)r * n + k] -= f * inv[(size_t)c * n + k];
+            }
+        }
+    }
+    return inv;
+}
+
+// Lm: the coarsest level's local matrices on the HOST; returns the n x n inverse (n = scalar nodes)
+template <int NODES>
+inline std::vector<double> trimg_coarse_inverse(const TriLevel& g, const double* Lm, int& n_out) {
+    const TriLevel one{g.nx, g.ny, 1, g.fixed_boundary};
+    const int n = (int)trimg_num_nodes<NODES>(one);
+    const size_t nt = trimg_num_tri(one);
+    std::vector<double> A((size_t)n * n, 0.0), e(n), col(n);
+    for (int j = 0; j < n; ++j) {
+        std::fill(e.begin(), e.end(), 0.0);
+        e[j] = 1.0;
+        std::fill(col.begin(), col.end(), 0.0);
+        for (size_t t = 0; t < nt; ++t) trimg_body_apply<NODES>(one, Lm, nt, e.data(), col.data(), t, TriSerialAdd{});
+        for (int i = 0; i < n; ++i) A[(size_t)i * n + j] = col[i];
+    }
+    for (int i = 0; i < n; ++i)
+        if (A[(size_t)i * n + i] == 0.0) A[(size_t)i * n + i] = 1.0;
+    n_out = n;
+    return trimg_dense_inverse(std::move(A), n);
 }
 
 // ---------------------------------------------------------------------------------------------
