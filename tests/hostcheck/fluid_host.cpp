@@ -304,6 +304,23 @@ void hc_trimg_restrict(int kind, int nxf, int nyf, const double* rf, double* rc)
     }
 }
 
+// z = V-cycle(r) of hierarchy `kind` (0 velocity, 1 pressure Darcy Laplacian)
+void hc_trimg_vcycle(int nx, int ny, double W, double H, double q, double rmin, double rmax, double visc,
+                     const double* rho, int kind, const double* r, double* z) {
+    HostFluid f(nx, ny, W, H, q, rmin, rmax, visc);
+    f.set_density(rho);
+    tmx::TriMGParams prm;
+    if (kind == 0) {
+        HostMG<6> mg;
+        mg.build(tmx::TriLevel{nx, ny, 2, 1}, velocity_local_matrices(f), 16, 4);
+        mg.precondition(r, z, prm);
+    } else {
+        HostMG<3> mg;
+        mg.build(tmx::TriLevel{nx, ny, 1, 0}, darcy_local_matrices(f, rho), 16, 4);
+        mg.precondition(r, z, prm);
+    }
+}
+
 // the state solve with the multigrid preconditioner (velocity V-cycle | M_p^-1 + Darcy V-cycle)
 int hc_fluid_solve_mg(int nx, int ny, double W, double H, double q, double rmin, double rmax, double visc,
                       const double* rho, const double* g_boundary, double rtol, int maxit, double* up,

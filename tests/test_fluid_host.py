@@ -288,3 +288,35 @@ def test_multigrid_preconditioned_solve_matches_oracle_with_few_iterations(hc_mg
     assert its > 0, (its, relres.value)
     pr.calculate_objective(rho)
     assert np.abs(up[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+
+
+def test_vcycles_are_symmetric_positive_definite(hc_mg, repo_root):
+    """MINRES needs a symmetric positive definite preconditioner: the V-cycle (Chebyshev pre-smoothing
+    from zero, coarse correction, the adjoint post-smoothing) must satisfy <V x, y> = <x, V y> and
+    <V x, x> > 0, and contract the error: rho(I - V A) < 1."""
+    common = [I, I, D, D, D, D, D, D]
+    hc_mg.hc_trimg_vcycle.argtypes = common + [P, I, P, P]
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, 8, "diffuser", seed=4)
+    rng = np.random.default_rng(8)
+    bmask = np.repeat(_boundary_mask(m), 2)
+    for kind, n in ((0, m.nu), (1, m.n1)):
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        if kind == 0:
+            x[bmask] = 0.0
+            y[bmask] = 0.0
+        vx, vy = np.zeros(n), np.zeros(n)
+        hc_mg.hc_trimg_vcycle(*args, ptr(rho), kind, ptr(x), ptr(vx))
+        hc_mg.hc_trimg_vcycle(*args, ptr(rho), kind, ptr(y), ptr(vy))
+        assert abs(vx @ y - x @ vy) < 1e-10 * max(abs(vx @ y), 1e-300), kind
+        assert vx @ x > 0 and vy @ y > 0
+        # error contraction of the stationary iteration e <- (I - V A) e, A applied through level 0
+        e = x.copy()
+        norms = []
+        for _ in range(8):
+            ae, ve = np.zeros(n), np.zeros(n)
+            hc_mg.hc_trimg_level_apply(*args, ptr(rho), kind, 0, ptr(e), ptr(ae))
+            hc_mg.hc_trimg_vcycle(*args, ptr(rho), kind, ptr(ae), ptr(ve))
+            e = e - ve
+            norms.append(np.linalg.norm(e))
+        # measured: ~0.58 per cycle for the velocity block (P2, 2 smoothing steps), better for the P1 Laplacian
+        assert norms[-1] < 0.7 * norms[-2] or norms[-1] < 1e-8 * norms[0], (kind, norms)
