@@ -320,3 +320,44 @@ def test_vcycles_are_symmetric_positive_definite(hc_mg, repo_root):
             norms.append(np.linalg.norm(e))
         # measured: ~0.58 per cycle for the velocity block (P2, 2 smoothing steps), better for the P1 Laplacian
         assert norms[-1] < 0.7 * norms[-2] or norms[-1] < 1e-8 * norms[0], (kind, norms)
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA driver itself (FluidSolver / CudaTriMG) run serially through tests/hostcheck/cuda_host_shim.h
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def driver():
+    build = os.path.join(HERE, "_build")
+    os.makedirs(build, exist_ok=True)
+    so = os.path.join(build, "libfluid_cuda_host.so")
+    src = os.path.join(HERE, "hostcheck", "fluid_cuda_host.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(HERE, "hostcheck"), "-shared", "-fPIC",
+                           src, "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.hc_driver_solve.argtypes = [I, I, D, D, D, D, D, D, P, P, D, I, I, P, P, P]
+    lib.hc_driver_solve.restype = I
+    return lib
+
+
+@pytest.mark.parametrize("design,N", [("diffuser", 16), ("twin_pipe", 8), ("pipe_bend", 10)])
+def test_cuda_driver_on_the_host_matches_oracle_with_both_preconditioners(driver, hc_mg, repo_root, design, N):
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, N, design, seed=13)
+    obj_o = pr.calculate_objective(rho)
+    grad_o = pr.calculate_objective_gradient()
+    counts = {}
+    for precond in (0, 1):
+        up, rhs, out3 = np.zeros(m.nu + m.n1), np.zeros(m.n1), np.zeros(3)
+        its = driver.hc_driver_solve(*args, ptr(rho), ptr(g), 1e-11, 20000, precond, ptr(up), ptr(rhs), ptr(out3))
+        assert its > 0 and out3[2] == 0.0, (precond, its, list(out3))
+        assert np.abs(up[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+        assert abs(out3[1] - obj_o) < 1e-8 * obj_o
+        assert np.abs(rhs - pr.M1 @ grad_o).max() < 1e-7 * np.abs(rhs).max()
+        counts[precond] = its
+    # the same iteration counts as the element-level host check (same algorithm, same order)
+    relres = D(0.0)
+    up = np.zeros(m.nu + m.n1)
+    assert counts[0] == hc_mg.hc_fluid_solve(*args, ptr(rho), ptr(g), 1e-11, 20000, ptr(up), ctypes.byref(relres))
+    if m.nx % 2 == 0 and m.ny % 2 == 0:
+        assert abs(counts[1] - hc_mg.hc_fluid_solve_mg(*args, ptr(rho), ptr(g), 1e-11, 20000, ptr(up),
+                                                       ctypes.byref(relres))) <= 2
+        assert counts[1] < counts[0]

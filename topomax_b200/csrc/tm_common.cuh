@@ -35,6 +35,10 @@ struct CudaFailure {
         }                                                                                      \
     } while (0)
 
+// kernel launch through one macro: the serial host build of the fluid driver (tests/hostcheck)
+// replaces it by a plain call
+#define TM_LAUNCH(kernel, grid, block, stream) kernel<<<(grid), (block), 0, (stream)>>>
+
 #define TM_CHECK_LAUNCH()            \
     do {                             \
         ++::tmx::g_launches;         \

@@ -3,17 +3,21 @@
 // header of tm_fluid.cuh for what is deliberately simple here.)
 #pragma once
 
-#include <cuda_runtime.h>
-
 #include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#ifdef TM_HOST_SHIM  // serial CPU build of this driver for the CPU tests (tests/hostcheck/cuda_host_shim.h)
+#include "cuda_host_shim.h"
+#else
+#include <cuda_runtime.h>
+
 #include "tm_common.cuh"
+#include "tm_vec.cuh"
+#endif
 #include "tm_fluid.cuh"
 #include "tm_trimg_cuda.cuh"
-#include "tm_vec.cuh"
 
 namespace tmx {
 
@@ -218,25 +222,25 @@ class FluidSolver {
     void set_density(const double* rho, double q) {
         if (!(q > 0.0)) throw std::runtime_error("fluid: the penalisation q must be > 0");
         g_.q = q;
-        fluid_mass_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, rho, Me_, ntri_);
+        TM_LAUNCH(fluid_mass_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, Me_, ntri_);
         TM_CHECK_LAUNCH();
-        fluid_diag_init_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(g_, diag_, n_);
+        TM_LAUNCH(fluid_diag_init_kernel, vec_grid(), kVecThreads, stream_)(g_, diag_, n_);
         TM_CHECK_LAUNCH();
-        fluid_diag_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, Me_, ntri_, diag_);
+        TM_LAUNCH(fluid_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, diag_);
         TM_CHECK_LAUNCH();
-        fluid_schur_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, diag_, ntri_);
+        TM_LAUNCH(fluid_schur_kernel, tri_grid(), 128, stream_)(d_tab_, g_, diag_, ntri_);
         TM_CHECK_LAUNCH();
         if (precond_mode_ == 1) {
             if (!mg_vel_.planned()) {
                 mg_vel_.plan(TriLevel{g_.nx, g_.ny, 2, 1}, max_blocks_);
                 mg_prs_.plan(TriLevel{g_.nx, g_.ny, 1, 0}, max_blocks_);
                 alloc(mp_diag_, n1_);
-                fluid_pmass_diag_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, mp_diag_, ntri_);
+                TM_LAUNCH(fluid_pmass_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, mp_diag_, ntri_);
                 TM_CHECK_LAUNCH();
             }
-            fluid_vel_local_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, Me_, mg_vel_.level_matrices(0), ntri_);
+            TM_LAUNCH(fluid_vel_local_kernel, tri_grid(), 128, stream_)(d_tab_, Me_, mg_vel_.level_matrices(0), ntri_);
             TM_CHECK_LAUNCH();
-            fluid_darcy_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, rho, mg_prs_.level_matrices(0), ntri_);
+            TM_LAUNCH(fluid_darcy_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, mg_prs_.level_matrices(0), ntri_);
             TM_CHECK_LAUNCH();
             mg_vel_.setup(stream_, rs_, sc_, h_sc_);
             mg_prs_.setup(stream_, rs_, sc_, h_sc_);
@@ -250,13 +254,13 @@ class FluidSolver {
         TM_CUDA(cudaMemsetAsync(xg_, 0, n_ * sizeof(double), stream_));
         TM_CUDA(cudaMemcpyAsync(xg_, boundary_velocity, nu_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
         apply_mode(xg_, b_, 1);
-        fluid_sum_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n1_, b_ + nu_, rs_, sc_);
+        TM_LAUNCH(fluid_sum_kernel, vec_grid(), kVecThreads, stream_)(n1_, b_ + nu_, rs_, sc_);
         TM_CHECK_LAUNCH();
-        fluid_rhs_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, nu_, b_, sc_, 1.0 / (double)n1_);
+        TM_LAUNCH(fluid_rhs_kernel, vec_grid(), kVecThreads, stream_)(n_, nu_, b_, sc_, 1.0 / (double)n1_);
         TM_CHECK_LAUNCH();
         DVec b{b_}, x{x_};
         const MinresResult r = fluid_minres(*this, b, x, rtol, maxit);
-        fluid_finish_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, nu_, x_, xg_, up);
+        TM_LAUNCH(fluid_finish_kernel, vec_grid(), kVecThreads, stream_)(n_, nu_, x_, xg_, up);
         TM_CHECK_LAUNCH();
         TM_CUDA(cudaStreamSynchronize(stream_));
         return r;
@@ -264,7 +268,7 @@ class FluidSolver {
 
     double objective(const double* u) {
         need_density();
-        fluid_objective_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, Me_, ntri_, u, rs_, sc_);
+        TM_LAUNCH(fluid_objective_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, u, rs_, sc_);
         TM_CHECK_LAUNCH();
         return read_scalar();
     }
@@ -272,7 +276,7 @@ class FluidSolver {
     void sens_rhs(const double* rho, const double* u, double* out) {
         if (!(g_.q > 0.0)) throw std::runtime_error("fluid: set the density / penalisation first");
         TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(double), stream_));
-        fluid_sens_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, rho, u, out, ntri_);
+        TM_LAUNCH(fluid_sens_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, u, out, ntri_);
         TM_CHECK_LAUNCH();
     }
 
@@ -280,7 +284,7 @@ class FluidSolver {
     void apply_mode(const double* x, double* y, int mode) {
         need_density();
         TM_CUDA(cudaMemsetAsync(y, 0, n_ * sizeof(double), stream_));
-        fluid_apply_kernel<<<tri_grid(), 128, 0, stream_>>>(d_tab_, g_, Me_, ntri_, x, y, mode);
+        TM_LAUNCH(fluid_apply_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, x, y, mode);
         TM_CHECK_LAUNCH();
     }
     const double* diagonal() const { return diag_; }
@@ -293,7 +297,7 @@ class FluidSolver {
         TM_CUDA(cudaMemcpyAsync(b.p, a.p, n_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
     }
     void scale(DVec& a, double s) {
-        fluid_scale_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, a.p, s);
+        TM_LAUNCH(fluid_scale_kernel, vec_grid(), kVecThreads, stream_)(n_, a.p, s);
         TM_CHECK_LAUNCH();
     }
     void apply(const DVec& x, DVec& y) { apply_mode(x.p, y.p, 0); }
@@ -301,25 +305,25 @@ class FluidSolver {
         if (precond_mode_ == 1) {
             mg_vel_.precondition(r.p, z.p, mg_prm_);
             mg_prs_.precondition(r.p + nu_, z.p + nu_, mg_prm_);
-            fluid_pmass_add_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n1_, mp_diag_, r.p + nu_, z.p + nu_);
+            TM_LAUNCH(fluid_pmass_add_kernel, vec_grid(), kVecThreads, stream_)(n1_, mp_diag_, r.p + nu_, z.p + nu_);
             TM_CHECK_LAUNCH();
             return;
         }
-        fluid_precond_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, diag_, r.p, z.p);
+        TM_LAUNCH(fluid_precond_kernel, vec_grid(), kVecThreads, stream_)(n_, diag_, r.p, z.p);
         TM_CHECK_LAUNCH();
     }
     double dot(const DVec& a, const DVec& b) {
-        dot_kernel<double><<<vec_grid(), kVecThreads, 0, stream_>>>(n_, a.p, b.p, rs_, sc_);
+        TM_LAUNCH(dot_kernel<double>, vec_grid(), kVecThreads, stream_)(n_, a.p, b.p, rs_, sc_);
         TM_CHECK_LAUNCH();
         return read_scalar();
     }
     void axpy2(DVec& y, double a, const DVec& p, double b, const DVec& q) {
-        fluid_axpy2_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, y.p, a, p.p, b, q.p);
+        TM_LAUNCH(fluid_axpy2_kernel, vec_grid(), kVecThreads, stream_)(n_, y.p, a, p.p, b, q.p);
         TM_CHECK_LAUNCH();
     }
     void direction(DVec& wn, const DVec& z, double a3, const DVec& wo, double a2, const DVec& w, double inv_a1,
                    DVec& x, double step) {
-        fluid_direction_kernel<<<vec_grid(), kVecThreads, 0, stream_>>>(n_, wn.p, z.p, a3, wo.p, a2, w.p, inv_a1,
+        TM_LAUNCH(fluid_direction_kernel, vec_grid(), kVecThreads, stream_)(n_, wn.p, z.p, a3, wo.p, a2, w.p, inv_a1,
                                                                        x.p, step);
         TM_CHECK_LAUNCH();
     }

@@ -3,14 +3,18 @@
 // NODES = 3: pressure "Darcy" Laplacian).  Opt-in preconditioner of the fluid solver.
 #pragma once
 
-#include <cuda_runtime.h>
-
 #include <stdexcept>
 #include <vector>
 
+#ifdef TM_HOST_SHIM  // serial CPU build for the CPU tests (tests/hostcheck/cuda_host_shim.h)
+#include "cuda_host_shim.h"
+#else
+#include <cuda_runtime.h>
+
 #include "tm_common.cuh"
-#include "tm_trimg.cuh"
 #include "tm_vec.cuh"
+#endif
+#include "tm_trimg.cuh"
 
 namespace tmx {
 
@@ -157,37 +161,37 @@ class CudaTriMG {
         const int L = levels();
         for (int l = 0; l + 1 < L; ++l) {
             const size_t ntc = trimg_num_tri(geo_[l + 1]);
-            trimg_coarsen_kernel<NODES><<<grid(ntc, 128), 128, 0, st>>>(tab_, geo_[l], Lm_[l], trimg_num_tri(geo_[l]),
+            TM_LAUNCH(trimg_coarsen_kernel<NODES>, grid(ntc, 128), 128, st)(tab_, geo_[l], Lm_[l], trimg_num_tri(geo_[l]),
                                                                        geo_[l + 1], Lm_[l + 1], ntc);
             TM_CHECK_LAUNCH();
         }
         for (int l = 0; l < L; ++l) {
             const size_t n = size(l), nt = trimg_num_tri(geo_[l]);
-            trimg_diag_init_kernel<NODES><<<grid(n, 256), 256, 0, st>>>(geo_[l], diag_[l], n);
+            TM_LAUNCH(trimg_diag_init_kernel<NODES>, grid(n, 256), 256, st)(geo_[l], diag_[l], n);
             TM_CHECK_LAUNCH();
-            trimg_diag_kernel<NODES><<<grid(nt, 128), 128, 0, st>>>(geo_[l], Lm_[l], nt, diag_[l]);
+            TM_LAUNCH(trimg_diag_kernel<NODES>, grid(nt, 128), 128, st)(geo_[l], Lm_[l], nt, diag_[l]);
             TM_CHECK_LAUNCH();
         }
         // lambda_max(D^-1 A) per level by power iteration (30 steps, like the host check)
         for (int l = 0; l + 1 < L; ++l) {
             const size_t n = size(l);
             double *v = vec(l, TRIMG_D), *w = vec(l, TRIMG_E);
-            trimg_fill_kernel<<<grid(n, 256), 256, 0, st>>>(n, v);
+            TM_LAUNCH(trimg_fill_kernel, grid(n, 256), 256, st)(n, v);
             TM_CHECK_LAUNCH();
             double lam = 1.0, vv = 0.0;
-            dot_kernel<double><<<grid(n, kVecThreads), kVecThreads, 0, st>>>(n, v, v, rs, d_scalar);
+            TM_LAUNCH(dot_kernel<double>, grid(n, kVecThreads), kVecThreads, st)(n, v, v, rs, d_scalar);
             TM_CHECK_LAUNCH();
             vv = read(d_scalar, h_scalar);
             for (int it = 0; it < 30; ++it) {
                 apply(l, v, w);
-                trimg_scale_diag_kernel<<<grid(n, 256), 256, 0, st>>>(n, diag_[l], w);
+                TM_LAUNCH(trimg_scale_diag_kernel, grid(n, 256), 256, st)(n, diag_[l], w);
                 TM_CHECK_LAUNCH();
-                dot_kernel<double><<<grid(n, kVecThreads), kVecThreads, 0, st>>>(n, w, w, rs, d_scalar);
+                TM_LAUNCH(dot_kernel<double>, grid(n, kVecThreads), kVecThreads, st)(n, w, w, rs, d_scalar);
                 TM_CHECK_LAUNCH();
                 const double ww = read(d_scalar, h_scalar);
                 if (!(ww > 0.0) || !(vv > 0.0)) break;
                 lam = std::sqrt(ww / vv);
-                trimg_scale_kernel<<<grid(n, 256), 256, 0, st>>>(n, w, v, 1.0 / std::sqrt(ww));
+                TM_LAUNCH(trimg_scale_kernel, grid(n, 256), 256, st)(n, w, v, 1.0 / std::sqrt(ww));
                 TM_CHECK_LAUNCH();
                 vv = 1.0;
             }
@@ -219,40 +223,40 @@ class CudaTriMG {
     void apply(int l, const double* x, double* y) {
         const size_t nt = trimg_num_tri(geo_[l]);
         TM_CUDA(cudaMemsetAsync(y, 0, size(l) * sizeof(double), stream_));
-        trimg_apply_kernel<NODES><<<grid(nt, 128), 128, 0, stream_>>>(geo_[l], Lm_[l], nt, x, y);
+        TM_LAUNCH(trimg_apply_kernel<NODES>, grid(nt, 128), 128, stream_)(geo_[l], Lm_[l], nt, x, y);
         TM_CHECK_LAUNCH();
     }
     void residual(int l, Vec b, Vec x, Vec r) {
         apply(l, x, r);
-        trimg_residual_kernel<<<grid(size(l), 256), 256, 0, stream_>>>(size(l), b, r);
+        TM_LAUNCH(trimg_residual_kernel, grid(size(l), 256), 256, stream_)(size(l), b, r);
         TM_CHECK_LAUNCH();
     }
     void cheb_first(int l, Vec b, Vec d, Vec x, double s) {
-        trimg_cheb_first_kernel<<<grid(size(l), 256), 256, 0, stream_>>>(size(l), diag_[l], b, d, x, s);
+        TM_LAUNCH(trimg_cheb_first_kernel, grid(size(l), 256), 256, stream_)(size(l), diag_[l], b, d, x, s);
         TM_CHECK_LAUNCH();
     }
     void cheb_next(int l, Vec r, Vec d, Vec x, double c1, double c2) {
-        trimg_cheb_next_kernel<<<grid(size(l), 256), 256, 0, stream_>>>(size(l), diag_[l], r, d, x, c1, c2);
+        TM_LAUNCH(trimg_cheb_next_kernel, grid(size(l), 256), 256, stream_)(size(l), diag_[l], r, d, x, c1, c2);
         TM_CHECK_LAUNCH();
     }
     void restrict_to(int l, Vec rf, Vec bc) {
         const size_t nodes = trimg_num_nodes<NODES>(geo_[l]);
         TM_CUDA(cudaMemsetAsync(bc, 0, size(l + 1) * sizeof(double), stream_));
-        trimg_restrict_kernel<NODES><<<grid(nodes, 256), 256, 0, stream_>>>(geo_[l], geo_[l + 1], rf, bc, nodes);
+        TM_LAUNCH(trimg_restrict_kernel<NODES>, grid(nodes, 256), 256, stream_)(geo_[l], geo_[l + 1], rf, bc, nodes);
         TM_CHECK_LAUNCH();
     }
     void prolong_add(int l, Vec xc, Vec xf) {
         const size_t nodes = trimg_num_nodes<NODES>(geo_[l]);
-        trimg_prolong_kernel<NODES><<<grid(nodes, 256), 256, 0, stream_>>>(geo_[l], geo_[l + 1], xc, xf, nodes);
+        TM_LAUNCH(trimg_prolong_kernel<NODES>, grid(nodes, 256), 256, stream_)(geo_[l], geo_[l + 1], xc, xf, nodes);
         TM_CHECK_LAUNCH();
     }
     void coarse_solve(Vec b, Vec x) {
         const int nc = geo_.back().ncomp;
-        trimg_coarse_solve_kernel<<<grid((size_t)ncoarse_ * nc, 128), 128, 0, stream_>>>(ncoarse_, nc, inv_, b, x);
+        TM_LAUNCH(trimg_coarse_solve_kernel, grid((size_t)ncoarse_ * nc, 128), 128, stream_)(ncoarse_, nc, inv_, b, x);
         TM_CHECK_LAUNCH();
     }
     void add(int l, Vec e, Vec x) {
-        trimg_add_kernel<<<grid(size(l), 256), 256, 0, stream_>>>(size(l), e, x);
+        TM_LAUNCH(trimg_add_kernel, grid(size(l), 256), 256, stream_)(size(l), e, x);
         TM_CHECK_LAUNCH();
     }
 
