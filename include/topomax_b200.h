@@ -214,7 +214,9 @@ int tm_fluid_set_stream(tm_fluid_handle h, void* stream);
 /* option 1: MINRES preconditioner, 0 = diagonal (default), 1 = multigrid on per-triangle Galerkin
  * matrices (one V-cycle per velocity component on M_r + K; pressure: M_p^-1 + a V-cycle on the P1
  * Laplacian int (1/r) grad.grad) -- needs cell counts with enough factors of two; options 2 / 3:
- * Chebyshev-Jacobi smoothing steps on the finest / the coarser levels (default 2 / 3) */
+ * Chebyshev-Jacobi smoothing steps on the finest / the coarser levels (default 2 / 3); option 4:
+ * warm start from the previous solve's solution (default 0), tolerance still relative to the
+ * original right-hand side, dropped when its residual is not smaller than the zero guess's */
 int tm_fluid_set_option(tm_fluid_handle h, int option, double value);
 int tm_fluid_set_density(tm_fluid_handle h, const double* rho, double q);
 int tm_fluid_state_solve(tm_fluid_handle h, const double* boundary_velocity, double rtol, int maxit, double* up,

@@ -7,6 +7,29 @@
 
 extern "C" {
 
+// two successive solves (densities rho1 then rho2) on one solver object, as in an optimisation run;
+// returns the iterations of the SECOND solve (negative if not converged), its solution in up
+int hc_driver_sequence(int nx, int ny, double W, double H, double q, double rmin, double rmax, double visc,
+                       const double* rho1, const double* rho2, const double* g_boundary, double rtol, int maxit,
+                       int preconditioner, int warm_start, double* up, double* out3) {
+    try {
+        tmx::FluidSolver solver(nx, ny, W, H, visc, rmin, rmax, 0);
+        if (preconditioner) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+        solver.set_option(tmx::TM_FLUID_OPT_WARM_START, warm_start ? 1.0 : 0.0);
+        solver.set_density(rho1, q);
+        const tmx::MinresResult r1 = solver.solve(g_boundary, rtol, maxit, up);
+        out3[0] = r1.iterations;
+        solver.set_density(rho2, q);
+        const tmx::MinresResult r2 = solver.solve(g_boundary, rtol, maxit, up);
+        out3[1] = r2.relres;
+        out3[2] = solver.last_solve_was_warm() ? 1.0 : 0.0;
+        return r2.converged ? r2.iterations : -r2.iterations;
+    } catch (const std::exception& e) {
+        out3[2] = -1.0;
+        return -1;
+    }
+}
+
 // returns MINRES iterations (negative if not converged); up = [u | p]; out3 = {relres, objective, 0}
 int hc_driver_solve(int nx, int ny, double W, double H, double q, double rmin, double rmax, double visc,
                     const double* rho, const double* g_boundary, double rtol, int maxit, int preconditioner,

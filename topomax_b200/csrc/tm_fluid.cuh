@@ -425,8 +425,11 @@ struct MinresResult {
     bool converged = false;
 };
 
+// `ref_norm` > 0: the tolerance is relative to it instead of the initial residual norm (warm starts:
+// b is then the residual of the initial guess and ref_norm the norm of the original right-hand side)
 template <class BK>
-MinresResult fluid_minres(BK& bk, const typename BK::Vec& b, typename BK::Vec& x, double rtol, int maxit) {
+MinresResult fluid_minres(BK& bk, const typename BK::Vec& b, typename BK::Vec& x, double rtol, int maxit,
+                          double ref_norm = 0.0) {
     using Vec = typename BK::Vec;
     MinresResult res;
     Vec& v_old = bk.work(0);
@@ -449,7 +452,12 @@ MinresResult fluid_minres(BK& bk, const typename BK::Vec& b, typename BK::Vec& x
         return res;
     }
     double eta = gamma;
-    const double eta0 = gamma;
+    const double eta0 = ref_norm > 0.0 ? ref_norm : gamma;
+    if (gamma <= rtol * eta0) {  // the initial guess is already good enough
+        res.relres = gamma / eta0;
+        res.converged = true;
+        return res;
+    }
     double s_old = 0.0, s = 0.0, c_old = 1.0, c = 1.0;
     Vec* pv_old = &v_old;
     Vec* pv = &v;

@@ -150,7 +150,8 @@ __global__ void fluid_pmass_add_kernel(size_t n, const double* __restrict__ diag
     TM_GRID_STRIDE(i, n) z[i] += r[i] / diag[i];
 }
 
-enum { TM_FLUID_OPT_PRECOND = 1, TM_FLUID_OPT_FINE_STEPS = 2, TM_FLUID_OPT_COARSE_STEPS = 3 };
+enum { TM_FLUID_OPT_PRECOND = 1, TM_FLUID_OPT_FINE_STEPS = 2, TM_FLUID_OPT_COARSE_STEPS = 3,
+       TM_FLUID_OPT_WARM_START = 4 };
 
 class FluidSolver {
    public:
@@ -214,6 +215,10 @@ class FluidSolver {
                 break;
             case TM_FLUID_OPT_FINE_STEPS: mg_prm_.fine_steps = std::max(1, (int)value); break;
             case TM_FLUID_OPT_COARSE_STEPS: mg_prm_.coarse_steps = std::max(1, (int)value); break;
+            case TM_FLUID_OPT_WARM_START:
+                warm_ = value != 0.0;
+                have_prev_ = false;
+                break;
             default: throw std::runtime_error("fluid: unknown option " + std::to_string(opt));
         }
     }
@@ -259,7 +264,36 @@ class FluidSolver {
         TM_LAUNCH(fluid_rhs_kernel, vec_grid(), kVecThreads, stream_)(n_, nu_, b_, sc_, 1.0 / (double)n1_);
         TM_CHECK_LAUNCH();
         DVec b{b_}, x{x_};
-        const MinresResult r = fluid_minres(*this, b, x, rtol, maxit);
+        // warm start (opt-in): solve for the correction of the previous solution, to a tolerance
+        // relative to the ORIGINAL right-hand side; dropped when its residual is not smaller
+        double ref = 0.0;
+        bool warm = false;
+        if (warm_ && have_prev_) {
+            DVec zb = work(0), ax = work(1), xp{xprev_};
+            precond(b, zb);
+            ref = std::sqrt(std::fmax(dot(zb, b), 0.0));
+            apply(xp, ax);
+            axpy2(b, -1.0, ax, 0.0, ax);  // b <- b - A x_prev
+            precond(b, zb);
+            const double res0 = std::sqrt(std::fmax(dot(zb, b), 0.0));
+            if (res0 < ref) {
+                warm = true;
+            } else {
+                axpy2(b, 1.0, ax, 0.0, ax);  // restore the right-hand side
+                ref = 0.0;
+            }
+        }
+        const MinresResult r = fluid_minres(*this, b, x, rtol, maxit, ref);
+        if (warm) {
+            DVec xp{xprev_};
+            axpy2(x, 1.0, xp, 0.0, xp);  // x <- x_prev + correction
+        }
+        if (warm_) {
+            if (!xprev_) alloc(xprev_, n_);
+            TM_CUDA(cudaMemcpyAsync(xprev_, x_, n_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+            have_prev_ = true;
+        }
+        last_warm_ = warm;
         TM_LAUNCH(fluid_finish_kernel, vec_grid(), kVecThreads, stream_)(n_, nu_, x_, xg_, up);
         TM_CHECK_LAUNCH();
         TM_CUDA(cudaStreamSynchronize(stream_));
@@ -288,6 +322,7 @@ class FluidSolver {
         TM_CHECK_LAUNCH();
     }
     const double* diagonal() const { return diag_; }
+    bool last_solve_was_warm() const { return last_warm_; }
     size_t n() const { return n_; }
 
     // ---- back-end interface of fluid_minres
@@ -351,6 +386,8 @@ class FluidSolver {
     FluidTables* d_tab_ = nullptr;
     double *Me_ = nullptr, *diag_ = nullptr, *b_ = nullptr, *x_ = nullptr, *xg_ = nullptr, *sc_ = nullptr;
     double* mp_diag_ = nullptr;
+    double* xprev_ = nullptr;
+    bool warm_ = false, have_prev_ = false, last_warm_ = false;
     int precond_mode_ = 0;
     TriMGParams mg_prm_;
     CudaTriMG<6> mg_vel_;
