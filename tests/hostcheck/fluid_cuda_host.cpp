@@ -14,7 +14,8 @@ int hc_driver_sequence(int nx, int ny, double W, double H, double q, double rmin
                        int preconditioner, int warm_start, double* up, double* out3) {
     try {
         tmx::FluidSolver solver(nx, ny, W, H, visc, rmin, rmax, 0);
-        if (preconditioner) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+        if (preconditioner & 1) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+        if (preconditioner & 2) solver.set_option(tmx::TM_FLUID_OPT_DEVICE_SCALARS, 1.0);
         solver.set_option(tmx::TM_FLUID_OPT_WARM_START, warm_start ? 1.0 : 0.0);
         solver.set_density(rho1, q);
         const tmx::MinresResult r1 = solver.solve(g_boundary, rtol, maxit, up);
@@ -36,7 +37,11 @@ int hc_driver_solve(int nx, int ny, double W, double H, double q, double rmin, d
                     double* up, double* sens_rhs, double* out3) {
     try {
         tmx::FluidSolver solver(nx, ny, W, H, visc, rmin, rmax, 0);
-        if (preconditioner) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+        if (preconditioner & 1) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+        if (preconditioner & 2) {  // bit 1: MINRES scalars resident on the "device", checked every 7 iterations
+            solver.set_option(tmx::TM_FLUID_OPT_DEVICE_SCALARS, 1.0);
+            solver.set_option(tmx::TM_FLUID_OPT_CHECK_EVERY, 7.0);
+        }
         solver.set_density(rho, q);
         const tmx::MinresResult r = solver.solve(g_boundary, rtol, maxit, up);
         out3[0] = r.relres;

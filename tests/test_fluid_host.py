@@ -384,3 +384,30 @@ def test_warm_start_keeps_the_solution_and_saves_iterations(driver, repo_root, p
     # a Krylov method only gains the digits the guess already has: 243 -> 226 (diagonal) for a 2 %
     # change of a random density at rtol 1e-10; the gain grows as the design settles
     assert its[1] < its[0], its
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_minres_with_device_resident_scalars(driver, repo_root, precond):
+    """TM_FLUID_OPT_DEVICE_SCALARS: the Lanczos / Givens recurrences advance in one-thread scalar steps
+    on the device and the host looks at the residual every 7 iterations: same solution, and the
+    iteration count is the host-scalar count rounded up to the next check."""
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, 16, "diffuser", seed=31)
+    pr.calculate_objective(rho)
+    counts = {}
+    for mode in (precond, precond | 2):
+        up, out3 = np.zeros(m.nu + m.n1), np.zeros(3)
+        its = driver.hc_driver_solve(*args, ptr(rho), ptr(g), 1e-10, 20000, mode, ptr(up), None, ptr(out3))
+        assert its > 0 and out3[2] == 0.0, (mode, its, list(out3))
+        assert np.abs(up[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+        counts[mode] = its
+    host_its, dev_its = counts[precond], counts[precond | 2]
+    assert dev_its % 7 == 0 and host_its <= dev_its < host_its + 7, counts
+    # with a warm start as well
+    driver.hc_driver_sequence.argtypes = [I, I, D, D, D, D, D, D, P, P, P, D, I, I, I, P, P]
+    driver.hc_driver_sequence.restype = I
+    rho2 = np.clip(rho + 0.01, 0.01, 0.99)
+    pr.calculate_objective(rho2)
+    up, out3 = np.zeros(m.nu + m.n1), np.zeros(3)
+    its = driver.hc_driver_sequence(*args, ptr(rho), ptr(rho2), ptr(g), 1e-10, 20000, precond | 2, 1, ptr(up), ptr(out3))
+    assert its > 0 and out3[2] == 1.0
+    assert np.abs(up[:m.nu] - pr.u).max() < 2e-7 * np.abs(pr.u).max()

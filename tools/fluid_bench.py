@@ -33,11 +33,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--state_rtol", type=float, default=1e-10)
     ap.add_argument("--preconditioner", choices=("diagonal", "multigrid"), default="diagonal")
+    ap.add_argument("--device_scalars", action="store_true", help="MINRES scalars resident on the device")
+    ap.add_argument("--warm_start", action="store_true")
     args = ap.parse_args()
     lib = _lib.load_library()
     tmp = tempfile.mkdtemp(prefix="tm_fluid_bench_")
     solver = FEMSolver(args.N, args.design, data_path=tmp, verbose=False,
-                       problem_options={"state_rtol": args.state_rtol, "preconditioner": args.preconditioner})
+                       problem_options={"state_rtol": args.state_rtol, "preconditioner": args.preconditioner,
+                                        "device_scalars": args.device_scalars, "warm_start": args.warm_start})
     problem = solver.problem
     problem.set_penalization(solver.parameters.penalties[-1])
     rho = solver.rho.tensor
@@ -92,7 +95,8 @@ def main():
         "ms_per_step": ms, "wall_s": wall, "steps": args.steps, "warmup": args.warmup, "dtype": "f64",
         "config": {"workload": f"{os.path.basename(args.design)} N={args.N} (nx={solver.mesh.nx}, ny={solver.mesh.ny}; "
                                "Taylor-Hood P2/P1, fp64)", "velocity_dofs": problem.nu, "pressure_dofs": problem.n1,
-                   "state_rtol": args.state_rtol, "preconditioner": args.preconditioner},
+                   "state_rtol": args.state_rtol, "preconditioner": args.preconditioner,
+                   "device_scalars": args.device_scalars, "warm_start": args.warm_start},
         "minres_iterations_by_solve": its, "gpu_launches": lib.tm_launch_count() - launches0,
         "objective_trace": objectives,
         "roofline": {"bound": "hbm", "kernel": "fluid_apply_kernel (+ memset of y)", "achieved": achieved,

@@ -506,4 +506,129 @@ MinresResult fluid_minres(BK& bk, const typename BK::Vec& b, typename BK::Vec& x
     return res;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same MINRES with its Lanczos / Givens scalars RESIDENT ON THE DEVICE: the vector kernels read
+// their coefficients from a small array S, two one-thread "scalar steps" advance the recurrences, and
+// the host reads the residual estimate back only every `check_every` iterations (no synchronisation
+// per iteration: the prerequisite for replaying an iteration from a CUDA graph).  Iterations past
+// convergence inside a check interval are harmless (the residual norm is non-increasing).
+// ---------------------------------------------------------------------------------------------
+enum {
+    MS_GAMMA = 0, MS_GAMMA_OLD = 1, MS_ETA = 2, MS_ETA0 = 3, MS_S_OLD = 4, MS_S = 5, MS_C_OLD = 6, MS_C = 7,
+    MS_DELTA = 8, MS_GNEW_SQ = 9, MS_COEF_V = 10, MS_COEF_VOLD = 11, MS_A3 = 12, MS_A2 = 13, MS_INV_A1 = 14,
+    MS_STEP = 15, MS_INV_GAMMA = 16, MS_RELRES = 17, MS_BREAKDOWN = 18, MS_ITER = 19, MS_COUNT = 24
+};
+
+// start: S[MS_GNEW_SQ] holds z1 . v1
+TM_HD void minres_scalar_init(double* S, double ref_norm) {
+    const double gamma = sqrt(S[MS_GNEW_SQ] > 0.0 ? S[MS_GNEW_SQ] : 0.0);
+    S[MS_GAMMA] = gamma;
+    S[MS_GAMMA_OLD] = 1.0;
+    S[MS_ETA] = gamma;
+    S[MS_ETA0] = ref_norm > 0.0 ? ref_norm : gamma;
+    S[MS_S_OLD] = 0.0;
+    S[MS_S] = 0.0;
+    S[MS_C_OLD] = 1.0;
+    S[MS_C] = 1.0;
+    S[MS_INV_GAMMA] = gamma > 0.0 ? 1.0 / gamma : 0.0;
+    S[MS_RELRES] = S[MS_ETA0] > 0.0 ? gamma / S[MS_ETA0] : 0.0;
+    S[MS_BREAKDOWN] = gamma > 0.0 ? 0.0 : 1.0;
+    S[MS_ITER] = 0.0;
+}
+// after delta = (A z) . z: coefficients of  v_new -= (delta/gamma) v + (gamma/gamma_old) v_old
+TM_HD void minres_scalar_a(double* S) {
+    const double gamma = S[MS_GAMMA], gamma_old = S[MS_GAMMA_OLD];
+    S[MS_COEF_V] = gamma > 0.0 ? -S[MS_DELTA] / gamma : 0.0;
+    S[MS_COEF_VOLD] = gamma_old > 0.0 ? -gamma / gamma_old : 0.0;
+}
+// after gamma_new^2 = z_new . v_new: Givens rotation, direction coefficients, residual, rotation of names
+TM_HD void minres_scalar_b(double* S) {
+    const double gamma = S[MS_GAMMA], delta = S[MS_DELTA];
+    const double gamma_new = sqrt(S[MS_GNEW_SQ] > 0.0 ? S[MS_GNEW_SQ] : 0.0);
+    const double c = S[MS_C], c_old = S[MS_C_OLD], s = S[MS_S], s_old = S[MS_S_OLD];
+    const double a0 = c * delta - c_old * s * gamma;
+    const double a1 = sqrt(a0 * a0 + gamma_new * gamma_new);
+    const double a2 = s * delta + c_old * c * gamma;
+    const double a3 = s_old * gamma;
+    const bool dead = S[MS_BREAKDOWN] != 0.0 || !(a1 > 0.0);
+    const double c_new = dead ? 1.0 : a0 / a1, s_new = dead ? 0.0 : gamma_new / a1;
+    S[MS_A3] = a3;
+    S[MS_A2] = a2;
+    S[MS_INV_A1] = dead ? 0.0 : 1.0 / a1;
+    S[MS_STEP] = dead ? 0.0 : c_new * S[MS_ETA];
+    if (!dead) {
+        S[MS_ETA] = -s_new * S[MS_ETA];
+        S[MS_ITER] += 1.0;
+    }
+    S[MS_GAMMA_OLD] = gamma;
+    S[MS_GAMMA] = gamma_new;
+    S[MS_C_OLD] = c;
+    S[MS_C] = c_new;
+    S[MS_S_OLD] = s;
+    S[MS_S] = s_new;
+    S[MS_INV_GAMMA] = gamma_new > 0.0 ? 1.0 / gamma_new : 0.0;
+    if (!(gamma_new > 0.0)) S[MS_BREAKDOWN] = 1.0;  // Krylov space exhausted: later iterations are no-ops
+    const double eta = S[MS_ETA] < 0.0 ? -S[MS_ETA] : S[MS_ETA];
+    S[MS_RELRES] = S[MS_ETA0] > 0.0 ? eta / S[MS_ETA0] : 0.0;
+}
+
+// BK supplies the *_dev operations (coefficients named by their index in the device array) and
+// read_scalars(host double[MS_COUNT]).
+template <class BK>
+MinresResult fluid_minres_dev(BK& bk, const typename BK::Vec& b, typename BK::Vec& x, double rtol, int maxit,
+                              int check_every, double ref_norm = 0.0) {
+    using Vec = typename BK::Vec;
+    MinresResult res;
+    Vec* pv_old = &bk.work(0);
+    Vec* pv = &bk.work(1);
+    Vec* pv_new = &bk.work(2);
+    Vec* pz = &bk.work(3);
+    Vec* pz_new = &bk.work(4);
+    Vec* pw_old = &bk.work(5);
+    Vec* pw = &bk.work(6);
+    Vec* pw_new = &bk.work(7);
+    bk.zero(x);
+    bk.zero(*pv_old);
+    bk.zero(*pw_old);
+    bk.zero(*pw);
+    bk.copy(b, *pv);
+    bk.precond(*pv, *pz);
+    bk.dot_dev(*pz, *pv, MS_GNEW_SQ);
+    bk.scalar_init(ref_norm);
+    double S[MS_COUNT];
+    bk.read_scalars(S);
+    res.relres = S[MS_RELRES];
+    if (S[MS_BREAKDOWN] != 0.0 || S[MS_RELRES] <= rtol) {
+        res.converged = true;
+        return res;
+    }
+    if (check_every < 1) check_every = 1;
+    for (int j = 1; j <= maxit; ++j) {
+        bk.scale_dev(*pz, MS_INV_GAMMA);
+        bk.apply(*pz, *pv_new);
+        bk.dot_dev(*pv_new, *pz, MS_DELTA);
+        bk.scalar_a();
+        bk.axpy2_dev(*pv_new, MS_COEF_V, *pv, MS_COEF_VOLD, *pv_old);
+        bk.precond(*pv_new, *pz_new);
+        bk.dot_dev(*pz_new, *pv_new, MS_GNEW_SQ);
+        bk.scalar_b();
+        bk.direction_dev(*pw_new, *pz, MS_A3, *pw_old, MS_A2, *pw, MS_INV_A1, x, MS_STEP);
+        Vec* t = pv_old; pv_old = pv; pv = pv_new; pv_new = t;
+        t = pz; pz = pz_new; pz_new = t;
+        t = pw_old; pw_old = pw; pw = pw_new; pw_new = t;
+        if (j % check_every == 0 || j == maxit) {
+            bk.read_scalars(S);
+            res.iterations = (int)S[MS_ITER];
+            res.relres = S[MS_RELRES];
+            if (!(res.relres == res.relres)) break;
+            if (res.relres <= rtol || S[MS_BREAKDOWN] != 0.0) {
+                res.converged = true;
+                break;
+            }
+        }
+    }
+    return res;
+}
+
 }  // namespace tmx

@@ -150,8 +150,38 @@ __global__ void fluid_pmass_add_kernel(size_t n, const double* __restrict__ diag
     TM_GRID_STRIDE(i, n) z[i] += r[i] / diag[i];
 }
 
+// ---- MINRES with device-resident scalars (opt-in): coefficients come from the array S
+__global__ void fluid_scalar_init_kernel(double* S, double ref_norm) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) minres_scalar_init(S, ref_norm);
+}
+__global__ void fluid_scalar_a_kernel(double* S) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) minres_scalar_a(S);
+}
+__global__ void fluid_scalar_b_kernel(double* S) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) minres_scalar_b(S);
+}
+__global__ void fluid_scale_dev_kernel(size_t n, double* x, const double* __restrict__ S, int is) {
+    const double s = S[is];
+    TM_GRID_STRIDE(i, n) x[i] *= s;
+}
+__global__ void fluid_axpy2_dev_kernel(size_t n, double* y, const double* __restrict__ S, int ia,
+                                       const double* __restrict__ p, int ib, const double* __restrict__ q) {
+    const double a = S[ia], b = S[ib];
+    TM_GRID_STRIDE(i, n) y[i] += a * p[i] + b * q[i];
+}
+__global__ void fluid_direction_dev_kernel(size_t n, double* __restrict__ wn, const double* __restrict__ z,
+                                           const double* __restrict__ S, int i3, const double* __restrict__ wo, int i2,
+                                           const double* __restrict__ w, int i1, double* __restrict__ x, int istep) {
+    const double a3 = S[i3], a2 = S[i2], inv_a1 = S[i1], step = S[istep];
+    TM_GRID_STRIDE(i, n) {
+        const double v = (z[i] - a3 * wo[i] - a2 * w[i]) * inv_a1;
+        wn[i] = v;
+        x[i] += step * v;
+    }
+}
+
 enum { TM_FLUID_OPT_PRECOND = 1, TM_FLUID_OPT_FINE_STEPS = 2, TM_FLUID_OPT_COARSE_STEPS = 3,
-       TM_FLUID_OPT_WARM_START = 4 };
+       TM_FLUID_OPT_WARM_START = 4, TM_FLUID_OPT_DEVICE_SCALARS = 5, TM_FLUID_OPT_CHECK_EVERY = 6 };
 
 class FluidSolver {
    public:
@@ -198,6 +228,7 @@ class FluidSolver {
         cudaFree(d_tab_);
         cudaFree(rs_.counter);
         cudaFreeHost(h_sc_);
+        if (h_ms_) cudaFreeHost(h_ms_);
         if (own_stream_) cudaStreamDestroy(own_stream_);
     }
     FluidSolver(const FluidSolver&) = delete;
@@ -219,6 +250,8 @@ class FluidSolver {
                 warm_ = value != 0.0;
                 have_prev_ = false;
                 break;
+            case TM_FLUID_OPT_DEVICE_SCALARS: dev_scalars_ = value != 0.0; break;
+            case TM_FLUID_OPT_CHECK_EVERY: check_every_ = std::max(1, (int)value); break;
             default: throw std::runtime_error("fluid: unknown option " + std::to_string(opt));
         }
     }
@@ -283,7 +316,12 @@ class FluidSolver {
                 ref = 0.0;
             }
         }
-        const MinresResult r = fluid_minres(*this, b, x, rtol, maxit, ref);
+        if (dev_scalars_ && !ms_) {
+            alloc(ms_, MS_COUNT);
+            TM_CUDA(cudaMallocHost(&h_ms_, sizeof(double) * MS_COUNT));
+        }
+        const MinresResult r = dev_scalars_ ? fluid_minres_dev(*this, b, x, rtol, maxit, check_every_, ref)
+                                            : fluid_minres(*this, b, x, rtol, maxit, ref);
         if (warm) {
             DVec xp{xprev_};
             axpy2(x, 1.0, xp, 0.0, xp);  // x <- x_prev + correction
@@ -363,6 +401,43 @@ class FluidSolver {
         TM_CHECK_LAUNCH();
     }
 
+    // ---- additional back-end interface of fluid_minres_dev
+    void dot_dev(const DVec& a, const DVec& b, int idx) {
+        TM_LAUNCH(dot_kernel<double>, vec_grid(), kVecThreads, stream_)(n_, a.p, b.p, rs_, ms_ + idx);
+        TM_CHECK_LAUNCH();
+    }
+    void scalar_init(double ref_norm) {
+        TM_LAUNCH(fluid_scalar_init_kernel, 1, 32, stream_)(ms_, ref_norm);
+        TM_CHECK_LAUNCH();
+    }
+    void scalar_a() {
+        TM_LAUNCH(fluid_scalar_a_kernel, 1, 32, stream_)(ms_);
+        TM_CHECK_LAUNCH();
+    }
+    void scalar_b() {
+        TM_LAUNCH(fluid_scalar_b_kernel, 1, 32, stream_)(ms_);
+        TM_CHECK_LAUNCH();
+    }
+    void scale_dev(DVec& a, int is) {
+        TM_LAUNCH(fluid_scale_dev_kernel, vec_grid(), kVecThreads, stream_)(n_, a.p, ms_, is);
+        TM_CHECK_LAUNCH();
+    }
+    void axpy2_dev(DVec& y, int ia, const DVec& p, int ib, const DVec& q) {
+        TM_LAUNCH(fluid_axpy2_dev_kernel, vec_grid(), kVecThreads, stream_)(n_, y.p, ms_, ia, p.p, ib, q.p);
+        TM_CHECK_LAUNCH();
+    }
+    void direction_dev(DVec& wn, const DVec& z, int i3, const DVec& wo, int i2, const DVec& w, int i1, DVec& x,
+                       int istep) {
+        TM_LAUNCH(fluid_direction_dev_kernel, vec_grid(), kVecThreads, stream_)(n_, wn.p, z.p, ms_, i3, wo.p, i2, w.p,
+                                                                               i1, x.p, istep);
+        TM_CHECK_LAUNCH();
+    }
+    void read_scalars(double* out) {
+        TM_CUDA(cudaMemcpyAsync(h_ms_, ms_, sizeof(double) * MS_COUNT, cudaMemcpyDeviceToHost, stream_));
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        for (int i = 0; i < MS_COUNT; ++i) out[i] = h_ms_[i];
+    }
+
    private:
     void alloc(double*& p, size_t count) {
         TM_CUDA(cudaMalloc(&p, count * sizeof(double)));
@@ -388,6 +463,9 @@ class FluidSolver {
     double* mp_diag_ = nullptr;
     double* xprev_ = nullptr;
     bool warm_ = false, have_prev_ = false, last_warm_ = false;
+    double *ms_ = nullptr, *h_ms_ = nullptr;  // MINRES scalars on the device / their pinned mirror
+    bool dev_scalars_ = false;
+    int check_every_ = 10;
     int precond_mode_ = 0;
     TriMGParams mg_prm_;
     CudaTriMG<6> mg_vel_;

@@ -135,7 +135,8 @@ class FEMSolver(Solver):
                 raise NotImplementedError("the fluid problem runs on one GPU (SURVEY.md section 8f-3)")
             from .fluid_problem import FluidProblem
             options = {k: v for k, v in self.problem_options.items()
-                       if k in ("state_rtol", "state_max_iterations", "projection_rtol", "preconditioner", "warm_start")
+                       if k in ("state_rtol", "state_max_iterations", "projection_rtol", "preconditioner", "warm_start",
+                                "device_scalars")
                        and not (k == "preconditioner" and v == "jacobi")}
             return FluidProblem(self.mesh, problem_parameters, self.parameters,
                                 control_space=self.control_space, **options)
