@@ -158,3 +158,22 @@ def test_multigrid_preconditioner_same_solution_fewer_iterations(repo_root, desi
     assert np.abs(mg.u.tensor.cpu().numpy() - pr.u).max() < 1e-7 * np.abs(pr.u).max()
     its_d, its_m = problem.solve_log[-1]["iterations"], mg.solve_log[-1]["iterations"]
     assert its_m < 0.6 * its_d, (its_m, its_d)      # host check: 94 vs 243 at N=16, 102 vs 492 at N=32
+
+
+@pytest.mark.skipif(os.environ.get("TM_TEST_FLUID_MG") != "1",
+                    reason="opt-in solver variants (device-resident MINRES scalars, warm start): checked through the "
+                           "host build of the driver, not yet run on hardware; opt in with TM_TEST_FLUID_MG=1")
+@pytest.mark.parametrize("options", [dict(device_scalars=True), dict(warm_start=True),
+                                     dict(device_scalars=True, warm_start=True, preconditioner="multigrid")])
+def test_optin_solver_variants_reproduce_the_default_run(repo_root, tmp_path, options):
+    from FEM_src.solver import FEMSolver
+
+    design = os.path.join(repo_root, "designs", "diffuser.json")
+    base = FEMSolver(16, design, data_path=str(tmp_path / "a"), skip_multiple=999, verbose=False)
+    ref = base.solve(fixed_iterations=4)
+    variant = FEMSolver(16, design, data_path=str(tmp_path / "b"), skip_multiple=999, verbose=False,
+                        problem_options=options)
+    got = variant.solve(fixed_iterations=4)
+    trace = max(abs(a - b) / abs(b) for a, b in zip(got["objectives"], ref["objectives"]))
+    assert trace < 1e-7, (options, trace)
+    assert np.abs(variant.to_array(variant.rho) - base.to_array(base.rho)).max() < 1e-6

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader
 nvidia-smi topo -m | head -12
 timeout 120 python -m pytest tests/test_gpu_z_p2p_loopback.py -q 2>&1 | tail -3
-TM_TEST_FLUID_MG=1 timeout 200 python -m pytest tests/test_gpu_z_fluid.py -q -k multigrid 2>&1 | tail -15 | tee gpurun_out/r2_fluid_mg.txt
+TM_TEST_FLUID_MG=1 timeout 200 python -m pytest tests/test_gpu_z_fluid.py -q -k "multigrid or optin" 2>&1 | tail -15 | tee gpurun_out/r2_fluid_mg.txt
 TM_TEST_P2P=1 timeout 700 python -m pytest tests/test_gpu_sharded.py -q -x 2>&1 | tail -15 | tee gpurun_out/r2_p2p_sharded.txt
 for mode in 0 1; do
   TM_P2P=$mode timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
