@@ -212,3 +212,28 @@ def test_weak_scaling_resolution_keeps_equal_strips(repo_root):
         got = bench.mesh_of(design, n)
         assert got == mesh and got[1] % world == 0
         assert abs(got[0] * got[1] / (base[0] * base[1]) / world - 1) < 0.01
+
+
+def test_committed_bench_lines_keep_the_contract(repo_root):
+    """The JSON line bench.py printed on the B200 (committed under profiles/) carries every key of the
+    measurement contract; guards the schema against edits of bench.py made without a GPU at hand."""
+    import json
+
+    full = json.load(open(os.path.join(repo_root, "profiles", "r1j_bench.json")))
+    last = json.load(open(os.path.join(repo_root, "profiles", "r1l_bench_nocpu.json")))
+    for line in (full, last):
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                    "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in line, key
+        assert line["metric"] == "mirror_descent_iters_per_sec" and line["dtype"] == "f64"
+        assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["vs_baseline"] is None
+        assert "workload" in line["config"] and "model" not in line["config"]
+        assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] != line["value"]
+        roof = line["roofline"]
+        assert set(roof) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+        assert roof["bound"] == "hbm" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+        assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+        assert line["gpu_launches"] > 0
+    cpu = full["cpu_baseline"]
+    assert set(cpu) >= {"value", "unit", "cores", "kind", "sample"} and cpu["kind"] in ("port", "reference")
