@@ -1,5 +1,5 @@
 """Command-line entry, same positional arguments and -d/-k flags as the reference's run.py
-(reference: run.py:5-84).  Only the FEM elasticity path exists here.
+(reference: run.py:5-84).  FEM back-end only: elasticity designs (the hot path) and fluid designs.
 
     python run.py designs/cantilever.json 40 [-d output] [-k 1] [--dtype float64]
 """

@@ -163,8 +163,9 @@ def test_multigrid_preconditioner_same_solution_fewer_iterations(repo_root, desi
 @pytest.mark.skipif(os.environ.get("TM_TEST_FLUID_MG") != "1",
                     reason="opt-in solver variants (device-resident MINRES scalars, warm start): checked through the "
                            "host build of the driver, not yet run on hardware; opt in with TM_TEST_FLUID_MG=1")
-@pytest.mark.parametrize("options", [dict(device_scalars=True), dict(warm_start=True),
-                                     dict(device_scalars=True, warm_start=True, preconditioner="multigrid")])
+@pytest.mark.parametrize("options", [dict(fluid_device_scalars=True), dict(fluid_warm_start=True),
+                                     dict(fluid_device_scalars=True, fluid_warm_start=True,
+                                          fluid_preconditioner="multigrid")])
 def test_optin_solver_variants_reproduce_the_default_run(repo_root, tmp_path, options):
     from FEM_src.solver import FEMSolver
 

@@ -237,3 +237,11 @@ def test_committed_bench_lines_keep_the_contract(repo_root):
         assert line["gpu_launches"] > 0
     cpu = full["cpu_baseline"]
     assert set(cpu) >= {"value", "unit", "cores", "kind", "sample"} and cpu["kind"] in ("port", "reference")
+
+
+def test_fluid_solver_variants_stay_off_unless_named(repo_root):
+    """run.py / bench.py pass the ELASTICITY options "preconditioner" and "warm_start"; they must not
+    switch on the fluid solver's opt-in variants, which have their own keys."""
+    src = open(os.path.join(repo_root, "topomax_b200", "fem_solver.py")).read()
+    assert '"fluid_preconditioner": "preconditioner"' in src and '"fluid_warm_start": "warm_start"' in src
+    assert '"preconditioner": "preconditioner"' not in src and '"warm_start": "warm_start"' not in src

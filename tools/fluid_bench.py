@@ -39,8 +39,9 @@ def main():
     lib = _lib.load_library()
     tmp = tempfile.mkdtemp(prefix="tm_fluid_bench_")
     solver = FEMSolver(args.N, args.design, data_path=tmp, verbose=False,
-                       problem_options={"state_rtol": args.state_rtol, "preconditioner": args.preconditioner,
-                                        "device_scalars": args.device_scalars, "warm_start": args.warm_start})
+                       problem_options={"state_rtol": args.state_rtol, "fluid_preconditioner": args.preconditioner,
+                                        "fluid_device_scalars": args.device_scalars,
+                                        "fluid_warm_start": args.warm_start})
     problem = solver.problem
     problem.set_penalization(solver.parameters.penalties[-1])
     rho = solver.rho.tensor

@@ -134,10 +134,12 @@ class FEMSolver(Solver):
             if self.world > 1:
                 raise NotImplementedError("the fluid problem runs on one GPU (SURVEY.md section 8f-3)")
             from .fluid_problem import FluidProblem
-            options = {k: v for k, v in self.problem_options.items()
-                       if k in ("state_rtol", "state_max_iterations", "projection_rtol", "preconditioner", "warm_start",
-                                "device_scalars")
-                       and not (k == "preconditioner" and v == "jacobi")}
+            # the elasticity options "preconditioner" / "warm_start" name other things: the fluid
+            # solver's opt-in variants have their own keys and stay off unless asked for by name
+            rename = {"state_rtol": "state_rtol", "state_max_iterations": "state_max_iterations",
+                      "projection_rtol": "projection_rtol", "fluid_preconditioner": "preconditioner",
+                      "fluid_warm_start": "warm_start", "fluid_device_scalars": "device_scalars"}
+            options = {rename[k]: v for k, v in self.problem_options.items() if k in rename}
             return FluidProblem(self.mesh, problem_parameters, self.parameters,
                                 control_space=self.control_space, **options)
         raise ValueError(
