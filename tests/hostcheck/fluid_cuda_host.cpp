@@ -38,6 +38,7 @@ int hc_driver_solve(int nx, int ny, double W, double H, double q, double rmin, d
     try {
         tmx::FluidSolver solver(nx, ny, W, H, visc, rmin, rmax, 0);
         if (preconditioner & 1) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+        if (preconditioner & 4) solver.set_option(tmx::TM_FLUID_OPT_DETERMINISTIC, 1.0);  // bit 2: gather kernels
         if (preconditioner & 2) {  // bit 1: MINRES scalars resident on the "device", checked every 7 iterations
             solver.set_option(tmx::TM_FLUID_OPT_DEVICE_SCALARS, 1.0);
             solver.set_option(tmx::TM_FLUID_OPT_CHECK_EVERY, 7.0);

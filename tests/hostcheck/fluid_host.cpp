@@ -2,6 +2,7 @@
 // and the MINRES loop of the CUDA fluid path, run serially so that they can be checked against the
 // oracle without a GPU.  Test infrastructure only (tests/test_fluid_host.py).
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../topomax_b200/csrc/tm_fluid.cuh"
@@ -81,6 +82,7 @@ template <int NODES>
 struct HostMG {
     using Vec = double*;
     static constexpr int NE = NODES * (NODES + 1) / 2;
+    static constexpr int kNodes = NODES;
     std::vector<tmx::TriLevel> geo;
     std::vector<std::vector<double>> Lm, diag, store;
     std::vector<double> lmax_, inv;
@@ -282,6 +284,36 @@ int hc_trimg_level_apply(int nx, int ny, double W, double H, double q, double rm
     if (level >= mg.levels()) return -mg.levels();
     mg.apply(level, x, y);
     return mg.levels();
+}
+// the gather form of the level operator (every node written once) against the scatter form
+double hc_trimg_gather_vs_scatter(int nx, int ny, double W, double H, double q, double rmin, double rmax,
+                                  double visc, const double* rho, int kind, int level, const double* x) {
+    HostFluid f(nx, ny, W, H, q, rmin, rmax, visc);
+    f.set_density(rho);
+    double worst = 0.0;
+    auto compare = [&](auto& mg) {
+        if (level >= mg.levels()) { worst = -1.0; return; }
+        const size_t n = mg.size(level);
+        std::vector<double> ys(n), yg(n, 123.0);
+        mg.apply(level, x, ys.data());
+        const size_t nodes = n / mg.geo[level].ncomp;
+        for (size_t k = 0; k < nodes; ++k)
+            tmx::trimg_body_apply_gather<std::remove_reference_t<decltype(mg)>::kNodes>(
+                mg.geo[level], mg.Lm[level].data(), tmx::trimg_num_tri(mg.geo[level]), x, yg.data(), k);
+        double scale = 0.0;
+        for (size_t i = 0; i < n; ++i) scale = std::max(scale, std::fabs(ys[i]));
+        for (size_t i = 0; i < n; ++i) worst = std::max(worst, std::fabs(ys[i] - yg[i]) / (scale > 0 ? scale : 1.0));
+    };
+    if (kind == 0) {
+        HostMG<6> mg;
+        mg.build(tmx::TriLevel{nx, ny, 2, 1}, velocity_local_matrices(f), 16, 1);
+        compare(mg);
+    } else {
+        HostMG<3> mg;
+        mg.build(tmx::TriLevel{nx, ny, 1, 0}, darcy_local_matrices(f, rho), 16, 1);
+        compare(mg);
+    }
+    return worst;
 }
 void hc_trimg_prolong(int kind, int nxf, int nyf, const double* xc, double* xf) {
     if (kind == 0) {

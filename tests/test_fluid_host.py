@@ -411,3 +411,26 @@ def test_minres_with_device_resident_scalars(driver, repo_root, precond):
     its = driver.hc_driver_sequence(*args, ptr(rho), ptr(rho2), ptr(g), 1e-10, 20000, precond | 2, 1, ptr(up), ptr(out3))
     assert its > 0 and out3[2] == 1.0
     assert np.abs(up[:m.nu] - pr.u).max() < 2e-7 * np.abs(pr.u).max()
+
+
+@pytest.mark.parametrize("design,N", [("diffuser", 16), ("twin_pipe", 8)])
+def test_deterministic_gather_mode_matches_the_scatter_mode(driver, repo_root, design, N):
+    """TM_FLUID_OPT_DETERMINISTIC: every scatter-with-atomics work item replaced by its gather form
+    (one work item per output entry, fixed summation order): same operator, diagonals, sensitivity,
+    transfers and therefore the same iteration counts (+-1) and solution, with both preconditioners."""
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, N, design, seed=17)
+    pr.calculate_objective(rho)
+    grad_o = pr.calculate_objective_gradient()
+    for precond in (0, 1):
+        res = {}
+        for mode in (precond, precond | 4):
+            up, rhs, out3 = np.zeros(m.nu + m.n1), np.zeros(m.n1), np.zeros(3)
+            its = driver.hc_driver_solve(*args, ptr(rho), ptr(g), 1e-11, 20000, mode, ptr(up), ptr(rhs), ptr(out3))
+            assert its > 0 and out3[2] == 0.0, (mode, its, list(out3))
+            res[mode] = (its, up.copy(), rhs.copy(), out3[1])
+        (i0, u0, r0, o0), (i1, u1, r1, o1) = res[precond], res[precond | 4]
+        assert abs(i0 - i1) <= 1, (precond, i0, i1)
+        assert np.abs(u0[:m.nu] - u1[:m.nu]).max() < 1e-8 * np.abs(u0[:m.nu]).max()
+        assert np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max() and abs(o0 - o1) < 1e-9 * abs(o0)
+        assert np.abs(u1[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+        assert np.abs(r1 - pr.M1 @ grad_o).max() < 1e-7 * np.abs(r1).max()

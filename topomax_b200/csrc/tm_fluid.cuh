@@ -24,6 +24,7 @@
 #include <cstddef>
 
 #include "tm_element.cuh"  // TM_HD
+#include "tm_trimg.cuh"    // node -> incident triangles (gather forms)
 
 namespace tmx {
 
@@ -412,6 +413,153 @@ TM_HD void fluid_body_sens(const FluidTables& T, const FluidGeom& g, const doubl
     fluid_tri_sens(T, g, rho3, ux, uy, o);
 #pragma unroll
     for (int c = 0; c < 3; ++c) add(&out[vert[c]], o[c]);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Gather forms of the scatter work items above (opt-in "deterministic" mode): one work item per
+// OUTPUT entry, which walks the triangles incident to its node (trimg_incident) in a fixed order and
+// writes once -- no atomics, no memset, bit-reproducible sums.  Work item k < n2 is lattice node k
+// (both velocity components), k >= n2 is vertex k - n2 (pressure / continuity row).
+// ---------------------------------------------------------------------------------------------
+TM_HD void fluid_body_apply_gather(const FluidTables& T, const FluidGeom& g, const double* Me_all, size_t ntri,
+                                   const double* x, double* y, size_t k, int mode) {
+    const size_t n2 = (size_t)g.Lx * g.Ly, nu = 2 * n2;
+    size_t tri[6];
+    int local[6];
+    if (k < n2) {
+        const TriLevel lv{g.nx, g.ny, 2, 1};
+        const int cnt = trimg_incident<6>(lv, k, tri, local);
+        double sx = 0.0, sy = 0.0;
+        bool boundary = false;
+        for (int q = 0; q < cnt; ++q) {
+            int cx, cy, t, node[6], vert[3];
+            bool interior[6];
+            fluid_tid_to_cell(g, tri[q], cx, cy, t);
+            fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+            const int i = local[q];
+            if (!interior[i]) {
+                boundary = true;
+                break;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const bool use = mode == 0 ? interior[j] : !interior[j];
+                if (!use) continue;
+                const double a = Me_all[(size_t)fluid_sym(i, j) * ntri + tri[q]] + T.Kref[t][i][j];
+                sx += a * x[2 * (size_t)node[j]];
+                sy += a * x[2 * (size_t)node[j] + 1];
+            }
+            if (mode == 0)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double p = x[nu + vert[c]];
+                    sx -= T.Dloc[t][c][i][0] * p;
+                    sy -= T.Dloc[t][c][i][1] * p;
+                }
+        }
+        y[2 * k] = boundary ? 0.0 : sx;
+        y[2 * k + 1] = boundary ? 0.0 : sy;
+    } else {
+        const size_t v = k - n2;
+        const TriLevel lv{g.nx, g.ny, 1, 0};
+        const int cnt = trimg_incident<3>(lv, v, tri, local);
+        double s = 0.0;
+        for (int q = 0; q < cnt; ++q) {
+            int cx, cy, t, node[6], vert[3];
+            bool interior[6];
+            fluid_tid_to_cell(g, tri[q], cx, cy, t);
+            fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+            const int c = local[q];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const bool use = mode == 0 ? interior[j] : !interior[j];
+                if (!use) continue;
+                s += T.Dloc[t][c][j][0] * x[2 * (size_t)node[j]] + T.Dloc[t][c][j][1] * x[2 * (size_t)node[j] + 1];
+            }
+        }
+        y[nu + v] = -s;
+    }
+}
+
+// the whole preconditioner diagonal in two gather passes: velocity entries (pass 0), then the
+// pressure entries, which read the velocity ones (pass 1)
+TM_HD void fluid_body_diag_gather(const FluidTables& T, const FluidGeom& g, const double* Me_all, size_t ntri,
+                                  double* diag, size_t k, int pass) {
+    const size_t n2 = (size_t)g.Lx * g.Ly, nu = 2 * n2;
+    size_t tri[6];
+    int local[6];
+    if (pass == 0) {
+        if (k >= n2) return;
+        const TriLevel lv{g.nx, g.ny, 2, 1};
+        const int cnt = trimg_incident<6>(lv, k, tri, local);
+        double a = 0.0;
+        bool boundary = false;
+        for (int q = 0; q < cnt; ++q) {
+            int cx, cy, t, node[6], vert[3];
+            bool interior[6];
+            fluid_tid_to_cell(g, tri[q], cx, cy, t);
+            fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+            if (!interior[local[q]]) {
+                boundary = true;
+                break;
+            }
+            a += Me_all[(size_t)fluid_sym(local[q], local[q]) * ntri + tri[q]] + T.Kref[t][local[q]][local[q]];
+        }
+        diag[2 * k] = diag[2 * k + 1] = boundary ? 1.0 : a;
+    } else {
+        if (k < n2) return;
+        const size_t v = k - n2;
+        const TriLevel lv{g.nx, g.ny, 1, 0};
+        const int cnt = trimg_incident<3>(lv, v, tri, local);
+        double s = 0.0;
+        for (int q = 0; q < cnt; ++q) {
+            int cx, cy, t, node[6], vert[3];
+            bool interior[6];
+            fluid_tid_to_cell(g, tri[q], cx, cy, t);
+            fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+            const int c = local[q];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (interior[j]) {
+                    s += T.Dloc[t][c][j][0] * T.Dloc[t][c][j][0] / diag[2 * (size_t)node[j]];
+                    s += T.Dloc[t][c][j][1] * T.Dloc[t][c][j][1] / diag[2 * (size_t)node[j] + 1];
+                }
+        }
+        diag[nu + v] = s;
+    }
+}
+
+// sensitivity right-hand side of vertex v, and the P1 mass diagonal, by gather
+TM_HD void fluid_body_sens_gather(const FluidTables& T, const FluidGeom& g, const double* rho, const double* u,
+                                  double* out, size_t v) {
+    size_t tri[6];
+    int local[6];
+    const TriLevel lv{g.nx, g.ny, 1, 0};
+    const int cnt = trimg_incident<3>(lv, v, tri, local);
+    double s = 0.0;
+    for (int q = 0; q < cnt; ++q) {
+        int cx, cy, t, node[6], vert[3];
+        bool interior[6];
+        fluid_tid_to_cell(g, tri[q], cx, cy, t);
+        fluid_tri_nodes(g, cx, cy, t, node, vert, interior);
+        const double rho3[3] = {rho[vert[0]], rho[vert[1]], rho[vert[2]]};
+        double ux[6], uy[6], o[3];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            ux[j] = u[2 * (size_t)node[j]];
+            uy[j] = u[2 * (size_t)node[j] + 1];
+        }
+        fluid_tri_sens(T, g, rho3, ux, uy, o);
+        s += o[local[q]];
+    }
+    out[v] = s;
+}
+TM_HD void fluid_body_pmass_diag_gather(const FluidTables& T, const FluidGeom& g, double* diag, size_t v) {
+    size_t tri[6];
+    int local[6];
+    const TriLevel lv{g.nx, g.ny, 1, 0};
+    diag[v] = trimg_incident<3>(lv, v, tri, local) * (T.area / 6.0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -86,6 +86,28 @@ __global__ void __launch_bounds__(128) fluid_sens_kernel(const FluidTables* __re
     TM_FLUID_TRI_LOOP(tid, ntri) fluid_body_sens(*T, g, rho, u, out, tid, FluidAtomicAdd{});
 }
 
+// ---- gather forms (opt-in deterministic mode): one work item per output entry
+__global__ void __launch_bounds__(128) fluid_apply_gather_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                                 const double* __restrict__ Me, size_t ntri,
+                                                                 const double* __restrict__ x, double* __restrict__ y,
+                                                                 size_t items, int mode) {
+    TM_GRID_STRIDE(k, items) fluid_body_apply_gather(*T, g, Me, ntri, x, y, k, mode);
+}
+__global__ void fluid_diag_gather_kernel(const FluidTables* __restrict__ T, FluidGeom g, const double* __restrict__ Me,
+                                         size_t ntri, double* diag, size_t items, int pass) {
+    TM_GRID_STRIDE(k, items) fluid_body_diag_gather(*T, g, Me, ntri, diag, k, pass);
+}
+__global__ void __launch_bounds__(128) fluid_sens_gather_kernel(const FluidTables* __restrict__ T, FluidGeom g,
+                                                                const double* __restrict__ rho,
+                                                                const double* __restrict__ u, double* __restrict__ out,
+                                                                size_t verts) {
+    TM_GRID_STRIDE(v, verts) fluid_body_sens_gather(*T, g, rho, u, out, v);
+}
+__global__ void fluid_pmass_diag_gather_kernel(const FluidTables* __restrict__ T, FluidGeom g, double* diag,
+                                               size_t verts) {
+    TM_GRID_STRIDE(v, verts) fluid_body_pmass_diag_gather(*T, g, diag, v);
+}
+
 // ---- vector kernels of the MINRES loop (combined vector [u | p])
 __global__ void fluid_precond_kernel(size_t n, const double* __restrict__ diag, const double* __restrict__ r,
                                      double* __restrict__ z) {
@@ -181,7 +203,8 @@ __global__ void fluid_direction_dev_kernel(size_t n, double* __restrict__ wn, co
 }
 
 enum { TM_FLUID_OPT_PRECOND = 1, TM_FLUID_OPT_FINE_STEPS = 2, TM_FLUID_OPT_COARSE_STEPS = 3,
-       TM_FLUID_OPT_WARM_START = 4, TM_FLUID_OPT_DEVICE_SCALARS = 5, TM_FLUID_OPT_CHECK_EVERY = 6 };
+       TM_FLUID_OPT_WARM_START = 4, TM_FLUID_OPT_DEVICE_SCALARS = 5, TM_FLUID_OPT_CHECK_EVERY = 6,
+       TM_FLUID_OPT_DETERMINISTIC = 7 };
 
 class FluidSolver {
    public:
@@ -251,6 +274,12 @@ class FluidSolver {
                 have_prev_ = false;
                 break;
             case TM_FLUID_OPT_DEVICE_SCALARS: dev_scalars_ = value != 0.0; break;
+            case TM_FLUID_OPT_DETERMINISTIC:  // gather kernels: no atomics, bit-reproducible
+                deterministic_ = value != 0.0;
+                mg_vel_.set_deterministic(deterministic_);
+                mg_prs_.set_deterministic(deterministic_);
+                have_density_ = false;
+                break;
             case TM_FLUID_OPT_CHECK_EVERY: check_every_ = std::max(1, (int)value); break;
             default: throw std::runtime_error("fluid: unknown option " + std::to_string(opt));
         }
@@ -262,18 +291,31 @@ class FluidSolver {
         g_.q = q;
         TM_LAUNCH(fluid_mass_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, Me_, ntri_);
         TM_CHECK_LAUNCH();
-        TM_LAUNCH(fluid_diag_init_kernel, vec_grid(), kVecThreads, stream_)(g_, diag_, n_);
-        TM_CHECK_LAUNCH();
-        TM_LAUNCH(fluid_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, diag_);
-        TM_CHECK_LAUNCH();
-        TM_LAUNCH(fluid_schur_kernel, tri_grid(), 128, stream_)(d_tab_, g_, diag_, ntri_);
-        TM_CHECK_LAUNCH();
+        if (deterministic_) {
+            const size_t items = nu_ / 2 + n1_;
+            for (int pass = 0; pass < 2; ++pass) {
+                TM_LAUNCH(fluid_diag_gather_kernel, vec_grid(), kVecThreads, stream_)(d_tab_, g_, Me_, ntri_, diag_,
+                                                                                     items, pass);
+                TM_CHECK_LAUNCH();
+            }
+        } else {
+            TM_LAUNCH(fluid_diag_init_kernel, vec_grid(), kVecThreads, stream_)(g_, diag_, n_);
+            TM_CHECK_LAUNCH();
+            TM_LAUNCH(fluid_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, diag_);
+            TM_CHECK_LAUNCH();
+            TM_LAUNCH(fluid_schur_kernel, tri_grid(), 128, stream_)(d_tab_, g_, diag_, ntri_);
+            TM_CHECK_LAUNCH();
+        }
         if (precond_mode_ == 1) {
             if (!mg_vel_.planned()) {
                 mg_vel_.plan(TriLevel{g_.nx, g_.ny, 2, 1}, max_blocks_);
                 mg_prs_.plan(TriLevel{g_.nx, g_.ny, 1, 0}, max_blocks_);
                 alloc(mp_diag_, n1_);
-                TM_LAUNCH(fluid_pmass_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, mp_diag_, ntri_);
+                if (deterministic_) {
+                    TM_LAUNCH(fluid_pmass_diag_gather_kernel, vec_grid(), kVecThreads, stream_)(d_tab_, g_, mp_diag_, n1_);
+                } else {
+                    TM_LAUNCH(fluid_pmass_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, mp_diag_, ntri_);
+                }
                 TM_CHECK_LAUNCH();
             }
             TM_LAUNCH(fluid_vel_local_kernel, tri_grid(), 128, stream_)(d_tab_, Me_, mg_vel_.level_matrices(0), ntri_);
@@ -347,6 +389,11 @@ class FluidSolver {
 
     void sens_rhs(const double* rho, const double* u, double* out) {
         if (!(g_.q > 0.0)) throw std::runtime_error("fluid: set the density / penalisation first");
+        if (deterministic_) {
+            TM_LAUNCH(fluid_sens_gather_kernel, vec_grid(), 128, stream_)(d_tab_, g_, rho, u, out, n1_);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(double), stream_));
         TM_LAUNCH(fluid_sens_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, u, out, ntri_);
         TM_CHECK_LAUNCH();
@@ -355,6 +402,12 @@ class FluidSolver {
     // y = Op x (mode 0) or the lifting of boundary values (mode 1); exposed for the parity tests
     void apply_mode(const double* x, double* y, int mode) {
         need_density();
+        if (deterministic_) {
+            const size_t items = nu_ / 2 + n1_;
+            TM_LAUNCH(fluid_apply_gather_kernel, vec_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, x, y, items, mode);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         TM_CUDA(cudaMemsetAsync(y, 0, n_ * sizeof(double), stream_));
         TM_LAUNCH(fluid_apply_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, x, y, mode);
         TM_CHECK_LAUNCH();
@@ -464,7 +517,7 @@ class FluidSolver {
     double* xprev_ = nullptr;
     bool warm_ = false, have_prev_ = false, last_warm_ = false;
     double *ms_ = nullptr, *h_ms_ = nullptr;  // MINRES scalars on the device / their pinned mirror
-    bool dev_scalars_ = false;
+    bool dev_scalars_ = false, deterministic_ = false;
     int check_every_ = 10;
     int precond_mode_ = 0;
     TriMGParams mg_prm_;

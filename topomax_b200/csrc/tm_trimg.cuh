@@ -276,6 +276,145 @@ TM_HD void trimg_body_restrict(const TriLevel& gf, const TriLevel& gc, const dou
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Node -> incident triangles (for gather-type kernels: every node written once, fixed summation
+// order).  Returns the number of incident (triangle id, local node index) pairs of node `n`.
+//   vertex (ix, iy):   cell (ix, iy) A:0 B:0 | cell (ix-1, iy) A:1 | cell (ix, iy-1) B:1 |
+//                      cell (ix-1, iy-1) A:2 B:2
+//   P2 lattice node (i, j), by parity:  (even, even) the vertex rule;  (odd, even) horizontal edge:
+//   cell below B:4, cell above A:3;  (even, odd) vertical edge: cell left A:4, cell right B:3;
+//   (odd, odd) the diagonal of its cell: A:5, B:5.
+// ---------------------------------------------------------------------------------------------
+template <int NODES>
+TM_HD int trimg_incident(const TriLevel& g, size_t n, size_t (&tri)[6], int (&local)[6]) {
+    int cnt = 0;
+    auto push = [&](int cx, int cy, int t, int k) {
+        if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) return;
+        tri[cnt] = 2 * ((size_t)cy * g.nx + cx) + t;
+        local[cnt] = k;
+        ++cnt;
+    };
+    int ix, iy;
+    bool vertex = true;
+    if (NODES == 6) {
+        const int Lx = 2 * g.nx + 1;
+        const int j = (int)(n / Lx), i = (int)(n - (size_t)j * Lx);
+        const bool io = i & 1, jo = j & 1;
+        ix = i >> 1;
+        iy = j >> 1;
+        if (io && !jo) {  // horizontal edge between vertices ix and ix+1 on vertex row iy
+            vertex = false;
+            push(ix, iy - 1, 1, 4);
+            push(ix, iy, 0, 3);
+        } else if (!io && jo) {  // vertical edge between vertex rows iy and iy+1 on vertex column ix
+            vertex = false;
+            push(ix - 1, iy, 0, 4);
+            push(ix, iy, 1, 3);
+        } else if (io && jo) {
+            vertex = false;
+            push(ix, iy, 0, 5);
+            push(ix, iy, 1, 5);
+        }
+    } else {
+        iy = (int)(n / (g.nx + 1));
+        ix = (int)(n - (size_t)iy * (g.nx + 1));
+    }
+    if (vertex) {
+        push(ix, iy, 0, 0);
+        push(ix, iy, 1, 0);
+        push(ix - 1, iy, 0, 1);
+        push(ix, iy - 1, 1, 1);
+        push(ix - 1, iy - 1, 0, 2);
+        push(ix - 1, iy - 1, 1, 2);
+    }
+    return cnt;
+}
+
+// y[n] = (A x)[n] by gathering over the incident triangles (deterministic; Dirichlet rows give 0)
+template <int NODES>
+TM_HD void trimg_body_apply_gather(const TriLevel& g, const double* Lm, size_t ntri, const double* x, double* y,
+                                   size_t n) {
+    size_t tri[6];
+    int local[6];
+    const int cnt = trimg_incident<NODES>(g, n, tri, local);
+    double acc[2] = {0.0, 0.0};  // ncomp <= 2
+    bool fixed_node = false;
+    for (int q = 0; q < cnt; ++q) {
+        int cx, cy, t, node[NODES];
+        bool in[NODES];
+        trimg_tid_to_cell(g, tri[q], cx, cy, t);
+        trimg_nodes<NODES>(g, cx, cy, t, node, in);
+        const int i = local[q];
+        if (!in[i]) {
+            fixed_node = true;
+            break;
+        }
+        for (int c = 0; c < g.ncomp; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NODES; ++j)
+                if (in[j]) s += Lm[(size_t)trimg_sym<NODES>(i, j) * ntri + tri[q]] * x[(size_t)node[j] * g.ncomp + c];
+            acc[c] += s;
+        }
+    }
+    for (int c = 0; c < g.ncomp; ++c) y[n * g.ncomp + c] = fixed_node ? 0.0 : acc[c];
+}
+
+
+// diagonal by gather (Dirichlet nodes: 1)
+template <int NODES>
+TM_HD void trimg_body_diag_gather(const TriLevel& g, const double* Lm, size_t ntri, double* diag, size_t n) {
+    size_t tri[6];
+    int local[6];
+    const int cnt = trimg_incident<NODES>(g, n, tri, local);
+    double acc = 0.0;
+    bool fixed_node = false;
+    for (int q = 0; q < cnt; ++q) {
+        int cx, cy, t, node[NODES];
+        bool in[NODES];
+        trimg_tid_to_cell(g, tri[q], cx, cy, t);
+        trimg_nodes<NODES>(g, cx, cy, t, node, in);
+        if (!in[local[q]]) {
+            fixed_node = true;
+            break;
+        }
+        acc += Lm[(size_t)trimg_sym<NODES>(local[q], local[q]) * ntri + tri[q]];
+    }
+    for (int c = 0; c < g.ncomp; ++c) diag[n * g.ncomp + c] = fixed_node ? 1.0 : acc;
+}
+
+// r_c[nc] = (P^T r_f)[nc] by gather: the fine nodes whose transfer stencil can contain coarse node nc
+// lie within one coarse cell of it; each is asked for its stencil (the same function the scatter form
+// and the prolongation use), so this is the exact transpose with a fixed summation order.
+template <int NODES>
+TM_HD void trimg_body_restrict_gather(const TriLevel& gf, const TriLevel& gc, const double* rf, double* rc,
+                                      size_t nc) {
+    const int span = NODES == 6 ? 4 : 2;                  // fine node steps per coarse cell
+    const int cstep = NODES == 6 ? 2 : 2;                 // fine node steps per coarse NODE step
+    const int Lxc = NODES == 6 ? 2 * gc.nx + 1 : gc.nx + 1;
+    const int Lxf = NODES == 6 ? 2 * gf.nx + 1 : gf.nx + 1, Lyf = NODES == 6 ? 2 * gf.ny + 1 : gf.ny + 1;
+    const int jc = (int)(nc / Lxc), ic = (int)(nc - (size_t)jc * Lxc);
+    const int i0 = ic * cstep, j0 = jc * cstep;           // the coarse node on the fine lattice
+    double acc[2] = {0.0, 0.0};
+    for (int j = j0 - span; j <= j0 + span; ++j) {
+        if (j < 0 || j >= Lyf) continue;
+        for (int i = i0 - span; i <= i0 + span; ++i) {
+            if (i < 0 || i >= Lxf) continue;
+            int cnode[NODES];
+            double w[NODES];
+            bool cin[NODES];
+            const size_t nf = (size_t)j * Lxf + i;
+            if (!trimg_transfer_stencil<NODES>(gf, gc, nf, cnode, w, cin)) continue;
+#pragma unroll
+            for (int k = 0; k < NODES; ++k)
+                if ((size_t)cnode[k] == nc && cin[k] && w[k] != 0.0)
+                    for (int c = 0; c < gf.ncomp; ++c) acc[c] += w[k] * rf[nf * gf.ncomp + c];
+        }
+    }
+    for (int c = 0; c < gf.ncomp; ++c) rc[nc * gf.ncomp + c] = acc[c];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Coarsest level: explicit inverse of the assembled scalar operator, built on the host from the
 // level's local matrices (both back-ends).  Dirichlet rows (empty after assembly) become identity.

@@ -67,6 +67,23 @@ __global__ void trimg_restrict_kernel(TriLevel gf, TriLevel gc, const double* __
                                       size_t nodes) {
     TM_GRID_STRIDE(nf, nodes) trimg_body_restrict<NODES>(gf, gc, rf, rc, nf, TriAtomicAdd{});
 }
+// gather forms (deterministic mode): one work item per output node, no atomics, no memset
+template <int NODES>
+__global__ void __launch_bounds__(128) trimg_apply_gather_kernel(TriLevel g, const double* __restrict__ Lm, size_t ntri,
+                                                                 const double* __restrict__ x, double* __restrict__ y,
+                                                                 size_t nodes) {
+    TM_GRID_STRIDE(n, nodes) trimg_body_apply_gather<NODES>(g, Lm, ntri, x, y, n);
+}
+template <int NODES>
+__global__ void trimg_diag_gather_kernel(TriLevel g, const double* __restrict__ Lm, size_t ntri, double* diag,
+                                         size_t nodes) {
+    TM_GRID_STRIDE(n, nodes) trimg_body_diag_gather<NODES>(g, Lm, ntri, diag, n);
+}
+template <int NODES>
+__global__ void trimg_restrict_gather_kernel(TriLevel gf, TriLevel gc, const double* __restrict__ rf,
+                                             double* __restrict__ rc, size_t cnodes) {
+    TM_GRID_STRIDE(nc, cnodes) trimg_body_restrict_gather<NODES>(gf, gc, rf, rc, nc);
+}
 // r = b - r   (r holds A x)
 __global__ void trimg_residual_kernel(size_t n, const double* __restrict__ b, double* r) {
     TM_GRID_STRIDE(i, n) r[i] = b[i] - r[i];
@@ -153,6 +170,7 @@ class CudaTriMG {
         TM_CUDA(cudaMemcpy(tab_, &tab, sizeof(tab), cudaMemcpyHostToDevice));
     }
     bool planned() const { return !geo_.empty(); }
+    void set_deterministic(bool on) { deterministic_ = on; }
     double* level_matrices(int l) { return Lm_[l]; }
 
     // Galerkin coarse matrices, diagonals, smoothing bounds and the coarsest inverse from level 0
@@ -167,6 +185,12 @@ class CudaTriMG {
         }
         for (int l = 0; l < L; ++l) {
             const size_t n = size(l), nt = trimg_num_tri(geo_[l]);
+            if (deterministic_) {
+                const size_t nodes = trimg_num_nodes<NODES>(geo_[l]);
+                TM_LAUNCH(trimg_diag_gather_kernel<NODES>, grid(nodes, 256), 256, st)(geo_[l], Lm_[l], nt, diag_[l], nodes);
+                TM_CHECK_LAUNCH();
+                continue;
+            }
             TM_LAUNCH(trimg_diag_init_kernel<NODES>, grid(n, 256), 256, st)(geo_[l], diag_[l], n);
             TM_CHECK_LAUNCH();
             TM_LAUNCH(trimg_diag_kernel<NODES>, grid(nt, 128), 128, st)(geo_[l], Lm_[l], nt, diag_[l]);
@@ -222,6 +246,12 @@ class CudaTriMG {
     Vec vec(int l, int which) { return store_[l] + (size_t)which * size(l); }
     void apply(int l, const double* x, double* y) {
         const size_t nt = trimg_num_tri(geo_[l]);
+        if (deterministic_) {
+            const size_t nodes = trimg_num_nodes<NODES>(geo_[l]);
+            TM_LAUNCH(trimg_apply_gather_kernel<NODES>, grid(nodes, 128), 128, stream_)(geo_[l], Lm_[l], nt, x, y, nodes);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         TM_CUDA(cudaMemsetAsync(y, 0, size(l) * sizeof(double), stream_));
         TM_LAUNCH(trimg_apply_kernel<NODES>, grid(nt, 128), 128, stream_)(geo_[l], Lm_[l], nt, x, y);
         TM_CHECK_LAUNCH();
@@ -240,6 +270,13 @@ class CudaTriMG {
         TM_CHECK_LAUNCH();
     }
     void restrict_to(int l, Vec rf, Vec bc) {
+        if (deterministic_) {
+            const size_t cnodes = trimg_num_nodes<NODES>(geo_[l + 1]);
+            TM_LAUNCH(trimg_restrict_gather_kernel<NODES>, grid(cnodes, 128), 128, stream_)(geo_[l], geo_[l + 1], rf, bc,
+                                                                                           cnodes);
+            TM_CHECK_LAUNCH();
+            return;
+        }
         const size_t nodes = trimg_num_nodes<NODES>(geo_[l]);
         TM_CUDA(cudaMemsetAsync(bc, 0, size(l + 1) * sizeof(double), stream_));
         TM_LAUNCH(trimg_restrict_kernel<NODES>, grid(nodes, 256), 256, stream_)(geo_[l], geo_[l + 1], rf, bc, nodes);
@@ -289,6 +326,7 @@ class CudaTriMG {
     double* inv_ = nullptr;
     TriCoarsenTable<NODES>* tab_ = nullptr;
     int ncoarse_ = 0, max_blocks_ = 148 * 16;
+    bool deterministic_ = false;
     cudaStream_t stream_ = nullptr;
 };
 

@@ -138,7 +138,8 @@ class FEMSolver(Solver):
             # solver's opt-in variants have their own keys and stay off unless asked for by name
             rename = {"state_rtol": "state_rtol", "state_max_iterations": "state_max_iterations",
                       "projection_rtol": "projection_rtol", "fluid_preconditioner": "preconditioner",
-                      "fluid_warm_start": "warm_start", "fluid_device_scalars": "device_scalars"}
+                      "fluid_warm_start": "warm_start", "fluid_device_scalars": "device_scalars",
+                      "fluid_deterministic": "deterministic"}
             options = {rename[k]: v for k, v in self.problem_options.items() if k in rename}
             return FluidProblem(self.mesh, problem_parameters, self.parameters,
                                 control_space=self.control_space, **options)
