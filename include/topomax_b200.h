@@ -220,7 +220,9 @@ int tm_fluid_set_stream(tm_fluid_handle h, void* stream);
  * option 5: keep the MINRES scalars on the device (one-thread scalar steps, no synchronisation per
  * iteration; default 0) and option 6: iterations between the residual read-backs then (default 10);
  * option 7: deterministic mode -- gather kernels (one work item per output entry, fixed summation
- * order, no atomics) instead of the per-triangle scatter kernels (default 0) */
+ * order, no atomics) instead of the per-triangle scatter kernels (default 0); option 8: six MINRES
+ * iterations (the period of the vector roles) captured once per solve and replayed as a CUDA graph
+ * (implies option 5; default 0) */
 int tm_fluid_set_option(tm_fluid_handle h, int option, double value);
 int tm_fluid_set_density(tm_fluid_handle h, const double* rho, double q);
 int tm_fluid_state_solve(tm_fluid_handle h, const double* boundary_velocity, double rtol, int maxit, double* up,

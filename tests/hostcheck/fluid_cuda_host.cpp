@@ -3,6 +3,7 @@
 // sequence, "device memory" = malloc.  Checks what the element-level host build
 // (fluid_host.cpp) cannot: buffer sizes, offsets, level bookkeeping, option handling.
 #define TM_HOST_SHIM 1
+#include <cstdio>
 #include "../../topomax_b200/csrc/tm_fluid_cuda.cuh"
 
 extern "C" {
@@ -39,6 +40,10 @@ int hc_driver_solve(int nx, int ny, double W, double H, double q, double rmin, d
         tmx::FluidSolver solver(nx, ny, W, H, visc, rmin, rmax, 0);
         if (preconditioner & 1) solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
         if (preconditioner & 4) solver.set_option(tmx::TM_FLUID_OPT_DETERMINISTIC, 1.0);  // bit 2: gather kernels
+        if (preconditioner & 8) {  // bit 3: six iterations replayed from a captured graph, residual every 12
+            solver.set_option(tmx::TM_FLUID_OPT_GRAPH, 1.0);
+            solver.set_option(tmx::TM_FLUID_OPT_CHECK_EVERY, 12.0);
+        }
         if (preconditioner & 2) {  // bit 1: MINRES scalars resident on the "device", checked every 7 iterations
             solver.set_option(tmx::TM_FLUID_OPT_DEVICE_SCALARS, 1.0);
             solver.set_option(tmx::TM_FLUID_OPT_CHECK_EVERY, 7.0);
@@ -54,6 +59,7 @@ int hc_driver_solve(int nx, int ny, double W, double H, double q, double rmin, d
         if (r2.iterations != r.iterations) return -100000 - r2.iterations;
         return r.converged ? r.iterations : -r.iterations;
     } catch (const std::exception& e) {
+        std::fprintf(stderr, "hc_driver_solve: %s\n", e.what());
         out3[2] = 1.0;
         return -1;
     }

@@ -434,3 +434,23 @@ def test_deterministic_gather_mode_matches_the_scatter_mode(driver, repo_root, d
         assert np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max() and abs(o0 - o1) < 1e-9 * abs(o0)
         assert np.abs(u1[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
         assert np.abs(r1 - pr.M1 @ grad_o).max() < 1e-7 * np.abs(r1).max()
+
+
+@pytest.mark.parametrize("precond", [0, 1, 5])
+def test_minres_replayed_from_a_captured_graph(driver, repo_root, precond):
+    """TM_FLUID_OPT_GRAPH: six iterations (the period of the vector roles) are captured once per solve and
+    replayed.  The CUDA shim models stream capture -- launches and async memory operations are recorded,
+    not executed, and anything illegal inside a capture throws -- so the contents and the legality of
+    the captured block (including the multigrid V-cycles, precond = 1, and the gather kernels, 5) are
+    checked here; the count is the host-scalar count rounded up to the 12-iteration check."""
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, 16, "diffuser", seed=41)
+    pr.calculate_objective(rho)
+    counts = {}
+    for mode in (precond, precond | 8):
+        up, out3 = np.zeros(m.nu + m.n1), np.zeros(3)
+        its = driver.hc_driver_solve(*args, ptr(rho), ptr(g), 1e-10, 20000, mode, ptr(up), None, ptr(out3))
+        assert its > 0 and out3[2] == 0.0, (mode, its, list(out3))
+        assert np.abs(up[:m.nu] - pr.u).max() < 1e-7 * np.abs(pr.u).max()
+        counts[mode] = its
+    plain, graph = counts[precond], counts[precond | 8]
+    assert graph % 12 == 0 and plain <= graph < plain + 12, counts

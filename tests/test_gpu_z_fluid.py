@@ -165,6 +165,7 @@ def test_multigrid_preconditioner_same_solution_fewer_iterations(repo_root, desi
                            "host build of the driver, not yet run on hardware; opt in with TM_TEST_FLUID_MG=1")
 @pytest.mark.parametrize("options", [dict(fluid_device_scalars=True), dict(fluid_warm_start=True), dict(fluid_deterministic=True),
                                      dict(fluid_deterministic=True, fluid_preconditioner="multigrid"),
+                                     dict(fluid_graph=True), dict(fluid_graph=True, fluid_preconditioner="multigrid"),
                                      dict(fluid_device_scalars=True, fluid_warm_start=True,
                                           fluid_preconditioner="multigrid")])
 def test_optin_solver_variants_reproduce_the_default_run(repo_root, tmp_path, options):

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--device_scalars", action="store_true", help="MINRES scalars resident on the device")
     ap.add_argument("--warm_start", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="gather kernels instead of scatter + atomics")
+    ap.add_argument("--graph", action="store_true", help="six MINRES iterations replayed from a CUDA graph")
     args = ap.parse_args()
     lib = _lib.load_library()
     tmp = tempfile.mkdtemp(prefix="tm_fluid_bench_")
@@ -43,7 +44,7 @@ def main():
                        problem_options={"state_rtol": args.state_rtol, "fluid_preconditioner": args.preconditioner,
                                         "fluid_device_scalars": args.device_scalars,
                                         "fluid_warm_start": args.warm_start,
-                                        "fluid_deterministic": args.deterministic})
+                                        "fluid_deterministic": args.deterministic, "fluid_graph": args.graph})
     problem = solver.problem
     problem.set_penalization(solver.parameters.penalties[-1])
     rho = solver.rho.tensor
@@ -100,7 +101,7 @@ def main():
                                "Taylor-Hood P2/P1, fp64)", "velocity_dofs": problem.nu, "pressure_dofs": problem.n1,
                    "state_rtol": args.state_rtol, "preconditioner": args.preconditioner,
                    "device_scalars": args.device_scalars, "warm_start": args.warm_start,
-                   "deterministic": args.deterministic},
+                   "deterministic": args.deterministic, "graph": args.graph},
         "minres_iterations_by_solve": its, "gpu_launches": lib.tm_launch_count() - launches0,
         "objective_trace": objectives,
         "roofline": {"bound": "hbm", "kernel": "fluid_apply_kernel (+ memset of y)", "achieved": achieved,

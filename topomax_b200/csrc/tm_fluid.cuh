@@ -779,4 +779,77 @@ MinresResult fluid_minres_dev(BK& bk, const typename BK::Vec& b, typename BK::Ve
     return res;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// ... and replayed from a captured graph.  The vector roles rotate with periods 3 (v), 2 (z) and 3 (w),
+// so after SIX iterations every pointer is back where it started: six iterations are captured once
+// per solve (bk.begin_capture / end_capture: nothing executes while capturing) and the graph is
+// replayed; the host looks at the residual every `check_every` iterations, rounded to whole blocks.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMinresGraphBlock = 6;
+
+template <class BK>
+MinresResult fluid_minres_graph(BK& bk, const typename BK::Vec& b, typename BK::Vec& x, double rtol, int maxit,
+                                int check_every, double ref_norm = 0.0) {
+    using Vec = typename BK::Vec;
+    MinresResult res;
+    Vec* pv_old = &bk.work(0);
+    Vec* pv = &bk.work(1);
+    Vec* pv_new = &bk.work(2);
+    Vec* pz = &bk.work(3);
+    Vec* pz_new = &bk.work(4);
+    Vec* pw_old = &bk.work(5);
+    Vec* pw = &bk.work(6);
+    Vec* pw_new = &bk.work(7);
+    bk.zero(x);
+    bk.zero(*pv_old);
+    bk.zero(*pw_old);
+    bk.zero(*pw);
+    bk.copy(b, *pv);
+    bk.precond(*pv, *pz);
+    bk.dot_dev(*pz, *pv, MS_GNEW_SQ);
+    bk.scalar_init(ref_norm);
+    double S[MS_COUNT];
+    bk.read_scalars(S);
+    res.relres = S[MS_RELRES];
+    if (S[MS_BREAKDOWN] != 0.0 || S[MS_RELRES] <= rtol) {
+        res.converged = true;
+        return res;
+    }
+    bk.begin_capture();
+    for (int k = 0; k < kMinresGraphBlock; ++k) {
+        bk.scale_dev(*pz, MS_INV_GAMMA);
+        bk.apply(*pz, *pv_new);
+        bk.dot_dev(*pv_new, *pz, MS_DELTA);
+        bk.scalar_a();
+        bk.axpy2_dev(*pv_new, MS_COEF_V, *pv, MS_COEF_VOLD, *pv_old);
+        bk.precond(*pv_new, *pz_new);
+        bk.dot_dev(*pz_new, *pv_new, MS_GNEW_SQ);
+        bk.scalar_b();
+        bk.direction_dev(*pw_new, *pz, MS_A3, *pw_old, MS_A2, *pw, MS_INV_A1, x, MS_STEP);
+        Vec* t = pv_old; pv_old = pv; pv = pv_new; pv_new = t;
+        t = pz; pz = pz_new; pz_new = t;
+        t = pw_old; pw_old = pw; pw = pw_new; pw_new = t;
+    }
+    bk.end_capture();
+    const int blocks_per_check = check_every > kMinresGraphBlock ? check_every / kMinresGraphBlock : 1;
+    int blocks = 0;
+    for (int it = 0; it < maxit; it += kMinresGraphBlock) {
+        bk.replay();
+        ++blocks;
+        if (blocks % blocks_per_check == 0 || it + kMinresGraphBlock >= maxit) {
+            bk.read_scalars(S);
+            res.iterations = (int)S[MS_ITER];
+            res.relres = S[MS_RELRES];
+            if (!(res.relres == res.relres)) break;
+            if (res.relres <= rtol || S[MS_BREAKDOWN] != 0.0) {
+                res.converged = true;
+                break;
+            }
+        }
+    }
+    bk.drop_graph();
+    return res;
+}
+
 }  // namespace tmx

@@ -204,7 +204,7 @@ __global__ void fluid_direction_dev_kernel(size_t n, double* __restrict__ wn, co
 
 enum { TM_FLUID_OPT_PRECOND = 1, TM_FLUID_OPT_FINE_STEPS = 2, TM_FLUID_OPT_COARSE_STEPS = 3,
        TM_FLUID_OPT_WARM_START = 4, TM_FLUID_OPT_DEVICE_SCALARS = 5, TM_FLUID_OPT_CHECK_EVERY = 6,
-       TM_FLUID_OPT_DETERMINISTIC = 7 };
+       TM_FLUID_OPT_DETERMINISTIC = 7, TM_FLUID_OPT_GRAPH = 8 };
 
 class FluidSolver {
    public:
@@ -252,6 +252,7 @@ class FluidSolver {
         cudaFree(rs_.counter);
         cudaFreeHost(h_sc_);
         if (h_ms_) cudaFreeHost(h_ms_);
+        drop_graph();
         if (own_stream_) cudaStreamDestroy(own_stream_);
     }
     FluidSolver(const FluidSolver&) = delete;
@@ -274,6 +275,10 @@ class FluidSolver {
                 have_prev_ = false;
                 break;
             case TM_FLUID_OPT_DEVICE_SCALARS: dev_scalars_ = value != 0.0; break;
+            case TM_FLUID_OPT_GRAPH:  // six MINRES iterations replayed from a captured graph (implies option 5)
+                use_graph_ = value != 0.0;
+                if (use_graph_) dev_scalars_ = true;
+                break;
             case TM_FLUID_OPT_DETERMINISTIC:  // gather kernels: no atomics, bit-reproducible
                 deterministic_ = value != 0.0;
                 mg_vel_.set_deterministic(deterministic_);
@@ -362,8 +367,9 @@ class FluidSolver {
             alloc(ms_, MS_COUNT);
             TM_CUDA(cudaMallocHost(&h_ms_, sizeof(double) * MS_COUNT));
         }
-        const MinresResult r = dev_scalars_ ? fluid_minres_dev(*this, b, x, rtol, maxit, check_every_, ref)
-                                            : fluid_minres(*this, b, x, rtol, maxit, ref);
+        const MinresResult r = use_graph_     ? fluid_minres_graph(*this, b, x, rtol, maxit, check_every_, ref)
+                               : dev_scalars_ ? fluid_minres_dev(*this, b, x, rtol, maxit, check_every_, ref)
+                                              : fluid_minres(*this, b, x, rtol, maxit, ref);
         if (warm) {
             DVec xp{xprev_};
             axpy2(x, 1.0, xp, 0.0, xp);  // x <- x_prev + correction
@@ -485,6 +491,21 @@ class FluidSolver {
                                                                                i1, x.p, istep);
         TM_CHECK_LAUNCH();
     }
+    // ---- stream capture of the iteration block of fluid_minres_graph
+    void begin_capture() { TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal)); }
+    void end_capture() {
+        cudaGraph_t graph = nullptr;
+        TM_CUDA(cudaStreamEndCapture(stream_, &graph));
+        drop_graph();
+        const cudaError_t e = cudaGraphInstantiate(&graph_exec_, graph, 0);
+        cudaGraphDestroy(graph);
+        TM_CUDA(e);
+    }
+    void replay() { TM_CUDA(cudaGraphLaunch(graph_exec_, stream_)); }
+    void drop_graph() {
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        graph_exec_ = nullptr;
+    }
     void read_scalars(double* out) {
         TM_CUDA(cudaMemcpyAsync(h_ms_, ms_, sizeof(double) * MS_COUNT, cudaMemcpyDeviceToHost, stream_));
         TM_CUDA(cudaStreamSynchronize(stream_));
@@ -517,7 +538,8 @@ class FluidSolver {
     double* xprev_ = nullptr;
     bool warm_ = false, have_prev_ = false, last_warm_ = false;
     double *ms_ = nullptr, *h_ms_ = nullptr;  // MINRES scalars on the device / their pinned mirror
-    bool dev_scalars_ = false, deterministic_ = false;
+    bool dev_scalars_ = false, deterministic_ = false, use_graph_ = false;
+    cudaGraphExec_t graph_exec_ = nullptr;
     int check_every_ = 10;
     int precond_mode_ = 0;
     TriMGParams mg_prm_;

@@ -139,7 +139,7 @@ class FEMSolver(Solver):
             rename = {"state_rtol": "state_rtol", "state_max_iterations": "state_max_iterations",
                       "projection_rtol": "projection_rtol", "fluid_preconditioner": "preconditioner",
                       "fluid_warm_start": "warm_start", "fluid_device_scalars": "device_scalars",
-                      "fluid_deterministic": "deterministic"}
+                      "fluid_deterministic": "deterministic", "fluid_graph": "graph"}
             options = {rename[k]: v for k, v in self.problem_options.items() if k in rename}
             return FluidProblem(self.mesh, problem_parameters, self.parameters,
                                 control_space=self.control_space, **options)

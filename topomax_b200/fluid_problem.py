@@ -111,7 +111,8 @@ class FluidProblem(Problem):
                  domain_parameters: DomainParameters, *, control_space: FunctionSpace | None = None,
                  state_rtol: float = 1e-10, state_max_iterations: int = 200000, projection_rtol: float = 1e-12,
                  preconditioner: str = "diagonal", warm_start: bool = False,
-                 device_scalars: bool = False, deterministic: bool = False, device=None):
+                 device_scalars: bool = False, deterministic: bool = False, graph: bool = False,
+                 device=None):
         """``preconditioner``: "diagonal" (default) or "multigrid" (V-cycles on per-triangle Galerkin
         matrices for the velocity block and the pressure's Darcy Laplacian; needs cell counts with
         enough factors of two; checked on the CPU, not yet run on hardware)."""
@@ -160,6 +161,9 @@ class FluidProblem(Problem):
         self.deterministic = bool(deterministic)  # gather kernels instead of scatter + atomics
         if self.deterministic:
             _lib.check(self.lib.tm_fluid_set_option(self._h, 7, 1.0))
+        self.graph = bool(graph)  # six MINRES iterations replayed from a captured CUDA graph
+        if self.graph:
+            _lib.check(self.lib.tm_fluid_set_option(self._h, 8, 1.0))
         self.solution_space = FunctionSpace(mesh, "CG", 2, dtype="float64", device=self.device)
         self.n1 = (mesh.nx + 1) * (mesh.ny + 1)
         self.nu = 2 * (2 * mesh.nx + 1) * (2 * mesh.ny + 1)
