@@ -8,8 +8,19 @@ optimisation are timed, so the density field evolves exactly as in a run.
     python bench.py [--gpus N] [--steps K] [--warmup W]              # CUDA arm
     python bench.py --impl reference [--steps K] [--warmup W]        # CPU arm (oracle port)
 
-Workload at N=1: designs/short_cantilever.json at N=512 (configs[1] of BASELINE.json; the
-reference's N truncation makes it nx=1020, ny=510, 4 167 722 displacement dofs), fp64.
+Workloads = the configurations BASELINE.json names, by GPU count (override: --design / --N):
+    1 GPU   designs/bridge.json N=2048       (12288 x 2048 cells, 201 383 938 displacement dofs)
+    2, 4    designs/triangle.json N=4096     (4096 x 4096 cells, 134 250 498 dofs), row strips
+    8       cantilever N=16384               (49152 x 16384 cells, 6 442 713 090 dofs), row strips
+plus, on one GPU, a separately labelled latency-bound line: designs/short_cantilever.json N=512.
+`value` at N > 1 is iterations/s x (global dofs / dofs of the 1-GPU workload): the whole-job rate
+normalised to the mesh the 1-GPU line runs (the meshes of BASELINE.json's configs differ).
+
+Every CUDA line checks itself: the displacement of the last timed state solve is handed to the
+INDEPENDENT CPU operator (oracle/c/elast_omp.c: numerical quadrature, plain C + OpenMP) and the line
+carries ||b - K_cpu u_gpu|| / ||b|| and the compliance u . K_cpu u against the GPU's u . b
+(`parity`); multi-GPU lines also compare their objective trace with a single-GPU run of the same
+mesh when that fits one GPU.
 """
 from __future__ import annotations
 
@@ -26,30 +37,49 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-DESIGN = "short_cantilever"
-FULL_N = 512
+# BASELINE.json configs by GPU count
+WORKLOADS = {1: ("bridge", 2048), 2: ("triangle", 4096), 4: ("triangle", 4096), 8: ("cantilever", 16384)}
+SECONDARY = ("short_cantilever", 512)  # configs[1]: latency-bound on a B200, reported separately
 METRIC = "mirror_descent_iters_per_sec"
 UNIT = "iter/s"
+RESIDUAL_BOUND = 1e-9    # ||b - K_cpu u_gpu|| / ||b||
+COMPLIANCE_BOUND = 1e-6  # |u.K_cpu u - u.b| / |u.b|   (north_star: compliance within 1e-6 per solve)
+FULL_CHECK_MAX_DOFS = 300_000_000  # rank-local dofs up to which the CPU operator runs on every row
+
+# stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's INFO lines
+# among them) is routed to stderr, where the driver looks for the communicator's rank count
+_REAL_STDOUT = None
 
 
-def workload_description(design, full_n, nx, ny):
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def workload_for(world):
+    key = max(k for k in WORKLOADS if k <= max(1, world))
+    return WORKLOADS[key]
+
+
+def workload_description(design, full_n, nx, ny, dtype="float64"):
     n_u = 2 * (2 * nx + 1) * (2 * ny + 1)
     return {
-        "workload": f"designs/{design}.json N={full_n} (nx={nx}, ny={ny}; vector-P2 / P1, fp64)",
+        "workload": f"designs/{design}.json N={full_n} (nx={nx}, ny={ny}; vector-P2 / P1, "
+                    f"{'fp64' if dtype == 'float64' else 'fp32'})",
         "n_cells": nx * ny, "n_density_dofs": (nx + 1) * (ny + 1), "n_displacement_dofs": n_u,
     }
-
-
-def weak_scaling_n(design_path, full_n, world):
-    """Resolution of the weak-scaling run on `world` GPUs: N * sqrt(world) (~world x the cells), with
-    the elements per unit length rounded down to a multiple of `world` so that every strip gets the
-    same number of cell rows (unchanged for 2 and 4 GPUs on the default design; 1448 -> 1440 on 8)."""
-    from topomax_b200.designs.design_parser import parse_design
-    dom, _ = parse_design(design_path)
-    shortest = min(dom.width, dom.height)
-    per_unit = int(int(round(full_n * world ** 0.5)) / shortest)
-    per_unit -= per_unit % world
-    return int(per_unit * shortest)
 
 
 def mesh_of(design_path, full_n):
@@ -57,6 +87,10 @@ def mesh_of(design_path, full_n):
     dom, _ = parse_design(design_path)
     n = int(full_n / min(dom.width, dom.height))
     return int(dom.width * n), int(dom.height * n)
+
+
+def design_file(name):
+    return name if os.path.isfile(name) else os.path.join(ROOT, "designs", f"{name}.json")
 
 
 class ClockSampler:
@@ -117,18 +151,11 @@ class ClockSampler:
         return out
 
 
-class Function_like:
-    """minimal stand-in so that FEMSolver.to_array can read an arbitrary device tensor"""
-
-    def __init__(self, tensor, solver):
-        self.tensor = tensor
-
-
-def measured_traffic(design, full_n, dtype, kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def measured_traffic(design, full_n, dtype, category):
+    """DRAM bytes per launch of a kernel from the committed ncu capture, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-            entry = json.load(fh).get(f"{design}:{full_n}:{dtype}:{kernel}")
+            entry = json.load(fh).get(f"{design}:{full_n}:{dtype}:{category}")
         return (entry["bytes_per_launch"], entry["source"]) if entry else (None, None)
     except Exception:
         return None, None
@@ -143,30 +170,158 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+KERNEL_OF = {
+    "fine_op_plain": "elast_apply_kernel<{T},xi,EP_PLAIN>", "fine_op_dot": "elast_apply_kernel<{T},xi,EP_DOT>",
+    "fine_op_resid": "elast_apply_kernel<{T},xi,EP_RESID>", "fine_op_cheb": "elast_apply_kernel<{T},xi,EP_CHEB>",
+    "fine_op_resid0": "elast_apply_kernel<{T},xi,EP_RESID0>", "fine_op_chebdot": "elast_apply_kernel<{T},xi,EP_CHEBDOT>",
+    "restrict": "mg_restrict_kernel<{T}>", "prolong": "mg_prolong_add_kernel<{T}>", "cheb_first": "cheb_first_kernel<{T}>",
+    "pcg_update": "pcg_update_kernel<{T}>", "pcg_direction": "pcg_direction_kernel<{T}>",
+    "reductions": "dot_kernel / pcg_start_kernel<{T}>", "tail": "tail_vcycle_kernel<{T}>",
+    "sensitivity": "sens_rhs_kernel<{T}>",
+}
+COMM_CATEGORIES = ("halo", "allreduce", "gather")
+
+
+def kernel_name(category, tname):
+    if category in KERNEL_OF:
+        return KERNEL_OF[category].format(T=tname)
+    if category.startswith("level") and category.endswith("_op"):
+        return f"elast_apply_kernel<{tname},stored moments,*> on multigrid level {category[5:-3]}"
+    return category
+
+
+# --------------------------------------------------------------------------------------
+# independent CPU operator check (oracle/c/elast_omp.c) of a GPU state solve
+# --------------------------------------------------------------------------------------
+def slab_operator_sums(d, nx, nyg, g0, nrows, u, b, xi, own=None, threads=0):
+    """The C + OpenMP quadrature operator on a slab of `nrows` cell rows starting at GLOBAL cell row g0
+    (numpy arrays: u, b of shape (2 nrows + 1, 2 nx + 1, 2), xi of shape (nrows + 1, nx + 1)).
+    Returns ([sum r^2, sum u.(K u), dofs checked], seconds of the apply, threads) over the lattice rows
+    whose stencil is complete inside the slab -- all but its first / last row unless that row is the
+    domain boundary -- intersected with the slab-local row range `own` when given."""
+    import numpy as np
+    from oracle.fem_oracle import lame
+    from oracle.omp_kernels import OmpElasticity
+
+    lda, mu = lame(d["E"], d["nu"])
+    Lx = 2 * nx + 1
+    at_bottom, at_top = g0 == 0, g0 + nrows == nyg
+    sides = [s for s in d["fixed_sides"] if s in ("Left", "Right")]
+    if "Bottom" in d["fixed_sides"] and at_bottom:
+        sides.append("Bottom")
+    if "Top" in d["fixed_sides"] and at_top:
+        sides.append("Top")
+    op = OmpElasticity(d["width"], d["height"] * nrows / nyg, nx, nrows, lda, mu, sides,
+                       p=d["penalties"][0], threads=threads)
+    t0 = time.perf_counter()
+    y = op.apply(np.ascontiguousarray(xi, dtype=np.float64).reshape(-1),
+                 np.ascontiguousarray(u, dtype=np.float64).reshape(-1)).reshape(u.shape)
+    seconds = time.perf_counter() - t0
+    j_lo = 0 if at_bottom else 1
+    j_hi = 2 * nrows + 1 if at_top else 2 * nrows
+    if own is not None:
+        j_lo, j_hi = max(j_lo, own[0]), min(j_hi, own[1])
+    res = (b - y)[j_lo:j_hi]
+    # Dirichlet rows are identity rows of the CPU operator (y = u there, and u = 0) and b_D = 0
+    # (FEM_src/pde_solver.py:125): they carry no residual
+    for col, side in ((0, "Left"), (Lx - 1, "Right")):
+        if side in sides:
+            res[:, col, :] = 0.0
+    if "Bottom" in sides and j_lo == 0 and j_hi > j_lo:
+        res[0] = 0.0
+    if "Top" in sides and j_hi == 2 * nrows + 1 and j_hi > j_lo:
+        res[-1] = 0.0
+    sums = np.array([float(np.vdot(res, res)), float(np.vdot(u[j_lo:j_hi], y[j_lo:j_hi])),
+                     float(max(j_hi - j_lo, 0) * Lx * 2)])
+    return sums, seconds, op.threads
+
+
+def cpu_operator_check(problem, solver_objective, design_path, world, threads=0, band_cells=256):
+    """Applies the C + OpenMP quadrature operator to the displacement the GPU returned.
+
+    Rank-local: the strip's stored lattice (owned rows + halo rows, refreshed by the solve) is a
+    standalone slab for the CPU operator; residual and energy are taken on the OWNED rows (their
+    stencils are complete inside the stored strip) and summed over ranks.  Strips above
+    FULL_CHECK_MAX_DOFS dofs check a band of `band_cells` cell rows at the bottom of the stored strip
+    (for rank > 0 that band straddles the boundary with the rank below: halo consistency)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle.md_oracle import read_design
+
+    eng = problem.engine
+    d = read_design(design_path)
+    nx, nyg, ny_loc = eng.nx, eng.ny, eng.ny_local
+    Lx = 2 * nx + 1
+    t_start = time.perf_counter()
+    bb = eng.dot_p2(problem.load, problem.load)  # collective: ||b||^2 over all ranks
+    full = eng.nu <= FULL_CHECK_MAX_DOFS
+    r0, r1 = (0, ny_loc) if full else (0, min(ny_loc, band_cells))
+    rows = slice(2 * r0, 2 * r1 + 1)
+    to_host = lambda t, shape: t.detach().reshape(shape)[rows].contiguous().cpu().numpy().astype(np.float64)
+    u = to_host(problem.u.tensor, (2 * ny_loc + 1, Lx, 2))
+    b = to_host(problem.load, (2 * ny_loc + 1, Lx, 2))
+    xi = problem.filtered_rho.tensor.detach().reshape(ny_loc + 1, nx + 1)[r0:r1 + 1].contiguous().cpu().numpy()
+    own = None
+    if full:
+        own_lo, own_hi, _ = eng.owned_p2_rows()
+        own = (own_lo - 2 * r0, own_hi - 2 * r0)
+    sums, t_apply, nthreads = slab_operator_sums(d, nx, nyg, eng.cl0 + r0, r1 - r0, u, b, xi, own, threads)
+    if world > 1:
+        t = torch.as_tensor(sums, dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t)
+        sums = t.cpu().numpy()
+    out = {
+        "check": "independent CPU operator (oracle/c/elast_omp.c: 16-point quadrature, C + OpenMP) applied to the "
+                 "GPU displacement of the last timed state solve",
+        "coverage": "every lattice row" if full else
+                    f"band sample: the lowest {r1 - r0} stored cell rows of every rank ({int(sums[2])} dofs)",
+        "relative_residual": float(np.sqrt(sums[0] / bb)) if bb > 0 else None,
+        "relative_residual_bound": RESIDUAL_BOUND,
+        "cpu_threads_per_rank": nthreads, "cpu_apply_seconds": round(t_apply, 3),
+    }
+    ok = out["relative_residual"] is not None and out["relative_residual"] <= RESIDUAL_BOUND
+    if full:
+        out["compliance_gpu"] = solver_objective
+        out["compliance_cpu_energy"] = float(sums[1])
+        out["compliance_rel_diff"] = abs(sums[1] - solver_objective) / abs(solver_objective)
+        out["compliance_bound"] = COMPLIANCE_BOUND
+        ok = ok and out["compliance_rel_diff"] <= COMPLIANCE_BOUND
+    out["ok"] = bool(ok)
+    out["seconds"] = round(time.perf_counter() - t_start, 2)
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm (assembly + sparse direct solves)
 # --------------------------------------------------------------------------------------
-def oracle_iteration_seconds(design_path, sample_n, steps, warmup):
-    """Times `steps` mirror-descent iterations of the oracle at resolution sample_n."""
+def oracle_iteration_seconds(design_path, sample_n, steps, warmup, budget_s=None):
+    """Times `steps` mirror-descent iterations of the oracle at resolution sample_n (after `warmup`
+    untimed ones).  Returns (times, solver, seconds of the first objective evaluation); stops early
+    with times = None when the first objective predicts the run would exceed budget_s."""
     from oracle.md_oracle import OracleSolver, expit, logit
 
     s = OracleSolver(sample_n, design_path)
     s.problem.set_penalization(s.design["penalties"][0])
     psi = logit(s.rho)
-    s.problem.calculate_objective(s.rho)
+    t0 = time.perf_counter()
+    s.bench_objectives = [s.problem.calculate_objective(s.rho)]
+    first = time.perf_counter() - t0
+    if budget_s is not None and 1.15 * first * (warmup + steps) > budget_s:
+        return None, s, first
     times = []
     for k in range(warmup + steps):
         t0 = time.perf_counter()
         psi = s.step(psi.copy(), s.step_size_at_iter(k))
         s.rho = expit(psi)
-        s.problem.calculate_objective(s.rho)
+        s.bench_objectives.append(s.problem.calculate_objective(s.rho))
         dt = time.perf_counter() - t0
         if k >= warmup:
             times.append(dt)
-    return times, s
+    return times, s, first
 
 
-def omp_kernel_baseline(design_path, full_n, max_iterations=60):
+def omp_kernel_baseline(design_path, full_n, max_iterations=20):
     """Like-for-like CPU *kernel* figure: the C + OpenMP matrix-free operator with
     Jacobi-PCG (oracle/c/elast_omp.c) on all host cores, at the FULL resolution of the GPU
     workload, for a bounded number of PCG iterations on the initial (uniform) design."""
@@ -181,11 +336,8 @@ def omp_kernel_baseline(design_path, full_n, max_iterations=60):
     lda, mu = lame(d["E"], d["nu"])
     op = OmpElasticity(d["width"], d["height"], nx, ny, lda, mu, d["fixed_sides"], p=d["penalties"][0])
     xi = np.full(op.n1, d["volume_fraction"])
-    if d["body_force"] is None:
-        b = StructuredMesh(d["width"], d["height"], nx, ny).load_vector(None, d["tractions"])
-    else:  # the P2 mass matrix of the body-force load is not worth assembling for a timing
-        b = np.zeros(op.nu)
-        b[1::2] = -1.0
+    b = np.zeros(op.nu)  # a timing: any right-hand side does (the P2 load assembly is not the subject)
+    b[1::2] = -1.0
     _, its, rel, sec = op.jacobi_pcg(xi, b, rtol=1e-10, maxit=max_iterations)
     return {"what": "C + OpenMP matrix-free P2 elasticity operator (quadrature) + Jacobi-PCG, fp64",
             "dof_iters_per_sec": op.nu * its / sec if sec > 0 else None, "cores": op.threads,
@@ -193,34 +345,66 @@ def omp_kernel_baseline(design_path, full_n, max_iterations=60):
             "seconds": sec}
 
 
-def pick_sample_n(full_n, steps_total, budget_s):
-    # sparse LU with nested dissection on a 2-D mesh: ~17 s at N=256 here, flops ~ N^3
-    for n in (full_n, 384, 256, 192, 128, 96, 64):
+def oracle_cost_estimate(design_path, n):
+    """Seconds per mirror-descent iteration of the scipy oracle (assembly + SuperLU with nested
+    dissection), calibrated on bridge N=64/128, triangle N=128/256 and short_cantilever N=192/256:
+    ~ c * dofs^1.5 + linear part, c = 1.7e-8 .. 2.9e-8 over those runs (2.4e-8 used; the arm re-scales the model
+    to the host it runs on from its first objective evaluation)."""
+    nx, ny = mesh_of(design_path, n)
+    dofs = 2 * (2 * nx + 1) * (2 * ny + 1)
+    return 2.4e-8 * dofs ** 1.5 + 4e-6 * dofs
+
+
+def pick_sample_n(design_path, full_n, iterations, budget_s):
+    from topomax_b200.designs.design_parser import parse_design
+    dom, _ = parse_design(design_path)
+    shortest = min(dom.width, dom.height)
+    cands = sorted({int(shortest * k) for k in (512, 384, 256, 192, 160, 128, 96, 80, 64, 48, 40, 32, 24, 16, 8)},
+                   reverse=True)
+    for n in cands:
         if n > full_n:
             continue
-        est = 22.0 * (n / 256.0) ** 3 + 3.0 * (n / 256.0) ** 2
-        if est * steps_total <= budget_s:
+        if oracle_cost_estimate(design_path, n) * iterations <= budget_s:
             return n
-    return 64
+    return cands[-1]
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    design_path = os.path.join(ROOT, "designs", f"{args.design}.json")
-    nx, ny = mesh_of(design_path, args.N)
-    warmup = min(args.warmup, 1)
-    sample_n = args.sample_n or pick_sample_n(args.N, warmup + args.steps, 240.0)
-    times, s = oracle_iteration_seconds(design_path, sample_n, args.steps, warmup)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    design, full_n = (args.design, args.N) if args.design else workload_for(world)
+    if args.N and not args.design:
+        full_n = args.N
+    design_path = design_file(design)
+    nx, ny = mesh_of(design_path, full_n)
+    warmup, steps = args.warmup, args.steps  # the same K and W as the CUDA arm is asked for
+    budget = args.reference_budget_s
+    sample_n = args.sample_n or pick_sample_n(design_path, full_n, warmup + steps, 0.7 * budget)
+    while True:
+        times, s, first = oracle_iteration_seconds(design_path, sample_n, steps, warmup, budget_s=budget)
+        if times is not None or args.sample_n:
+            break
+        smaller = pick_sample_n(design_path, sample_n - 1, warmup + steps, 0.7 * budget * (oracle_cost_estimate(
+            design_path, sample_n) / first))  # rescale the cost model to this host
+        if smaller >= sample_n:
+            smaller = max(8, sample_n // 2)
+        sample_n = smaller
     total = sum(times)
     value = len(times) / total
-    sample = (f"{len(times)} mirror-descent iteration(s) of the scipy oracle (CSR assembly + SuperLU with "
-              f"nested-dissection ordering in MUMPS' role) on designs/{args.design}.json at N={sample_n} "
-              f"(nx={s.mesh.nx}, ny={s.mesh.ny}, {s.mesh.nu} displacement dofs"
-              + ("" if sample_n == args.N else f"; bounded sample: the metric workload is N={args.N}") + ")")
-    cfg = workload_description(args.design, args.N, nx, ny)
-    cfg["reference_sample_N"] = sample_n
+    snx, sny = s.mesh.nx, s.mesh.ny
+    sample = (f"{len(times)} mirror-descent iteration(s) after {warmup} warm-up one(s) of the scipy oracle (CSR "
+              f"assembly + SuperLU with nested-dissection ordering in MUMPS' role: a fresh factorisation per solve, "
+              f"FEM_src/pde_solver.py:130-131) on designs/{design}.json at N={sample_n} (nx={snx}, ny={sny}, "
+              f"{s.mesh.nu} displacement dofs)"
+              + ("" if sample_n == full_n else
+                 f"; a BOUNDED SAMPLE: the CUDA arm's workload is N={full_n} ({nx * ny / (snx * sny):.0f}x the cells), "
+                 f"where a sparse direct solve does not fit the host's memory or the time limit"))
+    cfg = workload_description(design, sample_n, snx, sny)  # the workload this arm really ran
+    cfg.update({"cuda_arm_workload": workload_description(design, full_n, nx, ny)["workload"],
+                "same_config_as_cuda_arm": sample_n == full_n,
+                "like_for_like_pair": "the CUDA arm's cpu_baseline.same_config_pair times both arms at one N"})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
@@ -231,16 +415,84 @@ def run_reference_arm(args):
                          "split_seconds": {k: round(v, 3) for k, v in s.problem.timings.items()}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    try:
-        line["cpu_baseline"]["state_solve_kernel"] = omp_kernel_baseline(design_path, args.N)
-    except Exception as exc:  # the direct-solver figure above is the arm's value either way
-        line["cpu_baseline"]["state_solve_kernel"] = {"unavailable": repr(exc)}
-    print(json.dumps(line))
+    if not args.no_omp_baseline:
+        try:
+            line["cpu_baseline"]["state_solve_kernel"] = omp_kernel_baseline(
+                design_path, min(full_n, args.omp_max_n) if args.omp_max_n else full_n)
+        except Exception as exc:  # the direct-solver figure above is the arm's value either way
+            line["cpu_baseline"]["state_solve_kernel"] = {"unavailable": repr(exc)}
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------------------
+def md_loop(solver, problem, psi, rho, prev, k, n, objectives):
+    for _ in range(n):
+        prev.copy_(psi)
+        solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
+        objectives.append(problem.calculate_objective(solver.rho))
+        k += 1
+    return k
+
+
+def timed_device_run(design_path, full_n, args, *, steps, warmup, distributed, dtype="float64", mixed=False,
+                     options=None):
+    """Builds a solver and times `steps` device-resident mirror-descent iterations after `warmup`.
+    Returns a dict with the solver, timings, ledger and traces (used for the main line, the
+    latency-bound secondary line, the same-config pair and the single-GPU comparison)."""
+    import torch
+    import torch.distributed as dist
+    from topomax_b200.fem_solver import FEMSolver
+
+    world = dist.get_world_size() if distributed else 1
+    tmp = tempfile.mkdtemp(prefix="tm_bench_")
+    solver = FEMSolver(full_n, design_path, data_path=tmp, verbose=False, dtype=dtype, distributed=distributed,
+                       dist_levels=args.dist_levels,
+                       problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
+                                        "mixed_precision": mixed, "warm_start": not args.no_warm_start})
+    problem, engine = solver.problem, solver.problem.engine
+    for kv in (options if options is not None else args.engine_option):
+        key, val = kv.split("=")
+        engine.set_option(int(key), float(val))
+    problem.set_penalization(solver.parameters.penalties[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rho = solver.rho.tensor
+    psi = torch.log(rho / (1.0 - rho))
+    prev = torch.empty_like(psi)
+    objectives = [problem.calculate_objective(solver.rho)]
+    k = md_loop(solver, problem, psi, rho, prev, 0, warmup, objectives)
+    engine.ledger_read(reset=True)
+    log0 = len(problem.solve_log)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    state0 = (psi.clone(), rho.clone(), k)
+    barrier()
+    start.record()
+    k = md_loop(solver, problem, psi, rho, prev, k, steps, objectives)
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    return dict(solver=solver, problem=problem, engine=engine, psi=psi, rho=rho, prev=prev, k=k,
+                objectives=objectives, elapsed_ms=elapsed_ms, ledger=engine.ledger_read(reset=True),
+                solves=problem.solve_log[log0:log0 + steps], state0=state0, barrier=barrier)
+
+
+def ledger_totals(ledger):
+    hbm = sum(v["bytes"] for c, v in ledger.items() if c not in COMM_CATEGORIES)
+    link = sum(v["bytes"] for c, v in ledger.items() if c in COMM_CATEGORIES)
+    launches = sum(v["launches"] for v in ledger.values())
+    return hbm, link, launches
+
+
 def run_cuda_arm(args):
     import numpy as np
     import torch
@@ -249,8 +501,9 @@ def run_cuda_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries exactly one JSON line: keep NCCL's version banner off it
-    os.environ["NCCL_DEBUG"] = os.environ.get("TM_NCCL_DEBUG", "WARN")
+    # NCCL's communicator lines (rank counts, transports) go to stderr with everything else
+    os.environ.setdefault("NCCL_DEBUG", os.environ.get("TM_NCCL_DEBUG", "INFO"))
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (CUDA arm) needs a GPU; use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -258,159 +511,114 @@ def run_cuda_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from topomax_b200 import _lib
-    from topomax_b200.fem_solver import FEMSolver
-    from topomax_b200.solver import expit, logit
 
-    design_path = args.design if os.path.isfile(args.design) else os.path.join(ROOT, "designs", f"{args.design}.json")
-    tmp = tempfile.mkdtemp(prefix="tm_bench_")
-    # weak scaling: the same design at N * sqrt(world), i.e. ~world x the cells, cut into one
-    # strip of cell rows per GPU (NCCL halo exchange per operator application, all-reduced dots)
-    run_n = args.N if (world == 1 or args.exact_N) else weak_scaling_n(design_path, args.N, world)
-    base_nx, base_ny = mesh_of(design_path, args.N)
-    solver = FEMSolver(run_n, design_path, data_path=tmp, verbose=False, dtype=args.dtype,
-                       distributed=world > 1, dist_levels=args.dist_levels,
-                       problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
-                                        "mixed_precision": args.mixed, "warm_start": not args.no_warm_start})
-    problem, engine = solver.problem, solver.problem.engine
-    for kv in args.engine_option:
-        key, val = kv.split("=")
-        engine.set_option(int(key), float(val))
+    design, run_n = (args.design, args.N) if args.design else workload_for(world)
+    if args.N and not args.design:
+        run_n = args.N
+    design_path = design_file(design)
+    base_design, base_n = WORKLOADS[1]
+    base_nx, base_ny = mesh_of(design_file(base_design), base_n)
+    nu_base = 2 * (2 * base_nx + 1) * (2 * base_ny + 1)
+    esize = 8 if args.dtype == "float64" else 4
+    tname = "double" if esize == 8 else "float"
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    in_profiler = bool(os.environ.get("TM_PROFILER_RANGE"))  # ncu --profile-from-start off
+    if in_profiler:
+        # the profiled range is the timed region of a run whose warm-up is not profiled
+        torch.cuda.profiler.stop()
+    run = timed_device_run(design_path, run_n, args, steps=args.steps, warmup=args.warmup, distributed=world > 1,
+                           dtype=args.dtype, mixed=args.mixed) if not in_profiler else None
+    if in_profiler:
+        run = profiled_run(design_path, run_n, args, world)
+    clocks = sampler.stop()
+    solver, problem, engine = run["solver"], run["problem"], run["engine"]
+    psi, rho, prev, k, objectives = run["psi"], run["rho"], run["prev"], run["k"], run["objectives"]
+    barrier = run["barrier"]
+    elapsed_ms, solves, ledger = run["elapsed_ms"], run["solves"], run["ledger"]
     nx, ny = solver.mesh.nx, solver.mesh.ny
     n1, nu = engine.n1, engine.nu  # rank-local sizes (owned + halo rows)
     nu_global = 2 * (2 * nx + 1) * (2 * ny + 1)
-    nu_base = 2 * (2 * base_nx + 1) * (2 * base_ny + 1)
-    size_factor = nu_global / nu_base  # 1 on one GPU
-    esize = 8 if args.dtype == "float64" else 4
-    problem.set_penalization(solver.parameters.penalties[0])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident loop: W warm-up + K timed mirror-descent iterations
-    rho = solver.rho.tensor
-    psi = torch.log(rho / (1.0 - rho))
-    prev = torch.empty_like(psi)
-    objectives = [problem.calculate_objective(solver.rho)]
-    k = 0
-    for _ in range(args.warmup):
-        prev.copy_(psi)
-        solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
-        objectives.append(problem.calculate_objective(solver.rho))
-        k += 1
-
-    engine.set_option(_lib.OPT_PROFILE, 1)
-    engine.profile_read()
-    counts0 = engine.last_solve_stats()["fine_launches_total"]
-    log0 = len(problem.solve_log)
-    launches0 = engine.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    in_profiler = bool(os.environ.get("TM_PROFILER_RANGE"))  # ncu --profile-from-start off
-    if in_profiler:
-        torch.cuda.profiler.start()
-    psi_at_start, rho_at_start, k_at_start = psi.clone(), rho.clone(), k  # the e2e leg repeats these steps
-    start.record()
-    for _ in range(args.steps):
-        prev.copy_(psi)
-        solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
-        objectives.append(problem.calculate_objective(solver.rho))
-        k += 1
-    stop.record()
-    barrier()
-    if in_profiler:
-        torch.cuda.profiler.stop()
-    elapsed_ms = start.elapsed_time(stop)
-    clocks = sampler.stop()
-    prof = engine.profile_read()
-    counts1 = engine.last_solve_stats()["fine_launches_total"]
-    true_counts = {n: counts1[n] - counts0[n] for n in counts1}
-    launches = engine.launch_count() - launches0
-    # one extra, untimed iteration with every multigrid level instrumented (diagnostic only)
-    engine.set_option(_lib.OPT_PROFILE, 2)
-    prev.copy_(psi)
-    solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
-    objectives.append(problem.calculate_objective(solver.rho))
-    k += 1
-    engine.profile_read()
-    level_profile = getattr(engine, "last_level_profile", None)
-    engine.set_option(_lib.OPT_PROFILE, 0)
-    solves = problem.solve_log[log0:log0 + args.steps]
+    size_factor = nu_global / nu_base if not args.design else 1.0
+    raw_rate = args.steps / (elapsed_ms * 1e-3)
+    value = size_factor * raw_rate
     pcg_iters = sum(s["iterations"] for s in solves)
     fine_applies = sum(s["fine_applies"] for s in solves)
+    hbm_bytes, link_bytes, launches = ledger_totals(ledger)
 
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    raw_rate = args.steps / (elapsed_ms * 1e-3)
-    # whole-job aggregate: iterations/s normalised to the 1-GPU mesh (x global dofs / 1-GPU dofs)
-    value = size_factor * raw_rate
+    # ---- self-check of the last timed state solve against the independent CPU operator
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = cpu_operator_check(problem, objectives[-1], design_path, world,
+                                        threads=max(1, (os.cpu_count() or 1) // world))
+        except Exception as exc:
+            parity = {"ok": False, "error": repr(exc)}
+
+    # ---- one extra, untimed iteration with every launch event-timed by ledger category
+    engine.set_option(_lib.OPT_PROFILE, 3)
+    engine.ledger_read(reset=True)
+    k = md_loop(solver, problem, psi, rho, prev, k, 1, objectives)
+    torch.cuda.synchronize()
+    by_cat = engine.ledger_read(reset=True)
+    engine.set_option(_lib.OPT_PROFILE, 0)
+    instrumented_ms = sum(v["ms"] for v in by_cat.values())
 
     # ---- end to end through the reference-facing hooks with HOST buffers (numpy in/out):
-    # Solver.step + calculate_objective of src/solver.py.
-    # FEMSolver's numpy hooks count their own PCIe traffic (pinned staging inside _h2d/_d2h).
-    # Per step: psi goes up, psi_new comes down, the objective comes down; rho = expit(psi_new) is
-    # left on the device by FEMSolver.step (the reference loop's host-side expit + upload is not
-    # needed to evaluate the next objective).
-    # The leg repeats exactly the mirror-descent iterations of the device-timed region (same
-    # starting design, same PCG work).  Untimed first: the state at that point is re-established
-    # and the pinned staging buffers are allocated.
-    psi_host = None
+    # Solver.step + calculate_objective of src/solver.py.  Per step: psi goes up, psi_new comes down,
+    # the objective comes down (rho = expit(psi_new) is left on the device by FEMSolver.step).  On a
+    # sharded solver every rank's host process holds its own strip of psi (pinned staging each way).
+    # The leg repeats exactly the mirror-descent iterations of the device-timed region.
+    e2e_value, traffic = None, {"h2d": 0, "d2h": 0}
     if not args.no_e2e:
-        k = k_at_start
-        rho.copy_(rho_at_start)
+        psi0, rho0, k0 = run["state0"]
+        rho.copy_(rho0)
         objectives.append(problem.calculate_objective(solver.rho))
-        psi_host = solver.to_array(Function_like(psi_at_start, solver))
-        solver._h2d(psi_host)
-    solver.h2d_bytes = solver.d2h_bytes = 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(0 if args.no_e2e else args.steps):
-        psi_host = solver.step(psi_host, solver.step_size_at_iter(k))
-        objectives.append(problem.calculate_objective(solver.rho))
-        k += 1
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    traffic = {"h2d": solver.h2d_bytes, "d2h": solver.d2h_bytes}
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = None if args.no_e2e else size_factor * args.steps / float(t.item())
+        psi_host = solver.host_array(psi0)
+        solver._h2d(psi_host, local=True)  # allocates the pinned staging buffers (untimed)
+        solver.h2d_bytes = solver.d2h_bytes = 0
+        kk = k0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            psi_host = solver.step_local(psi_host, solver.step_size_at_iter(kk))
+            objectives.append(problem.calculate_objective(solver.rho))
+            kk += 1
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        traffic = {"h2d": solver.h2d_bytes, "d2h": solver.d2h_bytes}
+        t = torch.tensor([e2e_s, traffic["h2d"], traffic["d2h"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e2e_s, traffic = float(tmax[0].item()), {"h2d": int(t[1].item()), "d2h": int(t[2].item())}
+        e2e_value = size_factor * args.steps / e2e_s
 
     # ---- reported separately: the same iterations with the multigrid preconditioner in fp32 inside
     # the fp64 PCG (TM option 117).  Residual test, search directions and the converged displacement
-    # stay fp64 (parity: test_mixed_precision_preconditioner_keeps_fp64_accuracy); the headline
-    # `value` above is the all-fp64 run.
+    # stay fp64; the headline `value` above is the all-fp64 run.
     mixed_leg = None
     if world == 1 and esize == 8 and not args.mixed and not args.no_mixed_leg and args.preconditioner == "multigrid":
         engine.set_option(117, 1)
-        k = k_at_start
-        psi.copy_(psi_at_start)
-        rho.copy_(rho_at_start)
+        psi0, rho0, k0 = run["state0"]
+        psi.copy_(psi0)
+        rho.copy_(rho0)
         objectives_mixed = [problem.calculate_objective(solver.rho)]  # untimed: builds the fp32 hierarchy
         log1 = len(problem.solve_log)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         start.record()
-        for _ in range(args.steps):
-            prev.copy_(psi)
-            solver.step_device(prev, solver.step_size_at_iter(k), psi, rho)
-            objectives_mixed.append(problem.calculate_objective(solver.rho))
-            k += 1
+        md_loop(solver, problem, psi, rho, prev, k0, args.steps, objectives_mixed)
         stop.record()
         barrier()
-        t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = start.elapsed_time(stop)
         engine.set_option(117, 0)
         msolves = problem.solve_log[log1:log1 + args.steps]
         ref_obj = objectives[args.warmup:args.warmup + args.steps + 1]
         mixed_leg = {
-            "value": size_factor * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
-            "ms_per_step": float(t.item()) / args.steps,
+            "value": size_factor * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
             "pcg_iterations_by_solve": [s_["iterations"] for s_ in msolves],
             "last_relative_residual": msolves[-1]["relative_residual"] if msolves else None,
             "max_relative_objective_difference_vs_fp64_run": max(
@@ -418,67 +626,135 @@ def run_cuda_arm(args):
             "note": "fp32 V-cycle inside the fp64 PCG; NOT the headline value",
         }
 
+    # ---- multi-GPU: the same mesh on ONE GPU (rank 0), objective traces compared, when it fits
+    single_gpu = None
+    if world > 1 and not args.no_single_gpu_check and nu_global <= args.single_gpu_max_dofs:
+        n_obj = args.warmup + args.steps + 1
+        if rank == 0:
+            try:
+                one = timed_device_run(design_path, run_n, args, steps=args.steps, warmup=args.warmup,
+                                       distributed=False, dtype=args.dtype, mixed=args.mixed)
+                diffs = [abs(a - b) / abs(b) for a, b in zip(objectives[:n_obj], one["objectives"][:n_obj])]
+                single_gpu = {
+                    "what": f"the same {n_obj - 1} mirror-descent iterations of the same mesh on one GPU (rank 0, "
+                            f"unsharded engine)", "objective_trace_max_rel_diff": max(diffs),
+                    "bound": 1e-8, "ok": max(diffs) <= 1e-8,
+                    "ms_per_step_one_gpu": one["elapsed_ms"] / args.steps,
+                    "strong_scaling_speedup": (one["elapsed_ms"] / args.steps) / (elapsed_ms / args.steps),
+                    "pcg_iterations_one_gpu": [s_["iterations"] for s_ in one["solves"]],
+                }
+                del one
+            except Exception as exc:
+                single_gpu = {"ok": False, "error": repr(exc)}
+        dist.barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the fine-level operator with a fused epilogue.
-    # Algorithmic bytes per launch (every lattice vector once), with the
-    # default fine smoother degree 1: Chebyshev step  reads x, b, D^-1, xi, writes x_new (the
-    # direction d is neither read, c1 = 0, nor stored, last step); residual with the fused first
-    # step  reads b, D^-1, xi, writes x, r;  p.Ap  reads p, xi, writes Ap.
+    # ---- rooflines.  Step level ("per-step figure = sum of bytes / sum of time"): the
+    # algorithmic bytes of EVERY launch of the timed region, filed by the library's ledger (CUDA-graph
+    # replays included), over the timed region's device time.  Kernel level: the category with the
+    # largest time share in the instrumented iteration, over all multigrid levels.
     peak, peak_src = measured_peak_hbm()
-    es_mg = 4 if (args.mixed and esize == 8) else esize  # multigrid-side launches run in fp32 when mixed
-    alg_bytes = {
-        "cheb": (4 * nu + n1) * es_mg, "resid": (4 * nu + n1) * es_mg,
-        "dot": (2 * nu + n1) * esize, "plain": (2 * nu + n1) * es_mg,
-    }
-    # Event-timed launches are a sample (V-cycles replayed from a CUDA graph are not individually
-    # timed): time per epilogue = sampled mean x true launch count in the timed region
-    est_ms = {n: (p["ms"] / p["launches"] * true_counts[n]) if p["launches"] else 0.0 for n, p in prof.items()}
-    dominant = max(est_ms, key=est_ms.get)
-    d = prof[dominant]
-    avg_ms = d["ms"] / max(d["launches"], 1)
-    achieved = alg_bytes[dominant] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    kernel_ms = sum(est_ms.values())
+    step_ms = elapsed_ms / args.steps
+    step_gbps = hbm_bytes / args.steps / (step_ms * 1e-3) / 1e9
+    kernel_cats = {c: v for c, v in by_cat.items() if c not in COMM_CATEGORIES and c not in ("filter", "mirror_descent",
+                                                                                           "copies", "other")}
+    dominant = max(kernel_cats, key=lambda c: kernel_cats[c]["ms"]) if kernel_cats else None
+    d = by_cat.get(dominant, {"ms": 0.0, "bytes": 0.0, "launches": 0})
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     traffic_bytes, traffic_src = (None, None)
-    if world == 1 and not args.mixed:
-        traffic_bytes, traffic_src = measured_traffic(os.path.splitext(os.path.basename(design_path))[0], run_n,
-                                                      args.dtype, dominant)
+    if world == 1 and not args.mixed and dominant:
+        traffic_bytes, traffic_src = measured_traffic(design, run_n, args.dtype, dominant)
+    survey_roof = peak * 1e9 / (13.125 * esize) * world
+    dof_iters = pcg_iters * nu_global / (elapsed_ms * 1e-3)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic_bytes, "traffic_source": traffic_src, "peak_source": peak_src,
-        "kernel": f"elast_apply_kernel<{'double' if esize == 8 else 'float'},xi,EP_{dominant.upper()}>",
-        "algorithmic_bytes_per_launch": alg_bytes[dominant], "avg_launch_ms": avg_ms,
-        "launches_in_timed_region": true_counts[dominant], "launches_event_timed": d["launches"],
-        "share_of_step_time": kernel_ms / elapsed_ms,
-        "operator_ms_by_multigrid_level_one_untimed_step": level_profile,
-        "per_epilogue": {n: {"ms_sampled": p["ms"], "launches_sampled": p["launches"],
-                             "launches_true": true_counts[n], "ms_estimated": est_ms[n],
-                             "GBps": (alg_bytes[n] * p["launches"] / (p["ms"] * 1e-3) / 1e9) if p["ms"] > 0 else None}
-                         for n, p in prof.items()},
+        "kernel": kernel_name(dominant, tname) if dominant else None, "category": dominant,
+        "selection": "largest time share over ALL multigrid levels in one instrumented iteration (every launch "
+                     "event-timed on the launching stream, CUDA-graph replay off; run right after the timed region)",
+        "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+        "avg_launch_ms": d["ms"] / max(d["launches"], 1), "launches_in_instrumented_step": d["launches"],
+        "share_of_instrumented_step": d["ms"] / instrumented_ms if instrumented_ms > 0 else None,
+        "step": {
+            "what": "sum of the algorithmic bytes of every launch in the timed region / its device time, rank 0",
+            "algorithmic_bytes_per_step": hbm_bytes / args.steps, "ms_per_step": step_ms,
+            "achieved": step_gbps, "frac": step_gbps / peak,
+            "bytes_by_category_per_step": {c: v["bytes"] / args.steps for c, v in sorted(
+                ledger.items(), key=lambda kv: -kv[1]["bytes"]) if v["bytes"] > 0},
+            "interconnect_bytes_per_step": link_bytes / args.steps,
+        },
+        "survey_pcg_figure": {
+            "what": "PCG dof-iterations/s against the Jacobi-PCG roofline of SURVEY.md 8d, peak / (13.125 x 8 B) per GPU "
+                    "(a multigrid-preconditioned iteration moves ~3x the bytes of a Jacobi one and needs ~100x fewer)",
+            "dof_iters_per_sec": dof_iters, "roofline_dof_iters_per_sec": survey_roof, "frac": dof_iters / survey_roof,
+        },
+        "by_category_one_instrumented_step": {
+            c: {"ms": round(v["ms"], 4), "launches": v["launches"], "share": round(v["ms"] / instrumented_ms, 4),
+                "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+            for c, v in sorted(by_cat.items(), key=lambda kv: -kv[1]["ms"])},
+        "instrumented_step_ms": instrumented_ms,
     }
 
-    cpu_baseline = None
+    # ---- one GPU only: the latency-bound BASELINE config as a separately labelled line, the CPU
+    # baseline, and a like-for-like CPU/GPU pair at one resolution
+    secondary, cpu_baseline = None, None
+    if world == 1 and not args.design and not args.no_secondary:
+        sd, sn = SECONDARY
+        try:
+            sec = timed_device_run(design_file(sd), sn, args, steps=args.steps, warmup=args.warmup, distributed=False,
+                                   options=[])
+            snx, sny = sec["solver"].mesh.nx, sec["solver"].mesh.ny
+            s_hbm, _, s_launches = ledger_totals(sec["ledger"])
+            s_ms = sec["elapsed_ms"] / args.steps
+            secondary = {
+                "label": "latency-bound BASELINE config, NOT the headline",
+                "config": workload_description(sd, sn, snx, sny), "value": args.steps / (sec["elapsed_ms"] * 1e-3),
+                "unit": UNIT, "ms_per_step": s_ms, "steps": args.steps, "warmup": args.warmup,
+                "pcg_iterations_per_step": sum(s_["iterations"] for s_ in sec["solves"]) / args.steps,
+                "roofline_step_frac": s_hbm / args.steps / (s_ms * 1e-3) / 1e9 / peak, "gpu_launches": int(s_launches),
+                "parity": cpu_operator_check(sec["problem"], sec["objectives"][-1], design_file(sd), 1)
+                if not args.no_parity else None,
+            }
+            del sec
+        except Exception as exc:
+            secondary = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
-        sample_n = args.sample_n or 256
-        times, s = oracle_iteration_seconds(design_path, sample_n, 1, 0)
+        sample_n = args.sample_n or pick_sample_n(design_path, run_n, 2, 30.0)
+        times, s, first = oracle_iteration_seconds(design_path, sample_n, 1, 1)
+        cpu_value = 1.0 / times[0]
         cpu_baseline = {
-            "value": 1.0 / times[0], "unit": UNIT, "cores": 1, "kind": "port",
+            "value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
             "host_cores_available": os.cpu_count(),
-            "sample": (f"1 mirror-descent iteration of the scipy oracle (CSR assembly + SuperLU, nested "
-                       f"dissection) on designs/{args.design}.json at N={sample_n} (nx={s.mesh.nx}, "
+            "sample": (f"mirror-descent iteration 1 (after iteration 0 as warm-up) of the scipy oracle (CSR assembly + "
+                       f"SuperLU, nested dissection) on designs/{design}.json at N={sample_n} (nx={s.mesh.nx}, "
                        f"ny={s.mesh.ny}, {s.mesh.nu} displacement dofs): a bounded sample, "
-                       f"{(nx * ny) / (s.mesh.nx * s.mesh.ny):.1f}x fewer cells than the GPU workload"),
+                       f"{(nx * ny) / (s.mesh.nx * s.mesh.ny):.0f}x fewer cells than the GPU workload"),
             "split_seconds": {k2: round(v, 3) for k2, v in s.problem.timings.items()},
         }
-        try:
-            cpu_baseline["state_solve_kernel"] = omp_kernel_baseline(design_path, args.N)
+        try:  # the same iteration of the same mesh on the GPU: the one like-for-like ratio of this line
+            pair = timed_device_run(design_path, sample_n, args, steps=1, warmup=1, distributed=False, options=[])
+            gpu_value = 1.0 / (pair["elapsed_ms"] * 1e-3)
+            cpu_baseline["same_config_pair"] = {
+                "workload": workload_description(design, sample_n, s.mesh.nx, s.mesh.ny)["workload"],
+                "iteration": 1, "cpu_iter_per_s": cpu_value, "gpu_iter_per_s": gpu_value,
+                "gpu_over_cpu": gpu_value / cpu_value,
+                "objective_trace_max_rel_diff_gpu_vs_cpu": max(
+                    abs(a - b) / abs(b) for a, b in zip(pair["objectives"][:3], s.bench_objectives[:3])),
+            }
+            del pair
         except Exception as exc:
-            cpu_baseline["state_solve_kernel"] = {"unavailable": repr(exc)}
+            cpu_baseline["same_config_pair"] = {"error": repr(exc)}
+        if not args.no_omp_baseline:
+            try:
+                cpu_baseline["state_solve_kernel"] = omp_kernel_baseline(design_path, run_n)
+            except Exception as exc:
+                cpu_baseline["state_solve_kernel"] = {"unavailable": repr(exc)}
 
-    cfg = workload_description(args.design, run_n, nx, ny)
+    cfg = workload_description(design, run_n, nx, ny, args.dtype)
     cfg.update({
         "preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
         "parallelism": "1 GPU" if world == 1 else
@@ -486,13 +762,16 @@ def run_cuda_arm(args):
             "halo rows and scalar sums by the library's own kernels over peer-mapped NVLink windows (TM_OPT_P2P)"
             if engine.peer_memory_active else "NCCL halo exchange + all-reduce") +
         f", {engine.dist_levels} sharded multigrid levels",
-        "weak_scaling_N": run_n, "value_normalisation": f"iter/s x (global dofs / dofs of the N={args.N} mesh) = x{size_factor:.3f}",
-        "l2": f"working set of a state solve ~{10 * nu * esize / 1e6:.0f} MB of lattice vectors, larger than the 126 MB L2",
+        "value_normalisation": f"iter/s x (global dofs / dofs of the 1-GPU workload {base_design} N={base_n}) = "
+                               f"x{size_factor:.4f}",
+        "l2": f"working set of a state solve ~{10 * nu * esize / 1e6:.0f} MB of lattice vectors per GPU, larger than "
+              f"the 126 MB L2",
         "md_iterations_timed": [args.warmup, args.warmup + args.steps],
+        "e2e_host_buffers": "global numpy arrays" if world == 1 else "every rank's host process holds its strip",
     })
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": ("f64 (fp32 multigrid preconditioner)" if args.mixed else "f64") if esize == 8 else "f32",
         "data": "synthetic", "config": cfg, "clocks": clocks,
@@ -501,11 +780,14 @@ def run_cuda_arm(args):
                 "d2h_bytes_per_step": traffic["d2h"] // args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "parity": parity,
+        "single_gpu_comparison": single_gpu,
         "cpu_baseline": cpu_baseline,
+        "secondary": secondary,
         "raw_iters_per_sec": raw_rate,
         "mixed_precision_preconditioner": mixed_leg,
         "pcg": {"iterations_per_step": pcg_iters / args.steps,
-                "dof_iters_per_sec": pcg_iters * nu_global / (elapsed_ms * 1e-3),
+                "dof_iters_per_sec": dof_iters,
                 "fine_operator_applies_per_step": fine_applies / args.steps,
                 "state_solves": len(solves),
                 "warm_starts_kept": sum(1 for s in solves if s.get("warm_start_used")),
@@ -513,9 +795,43 @@ def run_cuda_arm(args):
                 "last_relative_residual": solves[-1]["relative_residual"] if solves else None},
         "objective_trace": objectives[: args.warmup + args.steps + 1],
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def profiled_run(design_path, run_n, args, world):
+    """ncu --profile-from-start off: warm up untimed, then bracket the timed region with the profiler
+    range (TM_PROFILER_RANGE=1)."""
+    import torch
+
+    class _Range:
+        def __enter__(self):
+            torch.cuda.profiler.start()
+
+        def __exit__(self, *a):
+            torch.cuda.profiler.stop()
+
+    # timed_device_run with the profiler range around its timed loop
+    global md_loop
+    plain_loop = md_loop
+    calls = {"n": 0}
+
+    def ranged_loop(*a, **kw):
+        calls["n"] += 1
+        if calls["n"] == 2:  # call 1 = warm-up, call 2 = the timed region
+            with _Range():
+                out = plain_loop(*a, **kw)
+                torch.cuda.synchronize()
+            return out
+        return plain_loop(*a, **kw)
+
+    md_loop = ranged_loop
+    try:
+        return timed_device_run(design_path, run_n, args, steps=args.steps, warmup=args.warmup,
+                                distributed=world > 1, dtype=args.dtype, mixed=args.mixed)
+    finally:
+        md_loop = plain_loop
 
 
 def main():
@@ -524,23 +840,40 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("cuda", "reference"), default="cuda")
-    ap.add_argument("--design", default=DESIGN)
-    ap.add_argument("--N", type=int, default=FULL_N)
+    ap.add_argument("--design", default="", help="override the workload (default: BASELINE.json's config for --gpus)")
+    ap.add_argument("--N", type=int, default=0)
     ap.add_argument("--dtype", choices=("float64", "float32"), default="float64")
     ap.add_argument("--preconditioner", choices=("multigrid", "jacobi"), default="multigrid")
     ap.add_argument("--state_rtol", type=float, default=1e-10)
     ap.add_argument("--sample_n", type=int, default=0, help="resolution of the CPU baseline sample")
+    ap.add_argument("--reference_budget_s", type=float, default=420.0, help="time budget of the CPU arm")
+    ap.add_argument("--omp_max_n", type=int, default=4096, help="CPU arm: largest N of the OpenMP kernel figure")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_omp_baseline", action="store_true")
+    ap.add_argument("--no_secondary", action="store_true", help="skip the latency-bound short_cantilever N=512 line")
+    ap.add_argument("--no_parity", action="store_true", help="skip the CPU-operator self-check")
+    ap.add_argument("--no_single_gpu_check", action="store_true")
+    ap.add_argument("--single_gpu_max_dofs", type=int, default=260_000_000)
     ap.add_argument("--dist_levels", type=int, default=0, help="sharded multigrid levels (0 = automatic)")
     ap.add_argument("--mixed", action="store_true", help="fp32 multigrid preconditioner inside the fp64 PCG (reported separately)")
     ap.add_argument("--engine_option", action="append", default=[], help="KEY=VALUE passed to tm_set_option (tuning studies)")
-    ap.add_argument("--exact_N", action="store_true", help="multi-GPU: run exactly --N (strong scaling of a named config)")
     ap.add_argument("--no_warm_start", action="store_true", help="state solves start from zero (study)")
     ap.add_argument("--no_mixed_leg", action="store_true", help="skip the separately reported fp32-preconditioner leg")
-    ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large meshes)")
+    ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--lean", action="store_true", help="main timed region + roofline only (studies, ncu runs)")
     args = ap.parse_args()
+    if args.lean:
+        args.no_cpu_baseline = args.no_secondary = args.no_mixed_leg = args.no_e2e = True
+        args.no_single_gpu_check = args.no_omp_baseline = True
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
+    if args.impl == "cuda" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # not launched through torch.distributed.run: do that here, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29611"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -37,10 +37,12 @@ enum { TM_PRECOND_JACOBI = 0, TM_PRECOND_MULTIGRID = 1 };
 /* integer / real options for tm_set_option */
 enum {
     TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
-    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 2; coarse levels 3) */
+    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 1; coarse levels 3) */
     TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
     TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (default 2)     */
-    TM_OPT_PROFILE = 5,      /* 1: time every fine-level operator launch with CUDA events */
+    TM_OPT_PROFILE = 5,      /* 1: time every fine-level operator launch with CUDA events; 2: the operator
+                                launches of every multigrid level; 3: every launch, by ledger category
+                                (tm_ledger_read).  2 and 3 switch CUDA-graph replay off: diagnostics only */
     TM_OPT_P2P = 130         /* sharded runs: halo exchange and scalar all-reduce by our own kernels over
                                 peer-mapped memory (NVLink) instead of NCCL calls; collective, set alike
                                 on every rank (default: env TM_P2P, else 0)                        */
@@ -170,6 +172,24 @@ int tm_last_solve_stats(tm_handle h, double* out, int n);
  * read, out[4..7] = launch counts.  tm_launch_count: kernels launched by the library so far. */
 int tm_profile_read(tm_handle h, double* out, int n);
 long long tm_launch_count(void);
+
+/* Measurement ledger (bench.py's step-level roofline, SURVEY.md section 8d "per-step figure = sum of
+ * bytes / sum of time"): every launch and collective of the engine files its ALGORITHMIC bytes
+ * (unique operand bytes read + written) under one of TM_LEDGER_CATEGORIES categories; launches
+ * replayed from a CUDA graph are filed with the totals recorded at capture.
+ *   out[0 .. C)        bytes per category since the last reset
+ *   out[C .. 2C)       launches (kernels, copies, collectives) per category
+ *   out[2C .. 3C)      milliseconds per category -- only with TM_OPT_PROFILE = 3, where every launch
+ *                      is followed by an event record and the gap between two records goes to the
+ *                      later one (launch gaps included: what the step really spends there)
+ * Categories: 0-5 level-0 operator by epilogue (plain, p.Ap, residual, Chebyshev, fused first step +
+ * residual, Chebyshev + r.z); 6-19 operator of multigrid level 1..14; 20 restriction; 21 prolongation;
+ * 22 first smoothing step; 23 PCG update; 24 PCG direction; 25 dots / norms; 26 copies, masks;
+ * 27 cluster tail; 28 coarsest solve; 29 filter; 30 mirror descent; 31 sensitivity; 32-34 hierarchy
+ * set-up (moments, diagonals, smoother bounds); 35 halo exchange; 36 all-reduce; 37 gather;
+ * 38 precision conversion; 39 other.  reset != 0 clears the ledger after reading. */
+enum { TM_LEDGER_CATEGORIES = 40 };
+int tm_ledger_read(tm_handle h, double* out, int n, int reset);
 
 /* Diagnostics for the parity tests: the multigrid hierarchy built for xi.
  *   op 0: out = A_level in          op 1: out(level) = P in(level+1)

@@ -256,36 +256,58 @@ class StructuredMesh:
             mi = M2 @ inside
             b[0::2] += fx * mi
             b[1::2] += fy * mi
-        for (side, center, length, tx, ty) in (tractions or []):
-            lo, hi = center - length / 2, center + length / 2
-            if side in ("Left", "Right"):
-                i = 0 if side == "Left" else self.Lx - 1
-                # pos[0] == 0.0 / == W exact compare on the node coordinate
-                on = self.xl[i] == (0.0 if side == "Left" else self.W)
-                s = self.yl
-                nodes = np.arange(self.Ly) * self.Lx + i
-            elif side in ("Top", "Bottom"):
-                j = 0 if side == "Bottom" else self.Ly - 1
-                on = self.yl[j] == (0.0 if side == "Bottom" else self.H)
-                s = self.xl
-                nodes = j * self.Lx + np.arange(self.Lx)
-            else:
+        tractions = list(tractions or [])
+        for (side, *_rest) in tractions:
+            if side not in ("Left", "Right", "Top", "Bottom"):
                 raise ValueError(f"Malformed side: {side}")
-            if not on:
-                continue
-            ind = ((s >= lo - DOLFIN_EPS) & (s <= hi + DOLFIN_EPS)).astype(np.float64)
-            # exact 1-D P2 mass per boundary edge (v0, mid, v1), by 3-point Gauss
+
+        def nodal_value(x, y):
+            """TractionExpression.eval at one node: every traction whose side passes through the node and
+            whose window contains it -- at a corner that includes tractions of BOTH adjacent sides."""
+            vx = vy = 0.0
+            for (side, center, length, tx, ty) in tractions:
+                lo, hi = center - length / 2, center + length / 2
+                if side == "Left":
+                    hit = x == 0.0 and lo - DOLFIN_EPS <= y <= hi + DOLFIN_EPS
+                elif side == "Right":
+                    hit = x == self.W and lo - DOLFIN_EPS <= y <= hi + DOLFIN_EPS
+                elif side == "Top":
+                    hit = y == self.H and lo - DOLFIN_EPS <= x <= hi + DOLFIN_EPS
+                else:
+                    hit = y == 0.0 and lo - DOLFIN_EPS <= x <= hi + DOLFIN_EPS
+                if hit:
+                    vx += tx
+                    vy += ty
+            return vx, vy
+
+        if tractions:
+            # ds runs over all four sides; on each boundary edge the P2 interpolant of the expression is
+            # fixed by its values at the edge's three nodes: exact 1-D P2 mass (v0, mid, v1), 3-point Gauss
             g, w = segment_rule(3)
             phi = np.array([[(1 - x) * (1 - 2 * x), 4 * x * (1 - x), x * (2 * x - 1)] for x in g])
-            acc = np.zeros(len(s))
-            ne = (len(s) - 1) // 2
-            for e in range(ne):
-                loc = [2 * e, 2 * e + 1, 2 * e + 2]
-                hlen = s[2 * e + 2] - s[2 * e]
-                Me = hlen * (phi.T * w) @ phi
-                acc[loc] += Me @ ind[loc]
-            b[2 * nodes] += tx * acc
-            b[2 * nodes + 1] += ty * acc
+            for side in ("Left", "Right", "Bottom", "Top"):
+                if side in ("Left", "Right"):
+                    i = 0 if side == "Left" else self.Lx - 1
+                    s = self.yl
+                    nodes = np.arange(self.Ly) * self.Lx + i
+                    vals = np.array([nodal_value(self.xl[i], y) for y in s])
+                else:
+                    j = 0 if side == "Bottom" else self.Ly - 1
+                    s = self.xl
+                    nodes = j * self.Lx + np.arange(self.Lx)
+                    vals = np.array([nodal_value(x, self.yl[j]) for x in s])
+                if not vals.any():
+                    continue
+                acc = np.zeros_like(vals)
+                for e in range((len(s) - 1) // 2):
+                    loc = [2 * e, 2 * e + 1, 2 * e + 2]
+                    if not vals[loc].any():
+                        continue
+                    hlen = s[2 * e + 2] - s[2 * e]
+                    Me = hlen * (phi.T * w) @ phi
+                    acc[loc] += Me @ vals[loc]
+                b[2 * nodes] += acc[:, 0]
+                b[2 * nodes + 1] += acc[:, 1]
         return b
 
     def dirichlet_mask(self, fixed_sides):

@@ -1,5 +1,5 @@
 """Sharded path vs single-GPU path on the same inputs.  Launched by tests/test_gpu_sharded.py as
-    python -m torch.distributed.run --nproc-per-node 2 tests/dist_check.py
+    python -m torch.distributed.run --nproc-per-node {2,4,8} tests/dist_check.py
 Every rank builds the global inputs from the same seed, runs the sharded engine on its strip and
 the gathered result is compared with an unsharded engine on rank 0's GPU."""
 import json
@@ -30,8 +30,11 @@ def main():
     report = {}
     want_p2p = os.environ.get("TM_P2P") == "1"
     p2p_seen = []
-    for case, (nx, ny, fixed, ld) in enumerate([(40, 32, [Side.LEFT], 2), (70, 52, [Side.BOTTOM, Side.TOP], 1),
-                                                (96, 64, [Side.LEFT, Side.RIGHT], 3)]):
+    # cell rows scale with the rank count so that every strip keeps >= 2^dist_levels rows (world 2: the
+    # meshes of round 1: 40x32, 70x52, 96x64)
+    for case, (nx, ny, fixed, ld) in enumerate([(40, 16 * world, [Side.LEFT], 2),
+                                                (70, 26 * world, [Side.BOTTOM, Side.TOP], 1),
+                                                (96, 32 * world, [Side.LEFT, Side.RIGHT], 3)]):
         W, H = 0.25 * nx, 0.25 * ny
         kw = dict(lame_lambda=1.3, lame_mu=0.8, filter_radius=0.3, fixed_sides=fixed)
         eng = Engine(nx, ny, W, H, rank=rank, nranks=world, dist_levels=ld, **kw)
@@ -109,17 +112,19 @@ def main():
     # the whole optimiser, sharded vs unsharded (device loop and the numpy-hook loop)
     from topomax_b200.fem_solver import FEMSolver
     design = os.path.join(ROOT, "designs", "cantilever.json")
-    sharded = FEMSolver(40, design, data_path=f"/tmp/tm_dist_{rank}", verbose=False, distributed=True, dist_levels=2)
+    N = 40 if world <= 4 else 64  # 40 cell rows cannot be cut into 8 strips of multiples of 4 rows
+    report["solver_N"] = N
+    sharded = FEMSolver(N, design, data_path=f"/tmp/tm_dist_{rank}", verbose=False, distributed=True, dist_levels=2)
     rs = sharded.solve(fixed_iterations=4)
     rho_s = sharded.to_array(sharded.rho)
-    single = FEMSolver(40, design, data_path=f"/tmp/tm_single_{rank}", verbose=False)
+    single = FEMSolver(N, design, data_path=f"/tmp/tm_single_{rank}", verbose=False)
     r1 = single.solve(fixed_iterations=4)
     report["solver_objectives"] = float(max(abs(a - b) / abs(b) for a, b in zip(rs["objectives"], r1["objectives"])))
     report["solver_rho"] = float(np.abs(rho_s - single.to_array(single.rho)).max())
-    hooks = FEMSolver(40, design, data_path=f"/tmp/tm_hooks_{rank}", skip_multiple=999, verbose=False, distributed=True,
+    hooks = FEMSolver(N, design, data_path=f"/tmp/tm_hooks_{rank}", skip_multiple=999, verbose=False, distributed=True,
                       dist_levels=2)
     hooks.solve_generic()
-    full = FEMSolver(40, design, data_path=f"/tmp/tm_full_{rank}", skip_multiple=999, verbose=False)
+    full = FEMSolver(N, design, data_path=f"/tmp/tm_full_{rank}", skip_multiple=999, verbose=False)
     full.solve()
     report["hooks_k"] = [hooks.last_result["k_final"], full.last_result["k_final"]]
     report["hooks_rho"] = float(np.abs(hooks.to_array(hooks.rho) - full.to_array(full.rho)).max())

@@ -1,0 +1,112 @@
+"""Correctness evidence AT the sizes bench.py measures: the parity tests of
+test_gpu_parity.py stop at N = 70 because the scipy oracle factorises; here
+
+* the GPU displacement of real mirror-descent iterations at the benchmark resolutions is handed to the
+  INDEPENDENT CPU operator (oracle/c/elast_omp.c: quadrature, C + OpenMP, shares nothing with the CUDA
+  kernels): ||b - K_cpu u_gpu|| / ||b|| <= 1e-9 and u . K_cpu u = u . b to 1e-6
+  (what "correct" means per solve: FEM_src/elasisity_problem.py:152-166);
+* one run against the FULL oracle (assembly + SuperLU) at N = 256, the largest size it finishes in ~1 min;
+* the fp32 engine's accuracy at a BASELINE config (north_star: "fp32 accuracy stated separately").
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _solver(repo_root, design, N, tmp_path, **kw):
+    from topomax_b200.fem_solver import FEMSolver
+    return FEMSolver(N, os.path.join(repo_root, "designs", f"{design}.json"), data_path=str(tmp_path),
+                     verbose=False, **kw)
+
+
+@pytest.mark.parametrize("design,N,iterations", [("short_cantilever", 512, 3), ("bridge", 2048, 2)])
+def test_benchmark_size_solves_pass_the_cpu_operator_check(repo_root, tmp_path, design, N, iterations):
+    import bench
+
+    if design == "bridge" and torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("bridge N=2048 needs ~60 GB of device memory")
+    solver = _solver(repo_root, design, N, tmp_path)
+    result = solver.solve(fixed_iterations=iterations)
+    parity = bench.cpu_operator_check(solver.problem, result["objectives"][-1],
+                                      os.path.join(repo_root, "designs", f"{design}.json"), 1)
+    stats = solver.problem.solve_log[-1]
+    print(f"{design} N={N}: PCG its={stats['iterations']} relres={stats['relative_residual']:.2e} -> {parity}")
+    assert parity["coverage"] == "every lattice row"
+    assert parity["relative_residual"] <= bench.RESIDUAL_BOUND, parity
+    assert parity["compliance_rel_diff"] <= bench.COMPLIANCE_BOUND, parity
+    # negative control on the same data: a 1e-4 relative change of ONE displacement value (the largest) must fail
+    u = solver.problem.u.tensor
+    u[int(torch.argmax(u.abs()))] *= 1.0 + 1e-4
+    bad = bench.cpu_operator_check(solver.problem, result["objectives"][-1],
+                                   os.path.join(repo_root, "designs", f"{design}.json"), 1)
+    assert not bad["ok"], bad
+
+
+def test_two_iterations_match_the_full_oracle_at_N256(repo_root, tmp_path):
+    """short_cantilever N=256 (510 x 255 cells, 1.04 M dofs): displacement, compliance and the design after
+    one mirror-descent iteration against assembly + SuperLU (the oracle pinned by the reference's golden
+    run).  North_star bars: 1e-6 on displacement and compliance per solve, 1e-4 L2 on the design."""
+    from oracle.md_oracle import OracleSolver, expit, logit
+
+    design = os.path.join(repo_root, "designs", "short_cantilever.json")
+    o = OracleSolver(256, design)
+    o.problem.set_penalization(o.design["penalties"][0])
+    obj0 = o.problem.calculate_objective(o.rho)
+    u0 = o.problem.u.copy()
+    psi = o.step(logit(o.rho), o.step_size_at_iter(0))
+    o.rho = expit(psi)
+    obj1 = o.problem.calculate_objective(o.rho)
+
+    s = _solver(repo_root, "short_cantilever", 256, tmp_path)
+    s.problem.set_penalization(s.parameters.penalties[0])
+    g0 = s.problem.calculate_objective(s.rho)
+    ug = s.problem.u.tensor.cpu().numpy()
+    err_u = np.linalg.norm(ug - u0) / np.linalg.norm(u0)
+    rho = s.rho.tensor
+    psi_g = torch.log(rho / (1.0 - rho))
+    prev = psi_g.clone()
+    s.step_device(prev, s.step_size_at_iter(0), psi_g, rho)
+    g1 = s.problem.calculate_objective(s.rho)
+    diff = rho.cpu().numpy() - o.rho
+    err_rho = float(np.sqrt(o.w @ diff ** 2))
+    print(f"N=256: objective {g0} vs {obj0}, u err {err_u:.2e}; after one iteration {g1} vs {obj1}, design L2 "
+          f"err {err_rho:.2e}")
+    assert abs(g0 - obj0) / abs(obj0) < 1e-6 and err_u < 1e-6
+    assert abs(g1 - obj1) / abs(obj1) < 1e-6 and err_rho < 1e-4
+
+
+def test_float32_accuracy_at_a_baseline_config(repo_root, tmp_path):
+    """north_star: "fp32 accuracy stated separately" -- at short_cantilever N=512 (BASELINE configs[1]): the
+    fp32 engine's state solve on the design reached after 3 fp64 iterations, against the fp64 solve of the
+    same field.  The numbers are printed (DESIGN.md quotes them) and bounded loosely."""
+    from topomax_b200 import _lib
+    from topomax_b200.engine import Engine
+
+    s = _solver(repo_root, "short_cantilever", 512, tmp_path)
+    s.solve(fixed_iterations=3)
+    p = s.problem
+    xi, u64, b64 = p.filtered_rho.tensor, p.u.tensor, p.load
+    c64 = p.engine.dot_p2(u64, b64)
+    e32 = Engine(s.mesh.nx, s.mesh.ny, s.mesh.width, s.mesh.height, lame_lambda=p.lamé_lda, lame_mu=p.lamé_mu,
+                 simp_min=p.penalizer.minimum, filter_radius=p.parameters.filter_radius,
+                 fixed_sides=p.parameters.fixed_sides, dtype="float32")
+    b32 = e32.load_vector(p.body_force, p.traction_term)
+    out = {}
+    for rtol in (1e-4, 1e-5, 1e-6):
+        try:
+            u32, info = e32.state_solve(xi.float(), b32, rtol=rtol, maxit=300)
+        except _lib.EngineError as exc:  # the fp32 residual recurrence stalls above the tolerance
+            out[rtol] = f"not reached ({exc})"
+            continue
+        err_u = float(torch.linalg.norm(u32.double() - u64) / torch.linalg.norm(u64))
+        c32 = float(torch.dot(u32.double(), b64))
+        out[rtol] = dict(iterations=info.iterations, relres=info.relative_residual, displacement_err=err_u,
+                         compliance_err=abs(c32 - c64) / abs(c64))
+    print("fp32 engine at short_cantilever N=512:", out)
+    first = out[1e-4]
+    assert isinstance(first, dict) and first["displacement_err"] < 5e-2 and first["compliance_err"] < 1e-2

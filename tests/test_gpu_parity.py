@@ -196,6 +196,35 @@ def test_load_vector_matches_oracle(repo_root, design, N):
     assert _rel(b, ref) < 1e-12
 
 
+@pytest.mark.parametrize("nx,ny", [(24, 10), (31, 17)])
+def test_traction_window_touching_a_corner_loads_the_adjacent_side(nx, ny):
+    """A corner node lies on two sides: TractionExpression.eval (FEM_src/elasisity_problem.py:47-70) gives it
+    the value of a traction on EITHER side whose window reaches the corner, so the P2 interpolant on the
+    adjacent side's corner edge carries load too (formerly a documented deviation of DESIGN.md section 4;
+    no reference fixture exists for tractions: oracle-pinned only)."""
+    from topomax_b200.designs.definitions import Side, Traction
+    W, H = 3.0, 1.0
+    mesh = StructuredMesh(W, H, nx, ny)
+    cases = [
+        [("Right", 0.9, 0.2, 0.0, -2.0)],                                   # window [0.8, 1.0] reaches the top-right corner
+        [("Top", 0.05, 0.1, 1.0, 0.5), ("Left", 0.5, 1.0, -1.0, 0.0)],      # both reach the top-left corner; Left spans the side
+        [("Bottom", 1.5, 3.0, 0.0, 1.0)],                                   # a whole side: both bottom corners
+        [("Right", 0.5, 0.2, 0.0, -1.0)],                                   # control: no corner involved
+    ]
+    eng = _engine(nx, ny, W, H)
+    for tr in cases:
+        ref = mesh.load_vector(None, tr)
+        b = eng.load_vector(None, [Traction(Side.from_string(s), c, l, (tx, ty)) for s, c, l, tx, ty in tr]).cpu().numpy()
+        tiny = 1e-13 * np.abs(ref).max()
+        assert np.count_nonzero(np.abs(b) > tiny) == np.count_nonzero(np.abs(ref) > tiny)
+        assert _rel(b, ref) < 1e-12
+    # the first case really loads the top side: the midpoint of the last top edge carries load
+    ref = mesh.load_vector(None, cases[0]).reshape(2 * ny + 1, 2 * nx + 1, 2)
+    assert abs(ref[2 * ny, 2 * nx - 1, 1]) > 0 and abs(ref[2 * ny - 1, 2 * nx, 1]) > 0
+    ctl = mesh.load_vector(None, cases[3]).reshape(2 * ny + 1, 2 * nx + 1, 2)
+    assert not ctl[2 * ny].any() and not ctl[0].any()
+
+
 def test_filter_matches_oracle_and_identity():
     nx, ny, W, H = 40, 24, 2.0, 1.2
     mesh = StructuredMesh(W, H, nx, ny)

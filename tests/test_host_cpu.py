@@ -199,19 +199,94 @@ def test_output_tree_round_trip(tmp_path):
     assert type(data_list[0][3]).__module__ == "src.utils"
 
 
-def test_weak_scaling_resolution_keeps_equal_strips(repo_root):
-    """bench.py --gpus N: ~N x the cells of the N=512 workload, elements per unit length a multiple
-    of the GPU count (equal strips of cell rows); the 1-GPU workload is the named config itself."""
+def test_bench_workloads_are_the_baseline_configs(repo_root):
+    """bench.py --gpus N runs the configuration BASELINE.json names for N GPUs (SURVEY.md App. B sizes)."""
     import bench
 
-    design = os.path.join(repo_root, "designs", "short_cantilever.json")
-    base = bench.mesh_of(design, 512)
-    assert base == (1020, 510)
-    for world, mesh in ((2, (1440, 720)), (4, (2040, 1020)), (8, (2880, 1440))):
-        n = bench.weak_scaling_n(design, 512, world)
-        got = bench.mesh_of(design, n)
-        assert got == mesh and got[1] % world == 0
-        assert abs(got[0] * got[1] / (base[0] * base[1]) / world - 1) < 0.01
+    expect = {1: ("bridge", 2048, (12288, 2048), 201383938), 2: ("triangle", 4096, (4096, 4096), 134250498),
+              4: ("triangle", 4096, (4096, 4096), 134250498), 8: ("cantilever", 16384, (49152, 16384), 6442713090)}
+    for world, (design, n, mesh, dofs) in expect.items():
+        assert bench.workload_for(world) == (design, n)
+        nx, ny = bench.mesh_of(bench.design_file(design), n)
+        assert (nx, ny) == mesh
+        assert bench.workload_description(design, n, nx, ny)["n_displacement_dofs"] == dofs
+    assert bench.mesh_of(bench.design_file("short_cantilever"), 512) == (1020, 510)  # the reference's N truncation
+    # the CPU arm's sample resolution stays within its budget under the calibrated cost model
+    for design in ("bridge", "triangle", "cantilever"):
+        n = bench.pick_sample_n(bench.design_file(design), 16384, 25, 300.0)
+        assert 8 <= n <= 512 and bench.oracle_cost_estimate(bench.design_file(design), n) * 25 <= 300.0
+
+
+@pytest.mark.parametrize("design,N", [("short_cantilever", 20), ("triangle", 12), ("bridge", 8)])
+def test_bench_cpu_operator_check_on_slabs(repo_root, design, N):
+    """bench.py's self-check (the C + OpenMP quadrature operator applied to a displacement) on the oracle's
+    direct solution: whole mesh, then cut into rank-like strips with halo rows (2 cell rows below, 1 above)
+    whose owned-row sums must add up to the whole, then a band sample.  A perturbed displacement must fail."""
+    import bench
+    from oracle.fem_oracle import StructuredMesh, lame, solve_spd
+    from oracle.md_oracle import read_design
+
+    path = bench.design_file(design)
+    d = read_design(path)
+    nx, ny = bench.mesh_of(path, N)
+    mesh = StructuredMesh(d["width"], d["height"], nx, ny)
+    lda, mu = lame(d["E"], d["nu"])
+    rng = np.random.default_rng(7)
+    xi = 0.1 + 0.8 * rng.random(mesh.n1)
+    fixed = mesh.dirichlet_mask(d["fixed_sides"])
+    b = mesh.load_vector(d["body_force"], d["tractions"])
+    K = mesh.elasticity_matrix(xi, lda, mu)
+    free = ~fixed
+    u = np.zeros(mesh.nu)
+    u[free] = solve_spd(K[free][:, free].tocsc(), b[free])
+    shape = (2 * ny + 1, 2 * nx + 1, 2)
+    U, B, XI = u.reshape(shape), np.where(fixed, 0.0, b).reshape(shape), xi.reshape(ny + 1, nx + 1)
+    bb = float(np.vdot(B, B))
+    whole, _, _ = bench.slab_operator_sums(d, nx, ny, 0, ny, U, B, XI)
+    assert np.sqrt(whole[0] / bb) < 1e-11 and whole[2] == mesh.nu
+    assert abs(whole[1] - u @ b) <= 1e-10 * abs(u @ b)
+    # three strips, the library's storage rule
+    cuts = [0, ny // 3, 2 * ny // 3, ny]
+    total = np.zeros(3)
+    for r in range(3):
+        c0, c1 = cuts[r], cuts[r + 1]
+        cl0, cl1 = max(0, c0 - 2), min(ny, c1 + 1)
+        own = (2 * (c0 - cl0), 2 * (c1 - cl0) + (1 if r == 2 else 0))
+        sl = slice(2 * cl0, 2 * cl1 + 1)
+        sums, _, _ = bench.slab_operator_sums(d, nx, ny, cl0, cl1 - cl0, U[sl], B[sl], XI[cl0:cl1 + 1], own)
+        total += sums
+    assert total[2] == mesh.nu
+    assert np.sqrt(total[0] / bb) < 1e-11 and abs(total[1] - whole[1]) <= 1e-10 * abs(whole[1])
+    # band sample in the middle of the mesh: incomplete first/last row excluded
+    g0, rows = ny // 4, max(2, ny // 3)
+    sl = slice(2 * g0, 2 * (g0 + rows) + 1)
+    band, _, _ = bench.slab_operator_sums(d, nx, ny, g0, rows, U[sl], B[sl], XI[g0:g0 + rows + 1])
+    assert band[2] == (2 * rows - 1) * (2 * nx + 1) * 2 and np.sqrt(band[0] / bb) < 1e-11
+    # negative control: a relative perturbation of 1e-6 of one interior value is seen
+    U2 = U.copy()
+    U2[ny, nx, 1] *= 1.0 + 1e-6
+    bad, _, _ = bench.slab_operator_sums(d, nx, ny, 0, ny, U2, B, XI)
+    assert np.sqrt(bad[0] / bb) > 1e-9
+
+
+def test_bench_reference_arm_line(repo_root):
+    """`bench.py --impl reference` prints exactly one JSON line on stdout whose config names the workload it
+    really ran, with the steps / warm-up it was asked for."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(repo_root, "bench.py"), "--impl", "reference", "--design",
+                          "triangle", "--N", "16", "--steps", "2", "--warmup", "1", "--no_omp_baseline"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1
+    assert "N=16" in line["config"]["workload"] and line["config"]["same_config_as_cuda_arm"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["value"] > 0 and line["unit"] == "iter/s" and line["metric"] == "mirror_descent_iters_per_sec"
 
 
 def test_committed_bench_lines_keep_the_contract(repo_root):

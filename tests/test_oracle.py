@@ -137,3 +137,24 @@ def test_oracle_point_evaluation_reproduces_polynomials():
     assert np.abs(grid[:, :, 0].ravel() - p1).max() < 1e-14
     with pytest.raises(ValueError):
         sample_function(mesh, p1, 1, 2, "corner", 2)
+
+
+def test_traction_corner_node_loads_both_sides():
+    """TractionExpression.eval is a function of the NODE (FEM_src/elasisity_problem.py:47-70): a corner node
+    inside the window of a traction on one side also feeds the P2 interpolant on the corner edge of the
+    adjacent side.  Totals: the own side integrates the indicator's interpolant, the adjacent corner edge adds
+    int phi_corner = h/6 times the value."""
+    from oracle.fem_oracle import StructuredMesh
+    W, H, nx, ny = 3.0, 1.0, 12, 4
+    mesh = StructuredMesh(W, H, nx, ny)
+    hy, hx = H / ny, W / nx
+    b = mesh.load_vector(None, [("Right", 0.875, 0.25, 0.0, -2.0)]).reshape(2 * ny + 1, 2 * nx + 1, 2)
+    # own side: nodes at y = 0.75 (vertex), 0.875 (mid), 1.0 (corner) carry -2: one full edge + the -2 at y=0.75
+    # seen from the edge below (v1 of that edge)
+    corner_edge_total = -2.0 * hx / 6   # int of the corner's P2 basis function over the top corner edge
+    corner_self = -2.0 * hx * 4 / 30    # of which this much lands on the corner dof itself
+    own = b[:, 2 * nx, 1].sum()         # right side, the shared corner dof included
+    assert abs(own - ((-2.0) * (hy + hy / 6) + corner_self)) < 1e-14
+    top = b[2 * ny, : 2 * nx, 1].sum()  # adjacent side without the shared corner dof
+    assert abs(top - (corner_edge_total - corner_self)) < 1e-14
+    assert not b[:, :, 0].any()

@@ -18,6 +18,7 @@ PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
 OPT_PRECOND, OPT_CHEB_DEGREE, OPT_CHECK_EVERY, OPT_MG_COARSE_CELLS = 1, 2, 3, 4
 OPT_PROFILE = 5
 OPT_P2P = 130
+LEDGER_CATEGORIES = 40
 OPT_CHEB_RATIO, OPT_EIG_SAFETY = 100, 101
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOT_CONVERGED = -1, -2, -3, -4
@@ -28,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "tm_load_vector", "tm_filter_apply", "tm_elast_matvec", "tm_elast_diag", "tm_state_solve",
     "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate", "tm_sample_field",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
-    "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
+    "tm_ledger_read", "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
     "tm_fluid_create", "tm_fluid_destroy", "tm_fluid_set_stream", "tm_fluid_set_option", "tm_fluid_set_density", "tm_fluid_state_solve",
     "tm_fluid_objective", "tm_fluid_sens_rhs", "tm_fluid_apply", "tm_p2p_selftest",
 )
@@ -107,6 +108,7 @@ def load_library() -> ctypes.CDLL:
         "tm_local_layout": ([V, POINTER(I), I], I),
         "tm_profile_read": ([V, POINTER(D), I], I),
         "tm_launch_count": ([], ctypes.c_longlong),
+        "tm_ledger_read": ([V, POINTER(D), I, I], I),
         "tm_mg_debug": ([V, V, I, I, V, V], I),
         "tm_mg_level_info": ([V, I, POINTER(I), POINTER(I)], I),
         "tm_dem_strain_energy": ([I, I, D, D, D, D, D, D, V, V, V, V, V, POINTER(D), V], I),

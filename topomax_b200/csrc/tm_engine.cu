@@ -97,6 +97,33 @@ struct SolveStats {
     bool converged = false;
 };
 
+// Measurement ledger (tm_ledger_read): every launch / collective of the engine files its
+// ALGORITHMIC bytes (unique operand bytes read + written) under one category.
+// Launches replayed from a CUDA graph are filed with the totals recorded at capture.  With
+// TM_OPT_PROFILE = 3 every launch is also followed by an event record, and the time between two
+// consecutive records is attributed to the category of the later one (one stream, in order: the
+// figure includes the launch gap in front of a kernel, i.e. what the step really spends there).
+enum LedgerCat {
+    LC_FINE_PLAIN = 0, LC_FINE_DOT, LC_FINE_RESID, LC_FINE_CHEB, LC_FINE_RESID0, LC_FINE_CHEBDOT,
+    LC_COARSE1 = 6,  // + (level - 1), levels 1 .. 14
+    LC_RESTRICT = 20, LC_PROLONG, LC_CHEB_FIRST, LC_PCG_UPDATE, LC_PCG_DIRECTION, LC_REDUCTIONS, LC_COPIES,
+    LC_TAIL, LC_COARSE_SOLVE, LC_FILTER, LC_MD, LC_SENS, LC_SETUP_COARSEN, LC_SETUP_DIAG, LC_SETUP_EIG,
+    LC_HALO, LC_ALLREDUCE, LC_GATHER, LC_CONVERT, LC_MISC, LC_COUNT = 40
+};
+struct Ledger {
+    double bytes[LC_COUNT], launches[LC_COUNT];
+    Ledger() { clear(); }
+    void clear() {
+        for (int i = 0; i < LC_COUNT; ++i) bytes[i] = launches[i] = 0.0;
+    }
+    void add(const Ledger& o) {
+        for (int i = 0; i < LC_COUNT; ++i) {
+            bytes[i] += o.bytes[i];
+            launches[i] += o.launches[i];
+        }
+    }
+};
+
 class EngineBase {
    public:
     virtual ~EngineBase() {}
@@ -123,6 +150,7 @@ class EngineBase {
     virtual void mg_debug(void* xi, int op, int level, const void* in, void* out) = 0;
     virtual int mg_level_info(int level, int* info) = 0;
     virtual void profile_read(double* out, int n) = 0;
+    virtual void ledger_read(double* out, int n, int reset) = 0;
     int device = 0;
 };
 
@@ -202,6 +230,8 @@ class Engine : public EngineBase {
             cudaEventDestroy(e.first);
             cudaEventDestroy(e.second);
         }
+        for (auto& m : ev_marks_) cudaEventDestroy(m.second);
+        for (auto& e : ev_free_) cudaEventDestroy(e);
         if (own_stream_) cudaStreamDestroy(own_stream_);
     }
 
@@ -224,7 +254,10 @@ class Engine : public EngineBase {
                 break;
             case 100: cheb_ratio_ = value; break;
             case 101: eig_safety_ = value; break;
-            case TM_OPT_PROFILE: profile_ = (int)value; break;  // 1: level-0 kernel, 2: every level
+            case TM_OPT_PROFILE:  // 1: level-0 kernel, 2: every level, 3: every launch by ledger category
+                profile_ = (int)value;
+                if (profile_ == 3 && ev_marks_.empty()) mark(-1);
+                break;
             case 102: blocks_per_sm_target_ = std::max(1, (int)value); break;
             case 103: min_rows_per_strip_ = std::max(1, (int)value); break;
             case 104: filter_persistent_ = value != 0.0; break;
@@ -410,6 +443,7 @@ class Engine : public EngineBase {
         dim3 blk(32, 8), grd(ceil_div(g0_.Lx, 32), ceil_div(g0_.Ly, 8));
         load_vector_kernel<T><<<grd, blk, 0, stream_>>>(s, (T*)b);
         TM_CHECK_LAUNCH();
+        acct(LC_MISC, sz(nu_));
     }
 
     // ------------------------------------------------------------------ filter
@@ -423,6 +457,7 @@ class Engine : public EngineBase {
             f_dinv_.ensure(n1_);
             p1_diag_kernel<T><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(p1_, alpha, beta, f_dinv_.p);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, sz(n1_));
             f_dinv_ready_ = true;
         }
         const bool use_fmg = filter_mg_mode_ == 1 ||
@@ -434,10 +469,13 @@ class Engine : public EngineBase {
             if (kind == 0) {
                 p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
                 rhs_p = f_rhs_.p;
-                if (out != in)
+                if (out != in) {
                     TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+                    acct(LC_FILTER, 2 * sz(n1_));
+                }
             } else {
                 TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
+                acct(LC_FILTER, sz(n1_));
             }
             f_p2_.ensure(n1_);
             if (filter_blocks_ == 0) {
@@ -488,6 +526,8 @@ class Engine : public EngineBase {
                 st.iters = (int)h_sc_[64];
                 st.relres = h_sc_[65];
                 st.converged = h_sc_[66] != 0.0;
+                // one Chebyshev-Jacobi iteration: read x, b, D^-1, d; write x, d
+                acct(LC_FILTER, 6.0 * st.iters * sz(n1_));
                 done = st.converged;  // otherwise continue with CG from the current iterate,
                 if (!done) filter_bounds_ready_ = false;  // ... and re-estimate the spectral bounds
             }
@@ -508,6 +548,7 @@ class Engine : public EngineBase {
                 TM_CUDA(cudaMemcpyAsync(h_sc_ + 64, result, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream_));
                 TM_CUDA(cudaStreamSynchronize(stream_));
                 const int cg_its = (int)h_sc_[64];
+                acct(LC_FILTER, 13.0 * cg_its * sz(n1_));  // one Jacobi-PCG iteration = 13 n1
                 st.iters += cg_its;
                 st.relres = h_sc_[65];
                 st.converged = h_sc_[66] != 0.0;
@@ -521,15 +562,20 @@ class Engine : public EngineBase {
             exchange_p1(in);
             p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
             rhs = f_rhs_.p;
-            if (out != in) TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            if (out != in) {
+                TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+                acct(LC_FILTER, 2 * sz(n1_));
+            }
             p1_apply(alpha, beta, out, f_Ap_.p, nullptr);
             waxpby_kernel<T><<<grid1d(p1_cnt_), kVecThreads, 0, stream_>>>(
                 p1_cnt_, 1.0, rhs + p1_off_, -1.0, f_Ap_.p + p1_off_, f_r_.p + p1_off_);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, 3 * sz(p1_cnt_));
         } else {
             rhs = in;
             TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
             TM_CUDA(cudaMemcpyAsync(f_r_.p, rhs, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            acct(LC_FILTER, 3 * sz(n1_));
         }
         auto apply_dot = [&](T* p, T* Ap) {
             exchange_p1(p);
@@ -539,7 +585,7 @@ class Engine : public EngineBase {
         auto precond = [&](T*) -> T* { return nullptr; };
         const int check = check_every_ > 0 ? check_every_ : 10;
         SolveStats st = pcg(p1_off_, p1_cnt_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, f_dinv_.p, apply_dot,
-                            precond, true, rtol, maxit, check);
+                            precond, true, rtol, maxit, check, true);
         exchange_p1(out);
         return st;
     }
@@ -588,6 +634,7 @@ class Engine : public EngineBase {
             nccl().Broadcast(ptr, ptr, (size_t)(j1 - j0) * row_elems, dtype, q, comm_, stream_);
         }
         nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+        acct(LC_GATHER, sz(((size_t)lv_ny_[l] + 1) * row_elems));
     }
 
     void fmg_apply(int l, int ep, const T* x, T* y, const T* b, double c1, double c2, double* dot_out) {
@@ -609,6 +656,10 @@ class Engine : public EngineBase {
                 break;
         }
         TM_CHECK_LAUNCH();
+        {   // operands: x, y (+ b; + D^-1, d read and written) + the 7 stencil planes of a coarse level
+            const double vecs = ep == P1EP_PLAIN || ep == P1EP_DOT ? 2.0 : (ep == P1EP_RESID ? 3.0 : 6.0);
+            acct(LC_FILTER, (vecs + (l > 0 ? 7.0 : 0.0)) * sz(F.n));
+        }
     }
 
     // one-off: Galerkin stencils, diagonals, smoother bounds, coarse factor (operator is constant)
@@ -717,6 +768,7 @@ class Engine : public EngineBase {
             cheb_first_kernel<T><<<grid1d(F.cnt), kVecThreads, 0, stream_>>>(
                 F.cnt, 1.0 / theta, F.dinv.p + F.off, b + F.off, F.d.p + F.off, F.x.p + F.off);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, 4 * sz(F.cnt));
             cur = F.x.p;
             k0 = 1;
         } else {
@@ -759,6 +811,7 @@ class Engine : public EngineBase {
             dim3 grd(ceil_div(C.L.g.nx + 1, 32), ceil_div(C.L.g.ny + 1, 8));
             p1mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(F.L.g, lv_ny_[l], gather ? C.gpiece : C.L.g, F.tmp.p, C.b.p);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, sz(F.n) + sz(C.n));
             if (gather) gather_p1_rows(l + 1, C.b.p);
             bs[l + 1] = C.b.p;
         }
@@ -766,6 +819,7 @@ class Engine : public EngineBase {
             FLevel& C = flevels_[nl - 1];
             p1mg_coarse_solve_kernel<T><<<1, 32, 0, stream_>>>((int)C.n, fcoarse_A_.p, bs[nl - 1], C.x.p);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, 2 * sz(C.n));
             xs[nl - 1] = C.x.p;
         }
         for (int l = nl - 1; l-- > 0;) {
@@ -775,6 +829,7 @@ class Engine : public EngineBase {
             dim3 grd(ceil_div(F.L.g.nx + 1, 32), ceil_div(F.L.g.ny + 1, 8));
             p1mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(F.L.g, C.L.g, xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, 2 * sz(F.n) + sz(C.n));
             xs[l] = fsmooth(l, bs[l], xs[l]);
         }
         return xs[0];
@@ -782,10 +837,11 @@ class Engine : public EngineBase {
 
     // graph replay of the filter V-cycle (the operator never changes: captured once per engine)
     T* fvcycle(T* r) {
-        if (!use_graph_ || (nranks_ > 1 && !graph_sharded_)) return fvcycle_body(r);
+        if (!use_graph_ || (nranks_ > 1 && !graph_sharded_) || profile_ >= 2) return fvcycle_body(r);
         if (fgraph_exec_ && fgraph_r_ == r) {
             TM_CUDA(cudaGraphLaunch(fgraph_exec_, stream_));
             ++g_launches;
+            led_.add(fgraph_led_);
             return fgraph_z_;
         }
         if (fgraph_exec_) {
@@ -795,14 +851,17 @@ class Engine : public EngineBase {
         const long long l0 = g_launches.load();
         cudaGraph_t graph = nullptr;
         TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        CaptureLedger cap(led_, capturing_);
         T* z = nullptr;
         try {
             z = fvcycle_body(r);
         } catch (...) {
+            cap.finish();
             cudaStreamEndCapture(stream_, &graph);
             if (graph) cudaGraphDestroy(graph);
             throw;
         }
+        fgraph_led_ = cap.finish();
         TM_CUDA(cudaStreamEndCapture(stream_, &graph));
         g_launches.store(l0);
         TM_CUDA(cudaGraphInstantiate(&fgraph_exec_, graph, 0));
@@ -819,15 +878,20 @@ class Engine : public EngineBase {
             exchange_p1(in);
             p1_apply(0.0, 1.0, in, f_rhs_.p, nullptr);  // rhs = M1 in
             rhs = f_rhs_.p;
-            if (out != in) TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            if (out != in) {
+                TM_CUDA(cudaMemcpyAsync(out, in, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+                acct(LC_FILTER, 2 * sz(n1_));
+            }
             p1_apply(alpha, beta, out, f_Ap_.p, nullptr);
             waxpby_kernel<T><<<grid1d(p1_cnt_), kVecThreads, 0, stream_>>>(
                 p1_cnt_, 1.0, rhs + p1_off_, -1.0, f_Ap_.p + p1_off_, f_r_.p + p1_off_);
             TM_CHECK_LAUNCH();
+            acct(LC_FILTER, 3 * sz(p1_cnt_));
         } else {
             rhs = in;
             TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(T), stream_));
             TM_CUDA(cudaMemcpyAsync(f_r_.p, rhs, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            acct(LC_FILTER, 3 * sz(n1_));
         }
         auto apply_dot = [&](T* p, T* Ap) {
             exchange_p1(p);
@@ -836,7 +900,7 @@ class Engine : public EngineBase {
         };
         auto precond = [&](T* r) -> T* { return fvcycle(r); };
         SolveStats st = pcg(p1_off_, p1_cnt_, rhs, out, f_r_.p, f_p_.p, f_Ap_.p, nullptr, apply_dot, precond, false,
-                            rtol, maxit, 1);
+                            rtol, maxit, 1, true);
         exchange_p1(out);
         return st;
     }
@@ -913,6 +977,7 @@ class Engine : public EngineBase {
         dim3 blk(32, 8), grd(ceil_div(g.nx, 32), ceil_div(g.ny, 8));
         mg_fine_moments_kernel<T><<<grd, blk, 0, stream_>>>(g, spec_, w0_.p);
         TM_CHECK_LAUNCH();
+        acct(LC_SETUP_COARSEN, sz(n1_) + 12 * sz((size_t)g.nx * g.ny));
     }
     // level-0 geometry bound to a density (its halo rows already exchanged)
     LevelGeom<T> fine_geom(const T* xi, bool compute) {
@@ -960,11 +1025,13 @@ class Engine : public EngineBase {
         // caller's allocator hands over from one solve to the next
         s_xi_.ensure(n1_);
         TM_CUDA(cudaMemcpyAsync(s_xi_.p, xi, n1_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        acct(LC_COPIES, 2 * sz(n1_));
         xi = s_xi_.p;
         LevelGeom<T> g = g0_;
         g.xi = xi;
         mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, b, s_b_.p);
         TM_CHECK_LAUNCH();
+        acct(LC_COPIES, 2 * sz(nu_));
 
         bool use_mg = precond_ == TM_PRECOND_MULTIGRID && nlevels_ >= 2;
         // mixed precision: the multigrid preconditioner runs in fp32 inside the fp64 PCG (the
@@ -990,6 +1057,7 @@ class Engine : public EngineBase {
         if (warm) {
             mask_fixed_kernel<T><<<grid1d(n2_), kVecThreads, 0, stream_>>>(g, u, u);
             TM_CHECK_LAUNCH();
+            acct(LC_COPIES, 2 * sz(nu_));
             exchange_p2(0, u);
             ApplyArgs<T> a = apply_args();
             a.x = u; a.y = s_r_.p; a.b = s_b_.p;
@@ -1004,6 +1072,9 @@ class Engine : public EngineBase {
                 dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, s_b_.p + p2_off_, s_b_.p + p2_off_, rs_,
                                                               sc_ + SC_TMP + 1);
                 TM_CHECK_LAUNCH();
+                ++g_launches;
+                acct(LC_REDUCTIONS, sz(p2_cnt_));
+                acct(LC_REDUCTIONS, sz(p2_cnt_));
                 sum_ranks(sc_ + SC_TMP, 2);
                 read_scalars();
                 if (!(h_sc_[SC_TMP] < h_sc_[SC_TMP + 1])) warm = false;
@@ -1013,6 +1084,7 @@ class Engine : public EngineBase {
         if (!warm) {
             TM_CUDA(cudaMemsetAsync(u, 0, nu_ * sizeof(T), stream_));
             TM_CUDA(cudaMemcpyAsync(s_r_.p, s_b_.p, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            acct(LC_COPIES, 3 * sz(nu_));
         }
 
         auto apply_dot = [&](T* pp, T* Ap) {
@@ -1040,6 +1112,7 @@ class Engine : public EngineBase {
         dot_kernel<T><<<grid1d(p2_cnt_), kVecThreads, 0, stream_>>>(
             p2_cnt_, (const T*)u + p2_off_, (const T*)b + p2_off_, rs_, sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        acct(LC_REDUCTIONS, 2 * sz(p2_cnt_));
         sum_ranks(sc_ + SC_TMP, 1);
         read_scalars();
         return h_sc_[SC_TMP];
@@ -1056,6 +1129,7 @@ class Engine : public EngineBase {
             sens_rhs_kernel<T, false><<<grid2d_p1(), dim3(32, 8), 0, stream_>>>(g, spec_, p1_.own_iy0,
                                                                                p1_.own_iy1, (const T*)u, (T*)out);
         TM_CHECK_LAUNCH();
+        acct(LC_SENS, sz(nu_) + 2 * sz(n1_));
     }
 
     // ------------------------------------------------------------------ mirror descent
@@ -1063,12 +1137,14 @@ class Engine : public EngineBase {
         waxpby_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(n1_, 1.0, (const T*)psi, -alpha,
                                                                   (const T*)g, (T*)half);
         TM_CHECK_LAUNCH();
+        acct(LC_MD, 3 * sz(n1_));
     }
 
     void md_volume(const void* half, double c, double* vol, double* dvol) override {
         md_volume_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(p1_, (const T*)half, c, rs_,
                                                                      sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        acct(LC_MD, sz(n1_));
         sum_ranks(sc_ + SC_TMP, 2);
         read_scalars();
         *vol = h_sc_[SC_TMP];
@@ -1080,6 +1156,7 @@ class Engine : public EngineBase {
         md_apply_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(
             p1_, (const T*)half, c, (const T*)psi_prev, (T*)psi, (T*)rho, rs_, sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        acct(LC_MD, 4 * sz(n1_));
         sum_ranks(sc_ + SC_TMP, 2);
         read_scalars();
         *delta_sq = h_sc_[SC_TMP];
@@ -1090,6 +1167,7 @@ class Engine : public EngineBase {
         p1_integrate_kernel<T><<<grid1d(n1_), kVecThreads, 0, stream_>>>(p1_, (const T*)values, rs_,
                                                                         sc_ + SC_TMP);
         TM_CHECK_LAUNCH();
+        acct(LC_MD, sz(n1_));
         sum_ranks(sc_ + SC_TMP, 1);
         read_scalars();
         return h_sc_[SC_TMP];
@@ -1156,6 +1234,36 @@ class Engine : public EngineBase {
             std::vector<double> t(n, 0.0);
             inner_->profile_read(t.data(), n);
             for (int i = 0; i < n; ++i) out[i] += t[i];
+        }
+    }
+
+    // out[0 .. LC_COUNT) algorithmic bytes, [LC_COUNT .. 2 LC_COUNT) launches, [2 LC_COUNT .. 3 LC_COUNT)
+    // milliseconds (TM_OPT_PROFILE = 3 only) per LedgerCat since the last reset
+    void ledger_read(double* out, int n, int reset) override {
+        TM_CUDA(cudaStreamSynchronize(stream_));
+        double ms[LC_COUNT];
+        for (int i = 0; i < LC_COUNT; ++i) ms[i] = 0.0;
+        for (size_t k = 1; k < ev_marks_.size(); ++k) {
+            float t = 0.f;
+            TM_CUDA(cudaEventElapsedTime(&t, ev_marks_[k - 1].second, ev_marks_[k].second));
+            if (ev_marks_[k].first >= 0) ms[ev_marks_[k].first] += t;
+        }
+        for (int i = 0; i < n; ++i) out[i] = 0.0;
+        for (int i = 0; i < LC_COUNT; ++i) {
+            if (i < n) out[i] = led_.bytes[i];
+            if (LC_COUNT + i < n) out[LC_COUNT + i] = led_.launches[i];
+            if (2 * LC_COUNT + i < n) out[2 * LC_COUNT + i] = ms[i];
+        }
+        if (inner_) {  // the fp32 twin (mixed precision) files its own launches
+            std::vector<double> t(n, 0.0);
+            inner_->ledger_read(t.data(), n, reset);
+            for (int i = 0; i < n; ++i) out[i] += t[i];
+        }
+        if (reset) {
+            led_.clear();
+            for (auto& m : ev_marks_) ev_free_.push_back(m.second);
+            ev_marks_.clear();
+            if (profile_ == 3) mark(-1);
         }
     }
 
@@ -1351,6 +1459,41 @@ class Engine : public EngineBase {
         return g;
     }
 
+    // ------------------------------------------------------------------ measurement ledger
+    double sz(size_t n) const { return (double)n * sizeof(T); }
+    void acct(int cat, double bytes) {
+        led_.bytes[cat] += bytes;
+        led_.launches[cat] += 1.0;
+        if (profile_ == 3 && !capturing_) mark(cat);
+    }
+    void mark(int cat) {
+        cudaEvent_t e = nullptr;
+        if (ev_free_.empty()) {
+            TM_CUDA(cudaEventCreate(&e));
+        } else {
+            e = ev_free_.back();
+            ev_free_.pop_back();
+        }
+        TM_CUDA(cudaEventRecord(e, stream_));
+        ev_marks_.push_back({cat, e});
+    }
+    // capture scope: launches recorded into a graph are filed when the graph is replayed
+    struct CaptureLedger {
+        Ledger saved;
+        Ledger& live;
+        bool& flag;
+        CaptureLedger(Ledger& l, bool& f) : saved(l), live(l), flag(f) {
+            live.clear();
+            flag = true;
+        }
+        Ledger finish() {
+            Ledger captured = live;
+            live = saved;
+            flag = false;
+            return captured;
+        }
+    };
+
     // ------------------------------------------------------------------ helpers
     int grid1d(size_t n) const {
         const size_t want = (n + kVecThreads - 1) / kVecThreads;
@@ -1392,9 +1535,11 @@ class Engine : public EngineBase {
             a.n = n;
             p2p_allreduce_kernel<<<1, 64, 0, stream_>>>(a);
             TM_CHECK_LAUNCH();
+            acct(LC_ALLREDUCE, 8.0 * n * nranks_);
             return;
         }
         nccl_check(nccl().AllReduce(p, p, (size_t)n, kNcclFloat64, kNcclSum, comm_, stream_), "ncclAllReduce");
+        acct(LC_ALLREDUCE, 8.0 * n * nranks_);
     }
 
     // halo exchange of a row-major local array: the `up` rows below my top edge go to rank+1,
@@ -1425,6 +1570,8 @@ class Engine : public EngineBase {
             else if (granule == 8) p2p_halo_kernel<uint2><<<blocks, 256, 0, stream_>>>(a);
             else p2p_halo_kernel<unsigned int><<<blocks, 256, 0, stream_>>>(a);
             TM_CHECK_LAUNCH();
+            // rows pushed to the neighbours + rows unpacked from the own mailboxes
+            acct(LC_HALO, 2.0 * ((!last ? 1 : 0) + (rank_ > 0 ? 1 : 0)) * (double)(up + down) * row_elems * sizeof(T));
             return;
         }
         const int dtype = sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32;
@@ -1438,6 +1585,7 @@ class Engine : public EngineBase {
             nccl().Recv(v + (size_t)(own0 - up) * row_elems, (size_t)up * row_elems, dtype, rank_ - 1, comm_, stream_);
         }
         nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+        acct(LC_HALO, 2.0 * ((!last ? 1 : 0) + (rank_ > 0 ? 1 : 0)) * (double)(up + down) * row_elems * sizeof(T));
     }
     // lattice vector of sharded level l: 4 rows up, 3 rows down
     void exchange_p2(int l, T* v) {
@@ -1478,6 +1626,7 @@ class Engine : public EngineBase {
             nccl().Broadcast(p, p, (size_t)(j1 - j0) * row_elems, dtype, q, comm_, stream_);
         }
         nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+        acct(LC_GATHER, sz((size_t)(cell_rows ? lv_ny_[l] : 2 * lv_ny_[l] + 1) * row_elems));
     }
 
     ApplyArgs<T> apply_args() const {
@@ -1562,6 +1711,15 @@ class Engine : public EngineBase {
 #undef TM_LAUNCH_APPLY_EP
 #undef TM_LAUNCH_APPLY
         TM_CHECK_LAUNCH();
+        {   // algorithmic bytes: every lattice vector the epilogue touches once + the coefficient source
+            const double nuv = 2.0 * g.Lx * g.Ly;
+            double vecs = 2.0;  // EP_PLAIN, EP_DOT: read x, write y
+            if (ep == EP_RESID) vecs = 3.0;  // + b
+            else if (ep == EP_RESID0) vecs = 4.0;  // read b, D^-1; write x, r
+            else if (ep_is_cheb(ep)) vecs = 4.0 + (a.c1 != T(0) ? 1.0 : 0.0) + (a.store_d ? 1.0 : 0.0);
+            const double coef = stored ? 12.0 * g.nx * g.ny : (double)(g.nx + 1) * (g.ny + 1);
+            acct(fine ? LC_FINE_PLAIN + ep : LC_COARSE1 + std::min(level, 14) - 1, (vecs * nuv + coef) * sizeof(T));
+        }
         if (timed) {
             TM_CUDA(cudaEventRecord(ev.second, stream_));
             prof_pending_.push_back({4 * level + ep_slot, ev});
@@ -1580,6 +1738,7 @@ class Engine : public EngineBase {
         else
             elast_diag_kernel<T, false><<<grd, blk, 0, stream_>>>(g, diag_tab_, dinv);
         TM_CHECK_LAUNCH();
+        acct(LC_SETUP_DIAG, (2.0 * g.Lx * g.Ly + (stored ? 12.0 * g.nx * g.ny : (double)(g.nx + 1) * (g.ny + 1))) * sizeof(T));
     }
 
     void p1_apply(double alpha, double beta, const T* x, T* y, double* dot_out) {
@@ -1590,6 +1749,7 @@ class Engine : public EngineBase {
         else
             p1_apply_kernel<T, false><<<grd, dim3(32, 8), 0, stream_>>>(p1_, alpha, beta, x, y, rs_, nullptr);
         TM_CHECK_LAUNCH();
+        acct(LC_FILTER, 2 * sz(n1_));
     }
 
     // ------------------------------------------------------------------ PCG
@@ -1598,12 +1758,17 @@ class Engine : public EngineBase {
     // nullptr when `jacobi` (then z = dinv r is fused into the vector kernels).
     template <class ApplyDot, class Precond>
     SolveStats pcg(size_t off, size_t n, const T* b, T* x, T* r, T* p, T* Ap, const T* dinv,
-                   ApplyDot apply_dot, Precond precond, bool jacobi, double rtol, int maxit, int check) {
+                   ApplyDot apply_dot, Precond precond, bool jacobi, double rtol, int maxit, int check,
+                   bool filter_solve = false) {
         SolveStats st;
         const int g1 = grid1d(n);
         const T* dv = dinv ? dinv + off : nullptr;
+        // ledger categories of the vector kernels (the filter's solves are filed as a whole)
+        const int lc_upd = filter_solve ? LC_FILTER : LC_PCG_UPDATE, lc_dir = filter_solve ? LC_FILTER : LC_PCG_DIRECTION,
+                  lc_red = filter_solve ? LC_FILTER : LC_REDUCTIONS;
         dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, b + off, b + off, rs_, sc_ + SC_BB);
         TM_CHECK_LAUNCH();
+        acct(lc_red, sz(n));
         sum_ranks(sc_ + SC_BB, 1);
         int cur = 0;
         if (jacobi) {
@@ -1614,6 +1779,7 @@ class Engine : public EngineBase {
                                                                        z + off, rs_);
         }
         TM_CHECK_LAUNCH();
+        acct(lc_red, 3 * sz(n));
         sum_ranks(sc_ + SC_RR, 1);
         sum_ranks(sc_ + cur, 1);
         read_scalars();
@@ -1634,12 +1800,14 @@ class Engine : public EngineBase {
                 pcg_update_kernel<T, true><<<g1, kVecThreads, 0, stream_>>>(
                     n, sc_, cur, cur ^ 1, x + off, r + off, p + off, Ap + off, dv, rs_);
                 TM_CHECK_LAUNCH();
+                acct(lc_upd, 7 * sz(n));
                 sum_ranks(sc_ + SC_RR, 1);
                 sum_ranks(sc_ + (cur ^ 1), 1);
             } else {
                 pcg_update_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(
                     n, sc_, cur, cur ^ 1, x + off, r + off, p + off, Ap + off, nullptr, rs_);
                 TM_CHECK_LAUNCH();
+                acct(lc_upd, 6 * sz(n));
                 sum_ranks(sc_ + SC_RR, 1);
             }
             st.iters = k + 1;
@@ -1666,12 +1834,14 @@ class Engine : public EngineBase {
                 } else {
                     dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(n, r + off, z + off, rs_, sc_ + (cur ^ 1));
                     TM_CHECK_LAUNCH();
+                    acct(lc_red, 2 * sz(n));
                     sum_ranks(sc_ + (cur ^ 1), 1);
                     pcg_direction_kernel<T, false><<<g1, kVecThreads, 0, stream_>>>(n, sc_, cur, cur ^ 1, -1,
                                                                                    p + off, r + off, z + off);
                 }
             }
             TM_CHECK_LAUNCH();
+            acct(lc_dir, (jacobi ? 4 : 3) * sz(n));
             cur ^= 1;
         }
         return st;
@@ -1890,6 +2060,7 @@ class Engine : public EngineBase {
             tail_assemble_kernel<T><<<ceil_div(V.toff[4] * V.npt * 2, 128), 128, 0, stream_>>>(
                 V, tail_cluster_used_, tail_host_.img_len, tail_img_.p);
             TM_CHECK_LAUNCH();
+            acct(LC_SETUP_COARSEN, 12 * sz((size_t)V.g.nx * V.g.ny) + sz((size_t)tail_cluster_used_ * tail_host_.img_len));
         }
     }
     // ... and the argument block (needs the smoother bounds, i.e. the host copy of lambda_max)
@@ -1951,6 +2122,7 @@ class Engine : public EngineBase {
         TM_CUDA(cudaLaunchKernelEx(&cfg, tail_vcycle_kernel<T>,
                                    reinterpret_cast<const TailArgs<T>*>(tail_dev_.p)));
         TM_CHECK_LAUNCH();
+        acct(LC_TAIL, 2 * sz(levels_[tail_first_].nu));
         const int D = tail_host_.degree;
         const int flips = std::max(D - 2, 0) + D;
         Level& L = levels_[tail_first_];
@@ -1964,13 +2136,14 @@ class Engine : public EngineBase {
         const int nl = nlevels_;
         graph_dirty_ = true;  // coefficients / smoother bounds change: re-capture the V-cycle
         graph_sampled_ = false;
-        bool steady = use_graph_ && nranks_ == 1 && profile_ != 2;
+        bool steady = use_graph_ && nranks_ == 1 && profile_ < 2;
         for (int l = 0; steady && l + 1 < nl; ++l) steady = levels_[l].eig_ready;
         if (!steady) {
             setup_device_part(xi);
         } else if (setup_graph_exec_ && setup_graph_xi_ == xi) {
             TM_CUDA(cudaGraphLaunch(setup_graph_exec_, stream_));
             ++g_launches;
+            led_.add(setup_graph_led_);
         } else {
             if (setup_graph_exec_) {
                 cudaGraphExecDestroy(setup_graph_exec_);
@@ -1981,14 +2154,17 @@ class Engine : public EngineBase {
             profile_ = 0;  // no event records inside a capture
             cudaGraph_t graph = nullptr;
             TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+            CaptureLedger cap(led_, capturing_);
             try {
                 setup_device_part(xi);
             } catch (...) {
+                cap.finish();
                 cudaStreamEndCapture(stream_, &graph);
                 if (graph) cudaGraphDestroy(graph);
                 profile_ = saved_profile;
                 throw;
             }
+            setup_graph_led_ = cap.finish();
             TM_CUDA(cudaStreamEndCapture(stream_, &graph));
             profile_ = saved_profile;
             g_launches.store(l0);
@@ -1997,6 +2173,7 @@ class Engine : public EngineBase {
             setup_graph_xi_ = xi;
             TM_CUDA(cudaGraphLaunch(setup_graph_exec_, stream_));
             ++g_launches;
+            led_.add(setup_graph_led_);
         }
         TM_CUDA(cudaMemcpyAsync(h_sc_ + SC_COUNT, eig_sc_, sizeof(double) * 2 * (nl - 1),
                                 cudaMemcpyDeviceToHost, stream_));
@@ -2034,6 +2211,8 @@ class Engine : public EngineBase {
                 mg_coarsen_moments_kernel<T, true><<<grd, blk, 0, stream_>>>(F.g, C.g.nx, C.g.ny, cell_off, own0,
                                                                             own1, co_tab_, C.W.p);
             TM_CHECK_LAUNCH();
+            acct(LC_SETUP_COARSEN, (F.g.W ? 12.0 * F.g.nx * F.g.ny : (double)(F.g.nx + 1) * (F.g.ny + 1)) * sizeof(T) +
+                                       12 * sz((size_t)C.g.nx * (own1 - own0)));
             if (C.sharded) exchange_w(l, C.W.p);
             if (gather) {
                 const size_t plane = (size_t)C.g.nx * C.g.ny;
@@ -2051,12 +2230,14 @@ class Engine : public EngineBase {
             if (!L.eig_ready) {
                 mg_seed_vector_kernel<T><<<grid1d(L.nu / 2), kVecThreads, 0, stream_>>>(L.g, L.eig.p);
                 TM_CHECK_LAUNCH();
+                acct(LC_SETUP_EIG, sz(L.nu));
                 its = eig_first_its_;  // the top of the spectrum is clustered: the power method is slow
                 L.eig_ready = true;
             }
             double* slot = eig_sc_ + 2 * l + 1;
             dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.cnt, L.eig.p + L.off, L.eig.p + L.off, rs_, slot);
             TM_CHECK_LAUNCH();
+            acct(LC_SETUP_EIG, sz(L.cnt));
             if (L.sharded) sum_ranks(slot, 1);
             for (int it = 0; it < its; ++it) {
                 exchange_p2(l, L.eig.p);
@@ -2067,8 +2248,10 @@ class Engine : public EngineBase {
                 normalize_scale_kernel<T><<<g1, kVecThreads, 0, stream_>>>(
                     L.cnt, L.dinv.p + L.off, L.tmp.p + L.off, L.eig.p + L.off, slot);
                 TM_CHECK_LAUNCH();
+                acct(LC_SETUP_EIG, 3 * sz(L.cnt));
                 dot_kernel<T><<<g1, kVecThreads, 0, stream_>>>(L.cnt, L.eig.p + L.off, L.eig.p + L.off, rs_, slot);
                 TM_CHECK_LAUNCH();
+                acct(LC_SETUP_EIG, sz(L.cnt));
                 if (L.sharded) sum_ranks(slot, 1);
             }
         }
@@ -2076,9 +2259,11 @@ class Engine : public EngineBase {
             Level& C = levels_[nl - 1];
             mg_coarse_factor_kernel<T><<<1, 256, 0, stream_>>>(C.g, coarse_A_.p);
             TM_CHECK_LAUNCH();
+            acct(LC_COARSE_SOLVE, 8.0 * C.nu * C.nu);
             coarse_Ainv_.ensure(C.nu * C.nu);
             mg_coarse_invert_kernel<<<1, 192, 0, stream_>>>((int)C.nu, coarse_A_.p, coarse_Ainv_.p);
             TM_CHECK_LAUNCH();
+            acct(LC_COARSE_SOLVE, 16.0 * C.nu * C.nu);
         }
     }
 
@@ -2108,6 +2293,7 @@ class Engine : public EngineBase {
         xi32_.ensure(n1_);
         convert_kernel<T, float><<<grid1d(n1_), kVecThreads, 0, stream_>>>(n1_, xi, xi32_.p);
         TM_CHECK_LAUNCH();
+        acct(LC_CONVERT, (sizeof(T) + 4.0) * n1_);
         if (in.levels_.empty()) in.build_levels();
         in.setup_hierarchy(xi32_.p);
         in.s_r_.ensure(nu_);
@@ -2118,9 +2304,11 @@ class Engine : public EngineBase {
         const int g1 = grid1d(p2_cnt_);
         convert_kernel<T, float><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, r + p2_off_, in.s_r_.p + p2_off_);
         TM_CHECK_LAUNCH();
+        acct(LC_CONVERT, (sizeof(T) + 4.0) * p2_cnt_);
         float* z = in.vcycle(in.s_r_.p);
         convert_kernel<float, T><<<g1, kVecThreads, 0, stream_>>>(p2_cnt_, z + p2_off_, s_z_.p + p2_off_);
         TM_CHECK_LAUNCH();
+        acct(LC_CONVERT, (sizeof(T) + 4.0) * p2_cnt_);
         return s_z_.p;
     }
 
@@ -2137,6 +2325,7 @@ class Engine : public EngineBase {
             launch_chain(cheb_first_kernel<T>, dim3(grid1d(L.cnt)), dim3(kVecThreads), L.cnt, 1.0 / theta,
                          (const T*)(L.dinv.p + L.off), b + L.off, L.d.p + L.off, L.x.p + L.off);
             TM_CHECK_LAUNCH();
+            acct(LC_CHEB_FIRST, 4 * sz(L.cnt));
             cur = L.x.p;
             k0 = 1;
         } else {
@@ -2174,13 +2363,14 @@ class Engine : public EngineBase {
     // path keeps stream launches because of its NCCL calls).  With TM_OPT_PROFILE on, the first
     // V-cycle of every solve runs un-captured so its level-0 launches can be event-timed.
     T* vcycle(T* r) {
-        if (!use_graph_ || (nranks_ > 1 && !graph_sharded_) || profile_ == 2) return vcycle_body(r);
+        if (!use_graph_ || (nranks_ > 1 && !graph_sharded_) || profile_ >= 2) return vcycle_body(r);
         if (graph_exec_ && graph_r_ == r && !graph_dirty_) {
             TM_CUDA(cudaGraphLaunch(graph_exec_, stream_));
             ++g_launches;
             ++stats_vcycles_;
             stats_fine_applies_ += graph_fine_applies_;
             for (int e = 0; e < 4; ++e) fine_ep_count_[e] += graph_ep_count_[e];
+            led_.add(graph_led_);
             vcycle_rz_ = graph_rz_;
             return graph_z_;
         }
@@ -2200,15 +2390,18 @@ class Engine : public EngineBase {
         profile_ = 0;
         cudaGraph_t graph = nullptr;
         TM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        CaptureLedger cap(led_, capturing_);
         T* z = nullptr;
         try {
             z = vcycle_body(r);
         } catch (...) {
+            cap.finish();
             cudaStreamEndCapture(stream_, &graph);
             if (graph) cudaGraphDestroy(graph);
             profile_ = saved_profile;
             throw;
         }
+        graph_led_ = cap.finish();
         TM_CUDA(cudaStreamEndCapture(stream_, &graph));
         profile_ = saved_profile;
         graph_fine_applies_ = stats_fine_applies_ - fa0;
@@ -2270,6 +2463,7 @@ class Engine : public EngineBase {
             launch_chain(mg_restrict_kernel<T>, grd, blk, L.g, gather ? C.gpiece : C.g, tr_tab_,
                          (const T*)L.tmp.p, C.b.p);
             TM_CHECK_LAUNCH();
+            acct(LC_RESTRICT, sz(L.nu) + sz(gather ? (size_t)(C.gpiece.own_j1 - C.gpiece.own_j0) * C.g.Lx * 2 : C.cnt));
             if (gather) gather_rows(l + 1, C.b.p, (size_t)C.g.Lx * 2, false);
             bs[l + 1] = C.b.p;
         }
@@ -2281,6 +2475,7 @@ class Engine : public EngineBase {
             Level& C = levels_[nl - 1];
             mg_coarse_apply_inverse_kernel<T><<<1, 192, 0, stream_>>>((int)C.nu, coarse_Ainv_.p, bs[nl - 1], C.x.p);
             TM_CHECK_LAUNCH();
+            acct(LC_COARSE_SOLVE, 8.0 * C.nu * C.nu);
             xs[nl - 1] = C.x.p;
         }
         for (int l = lbot; l-- > 0;) {
@@ -2290,6 +2485,7 @@ class Engine : public EngineBase {
             dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
             launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
+            acct(LC_PROLONG, 2 * sz(L.cnt) + sz(C.nu));
             // the V-cycle ends with the level-0 post-smoothing: its last step also returns r . z
             xs[l] = smooth(l, bs[l], xs[l], (l == 0 && (fuse_rz_ > 0 || (fuse_rz_ < 0 && p2_cnt_ >= ((size_t)1 << 24)))) ? sc_ + SC_RZV
                                                                                                  : nullptr);
@@ -2391,6 +2587,10 @@ class Engine : public EngineBase {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free_;
     int stats_iters_ = 0;
+    Ledger led_, graph_led_, fgraph_led_, setup_graph_led_;
+    bool capturing_ = false;
+    std::vector<std::pair<int, cudaEvent_t>> ev_marks_;
+    std::vector<cudaEvent_t> ev_free_;
 };
 
 }  // namespace tmx
@@ -2754,6 +2954,14 @@ int tm_last_solve_stats(tm_handle h, double* out, int n) {
 int tm_profile_read(tm_handle h, double* out, int n) {
     TM_REQUIRE_HANDLE(h);
     return guarded(h, [&] { h->impl->profile_read(out, n); });
+}
+int tm_ledger_read(tm_handle h, double* out, int n, int reset) {
+    TM_REQUIRE_HANDLE(h);
+    if (!out || n < 0) {
+        tmx::set_error("tm_ledger_read: bad argument");
+        return TM_ERR_INVALID;
+    }
+    return guarded(h, [&] { h->impl->ledger_read(out, n, reset); });
 }
 long long tm_launch_count(void) { return tmx::g_launches.load(); }
 int tm_mg_debug(tm_handle h, void* xi, int op, int level, const void* in, void* out) {

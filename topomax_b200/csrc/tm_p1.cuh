@@ -289,15 +289,25 @@ __device__ __forceinline__ bool inside_disc(const LoadSpec& s, int i, int j) {
     return dist < s.frad;
 }
 
-// nodal traction value of boundary node at lattice position p along side `side`
+// Nodal traction value of the boundary node at lattice position p along side `side`: the sum of
+// EVERY traction whose own side passes through the node and whose window contains it
+// (TractionExpression.eval, FEM_src/elasisity_problem.py:47-70, is evaluated at the node, whatever
+// facet is being integrated).  Away from the corners only tractions of `side` can match; a CORNER
+// node also picks up a traction of the adjacent side whose window reaches the corner, and through
+// the P2 interpolant on the corner edge of `side` that value loads this side too.
 __device__ __forceinline__ void traction_nodal(const LoadSpec& s, int side, int p, double& tx,
                                                double& ty) {
     tx = 0.0;
     ty = 0.0;
-    const bool vertical = side <= 1;
-    const double c = vertical ? lattice_coord(p, s.H, s.ny) : lattice_coord(p, s.W, s.nx);
+    const int Lx = 2 * s.nx + 1, Ly = 2 * s.ny + 1;
+    const int i = side == 0 ? 0 : (side == 1 ? Lx - 1 : p);
+    const int j = side == 2 ? Ly - 1 : (side == 3 ? 0 : p);
     for (int t = 0; t < s.ntractions; ++t) {
-        if (s.tside[t] != side) continue;
+        const int ts = s.tside[t];
+        const bool on = (ts == 0 && i == 0) || (ts == 1 && i == Lx - 1) || (ts == 2 && j == Ly - 1) ||
+                        (ts == 3 && j == 0);
+        if (!on) continue;
+        const double c = ts <= 1 ? lattice_coord(j, s.H, s.ny) : lattice_coord(i, s.W, s.nx);
         // df.between(c, (lo, hi)) with DOLFIN_EPS = 3e-16
         if (c >= __dsub_rn(s.tlo[t], 3.0e-16) && c <= __dadd_rn(s.thi[t], 3.0e-16)) {
             tx += s.tx[t];
@@ -342,10 +352,7 @@ __global__ void load_vector_kernel(const LoadSpec s, T* __restrict__ b) {
         else if (side == 1) { on = (i == Lx - 1); p = j; np = Ly; hlen = s.H / s.ny; }
         else if (side == 2) { on = (j == Ly - 1); p = i; np = Lx; hlen = s.W / s.nx; }
         else { on = (j == 0); p = i; np = Lx; hlen = s.W / s.nx; }
-        if (!on) continue;
-        bool any = false;
-        for (int t = 0; t < s.ntractions; ++t) any = any || (s.tside[t] == side);
-        if (!any) continue;
+        if (!on || s.ntractions == 0) continue;
         double a0 = 0.0, a1 = 0.0;
         const double c = hlen / 30.0;
         if (p & 1) {  // midpoint of edge (p-1, p, p+1)

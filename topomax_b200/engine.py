@@ -286,6 +286,25 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.tm_launch_count())
 
+    LEDGER_CATEGORIES = (
+        ["fine_op_plain", "fine_op_dot", "fine_op_resid", "fine_op_cheb", "fine_op_resid0", "fine_op_chebdot"]
+        + [f"level{lvl}_op" for lvl in range(1, 15)]
+        + ["restrict", "prolong", "cheb_first", "pcg_update", "pcg_direction", "reductions", "copies", "tail",
+           "coarse_solve", "filter", "mirror_descent", "sensitivity", "setup_moments", "setup_diag", "setup_eig",
+           "halo", "allreduce", "gather", "convert", "other"])
+
+    def ledger_read(self, reset: bool = True) -> dict:
+        """Per category: algorithmic bytes, launches and (``OPT_PROFILE`` = 3 only) milliseconds since the
+        last reset -- ``tm_ledger_read``."""
+        c = _lib.LEDGER_CATEGORIES
+        buf = (c_double * (3 * c))()
+        _lib.check(self.lib.tm_ledger_read(self._h, buf, 3 * c, 1 if reset else 0))
+        out = {}
+        for i, name in enumerate(self.LEDGER_CATEGORIES):
+            if buf[c + i]:
+                out[name] = {"bytes": buf[i], "launches": int(buf[c + i]), "ms": buf[2 * c + i]}
+        return out
+
     # ---------------------------------------------------------------- multigrid diagnostics
     def mg_levels(self):
         """[(nx, ny, dl, dr, db, dt)] per level of the hierarchy."""

@@ -154,8 +154,9 @@ class FEMSolver(Solver):
     h2d_bytes = 0
     d2h_bytes = 0
 
-    def _h2d(self, values: np.ndarray) -> torch.Tensor:
-        if self.world > 1:
+    def _h2d(self, values: np.ndarray, local: bool = False) -> torch.Tensor:
+        """``local``: ``values`` already is this rank's strip (owned + halo rows) of a sharded field."""
+        if self.world > 1 and not local:
             from . import sharding
             t = sharding.local_p1(self.problem.engine, values)
         else:
@@ -169,9 +170,9 @@ class FEMSolver(Solver):
         self.h2d_bytes += t.numel() * t.element_size()
         return t
 
-    def _d2h(self, tensor: torch.Tensor) -> np.ndarray:
+    def _d2h(self, tensor: torch.Tensor, local: bool = False) -> np.ndarray:
         self.d2h_bytes += tensor.numel() * tensor.element_size()
-        if self.world > 1:
+        if self.world > 1 and not local:
             from . import sharding
             return sharding.gather_p1(self.problem.engine, tensor)
         n = tensor.numel()
@@ -203,6 +204,19 @@ class FEMSolver(Solver):
         psi = torch.empty_like(prev)
         self.step_device(prev, step_size, psi, self.rho.tensor)
         return self._d2h(psi)
+
+    def host_array(self, tensor: torch.Tensor) -> np.ndarray:
+        """Host copy of a rank-local device field (the whole field on an unsharded solver)."""
+        return self._d2h(tensor, local=True)
+
+    def step_local(self, previous_psi_local: np.ndarray, step_size: float) -> np.ndarray:
+        """``step`` for a sharded solver whose HOST memory is distributed like the GPUs: every rank
+        passes and receives its own strip of psi (stored rows, halo rows included); one pinned
+        host-to-device and one device-to-host copy per rank, no gather.  On one GPU: ``step``."""
+        prev = self._h2d(previous_psi_local, local=True)
+        psi = torch.empty_like(prev)
+        self.step_device(prev, step_size, psi, self.rho.tensor)
+        return self._d2h(psi, local=True)
 
     def save_rho(self, rho: Function, file_root: str):
         rho_file = file_root + "_rho.dat"
