@@ -437,7 +437,7 @@ def md_loop(solver, problem, psi, rho, prev, k, n, objectives):
 
 
 def timed_device_run(design_path, full_n, args, *, steps, warmup, distributed, dtype="float64", mixed=False,
-                     options=None):
+                     options=None, sampler=None):
     """Builds a solver and times `steps` device-resident mirror-descent iterations after `warmup`.
     Returns a dict with the solver, timings, ledger and traces (used for the main line, the
     latency-bound secondary line, the same-config pair and the single-GPU comparison)."""
@@ -471,11 +471,14 @@ def timed_device_run(design_path, full_n, args, *, steps, warmup, distributed, d
     log0 = len(problem.solve_log)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     state0 = (psi.clone(), rho.clone(), k)
+    if sampler is not None:  # nvidia-smi clocks / throttle reasons DURING the timed region only
+        sampler.start()
     barrier()
     start.record()
     k = md_loop(solver, problem, psi, rho, prev, k, steps, objectives)
     stop.record()
     barrier()
+    clocks = sampler.stop() if sampler is not None else None
     elapsed_ms = start.elapsed_time(stop)
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
@@ -483,7 +486,7 @@ def timed_device_run(design_path, full_n, args, *, steps, warmup, distributed, d
         elapsed_ms = float(t.item())
     return dict(solver=solver, problem=problem, engine=engine, psi=psi, rho=rho, prev=prev, k=k,
                 objectives=objectives, elapsed_ms=elapsed_ms, ledger=engine.ledger_read(reset=True),
-                solves=problem.solve_log[log0:log0 + steps], state0=state0, barrier=barrier)
+                solves=problem.solve_log[log0:log0 + steps], state0=state0, barrier=barrier, clocks=clocks)
 
 
 def ledger_totals(ledger):
@@ -523,16 +526,15 @@ def run_cuda_arm(args):
     tname = "double" if esize == 8 else "float"
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
     in_profiler = bool(os.environ.get("TM_PROFILER_RANGE"))  # ncu --profile-from-start off
     if in_profiler:
         # the profiled range is the timed region of a run whose warm-up is not profiled
         torch.cuda.profiler.stop()
     run = timed_device_run(design_path, run_n, args, steps=args.steps, warmup=args.warmup, distributed=world > 1,
-                           dtype=args.dtype, mixed=args.mixed) if not in_profiler else None
+                           dtype=args.dtype, mixed=args.mixed, sampler=sampler) if not in_profiler else None
     if in_profiler:
         run = profiled_run(design_path, run_n, args, world)
-    clocks = sampler.stop()
+    clocks = run["clocks"]
     solver, problem, engine = run["solver"], run["problem"], run["engine"]
     psi, rho, prev, k, objectives = run["psi"], run["rho"], run["prev"], run["k"], run["objectives"]
     barrier = run["barrier"]

@@ -64,4 +64,35 @@ int hc_driver_solve(int nx, int ny, double W, double H, double q, double rmin, d
         return -1;
     }
 }
+
+// A mesh the multigrid cannot coarsen far enough: asking for the multigrid preconditioner
+// must fail cleanly, at set_option time, and leave a solver that still works with the diagonal one -- twice
+// over, since a caught error followed by a retry used to leave a half-planned hierarchy behind.
+// returns the iterations of the diagonal solve (negative: not converged), -99999 if nothing threw
+int hc_driver_uncoarsenable(int nx, int ny, double W, double H, double q, double rmin, double rmax, double visc,
+                            const double* rho, const double* g_boundary, double rtol, int maxit, double* up,
+                            double* out3) {
+    try {
+        tmx::FluidSolver solver(nx, ny, W, H, visc, rmin, rmax, 0);
+        int threw = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            try {
+                solver.set_option(tmx::TM_FLUID_OPT_PRECOND, 1.0);
+                solver.set_density(rho, q);
+            } catch (const std::exception&) {
+                ++threw;
+            }
+        }
+        solver.set_density(rho, q);
+        const tmx::MinresResult r = solver.solve(g_boundary, rtol, maxit, up);
+        out3[0] = r.relres;
+        out3[1] = solver.objective(up);
+        out3[2] = threw;
+        if (threw != 2) return -99999;
+        return r.converged ? r.iterations : -r.iterations;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "hc_driver_uncoarsenable: %s\n", e.what());
+        return -1;
+    }
+}
 }

@@ -363,6 +363,22 @@ def test_cuda_driver_on_the_host_matches_oracle_with_both_preconditioners(driver
         assert counts[1] < counts[0]
 
 
+def test_uncoarsenable_mesh_fails_cleanly_and_the_solver_stays_usable(driver, repo_root):
+    """50 x 50 cells halve once to 25 x 25: the coarsest velocity level (51^2 nodes) exceeds the dense
+    inverse's limit.  The multigrid request must throw (twice, no half-built state in between) and the
+    diagonal solver of the same object must still return the oracle's solution."""
+    driver.hc_driver_uncoarsenable.argtypes = [I, I, D, D, D, D, D, D, P, P, D, I, P, P]
+    driver.hc_driver_uncoarsenable.restype = I
+    s, pr, m, rho, args, g, interior = oracle_case(repo_root, 50, "diffuser", seed=5)
+    assert (m.nx, m.ny) == (50, 50)
+    obj_o = pr.calculate_objective(rho)
+    up, out3 = np.zeros(m.nu + m.n1), np.zeros(3)
+    its = driver.hc_driver_uncoarsenable(*args, ptr(rho), ptr(g), 1e-10, 40000, ptr(up), ptr(out3))
+    assert its > 0 and out3[2] == 2.0, (its, list(out3))
+    assert abs(out3[1] - obj_o) < 1e-7 * obj_o
+    assert np.abs(up[:m.nu] - pr.u).max() < 1e-6 * np.abs(pr.u).max()
+
+
 @pytest.mark.parametrize("precond", [0, 1])
 def test_warm_start_keeps_the_solution_and_saves_iterations(driver, repo_root, precond):
     """Opt-in warm start of the fluid solver (TM_FLUID_OPT_WARM_START): the second of two solves on

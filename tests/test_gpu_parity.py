@@ -597,8 +597,9 @@ def test_save_load_round_trip_and_plot_sampling(tmp_path):
     N = 20
     rmesh = RectangleMesh(1.0, 1.0, N, N)
     rng = np.random.default_rng(198)
-    for degree, problem in ((1, "design"), (2, "elasticity")):
-        space = FunctionSpace(rmesh, "CG", degree, device="cuda")
+    for degree, problem in ((1, "design"), (2, "elasticity"), ((2, 1), "fluid")):
+        space = FunctionSpace(rmesh, "TaylorHood", device="cuda") if problem == "fluid" else \
+            FunctionSpace(rmesh, "CG", degree, device="cuda")
         f = Function(space)
         f.vector()[:] = rng.random(space.dim())
         path = str(tmp_path / f"temp_{problem}.dat")
@@ -606,6 +607,15 @@ def test_save_load_round_trip_and_plot_sampling(tmp_path):
         g, mesh2, space2 = load_function(path)
         assert (mesh2.nx, mesh2.ny, space2.degree) == (N, N, degree)
         assert np.array_equal(f.vector()[:], g.vector()[:])
+        # the reference's call shape: mesh and function space passed positionally (FEM_src/utils.py:73-77)
+        g2, mesh3, space3 = load_function(path, rmesh, space)
+        assert mesh3 is rmesh and space3 is space and np.array_equal(f.vector()[:], g2.vector()[:])
+    # a design file in dolfin dof order (what the reference writes / reads) round-trips through the permutation
+    f = Function(FunctionSpace(rmesh, "CG", 1, device="cuda"))
+    f.vector()[:] = rng.random((N + 1) ** 2)
+    save_function(f, str(tmp_path / "dolfin_order.dat"), "design", ordering="dolfin")
+    back, *_ = load_function(str(tmp_path / "dolfin_order.dat"))
+    assert np.array_equal(f.vector()[:], back.vector()[:])
     rho, *_ = load_function(str(tmp_path / "temp_design.dat"))
     _, design_data = sample_function(rho, int(200 / 1.0), "center")
     assert design_data[:, :, 0].shape == (200, 200)

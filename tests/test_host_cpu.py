@@ -320,3 +320,62 @@ def test_fluid_solver_variants_stay_off_unless_named(repo_root):
     src = open(os.path.join(repo_root, "topomax_b200", "fem_solver.py")).read()
     assert '"fluid_preconditioner": "preconditioner"' in src and '"fluid_warm_start": "warm_start"' in src
     assert '"preconditioner": "preconditioner"' not in src and '"warm_start": "warm_start"' not in src
+
+
+def test_function_files_carry_their_ordering_and_reference_files_load(golden_dir):
+    """save_function / load_function data layer (reference: FEM_src/utils.py:47-109): files written here are
+    tagged row-major; a file WITHOUT the tag is the reference's (dolfin dof order) and a P1 design is mapped
+    through the dolfin permutation -- checked on the reference's own golden design; ordering='dolfin' writes a
+    file the reference reads; other spaces in dolfin order are refused, not silently permuted."""
+    import json
+
+    from topomax_b200.fem_solver import dolfin_p1_permutation, pack_function_data, unpack_function_data
+
+    gold = json.load(open(os.path.join(golden_dir, "triangle_N10_reference.json")))
+    dolfin_vec, lex = np.array(gold["rho_dolfin_order"]), np.array(gold["rho_lex"])
+    ref_file = {"N": 10, "domain_size": (1.0, 1.0), "problem": "design", "vector": dolfin_vec}  # as the reference writes it
+    vec, nx, ny, kind = unpack_function_data(ref_file)
+    assert (nx, ny, kind) == (10, 10, "P1") and np.array_equal(vec, lex)
+    ours = pack_function_data(lex, 10, (1.0, 1.0), "design")
+    assert ours["ordering"] == "row_major" and np.array_equal(unpack_function_data(ours)[0], lex)
+    theirs = pack_function_data(lex, 10, (1.0, 1.0), "design", ordering="dolfin")
+    assert "ordering" not in theirs and np.array_equal(theirs["vector"], dolfin_vec)
+    # a non-square mesh: the permutation is a bijection and round-trips
+    perm = dolfin_p1_permutation(7, 3)
+    assert sorted(perm.tolist()) == list(range(8 * 4))
+    v = np.arange(32.0)
+    assert np.array_equal(unpack_function_data(pack_function_data(v, 1, (7.0, 3.0), "design", "dolfin"))[0], v)
+    for problem, n in (("elasticity", 2 * 21 * 21), ("fluid", 2 * 21 * 21 + 11 * 11)):
+        tagged = pack_function_data(np.zeros(n), 10, (1.0, 1.0), problem)
+        assert unpack_function_data(tagged)[3] in ("P2", "TH")
+        untagged = {k: v for k, v in tagged.items() if k != "ordering"}
+        with pytest.raises(ValueError):
+            unpack_function_data(untagged)
+        with pytest.raises(ValueError):
+            pack_function_data(np.zeros(n), 10, (1.0, 1.0), problem, ordering="dolfin")
+    with pytest.raises(ValueError):
+        unpack_function_data({"N": 2, "domain_size": (1.0, 1.0), "problem": "nope", "vector": np.zeros(9)})
+
+
+def test_result_records_pickle_from_another_working_directory(tmp_path):
+    """IterationData / SolverResult pickle as src.utils.<name> (the reference's path); without the repo-root
+    src/ shim on sys.path the package registers itself under that name."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, pickle\n"
+        f"sys.path = [p for p in sys.path if p not in ('', {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})]\n"
+        "import importlib.util, types\n"
+        f"root = {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r}\n"
+        "pkg = types.ModuleType('topomax_b200'); pkg.__path__ = [root + '/topomax_b200']; sys.modules['topomax_b200'] = pkg\n"
+        "spec = importlib.util.spec_from_file_location('topomax_b200.utils', root + '/topomax_b200/utils.py')\n"
+        "m = importlib.util.module_from_spec(spec); sys.modules['topomax_b200.utils'] = m; spec.loader.exec_module(m)\n"
+        "d = m.IterationData((1.0, 2.0), 0.5, 3, 'x_rho.dat', 3.0)\n"
+        "blob = pickle.dumps(d)\n"
+        "assert b'src.utils' in blob\n"
+        "back = pickle.loads(blob)\n"
+        "assert back == d and type(back) is m.IterationData\n"
+        "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]

@@ -3039,12 +3039,14 @@ int tm_fluid_sens_rhs(tm_fluid_handle h, const double* rho, const double* u, dou
     return fluid_guarded(h, [&] {
         if (!rho || !u || !out) throw tmx::Invalid{"tm_fluid_sens_rhs: null argument"};
         h->impl->sens_rhs(rho, u, out);
+        h->impl->sync();
     });
 }
 int tm_fluid_apply(tm_fluid_handle h, const double* x, double* y, int mode) {
     return fluid_guarded(h, [&] {
         if (!x || !y || (mode != 0 && mode != 1)) throw tmx::Invalid{"tm_fluid_apply: bad argument"};
         h->impl->apply_mode(x, y, mode);
+        h->impl->sync();
     });
 }
 

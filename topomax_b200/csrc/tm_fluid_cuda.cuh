@@ -265,6 +265,10 @@ class FluidSolver {
         switch (opt) {
             case TM_FLUID_OPT_PRECOND:
                 if (value != 0.0 && value != 1.0) throw std::runtime_error("fluid: preconditioner must be 0 or 1");
+                if (value == 1.0) {  // can this mesh be coarsened far enough?  (throws; nothing has changed yet)
+                    CudaTriMG<6>::level_list(TriLevel{g_.nx, g_.ny, 2, 1});
+                    CudaTriMG<3>::level_list(TriLevel{g_.nx, g_.ny, 1, 0});
+                }
                 precond_mode_ = (int)value;
                 have_density_ = false;
                 break;
@@ -312,16 +316,20 @@ class FluidSolver {
             TM_CHECK_LAUNCH();
         }
         if (precond_mode_ == 1) {
-            if (!mg_vel_.planned()) {
+            // one flag for "both hierarchies planned and the pressure mass diagonal allocated": a failure
+            // anywhere in here (plan() leaves its object un-planned when it throws) is retried, cleanly,
+            // by the next call instead of running on half-built state
+            if (!mg_ready_) {
                 mg_vel_.plan(TriLevel{g_.nx, g_.ny, 2, 1}, max_blocks_);
                 mg_prs_.plan(TriLevel{g_.nx, g_.ny, 1, 0}, max_blocks_);
-                alloc(mp_diag_, n1_);
+                if (!mp_diag_) alloc(mp_diag_, n1_);
                 if (deterministic_) {
                     TM_LAUNCH(fluid_pmass_diag_gather_kernel, vec_grid(), kVecThreads, stream_)(d_tab_, g_, mp_diag_, n1_);
                 } else {
                     TM_LAUNCH(fluid_pmass_diag_kernel, tri_grid(), 128, stream_)(d_tab_, g_, mp_diag_, ntri_);
                 }
                 TM_CHECK_LAUNCH();
+                mg_ready_ = true;
             }
             TM_LAUNCH(fluid_vel_local_kernel, tri_grid(), 128, stream_)(d_tab_, Me_, mg_vel_.level_matrices(0), ntri_);
             TM_CHECK_LAUNCH();
@@ -393,17 +401,23 @@ class FluidSolver {
         return read_scalar();
     }
 
+    // NB the result is handed to OTHER objects (the elasticity engine's filter projects it, on the engine's
+    // own stream: two blocking streams order against the legacy stream only, not against each other), so
+    // the C entry tm_fluid_sens_rhs completes the stream before it returns (sync()), like solve() and
+    // objective() do; the same holds for tm_fluid_apply.
     void sens_rhs(const double* rho, const double* u, double* out) {
         if (!(g_.q > 0.0)) throw std::runtime_error("fluid: set the density / penalisation first");
         if (deterministic_) {
             TM_LAUNCH(fluid_sens_gather_kernel, vec_grid(), 128, stream_)(d_tab_, g_, rho, u, out, n1_);
             TM_CHECK_LAUNCH();
-            return;
+        } else {
+            TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(double), stream_));
+            TM_LAUNCH(fluid_sens_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, u, out, ntri_);
+            TM_CHECK_LAUNCH();
         }
-        TM_CUDA(cudaMemsetAsync(out, 0, n1_ * sizeof(double), stream_));
-        TM_LAUNCH(fluid_sens_kernel, tri_grid(), 128, stream_)(d_tab_, g_, rho, u, out, ntri_);
-        TM_CHECK_LAUNCH();
     }
+    // completes everything enqueued so far (the C entries that hand a result array back call it)
+    void sync() { TM_CUDA(cudaStreamSynchronize(stream_)); }
 
     // y = Op x (mode 0) or the lifting of boundary values (mode 1); exposed for the parity tests
     void apply_mode(const double* x, double* y, int mode) {
@@ -412,11 +426,11 @@ class FluidSolver {
             const size_t items = nu_ / 2 + n1_;
             TM_LAUNCH(fluid_apply_gather_kernel, vec_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, x, y, items, mode);
             TM_CHECK_LAUNCH();
-            return;
+        } else {
+            TM_CUDA(cudaMemsetAsync(y, 0, n_ * sizeof(double), stream_));
+            TM_LAUNCH(fluid_apply_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, x, y, mode);
+            TM_CHECK_LAUNCH();
         }
-        TM_CUDA(cudaMemsetAsync(y, 0, n_ * sizeof(double), stream_));
-        TM_LAUNCH(fluid_apply_kernel, tri_grid(), 128, stream_)(d_tab_, g_, Me_, ntri_, x, y, mode);
-        TM_CHECK_LAUNCH();
     }
     const double* diagonal() const { return diag_; }
     bool last_solve_was_warm() const { return last_warm_; }
@@ -535,6 +549,7 @@ class FluidSolver {
     FluidTables* d_tab_ = nullptr;
     double *Me_ = nullptr, *diag_ = nullptr, *b_ = nullptr, *x_ = nullptr, *xg_ = nullptr, *sc_ = nullptr;
     double* mp_diag_ = nullptr;
+    bool mg_ready_ = false;
     double* xprev_ = nullptr;
     bool warm_ = false, have_prev_ = false, last_warm_ = false;
     double *ms_ = nullptr, *h_ms_ = nullptr;  // MINRES scalars on the device / their pinned mirror

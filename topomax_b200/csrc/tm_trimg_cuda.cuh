@@ -139,20 +139,37 @@ class CudaTriMG {
     ~CudaTriMG() { release(); }
 
     // plan the levels and allocate; fine local matrices live in level_matrices(0), filled by the caller
-    void plan(TriLevel fine, int max_blocks, int min_cells = 4) {
-        release();
-        max_blocks_ = max_blocks;
-        geo_.assign(1, fine);
-        while (geo_.back().nx % 2 == 0 && geo_.back().ny % 2 == 0 && geo_.back().nx * geo_.back().ny > min_cells) {
-            TriLevel c = geo_.back();
+    // level list of a mesh; throws when the coarsest level would be too large for the dense inverse
+    static std::vector<TriLevel> level_list(TriLevel fine, int min_cells = 4) {
+        std::vector<TriLevel> geo(1, fine);
+        while (geo.back().nx % 2 == 0 && geo.back().ny % 2 == 0 && geo.back().nx * geo.back().ny > min_cells) {
+            TriLevel c = geo.back();
             c.nx /= 2;
             c.ny /= 2;
-            geo_.push_back(c);
+            geo.push_back(c);
         }
-        const TriLevel one{geo_.back().nx, geo_.back().ny, 1, geo_.back().fixed_boundary};
+        const TriLevel one{geo.back().nx, geo.back().ny, 1, geo.back().fixed_boundary};
         if (trimg_num_nodes<NODES>(one) > (size_t)kMaxCoarse)
             throw std::runtime_error("fluid multigrid: the mesh cannot be coarsened far enough (cell counts need "
                                      "more factors of two); use the diagonal preconditioner");
+        return geo;
+    }
+    // Exception safe: the level list is validated before any state changes, and a failure while
+    // allocating leaves the object un-planned (planned() == false), never half built.
+    void plan(TriLevel fine, int max_blocks, int min_cells = 4) {
+        std::vector<TriLevel> geo = level_list(fine, min_cells);  // may throw: nothing touched yet
+        release();
+        try {
+            plan_validated(std::move(geo), max_blocks);
+        } catch (...) {
+            release();
+            throw;
+        }
+    }
+    void plan_validated(std::vector<TriLevel> geo, int max_blocks) {
+        max_blocks_ = max_blocks;
+        geo_ = std::move(geo);
+        const TriLevel one{geo_.back().nx, geo_.back().ny, 1, geo_.back().fixed_boundary};
         const int L = (int)geo_.size();
         Lm_.assign(L, nullptr);
         diag_.assign(L, nullptr);
@@ -317,6 +334,10 @@ class CudaTriMG {
         owned_.clear();
         if (tab_) cudaFree(tab_);
         tab_ = nullptr;
+        inv_ = nullptr;
+        Lm_.clear();
+        diag_.clear();
+        store_.clear();
         geo_.clear();
     }
 

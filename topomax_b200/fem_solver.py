@@ -25,44 +25,104 @@ from .solver import MAX_ITERATIONS, Solver, find_volume_shift
 from .utils import Timer
 
 
-def save_function(f: Function, filename: str, problem: str, N: int | None = None, domain_size=None):
-    """Pickle ``{N, domain_size, problem, vector}`` (reference: FEM_src/utils.py:47-70).
-    ``vector`` is stored in this package's row-major node order, not dolfin's dof order."""
+def dolfin_p1_permutation(nx: int, ny: int) -> np.ndarray:
+    """``perm[d]`` = row-major vertex index of dolfin's P1 dof ``d`` on ``RectangleMesh(nx, ny)`` (default
+    "right" diagonal, serial): dofs sweep the diagonals from the top-left to the bottom-right corner,
+    i.e. vertices sorted by (ix - iy, ix).  Verified against the reference's golden file
+    tests/test_data/FEM/triangle/data/correct_rho.dat (11 x 11 vertices) -- the only
+    reference-written design file there is; other mesh shapes follow the same rule unverified."""
+    ix, iy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    ix, iy = ix.ravel(), iy.ravel()
+    return np.lexsort((ix, ix - iy))
+
+
+def pack_function_data(vector: np.ndarray, N: int, domain_size, problem: str, ordering: str = "row_major") -> dict:
+    """The dict ``save_function`` pickles (reference: FEM_src/utils.py:63-70).  ``ordering``:
+    ``"row_major"`` (default) stores this package's node order and says so in an extra ``"ordering"`` key
+    (the reference's reader ignores unknown keys but would misplace the values);
+    ``"dolfin"`` writes a file the REFERENCE's load_function reads correctly: dolfin's dof order, no extra
+    key -- available for P1 ("design") vectors, whose dof map is known (``dolfin_p1_permutation``)."""
+    vector = np.asarray(vector, dtype=np.float64)
+    data = {"N": N, "domain_size": domain_size, "problem": problem}
+    if ordering == "row_major":
+        data["vector"] = vector
+        data["ordering"] = "row_major"
+    elif ordering == "dolfin":
+        if problem != "design":
+            raise ValueError("ordering='dolfin' is available for P1 'design' vectors only (dolfin's dof map of the "
+                             "vector-P2 and Taylor-Hood spaces is not reconstructed here)")
+        w, h = domain_size
+        perm = dolfin_p1_permutation(int(w * N), int(h * N))
+        data["vector"] = vector[perm]
+    else:
+        raise ValueError(f"unknown ordering {ordering!r}")
+    return data
+
+
+def unpack_function_data(data: dict):
+    """(row-major vector, nx, ny, kind) of a pickled function dict, kind in {"P1", "P2", "TH"}.  A file
+    WITHOUT the ``"ordering"`` key was written by the reference (dolfin dof order): P1 vectors are mapped
+    through ``dolfin_p1_permutation``; vector-P2 / Taylor-Hood vectors in dolfin order are refused rather
+    than loaded silently permuted."""
+    problem = data["problem"]
+    kinds = {"design": "P1", "elasticity": "P2", "fluid": "TH"}
+    if problem not in kinds:
+        raise ValueError(f"load_function got malformed problem: {problem}")
+    w, h = data["domain_size"]
+    nx, ny = int(w * data["N"]), int(h * data["N"])
+    vector = np.asarray(data["vector"], dtype=np.float64)
+    ordering = data.get("ordering")
+    if ordering is None:
+        if problem != "design":
+            raise ValueError(f"{problem!r} file in dolfin dof order (written by the reference): only P1 'design' "
+                             "files can be re-ordered to this package's node order")
+        perm = dolfin_p1_permutation(nx, ny)
+        if vector.size != perm.size:
+            raise ValueError(f"design vector has {vector.size} entries, the {nx} x {ny} mesh {perm.size} vertices")
+        lex = np.empty_like(vector)
+        lex[perm] = vector
+        vector = lex
+    elif ordering != "row_major":
+        raise ValueError(f"unknown ordering {ordering!r} in function file")
+    return vector, nx, ny, kinds[problem]
+
+
+def save_function(f: Function, filename: str, problem: str, N: int | None = None, domain_size=None,
+                  *, ordering: str = "row_major"):
+    """Pickle ``{N, domain_size, problem, vector}`` (reference: FEM_src/utils.py:47-70), see
+    ``pack_function_data`` for the node order of ``vector``."""
     mesh = f.function_space().mesh()
     if N is None:
         N = int(round(1 / (mesh.hmin() / np.sqrt(2))))
     if domain_size is None:
         domain_size = mesh.domain_size
-    data = {
-        "N": N,
-        "domain_size": domain_size,
-        "problem": problem,
-        "vector": f.vector()[:].astype(np.float64),
-    }
     with open(filename, "wb") as fh:
-        pickle.dump(data, fh)
+        pickle.dump(pack_function_data(f.vector()[:], N, domain_size, problem, ordering), fh)
 
 
-def load_function(filename: str, *, dtype: str = "float64", device=None):
-    """Inverse of ``save_function`` (reference: FEM_src/utils.py:73-109): ``problem == 'design'``
-    gives a P1 function, ``'elasticity'`` a vector-P2 function; ``'fluid'`` (Taylor-Hood) is
-    outside this path."""
+def load_function(filename: str, mesh: RectangleMesh | None = None, function_space: FunctionSpace | None = None,
+                  *, dtype: str = "float64", device=None):
+    """Inverse of ``save_function`` with the reference's signature ``(filename, mesh=None,
+    function_space=None)`` (FEM_src/utils.py:73-109): ``problem == 'design'`` gives a P1 function,
+    ``'elasticity'`` a vector-P2 function, ``'fluid'`` the Taylor-Hood pair stored as ``[u | p]``.  Files
+    written by the reference itself (dolfin dof order, no ``"ordering"`` key) load through
+    ``unpack_function_data``."""
     with open(filename, "rb") as fh:
         data = pickle.load(fh)
-    if data["problem"] == "design":
-        degree = 1
-    elif data["problem"] == "elasticity":
-        degree = 2
-    elif data["problem"] == "fluid":
-        raise ValueError("load_function: the fluid problem is outside the accelerated path")
-    else:
-        raise ValueError(f"load_function got malformed problem: {data['problem']}")
-    w, h = data["domain_size"]
-    mesh = RectangleMesh(w, h, int(w * data["N"]), int(h * data["N"]))
-    space = FunctionSpace(mesh, "CG", degree, dtype=dtype, device=device)
-    f = Function(space)
-    f.vector()[:] = data["vector"]
-    return f, mesh, space
+    vector, nx, ny, kind = unpack_function_data(data)
+    if mesh is None:
+        w, h = data["domain_size"]
+        mesh = RectangleMesh(w, h, nx, ny)
+    if function_space is None:
+        if kind == "TH":
+            function_space = FunctionSpace(mesh, "TaylorHood", dtype=dtype, device=device)
+        else:
+            function_space = FunctionSpace(mesh, "CG", 1 if kind == "P1" else 2, dtype=dtype, device=device)
+    if function_space.dim() != vector.size:
+        raise ValueError(f"function file holds {vector.size} values, the function space has {function_space.dim()}")
+    f = Function(function_space)
+    f.vector()[:] = vector
+    return f, mesh, function_space
 
 
 class FEMSolver(Solver):
@@ -224,8 +284,8 @@ class FEMSolver(Solver):
             values = self.to_array(rho)  # collective
             if self.rank == 0:
                 mesh = self.mesh
-                data = {"N": int(round(1 / (mesh.hmin() / np.sqrt(2)))), "domain_size": mesh.domain_size,
-                        "problem": "design", "vector": values.astype(np.float64)}
+                data = pack_function_data(values, int(round(1 / (mesh.hmin() / np.sqrt(2)))), mesh.domain_size,
+                                          "design")
                 with open(rho_file, "wb") as fh:
                     pickle.dump(data, fh)
         else:

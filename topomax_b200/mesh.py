@@ -37,10 +37,12 @@ class FunctionSpace:
 
     def __init__(self, mesh: RectangleMesh, family: str = "CG", degree: int = 1, *,
                  dtype: str = "float64", device=None, local_rows: tuple[int, int] | None = None):
-        if family not in ("CG", "Lagrange", "P"):
+        if family in ("TaylorHood", "TH"):  # vector P2 x P1 (the fluid problem's state), stored as [u | p]
+            degree = (2, 1)
+        elif family not in ("CG", "Lagrange", "P"):
             raise ValueError(f"unsupported element family {family!r}")
-        if degree not in (1, 2):
-            raise ValueError("only P1 (scalar) and vector-P2 spaces exist on this path")
+        if degree not in (1, 2, (2, 1)):
+            raise ValueError("only P1 (scalar), vector-P2 and Taylor-Hood (vector P2 x P1) spaces exist on this path")
         self._mesh = mesh
         self.degree = degree
         self.dtype_name = dtype
@@ -50,8 +52,10 @@ class FunctionSpace:
         ny_stored = mesh.ny if local_rows is None else local_rows[1] - local_rows[0]
         if degree == 1:
             self.shape = (ny_stored + 1, mesh.nx + 1)
-        else:
+        elif degree == 2:
             self.shape = (2 * ny_stored + 1, 2 * mesh.nx + 1, 2)
+        else:  # flat [u | p]
+            self.shape = (2 * (2 * ny_stored + 1) * (2 * mesh.nx + 1) + (ny_stored + 1) * (mesh.nx + 1),)
 
     def mesh(self):
         return self._mesh

@@ -35,6 +35,34 @@ IterationData.__module__ = "src.utils"
 SolverResult.__module__ = "src.utils"
 
 
+def _register_reference_module_alias():
+    """Pickle stores the two records by reference as ``src.utils.<name>``.  When the repo-root ``src/`` shim
+    is not importable (package used from another working directory, or installed), register this module
+    under that name so that dumping and loading still work; an importable ``src.utils`` that already
+    carries the records (the shim, or the reference's own module) is left alone."""
+    import importlib
+    import sys
+    import types
+
+    try:
+        mod = importlib.import_module("src.utils")
+        if getattr(mod, "IterationData", None) is IterationData:
+            return
+        if hasattr(mod, "IterationData"):
+            return  # the reference's own src/utils.py: its classes pickle under the same path
+    except Exception:
+        pass
+    this = sys.modules[__name__]
+    pkg = sys.modules.get("src")
+    if pkg is None:
+        pkg = types.ModuleType("src")
+        pkg.__path__ = []  # a namespace stand-in
+        sys.modules["src"] = pkg
+    sys.modules["src.utils"] = this
+    setattr(pkg, "utils", this)
+
+
+
 class Timer:
     def __init__(self):
         self.restart()
@@ -95,3 +123,6 @@ def get_solver_data(solver: str, design: str, root_folder="output"):
             with open(data_path, "rb") as fh:
                 data_list.append((int(n_str), p_str, int(k_str[:-4]), pickle.load(fh)))
     return results, data_list
+
+
+_register_reference_module_alias()
