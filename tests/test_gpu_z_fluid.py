@@ -139,9 +139,7 @@ def test_penalty_continuation_and_hook_loop(repo_root, tmp_path):
     assert np.abs(hooks.to_array(hooks.rho) - ro["rho"]).max() < 1e-5
 
 
-@pytest.mark.skipif(os.environ.get("TM_TEST_FLUID_MG") != "1",
-                    reason="multigrid preconditioner of the fluid solver: checked on the CPU "
-                           "(tests/test_fluid_host.py), not yet run on hardware; opt in with TM_TEST_FLUID_MG=1")
+# (green on the B200 since round 2: profiles/r2a_fluid_optins_pytest.txt)
 @pytest.mark.parametrize("design,N", [("diffuser", 16), ("diffuser", 32), ("twin_pipe", 16)])
 def test_multigrid_preconditioner_same_solution_fewer_iterations(repo_root, design, N):
     s, problem, Function = make(repo_root, design, N, state_rtol=1e-11)
@@ -160,9 +158,6 @@ def test_multigrid_preconditioner_same_solution_fewer_iterations(repo_root, desi
     assert its_m < 0.6 * its_d, (its_m, its_d)      # host check: 94 vs 243 at N=16, 102 vs 492 at N=32
 
 
-@pytest.mark.skipif(os.environ.get("TM_TEST_FLUID_MG") != "1",
-                    reason="opt-in solver variants (device-resident MINRES scalars, warm start): checked through the "
-                           "host build of the driver, not yet run on hardware; opt in with TM_TEST_FLUID_MG=1")
 @pytest.mark.parametrize("options", [dict(fluid_device_scalars=True), dict(fluid_warm_start=True), dict(fluid_deterministic=True),
                                      dict(fluid_deterministic=True, fluid_preconditioner="multigrid"),
                                      dict(fluid_graph=True), dict(fluid_graph=True, fluid_preconditioner="multigrid"),
