@@ -144,6 +144,13 @@ int tm_md_halfstep(tm_handle h, const void* psi, const void* grad, double alpha,
 /* vol = int expit(half+c), dvol = int expit'(half+c)   reference: Solver.project,
  * src/solver.py:158-162 with FEMSolver.integrate, FEM_src/solver.py:81-84 */
 int tm_md_volume(tm_handle h, const void* half, double c, double* vol, double* dvol);
+/* Newton iteration for the volume shift c with int expit(half + c) = volume, the iterate resident on the
+ * device: scipy.optimize.newton(error, 0, fprime, tol, maxiter) of Solver.project, src/solver.py:166-174
+ * (c0 = 0, step p = c - f/f', converged when |p - c| <= tol), batches of iterates enqueued without a host
+ * round trip.  *status: 1 converged, 2 zero derivative, 0 not converged within maxit -- in the last two
+ * cases the caller falls back to the bracketing search of src/solver.py:175-186 through tm_md_volume. */
+int tm_md_project(tm_handle h, const void* half, double volume, double tol, int maxit, double* c, int* iters,
+                  int* status);
 /* psi = half + c, rho = expit(psi), *delta_sq = int (rho - expit(psi_prev))^2, *vol = int rho
  * reference: src/solver.py:186,262,286-288 */
 int tm_md_apply(tm_handle h, const void* half, double c, const void* psi_prev, void* psi,

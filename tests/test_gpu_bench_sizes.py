@@ -3,7 +3,8 @@ test_gpu_parity.py stop at N = 70 because the scipy oracle factorises; here
 
 * the GPU displacement of real mirror-descent iterations at the benchmark resolutions is handed to the
   INDEPENDENT CPU operator (oracle/c/elast_omp.c: quadrature, C + OpenMP, shares nothing with the CUDA
-  kernels): ||b - K_cpu u_gpu|| / ||b|| <= 1e-9 and u . K_cpu u = u . b to 1e-6
+  kernels): ||b - K_cpu u_gpu|| / ||b|| <= max(1e-9, 4 x its fp64 floor), u . K_cpu u = u . b to 1e-6 and
+  K_cpu x = K_gpu x to 1e-12 on a random vector
   (what "correct" means per solve: FEM_src/elasisity_problem.py:152-166, BASELINE.md section 5.4);
 * one run against the FULL oracle (assembly + SuperLU) at N = 256, the largest size it finishes in ~1 min;
 * the fp32 engine's accuracy at a BASELINE config (north_star: "fp32 accuracy stated separately").
@@ -37,8 +38,13 @@ def test_benchmark_size_solves_pass_the_cpu_operator_check(repo_root, tmp_path, 
     stats = solver.problem.solve_log[-1]
     print(f"{design} N={N}: PCG its={stats['iterations']} relres={stats['relative_residual']:.2e} -> {parity}")
     assert parity["coverage"] == "every lattice row"
-    assert parity["relative_residual"] <= bench.RESIDUAL_BOUND, parity
+    # <= 1e-9 unless the fp64 evaluation floor of ||b - K u|| / ||b|| at this size is higher (bridge N=2048:
+    # ~3e-9, see bench.cpu_operator_check); the residual of the oracle's DIRECT solutions sits at 1.8 x floor
+    assert parity["relative_residual"] <= parity["relative_residual_bound"] <= 4e-8, parity
+    assert parity["relative_residual"] <= 4.0 * max(parity["fp64_floor"], 2.5e-10), parity
     assert parity["compliance_rel_diff"] <= bench.COMPLIANCE_BOUND, parity
+    assert parity["operator_rel_diff_random_vector"] <= 1e-12, parity
+    assert parity["ok"], parity
     # negative control on the same data: a 1e-4 relative change of ONE displacement value (the largest) must fail
     u = solver.problem.u.tensor
     u[int(torch.argmax(u.abs()))] *= 1.0 + 1e-4

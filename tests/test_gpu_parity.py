@@ -297,6 +297,40 @@ def test_mirror_descent_kernels_match_numpy():
     assert abs(eng.integrate(torch.ones(mesh.n1, dtype=torch.float64).cuda()) - W * H) < 1e-13
 
 
+def test_device_resident_newton_projection_follows_scipy():
+    """tm_md_project: the Newton iterates of Solver.project (src/solver.py:166-174) with the iterate on the
+    device -- same root, same iteration count and the same converged / failed verdict as
+    scipy.optimize.newton on the device reductions; a flat derivative (|half| huge) must report failure so
+    that the caller falls back to the bracketing search like the reference."""
+    from scipy import optimize
+    nx, ny, W, H = 37, 21, 3.7, 2.1
+    rng = np.random.default_rng(9)
+    eng = _engine(nx, ny, W, H)
+    for scale, frac in ((1.0, 0.5), (4.0, 0.3), (0.2, 0.7), (12.0, 0.4)):
+        half = _t(scale * rng.standard_normal((nx + 1) * (ny + 1)))
+        volume = frac * W * H
+        calls = []
+
+        def err(c):
+            calls.append(c)
+            return eng.md_volume(half, c)[0] - volume
+
+        try:
+            c_ref, res = optimize.newton(err, 0, lambda c: eng.md_volume(half, c)[1], tol=1e-12, full_output=True)
+            ok_ref, its_ref = bool(res.converged), res.iterations
+        except RuntimeError:
+            ok_ref, its_ref, c_ref = False, 50, None
+        c, its, status = eng.md_project(half, volume, 1e-12, 50)
+        assert (status == 1) == ok_ref, (scale, frac, status, ok_ref)
+        if ok_ref:
+            assert c == c_ref and its == its_ref, (scale, frac, c, c_ref, its, its_ref)
+            assert abs(eng.md_volume(half, c)[0] - volume) < 1e-10 * W * H
+    # saturated sigmoid: expit' underflows to 0 -> zero derivative -> status 2 (scipy warns / fails likewise)
+    flat = _t(np.full((nx + 1) * (ny + 1), 800.0))
+    c, its, status = eng.md_project(flat, 0.5 * W * H, 1e-12, 50)
+    assert status == 2
+
+
 def _state_case(design, N, repo_root):
     from topomax_b200.designs.design_parser import parse_design
     path = os.path.join(repo_root, "designs", f"{design}.json")

@@ -242,12 +242,17 @@ def test_bench_cpu_operator_check_on_slabs(repo_root, design, N):
     shape = (2 * ny + 1, 2 * nx + 1, 2)
     U, B, XI = u.reshape(shape), np.where(fixed, 0.0, b).reshape(shape), xi.reshape(ny + 1, nx + 1)
     bb = float(np.vdot(B, B))
-    whole, _, _ = bench.slab_operator_sums(d, nx, ny, 0, ny, U, B, XI)
+    X = rng.standard_normal(shape)
+    Y = np.where(fixed, X.ravel(), K @ np.where(fixed, 0.0, X.ravel())).reshape(shape)  # the oracle's CSR operator
+    whole, _, _ = bench.slab_operator_sums(d, nx, ny, 0, ny, U, B, XI, x=X, y_gpu=Y)
     assert np.sqrt(whole[0] / bb) < 1e-11 and whole[2] == mesh.nu
+    assert np.sqrt(whole[4] / whole[5]) < 1e-13  # operator parity on a random vector
+    # the direct solution's residual sits within a small factor of the half-ulp perturbation floor
+    assert 0.2 < np.sqrt(whole[0] / whole[3]) < 4.0
     assert abs(whole[1] - u @ b) <= 1e-10 * abs(u @ b)
     # three strips, the library's storage rule
     cuts = [0, ny // 3, 2 * ny // 3, ny]
-    total = np.zeros(3)
+    total = np.zeros(6)
     for r in range(3):
         c0, c1 = cuts[r], cuts[r + 1]
         cl0, cl1 = max(0, c0 - 2), min(ny, c1 + 1)

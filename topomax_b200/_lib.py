@@ -27,7 +27,7 @@ ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOT_CONVERGED = -1, -2, -3, -4
 EXPORTED_SYMBOLS = (
     "tm_create", "tm_destroy", "tm_set_stream", "tm_set_option", "tm_last_error", "tm_version",
     "tm_load_vector", "tm_filter_apply", "tm_elast_matvec", "tm_elast_diag", "tm_state_solve",
-    "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_integrate", "tm_sample_field",
+    "tm_dot_p2", "tm_sens_rhs", "tm_md_halfstep", "tm_md_volume", "tm_md_apply", "tm_md_project", "tm_integrate", "tm_sample_field",
     "tm_last_solve_stats", "tm_mg_debug", "tm_mg_level_info", "tm_profile_read", "tm_launch_count",
     "tm_ledger_read", "tm_comm_unique_id", "tm_comm_init", "tm_local_layout", "tm_dem_strain_energy",
     "tm_fluid_create", "tm_fluid_destroy", "tm_fluid_set_stream", "tm_fluid_set_option", "tm_fluid_set_density", "tm_fluid_state_solve",
@@ -100,6 +100,7 @@ def load_library() -> ctypes.CDLL:
         "tm_md_halfstep": ([V, V, V, D, V], I),
         "tm_md_volume": ([V, V, D, POINTER(D), POINTER(D)], I),
         "tm_md_apply": ([V, V, D, V, V, V, POINTER(D), POINTER(D)], I),
+        "tm_md_project": ([V, V, D, D, I, POINTER(D), POINTER(I), POINTER(I)], I),
         "tm_integrate": ([V, V, POINTER(D)], I),
         "tm_sample_field": ([V, I, V, I, I, D, D, D, D, V], I),
         "tm_last_solve_stats": ([V, POINTER(D), I], I),

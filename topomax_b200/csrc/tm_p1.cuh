@@ -150,9 +150,11 @@ __device__ __forceinline__ double expit_d(double x) { return 1.0 / (1.0 + exp(-x
 
 // Volume-projection evaluation (reference: src/solver.py:158-162):
 //   out[0] = sum_i w_i expit(half_i + c),  out[1] = sum_i w_i expit'(half_i + c)
+// c_dev != nullptr: the shift is read from device memory (the device-resident Newton iteration)
 template <typename T>
 __global__ void md_volume_kernel(const P1Geom g, const T* __restrict__ half, double c,
-                                 ReduceScratch rs, double* out) {
+                                 ReduceScratch rs, double* out, const double* __restrict__ c_dev = nullptr) {
+    if (c_dev) c = *c_dev;
     double val[2] = {0.0, 0.0};
     const size_t n1 = (size_t)(g.nx + 1) * (g.ny + 1);
     for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n1;
@@ -166,6 +168,36 @@ __global__ void md_volume_kernel(const P1Geom g, const T* __restrict__ half, dou
     }
     double* const outs[2] = {out, out + 1};
     grid_reduce<2>(val, rs, outs);
+}
+
+// One Newton iterate of the volume projection on the device (reference: src/solver.py:166-174 =
+// scipy.optimize.newton(error, 0, fprime, tol=1e-12): p = p0 - f(p0)/f'(p0), converged when
+// |p - p0| <= tol; f(p0) == 0 returns p0; f'(p0) == 0 fails).  st = {c, done, iterations, status}
+// (status 1 converged, 2 zero derivative); vol[0] = sum w expit(half + c), vol[1] = its derivative.
+// A finished iteration turns the following updates into no-ops, so a batch can be enqueued blind.
+__global__ void md_newton_update_kernel(const double* __restrict__ vol, double volume, double tol,
+                                        double* __restrict__ st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || st[1] != 0.0) return;
+    const double c = st[0];
+    const double f = vol[0] - volume;
+    if (f == 0.0) {
+        st[1] = 1.0;
+        st[3] = 1.0;
+        return;
+    }
+    const double fder = vol[1];
+    if (fder == 0.0) {
+        st[1] = 1.0;
+        st[3] = 2.0;
+        return;
+    }
+    const double p = c - f / fder;
+    st[2] += 1.0;
+    st[0] = p;
+    if (fabs(p - c) <= tol) {
+        st[1] = 1.0;
+        st[3] = 1.0;
+    }
 }
 
 // psi = half + c; rho = expit(psi); out[0] = sum w (rho - expit(psi_prev))^2; out[1] = sum w rho

@@ -14,7 +14,8 @@ namespace tmx {
 
 // SC_RZV: r . z delivered by the V-cycle's last smoothing step (EP_CHEBDOT); a fixed slot, so that
 // the captured V-cycle graph can be replayed whichever of SC_RZ0/1 is current
-enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RR = 3, SC_BB = 4, SC_TMP = 5, SC_RZV = 8, SC_COUNT = 16 };
+// SC_NEWTON: {c, done, iterations, status} of the device-resident volume projection (md_newton_update_kernel)
+enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RR = 3, SC_BB = 4, SC_TMP = 5, SC_RZV = 8, SC_NEWTON = 10, SC_COUNT = 16 };
 
 constexpr int kVecThreads = 256;
 

@@ -78,7 +78,9 @@ class ElasticityProblem(Problem):
         """State solve  K(rho) u = b, u = 0 on the fixed sides; ``rho`` is the filtered density."""
         p = self.penalizer.assert_has_penalization()
         warm = self.warm_start and self.u is not None
-        u0 = self.u.tensor.clone() if warm else None
+        # warm start: the previous displacement is the initial guess and is overwritten IN PLACE by the new
+        # one (no clone: a lattice vector is 51 GB at N=16384); self.u is replaced by the result below
+        u0 = self.u.tensor if warm else None
         u, info = self.engine.state_solve(rho.tensor, self.load, p, rtol=self.state_rtol,
                                           maxit=self.state_max_iterations, u=u0, warm_start=warm)
         stats = self.engine.last_solve_stats()

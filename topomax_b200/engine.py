@@ -231,6 +231,15 @@ class Engine:
         _lib.check(self.lib.tm_md_volume(self._h, self._p(half, self.n1), float(c), byref(vol), byref(dvol)))
         return vol.value, dvol.value
 
+    def md_project(self, half, volume: float, tol: float = 1e-12, maxit: int = 50):
+        """Device-resident Newton iteration for the volume shift (``tm_md_project``): returns
+        ``(c, iterations, status)``, status 1 = converged, 2 = zero derivative, 0 = not converged."""
+        c, iters, status = c_double(0.0), c_int(0), c_int(0)
+        self._sync_stream()
+        _lib.check(self.lib.tm_md_project(self._h, self._p(half, self.n1), float(volume), float(tol), int(maxit),
+                                          byref(c), byref(iters), byref(status)))
+        return c.value, iters.value, status.value
+
     def md_apply(self, half, c: float, psi_prev, psi_out, rho_out):
         dsq, vol = c_double(0.0), c_double(0.0)
         self._sync_stream()

@@ -310,10 +310,19 @@ class FEMSolver(Solver):
         engine = self.problem.engine
         gradient = self.problem.calculate_objective_gradient()
         half = engine.md_halfstep(previous_psi, gradient.tensor, step_size)
-        c = find_volume_shift(
-            lambda c: engine.md_volume(half, c)[0] - self.volume,
-            lambda c: engine.md_volume(half, c)[1],
-        )
+        # Newton with the iterate on the device (same iterates as scipy.optimize.newton from 0, tol 1e-12,
+        # 50 iterations: src/solver.py:166-174); on failure the reference's own fallback, with the host
+        # calls it makes (Newton again would fail the same way, so straight to Brent on [-r, r])
+        c, _, status = engine.md_project(half, self.volume, 1e-12, 50)
+        if status != 1:
+            cache = {}
+
+            def pair(c):  # one launch + one read-back serves error(c) and error'(c)
+                if cache.get("c") != c:
+                    cache["c"], cache["v"] = c, engine.md_volume(half, c)
+                return cache["v"]
+
+            c = find_volume_shift(lambda c: pair(c)[0] - self.volume, lambda c: pair(c)[1])
         delta_sq, _ = engine.md_apply(half, c, previous_psi, psi_out, rho_out)
         return float(np.sqrt(delta_sq))
 
