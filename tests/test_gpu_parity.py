@@ -409,6 +409,27 @@ def test_multigrid_galerkin_and_transfer_adjoint(repo_root):
             assert abs(lhs - float(vc @ Rw)) < 1e-10 * max(1.0, abs(lhs))
 
 
+@pytest.mark.parametrize("nx,ny,fixed", [(8, 8, ["Left"]), (13, 7, ["Left", "Right"]), (22, 9, ["Bottom", "Top"]),
+                                         (150, 37, ["Left"]), (260, 131, []), (129, 70, ["Left", "Right", "Bottom", "Top"])])
+def test_tiled_restriction_is_bit_identical_to_the_gather(nx, ny, fixed):
+    """mg_restrict_tiled_kernel (shared-memory window, one stencil class per warp: the kernel the large levels
+    run) against mg_restrict_kernel on every level pair: same weights, same summation order, so EQUAL bits --
+    tile edges, odd sizes (overhanging coarse cells) and meshes narrower than one tile included."""
+    W, H = 0.1 * nx, 0.1 * ny
+    rng = np.random.default_rng(nx + ny)
+    mesh = StructuredMesh(W, H, nx, ny)
+    xi = _t(0.05 + 0.9 * rng.random(mesh.n1))
+    eng = _engine(nx, ny, W, H, lame_lambda=1.2, lame_mu=0.9, fixed_sides=_sides(fixed))
+    levels = eng.mg_levels()
+    for l in range(len(levels) - 2):
+        (fx, fy, *_), (cx, cy, *_) = levels[l], levels[l + 1]
+        nf, nc = 2 * (2 * fx + 1) * (2 * fy + 1), 2 * (2 * cx + 1) * (2 * cy + 1)
+        wf = _t(rng.standard_normal(nf))
+        gather = eng.mg_debug(xi, 2, l, wf, nc).cpu().numpy()
+        tiled = eng.mg_debug(xi, 7, l, wf, nc).cpu().numpy()
+        assert np.array_equal(gather, tiled), (nx, ny, l, np.abs(gather - tiled).max())
+
+
 def test_golden_triangle_end_to_end(repo_root, golden_dir, tmp_path):
     """reference tests/test_elasticity_solver.py:30-55 on the CUDA path."""
     import pickle

@@ -276,6 +276,7 @@ class Engine : public EngineBase {
             case 125: warm_guard_ = value != 0.0; break;
             case 126: pdl_ = value != 0.0; graph_dirty_ = true; break;
             case 127: fuse_rz_ = (int)value; graph_dirty_ = true; break;
+            case 128: restrict_tiled_ = value != 0.0; graph_dirty_ = true; break;
             case TM_OPT_P2P:  // collective: every rank must set it alike
                 p2p_want_ = value != 0.0;
                 graph_dirty_ = true;
@@ -1331,6 +1332,12 @@ class Engine : public EngineBase {
             dim3 grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
             mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, in, out);
             TM_CHECK_LAUNCH();
+        } else if (op == 7) {  // the shared-memory tiled restriction, whatever the level size
+            if (level + 1 >= nl) throw Invalid{"no coarser level"};
+            Level& C = levels_[level + 1];
+            mg_restrict_tiled_kernel<T><<<dim3(ceil_div(C.g.Lx, kRtTI), ceil_div(C.g.Ly, kRtTJ)), kRtThreads, 0, stream_>>>(
+                L.g, C.g, in, out);
+            TM_CHECK_LAUNCH();
         } else if (op == 3) {
             s_r_.ensure(nu_);
             TM_CUDA(cudaMemcpyAsync(s_r_.p, in, nu_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
@@ -1929,6 +1936,10 @@ class Engine : public EngineBase {
         }
         const size_t nc = levels_.back().nu;
         coarse_A_.ensure(nc * nc);
+        {   // stencil lists of the tiled restriction (tm_mg.cuh)
+            const RestrictLists rl = make_restrict_lists(tr_tab_);
+            TM_CUDA(cudaMemcpyToSymbol(c_restrict_lists, &rl, sizeof(rl)));
+        }
         plan_tail();
     }
 
@@ -2318,6 +2329,7 @@ class Engine : public EngineBase {
         in.blocks_per_sm_target_ = blocks_per_sm_target_; in.min_rows_per_strip_ = min_rows_per_strip_;
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
         in.fuse_first_ = fuse_first_;
+        in.restrict_tiled_ = restrict_tiled_;
         in.set_penalty(spec_.p);
         in.fuse_rz_ = 0;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
@@ -2494,8 +2506,12 @@ class Engine : public EngineBase {
             exchange_p2(l, L.tmp.p);
             const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
             dim3 blk(32, 8), grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
-            launch_chain(mg_restrict_kernel<T>, grd, blk, L.g, gather ? C.gpiece : C.g, tr_tab_,
-                         (const T*)L.tmp.p, C.b.p);
+            if (restrict_tiled_ && (long)C.g.Lx * C.g.Ly >= 16384)
+                launch_chain(mg_restrict_tiled_kernel<T>, dim3(ceil_div(C.g.Lx, kRtTI), ceil_div(C.g.Ly, kRtTJ)),
+                             dim3(kRtThreads), L.g, gather ? C.gpiece : C.g, (const T*)L.tmp.p, C.b.p);
+            else
+                launch_chain(mg_restrict_kernel<T>, grd, blk, L.g, gather ? C.gpiece : C.g, tr_tab_,
+                             (const T*)L.tmp.p, C.b.p);
             TM_CHECK_LAUNCH();
             acct(LC_RESTRICT, sz(L.nu) + sz(gather ? (size_t)(C.gpiece.own_j1 - C.gpiece.own_j0) * C.g.Lx * 2 : C.cnt));
             if (gather) gather_rows(l + 1, C.b.p, (size_t)C.g.Lx * 2, false);
@@ -2596,6 +2612,7 @@ class Engine : public EngineBase {
     T* setup_graph_xi_ = nullptr;
     bool filter_tb_ = true;
     bool pdl_ = true, pdl_active_ = false;  // option 126: programmatic dependent launch in V-cycles
+    bool restrict_tiled_ = true;            // option 128: shared-memory tiled restriction on the large levels
     bool warm_guard_ = true;   // option 125: drop a warm start whose residual exceeds the zero guess's
     int stats_warm_used_ = 0;  // last state solve: 1 if the caller's initial guess was kept
     int filter_tb_steps_ = 8, filter_tb_state_ = 0;  // state: 0 unplanned, 1 ready, -1 not usable

@@ -220,6 +220,110 @@ __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
     bc[2 * N + 1] = (T)a1;
 }
 
+// The same restriction through a shared-memory tile.  The gather kernel above issues, per warp of 32
+// coarse nodes, ~30 predicated loads whose active lanes sit 64 bytes apart (coarse neighbours are two
+// fine nodes apart and alternate between the 25-point vertex stencil and the 9-point edge stencils):
+// ~480 L1 wavefronts per warp, which is what bounds it (1.8 TB/s at 2e8 dofs, profiles/r2b).  Here a
+// block first copies the fine window of its 64 x 8 coarse tile into shared memory with coalesced loads,
+// the columns split into four planes by (column mod 4); then every warp handles 32 coarse nodes of ONE
+// stencil class (I = I0 + 2 lane + cx), whose reads of a given stencil entry are 32 consecutive 16-byte
+// words of one plane: conflict-free, 9 or 25 shared loads per node.  Same weights, same summation order
+// as restrict_node: bit-identical results.
+constexpr int kRtTI = 64, kRtTJ = 8, kRtThreads = 256;
+constexpr int kRtFW = 2 * kRtTI + 5;    // fine columns of the window: 2 I0 - 3 .. 2 (I0 + TI - 1) + 3
+constexpr int kRtFH = 2 * kRtTJ + 5;    // fine rows of the window
+constexpr int kRtPlane = 34;            // entries per plane and row: ceil(133 / 4), and = 2 mod 8 (bank spread)
+
+// The non-zero entries of the four 7 x 7 restriction stencils as lists of (shared-memory offset, weight),
+// split like restrict_node's two accumulators (even / odd dj + di) and kept in its (dj, di) order, so
+// that the sums are bit-identical to the gather kernel's.  Offsets are relative to
+// &sm[(2 Jr) * 4 kRtPlane + lane] for the class's column parity cx = class & 1.
+struct RestrictLists {
+    int n[4][2];
+    int off[4][2][28];
+    double w[4][2][28];
+};
+
+inline RestrictLists make_restrict_lists(const TransferTable& tab) {
+    RestrictLists L;
+    std::memset(&L, 0, sizeof(L));
+    for (int cls = 0; cls < 4; ++cls) {
+        const int cx = cls & 1;
+        for (int dj = -3; dj <= 3; ++dj)
+            for (int di = -3; di <= 3; ++di) {
+                const double w = tab.Rw[cls][7 * (dj + 3) + (di + 3)];
+                if (w == 0.0) continue;
+                const int acc = (dj + di) & 1;
+                const int m = 2 * cx + di + 3;  // window column = 4 lane + m
+                int& k = L.n[cls][acc];
+                L.off[cls][acc][k] = (dj + 3) * (4 * kRtPlane) + (m & 3) * kRtPlane + (m >> 2);
+                L.w[cls][acc][k] = w;
+                ++k;
+            }
+    }
+    return L;
+}
+
+// the lists live in constant memory (warp-uniform reads: constant cache, no load/store unit traffic);
+// uploaded by the engine when it builds its levels (the same universal numbers for every mesh)
+__constant__ RestrictLists c_restrict_lists;
+
+template <typename T>
+__global__ void __launch_bounds__(kRtThreads)
+mg_restrict_tiled_kernel(const LevelGeom<T> f, const LevelGeom<T> c, const T* __restrict__ r, T* __restrict__ bc) {
+    const RestrictLists* lists = &c_restrict_lists;
+    using V2 = typename MgVec2<T>::type;
+    __shared__ V2 sm[kRtFH * 4 * kRtPlane];
+    pdl_prologue();
+    const int I0 = blockIdx.x * kRtTI, J0 = blockIdx.y * kRtTJ;
+    const int jg_start = 2 * (J0 + c.j_off) - 3;  // global fine row of window row 0
+    const int i_start = 2 * I0 - 3;
+    for (int e = threadIdx.x; e < kRtFH * kRtFW; e += kRtThreads) {
+        const int row = e / kRtFW, cc = e - row * kRtFW;
+        const int i = i_start + cc, jg = jg_start + row, j = jg - f.j_off;
+        V2 v;
+        v.x = v.y = T(0);
+        if (i >= 0 && i < f.Lx && jg >= 0 && jg <= 2 * f.nyg && j >= 0 && j < f.Ly)
+            v = reinterpret_cast<const V2*>(r)[(size_t)j * f.Lx + i];
+        sm[row * (4 * kRtPlane) + (cc & 3) * kRtPlane + (cc >> 2)] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < (2 * kRtTJ) / (kRtThreads / 32); ++k) {
+        const int task = warp + (kRtThreads / 32) * k;
+        const int Jr = task >> 1, cx = task & 1;
+        const int I = I0 + 2 * lane + cx, J = J0 + Jr;
+        if (J >= c.Ly) continue;  // warp-uniform
+        const int cls = cx + 2 * ((J + c.j_off) & 1);  // one stencil class per warp
+        const V2* base = sm + (2 * Jr) * (4 * kRtPlane) + lane;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = lists->n[cls][h];
+            const int* off = lists->off[cls][h];
+            const double* w = lists->w[cls][h];
+            double s0 = 0.0, s1 = 0.0;
+            for (int q = 0; q < n; ++q) {
+                const V2 v = base[off[q]];
+                const double wq = w[q];
+                s0 += wq * (double)v.x;
+                s1 += wq * (double)v.y;
+            }
+            acc[h][0] = s0;
+            acc[h][1] = s1;
+        }
+        double a0 = acc[0][0] + acc[1][0], a1 = acc[0][1] + acc[1][1];
+        if (I < c.Lx && c.owns_row(J)) {
+            if (c.fixed(I, J)) a0 = a1 = 0.0;
+            V2 out;
+            out.x = (T)a0;
+            out.y = (T)a1;
+            reinterpret_cast<V2*>(bc)[(size_t)J * c.Lx + I] = out;
+        }
+    }
+}
+
 // x += P xc  (fine Dirichlet nodes untouched)
 template <typename T>
 __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
@@ -232,9 +336,12 @@ __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c
     if (f.fixed(i, j)) return;
     double a0, a1;
     prolong_node<T, false>(f, c, tab, xc, i, j, a0, a1);
-    const size_t n = (size_t)j * f.Lx + i;
-    x[2 * n] = (T)((double)x[2 * n] + a0);
-    x[2 * n + 1] = (T)((double)x[2 * n + 1] + a1);
+    using V2 = typename MgVec2<T>::type;
+    V2* xp = reinterpret_cast<V2*>(x) + ((size_t)j * f.Lx + i);  // one 16-byte access each way
+    V2 v = *xp;
+    v.x = (T)((double)v.x + a0);
+    v.y = (T)((double)v.y + a1);
+    *xp = v;
 }
 
 // ---------------------------------------------------------------------------------------
