@@ -289,14 +289,16 @@ def cpu_operator_check(problem, solver_objective, design_path, world, threads=0,
     rows = slice(2 * r0, 2 * r1 + 1)
     to_host = lambda t, shape: t.detach().reshape(shape)[rows].contiguous().cpu().numpy().astype(np.float64)
     xi_t = problem.filtered_rho.tensor
-    gen = torch.Generator(device=eng.device)
-    gen.manual_seed(4321 + eng.rank)
-    x_t = torch.randn(eng.nu, dtype=eng.dtype, device=eng.device, generator=gen)
-    y_t = eng.elast_matvec(xi_t, x_t, problem.penalizer.assert_has_penalization())  # refreshes x's halo rows
     lattice = (2 * ny_loc + 1, Lx, 2)
     u, b = to_host(problem.u.tensor, lattice), to_host(problem.load, lattice)
-    x, y_gpu = to_host(x_t, lattice), to_host(y_t, lattice)
-    del x_t, y_t
+    x = y_gpu = None
+    if full:  # (a band check keeps to the solve's own vectors: two more lattice vectors are 13 GB per GPU at N=16384)
+        gen = torch.Generator(device=eng.device)
+        gen.manual_seed(4321 + eng.rank)
+        x_t = torch.randn(eng.nu, dtype=eng.dtype, device=eng.device, generator=gen)
+        y_t = eng.elast_matvec(xi_t, x_t, problem.penalizer.assert_has_penalization())  # refreshes x's halo rows
+        x, y_gpu = to_host(x_t, lattice), to_host(y_t, lattice)
+        del x_t, y_t
     xi = xi_t.detach().reshape(ny_loc + 1, nx + 1)[r0:r1 + 1].contiguous().cpu().numpy()
     own = None
     if full:
@@ -323,7 +325,8 @@ def cpu_operator_check(problem, solver_objective, design_path, world, threads=0,
         "operator_rel_diff_random_vector": op_diff, "operator_bound": 1e-12,
         "cpu_threads_per_rank": nthreads, "cpu_apply_seconds": round(t_apply, 3),
     }
-    ok = residual is not None and residual <= out["relative_residual_bound"] and op_diff is not None and op_diff <= 1e-12
+    ok = residual is not None and residual <= out["relative_residual_bound"] and (
+        not full or (op_diff is not None and op_diff <= 1e-12))
     if full:
         out["compliance_gpu"] = solver_objective
         out["compliance_cpu_energy"] = float(sums[1])

@@ -229,6 +229,19 @@ __global__ void mg_restrict_kernel(const LevelGeom<T> f, const LevelGeom<T> c,
 // stencil class (I = I0 + 2 lane + cx), whose reads of a given stencil entry are 32 consecutive 16-byte
 // words of one plane: conflict-free, 9 or 25 shared loads per node.  Same weights, same summation order
 // as restrict_node: bit-identical results.
+// cp.async (LDGSTS): BYTES from global to shared memory without a register round trip; `valid` false
+// writes zeros (source size 0: nothing is read, the pointer only has to be a mapped address)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int src_bytes = valid ? BYTES : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(s), "l"(gmem), "n"(BYTES), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 constexpr int kRtTI = 64, kRtTJ = 8, kRtThreads = 256;
 constexpr int kRtFW = 2 * kRtTI + 5;    // fine columns of the window: 2 I0 - 3 .. 2 (I0 + TI - 1) + 3
 constexpr int kRtFH = 2 * kRtTJ + 5;    // fine rows of the window
@@ -278,15 +291,18 @@ mg_restrict_tiled_kernel(const LevelGeom<T> f, const LevelGeom<T> c, const T* __
     const int I0 = blockIdx.x * kRtTI, J0 = blockIdx.y * kRtTJ;
     const int jg_start = 2 * (J0 + c.j_off) - 3;  // global fine row of window row 0
     const int i_start = 2 * I0 - 3;
+    // Asynchronous global -> shared copies (cp.async, zero fill outside the lattice): all ~11 copies of a
+    // thread are in flight together and cost no registers.  (The first version loaded through registers,
+    // one LDG -> STS pair at a time: 62 % of its stall samples sat on that STS and it ran at 2.6 TB/s,
+    // profiles/r2d_ncu_restrict_tiled_v1.txt.)
     for (int e = threadIdx.x; e < kRtFH * kRtFW; e += kRtThreads) {
         const int row = e / kRtFW, cc = e - row * kRtFW;
         const int i = i_start + cc, jg = jg_start + row, j = jg - f.j_off;
-        V2 v;
-        v.x = v.y = T(0);
-        if (i >= 0 && i < f.Lx && jg >= 0 && jg <= 2 * f.nyg && j >= 0 && j < f.Ly)
-            v = reinterpret_cast<const V2*>(r)[(size_t)j * f.Lx + i];
-        sm[row * (4 * kRtPlane) + (cc & 3) * kRtPlane + (cc >> 2)] = v;
+        const bool ok = i >= 0 && i < f.Lx && jg >= 0 && jg <= 2 * f.nyg && j >= 0 && j < f.Ly;
+        const V2* src = reinterpret_cast<const V2*>(r) + (ok ? (size_t)j * f.Lx + i : (size_t)0);
+        cp_async_zfill<sizeof(V2)>(&sm[row * (4 * kRtPlane) + (cc & 3) * kRtPlane + (cc >> 2)], src, ok);
     }
+    cp_async_wait_all();
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
