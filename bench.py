@@ -581,7 +581,8 @@ def run_cuda_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # NCCL's communicator lines (rank counts, transports) go to stderr with everything else
-    os.environ.setdefault("NCCL_DEBUG", os.environ.get("TM_NCCL_DEBUG", "INFO"))
+    # (an inherited NCCL_DEBUG=WARN would hide them: the level is forced, TM_NCCL_DEBUG overrides)
+    os.environ["NCCL_DEBUG"] = os.environ.get("TM_NCCL_DEBUG", "INFO")
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (CUDA arm) needs a GPU; use --impl reference for the CPU arm")

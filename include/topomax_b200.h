@@ -45,7 +45,8 @@ enum {
                                 (tm_ledger_read).  2 and 3 switch CUDA-graph replay off: diagnostics only */
     TM_OPT_P2P = 130         /* sharded runs: halo exchange and scalar all-reduce by our own kernels over
                                 peer-mapped memory (NVLink) instead of NCCL calls; collective, set alike
-                                on every rank (default: env TM_P2P, else 0)                        */
+                                on every rank (default 1 since round 2; env TM_P2P=0 selects NCCL,
+                                which is also the fall-back when a peer window cannot be mapped)   */
 };
 
 /* Mesh, material and filter of one problem.
@@ -90,9 +91,9 @@ const char* tm_version(void);
  * broadcasts it (torch.distributed), every rank calls tm_comm_init: the engine then owns an
  * NCCL communicator for halo rows (ncclSend/Recv), dot products (ncclAllReduce) and the gather
  * of the first replicated multigrid level (ncclBroadcast).
- * With TM_OPT_P2P (or env TM_P2P=1) the halo rows and the scalar sums travel instead through
- * peer-mapped windows (cudaIpc) written and polled by the library's own kernels over NVLink
- * (csrc/tm_p2p.cuh); NCCL then only carries the window handles and the coarse-level gather.
+ * By default (TM_OPT_P2P = 1; env TM_P2P=0 or the option turn it off) the halo rows and the scalar sums
+ * travel instead through peer-mapped windows (cudaIpc) written and polled by the library's own kernels
+ * over NVLink (csrc/tm_p2p.cuh); NCCL then only carries the window handles and the coarse-level gather.
  * tm_local_layout: out = {rank, nranks, nx, ny_global, cl0, cl1, c0, c1, owns_top, dist_levels,
  * peer_memory_active}: this rank stores cell rows [cl0, cl1) and owns [c0, c1); local P1 arrays are
  * (cl1-cl0+1) x (nx+1), local P2 arrays (2(cl1-cl0)+1) x (2nx+1) x 2. */

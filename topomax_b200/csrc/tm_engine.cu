@@ -37,10 +37,13 @@ std::atomic<long long> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 const char* last_error() { return g_error.c_str(); }
 
-// peer-memory collectives are opt-in this round (TM_P2P=1 or TM_OPT_P2P): not yet run on hardware
+// Peer-memory halo exchange / all-reduce (tm_p2p.cuh) is the DEFAULT transport of sharded engines since
+// round 2 (green on 2 and 4 real peers; 139 ms against 203 ms per step under NCCL on the 4-GPU BASELINE
+// config, profiles/r2e_*); TM_P2P=0 or TM_OPT_P2P = 0 selects NCCL, which is also the automatic
+// fall-back when any rank cannot map a peer's window.
 static bool p2p_default() {
     const char* e = std::getenv("TM_P2P");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 struct Unsupported {
