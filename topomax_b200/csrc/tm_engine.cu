@@ -280,6 +280,7 @@ class Engine : public EngineBase {
             case 126: pdl_ = value != 0.0; graph_dirty_ = true; break;
             case 127: fuse_rz_ = (int)value; graph_dirty_ = true; break;
             case 128: restrict_tiled_ = value != 0.0; graph_dirty_ = true; break;
+            case 129: wave_aware_ = value != 0.0; graph_dirty_ = true; break;
             case TM_OPT_P2P:  // collective: every rank must set it alike
                 p2p_want_ = value != 0.0;
                 graph_dirty_ = true;
@@ -1716,6 +1717,36 @@ class Engine : public EngineBase {
         strips = std::max(strips, ceil_div(g.ny, 64));
         a.rows_per_strip = std::max(min_rows_per_strip_, ceil_div(g.ny, strips));
         strips = ceil_div(g.ny, a.rows_per_strip);
+        if (stored && wave_aware_) {
+            // Stored-moment levels: pick the strip height whose grid fills whole waves of resident blocks
+            // (bridge N=2048, level 2: 600 blocks on 444 resident slots = 1.35 waves ran at 3.6 TB/s, level 1
+            // at 1.8 waves at 4.8 TB/s, and 448 blocks = 1.01 waves costs two; profiles/r2b), weighed against
+            // the pre-roll row every strip re-evaluates.
+            if (stored_cap_ == 0) {
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &per_sm, elast_apply_kernel<T, true, EP_CHEB, 2, false>, kApplyWarps * 32, 0) != cudaSuccess ||
+                    per_sm < 1) {
+                    cudaGetLastError();
+                    per_sm = 3;
+                }
+                stored_cap_ = (long)per_sm * num_sms_;
+            }
+            // time model: whole waves of resident blocks, each marching h + 1 cell rows (a partly filled last
+            // wave costs a full one; a level below one wave is latency bound: the shortest march wins)
+            long best_t = -1;
+            int best_h = a.rows_per_strip;
+            for (int h = 64; h >= min_rows_per_strip_; --h) {
+                const long nb = (long)bx * ceil_div(g.ny, h);
+                const long t = (long)ceil_div(nb, stored_cap_) * (h + 1);
+                if (best_t < 0 || t < best_t) {  // ties: the taller strip (fewer redundant rows)
+                    best_t = t;
+                    best_h = h;
+                }
+            }
+            a.rows_per_strip = best_h;
+            strips = ceil_div(g.ny, a.rows_per_strip);
+        }
         dim3 grd(bx, strips), blk(kApplyWarps * 32);
         if ((long)bx * strips > rs_.capacity) throw Invalid{"reduction scratch too small"};
         const bool fine = g.nx == nx_ && g.nyg == nyg_;
@@ -2333,6 +2364,7 @@ class Engine : public EngineBase {
         in.use_graph_ = use_graph_; in.eig_first_its_ = eig_first_its_; in.profile_ = profile_;
         in.fuse_first_ = fuse_first_;
         in.restrict_tiled_ = restrict_tiled_;
+        in.wave_aware_ = wave_aware_;
         in.set_penalty(spec_.p);
         in.fuse_rz_ = 0;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
@@ -2616,6 +2648,8 @@ class Engine : public EngineBase {
     bool filter_tb_ = true;
     bool pdl_ = true, pdl_active_ = false;  // option 126: programmatic dependent launch in V-cycles
     bool restrict_tiled_ = true;            // option 128: shared-memory tiled restriction on the large levels
+    bool wave_aware_ = true;                // option 129: strip heights of the stored-moment levels fill whole waves
+    long stored_cap_ = 0;                   // resident blocks of the stored-moment operator kernel (whole GPU)
     bool warm_guard_ = true;   // option 125: drop a warm start whose residual exceeds the zero guess's
     int stats_warm_used_ = 0;  // last state solve: 1 if the caller's initial guess was kept
     int filter_tb_steps_ = 8, filter_tb_state_ = 0;  // state: 0 unplanned, 1 ready, -1 not usable
