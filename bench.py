@@ -496,7 +496,8 @@ def timed_device_run(design_path, full_n, args, *, steps, warmup, distributed, d
     solver = FEMSolver(full_n, design_path, data_path=tmp, verbose=False, dtype=dtype, distributed=distributed,
                        dist_levels=args.dist_levels,
                        problem_options={"preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
-                                        "mixed_precision": mixed, "warm_start": not args.no_warm_start})
+                                        "mixed_precision": mixed, "warm_start": not args.no_warm_start,
+                                        "warm_start_extrapolation": args.extrapolate})
     problem, engine = solver.problem, solver.problem.engine
     for kv in (options if options is not None else args.engine_option):
         key, val = kv.split("=")
@@ -944,6 +945,7 @@ def main():
     ap.add_argument("--mixed", action="store_true", help="fp32 multigrid preconditioner inside the fp64 PCG (reported separately)")
     ap.add_argument("--engine_option", action="append", default=[], help="KEY=VALUE passed to tm_set_option (tuning studies)")
     ap.add_argument("--no_warm_start", action="store_true", help="state solves start from zero (study)")
+    ap.add_argument("--extrapolate", action="store_true", help="warm start from 2 u_k - u_(k-1) (study)")
     ap.add_argument("--no_mixed_leg", action="store_true", help="skip the separately reported fp32-preconditioner leg")
     ap.add_argument("--no_e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--lean", action="store_true", help="main timed region + roofline only (studies, ncu runs)")

@@ -175,3 +175,36 @@ def test_optin_solver_variants_reproduce_the_default_run(repo_root, tmp_path, op
     trace = max(abs(a - b) / abs(b) for a, b in zip(got["objectives"], ref["objectives"]))
     assert trace < 1e-7, (options, trace)
     assert np.abs(variant.to_array(variant.rho) - base.to_array(base.rho)).max() < 1e-6
+
+
+def test_automatic_preconditioner_choice(repo_root):
+    """Default ``preconditioner="auto"``: multigrid + graph-replayed MINRES from 64 cells per short side when
+    the mesh coarsens far enough (profiles/r2d_fluid_bench.txt: 4-8x faster at N = 128 / 256), the diagonal
+    preconditioner below; same state and objective either way."""
+    from topomax_b200.designs.design_parser import parse_design
+    from topomax_b200.fluid_problem import FluidProblem
+    from topomax_b200.mesh import Function, RectangleMesh
+
+    assert FluidProblem.multigrid_pays_off(64, 64) and FluidProblem.multigrid_pays_off(256, 128)
+    assert not FluidProblem.multigrid_pays_off(32, 32)      # small: launch bound
+    assert not FluidProblem.multigrid_pays_off(100, 100)    # 25 x 25 coarsest cells: too large for the dense inverse
+    assert not FluidProblem.multigrid_pays_off(65, 64)      # odd: cannot be halved
+    path = os.path.join(repo_root, "designs", "diffuser.json")
+    dom, prm = parse_design(path)
+    mesh = RectangleMesh(dom.width, dom.height, 64, 64)
+    rng = np.random.default_rng(3)
+    auto = FluidProblem(mesh, prm, dom, state_rtol=1e-11)
+    diag = FluidProblem(mesh, prm, dom, state_rtol=1e-11, preconditioner="diagonal")
+    assert (auto.preconditioner, auto.graph) == ("multigrid", True) and diag.preconditioner == "diagonal"
+    small = FluidProblem(RectangleMesh(dom.width, dom.height, 20, 20), prm, dom)
+    assert (small.preconditioner, small.graph) == ("diagonal", False)
+    rho_values = 0.2 + 0.6 * rng.random((64 + 1) ** 2)
+    objs = []
+    for pr in (auto, diag):
+        pr.set_penalization(0.1)
+        rho = Function(pr.control_space)
+        rho.vector()[:] = rho_values
+        objs.append(pr.calculate_objective(rho))
+    assert abs(objs[0] - objs[1]) < 1e-8 * abs(objs[1])
+    assert torch.linalg.norm(auto.u.tensor - diag.u.tensor) < 1e-7 * torch.linalg.norm(diag.u.tensor)
+    assert auto.solve_log[-1]["iterations"] < 0.5 * diag.solve_log[-1]["iterations"]

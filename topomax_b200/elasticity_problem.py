@@ -8,6 +8,8 @@ with dolfin's assemble + MUMPS replaced by the kernels behind ``Engine``.
 """
 from __future__ import annotations
 
+import torch  # noqa: F401  (tensor handoff only)
+
 from .designs.definitions import DomainParameters, ElasticityParameters
 from .engine import Engine
 from .filter import AssembledP1Form, HelmholtzFilter
@@ -23,7 +25,8 @@ class ElasticityProblem(Problem):
                  domain_parameters: DomainParameters, elasticity_parameters: ElasticityParameters,
                  *, state_rtol: float = 1e-10, state_max_iterations: int = 200000,
                  filter_rtol: float = 1e-11, preconditioner: str = "multigrid",
-                 warm_start: bool = True, engine: Engine | None = None, mixed_precision: bool = False):
+                 warm_start: bool = True, engine: Engine | None = None, mixed_precision: bool = False,
+                 warm_start_extrapolation: bool = False):
         self.parameters = elasticity_parameters
         self.domain_size = (domain_parameters.width, domain_parameters.height)
         self.mesh = mesh
@@ -54,6 +57,11 @@ class ElasticityProblem(Problem):
         self.state_rtol = state_rtol
         self.state_max_iterations = state_max_iterations
         self.warm_start = warm_start
+        # optional: initial guess 2 u_k - u_{k-1} (linear extrapolation over the last two designs) instead of
+        # u_k; costs one more lattice vector; the engine still keeps whichever of {guess, 0} has the smaller
+        # residual, and the converged displacement meets the same tolerance
+        self.warm_start_extrapolation = warm_start_extrapolation
+        self._u_before: "torch.Tensor | None" = None
 
         self.solution_space = FunctionSpace(mesh, "CG", 2, dtype=control_space.dtype_name,
                                             device=self.engine.device, local_rows=control_space.local_rows)
@@ -81,6 +89,11 @@ class ElasticityProblem(Problem):
         # warm start: the previous displacement is the initial guess and is overwritten IN PLACE by the new
         # one (no clone: a lattice vector is 51 GB at N=16384); self.u is replaced by the result below
         u0 = self.u.tensor if warm else None
+        if warm and self.warm_start_extrapolation:
+            previous = u0.clone()
+            if self._u_before is not None:
+                u0.mul_(2.0).sub_(self._u_before)
+            self._u_before = previous
         u, info = self.engine.state_solve(rho.tensor, self.load, p, rtol=self.state_rtol,
                                           maxit=self.state_max_iterations, u=u0, warm_start=warm)
         stats = self.engine.last_solve_stats()

@@ -110,12 +110,16 @@ class FluidProblem(Problem):
     def __init__(self, mesh: RectangleMesh, fluid_parameters: FluidParameters,
                  domain_parameters: DomainParameters, *, control_space: FunctionSpace | None = None,
                  state_rtol: float = 1e-10, state_max_iterations: int = 200000, projection_rtol: float = 1e-12,
-                 preconditioner: str = "diagonal", warm_start: bool = False,
-                 device_scalars: bool = False, deterministic: bool = False, graph: bool = False,
+                 preconditioner: str = "auto", warm_start: bool = False,
+                 device_scalars: bool = False, deterministic: bool = False, graph: bool | None = None,
                  device=None):
-        """``preconditioner``: "diagonal" (default) or "multigrid" (V-cycles on per-triangle Galerkin
-        matrices for the velocity block and the pressure's Darcy Laplacian; needs cell counts with
-        enough factors of two; checked on the CPU, not yet run on hardware)."""
+        """``preconditioner``: "diagonal", "multigrid" (V-cycles on per-triangle Galerkin matrices for the
+        velocity block and the pressure's Darcy Laplacian; needs cell counts with enough factors of two) or
+        "auto" (default): multigrid, its MINRES iterations replayed from a CUDA graph, on meshes with at least
+        64 cells on the short side that can be coarsened far enough -- measured on the B200
+        (profiles/r2d_fluid_bench.txt): diffuser N=128 104 ms against 403 ms per mirror-descent iteration
+        (126 against ~5900 MINRES iterations), N=256 144 ms against 1211 ms -- and the diagonal preconditioner
+        on small meshes, which stay launch bound.  ``graph`` None follows the preconditioner choice."""
         self.parameters = fluid_parameters
         self.mesh = mesh
         self.domain_size = (domain_parameters.width, domain_parameters.height)
@@ -147,8 +151,13 @@ class FluidProblem(Problem):
                                             self.penalizer.minimum, self.penalizer.maximum,
                                             self.device.index or 0, byref(handle)))
         self._h = handle
-        if preconditioner not in ("diagonal", "multigrid"):
-            raise ValueError(f"preconditioner must be 'diagonal' or 'multigrid', got {preconditioner!r}")
+        if preconditioner not in ("diagonal", "multigrid", "auto"):
+            raise ValueError(f"preconditioner must be 'diagonal', 'multigrid' or 'auto', got {preconditioner!r}")
+        self.auto_preconditioner = preconditioner == "auto"
+        if self.auto_preconditioner:
+            preconditioner = "multigrid" if self.multigrid_pays_off(mesh.nx, mesh.ny) else "diagonal"
+            if graph is None:
+                graph = preconditioner == "multigrid"
         self.preconditioner = preconditioner
         if preconditioner == "multigrid":
             _lib.check(self.lib.tm_fluid_set_option(self._h, 1, 1.0))
@@ -208,14 +217,34 @@ class FluidProblem(Problem):
         self._sync_stream()
         _lib.check(self.lib.tm_fluid_set_density(self._h, self._ptr(rho.tensor, self.n1), q))
 
+    @staticmethod
+    def multigrid_pays_off(nx: int, ny: int) -> bool:
+        """Mirror of ``CudaTriMG::level_list``: the mesh halves while both cell counts are even and more than
+        four cells remain; the coarsest velocity level must fit the dense inverse (2048 scalar nodes)."""
+        if min(nx, ny) < 64:
+            return False
+        while nx % 2 == 0 and ny % 2 == 0 and nx * ny > 4:
+            nx, ny = nx // 2, ny // 2
+        return (2 * nx + 1) * (2 * ny + 1) <= 2048
+
     def forward(self, rho: Function) -> torch.Tensor:
         """State solve; returns the combined ``[velocity | pressure]`` device vector."""
         self.set_density(rho)
         up = torch.empty(self.nu + self.n1, dtype=torch.float64, device=self.device)
         iters, relres = c_int(0), c_double(0.0)
-        _lib.check(self.lib.tm_fluid_state_solve(self._h, self._ptr(self.boundary_velocity, self.nu),
-                                                 self.state_rtol, self.state_max_iterations,
-                                                 self._ptr(up, self.nu + self.n1), byref(iters), byref(relres)))
+        try:
+            _lib.check(self.lib.tm_fluid_state_solve(self._h, self._ptr(self.boundary_velocity, self.nu),
+                                                     self.state_rtol, self.state_max_iterations,
+                                                     self._ptr(up, self.nu + self.n1), byref(iters), byref(relres)))
+        except _lib.NotConverged:
+            if not (self.auto_preconditioner and self.preconditioner == "multigrid"):
+                raise
+            # the automatic choice must never cost a run: back to the diagonal preconditioner for good
+            self.preconditioner = "diagonal"
+            _lib.check(self.lib.tm_fluid_set_option(self._h, 8, 0.0))
+            _lib.check(self.lib.tm_fluid_set_option(self._h, 1, 0.0))
+            self.graph = False
+            return self.forward(rho)
         self.solve_log.append({"iterations": iters.value, "relative_residual": relres.value})
         return up
 
