@@ -1327,7 +1327,7 @@ class Engine : public EngineBase {
             if (level + 1 >= nl) throw Invalid{"no coarser level"};
             Level& C = levels_[level + 1];
             TM_CUDA(cudaMemsetAsync(out, 0, L.nu * sizeof(T), stream_));
-            dim3 grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
+            dim3 grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8 * kProlongRows));
             mg_prolong_add_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, in, out);
             TM_CHECK_LAUNCH();
         } else if (op == 2) {
@@ -2567,7 +2567,7 @@ class Engine : public EngineBase {
             Level& L = levels_[l];
             Level& C = levels_[l + 1];
             exchange_p2(l + 1, xs[l + 1]);
-            dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8));
+            dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8 * kProlongRows));
             launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
             acct(LC_PROLONG, 2 * sz(L.cnt) + sz(C.nu));
