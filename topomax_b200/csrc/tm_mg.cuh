@@ -182,14 +182,16 @@ __device__ __forceinline__ void restrict_node(const LevelGeom<T>& f, const Level
     a1 += e1;
 }
 
-// (P xc)(i, j) on the fine lattice (the caller skips fine Dirichlet nodes)
+// (P xc)(i, j) on the fine lattice (the caller skips fine Dirichlet nodes).  `Pw` = the 25 x 9 weight
+// table: TransferTable::Pw itself (kernel parameter space: fine for a few nodes, but an indexed constant
+// load per weight serialises over the warp's distinct indices) or a shared-memory copy of it.
 template <typename T, bool CG>
 __device__ __forceinline__ void prolong_node(const LevelGeom<T>& f, const LevelGeom<T>& c,
-                                             const TransferTable& tab, const T* __restrict__ xc, int i,
+                                             const double (*Pw)[9], const T* __restrict__ xc, int i,
                                              int j, double& a0, double& a1) {
     const int jg = j + f.j_off;  // global fine lattice row
     const int cx = min(i >> 2, c.nx - 1), cy = min(jg >> 2, c.nyg - 1);
-    const double* pw = tab.Pw[5 * (jg - 4 * cy) + (i - 4 * cx)];
+    const double* pw = Pw[5 * (jg - 4 * cy) + (i - 4 * cx)];
     a0 = 0.0;
     a1 = 0.0;
 #pragma unroll
@@ -341,9 +343,11 @@ mg_restrict_tiled_kernel(const LevelGeom<T> f, const LevelGeom<T> c, const T* __
 }
 
 // x += P xc  (fine Dirichlet nodes untouched).  A thread updates kProlongRows fine nodes of one lattice
-// column: their (up to 5 each) coarse loads and the x loads are all issued before the first use, and the
-// grid has 4x fewer, longer-lived blocks -- the one-node-per-thread version streamed at 3.5 TB/s
-// (profiles/r2d, r2h), limited by memory-level parallelism, not by bytes.  Same arithmetic per node.
+// column (their coarse loads and x loads are issued before the first use), and the weight table is
+// copied to shared memory first: ncu on the 2e8-dof level (profiles/r2i_ncu_prolong_constant_table.txt)
+// showed the kernel waiting on its INDEXED CONSTANT loads of the weights (short scoreboard 38 % + MIO
+// 10 % of the stall samples; 3.4 TB/s whatever the rows per thread) -- a warp holds four column classes,
+// so every `LDC c[0x0][R + ...]` replays four times.  Same arithmetic per node.
 constexpr int kProlongRows = 4;
 
 template <typename T>
@@ -351,6 +355,10 @@ __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c
                                       const TransferTable tab, const T* __restrict__ xc,
                                       T* __restrict__ x) {
     using V2 = typename MgVec2<T>::type;
+    __shared__ double s_pw[25][9];
+    for (int k = threadIdx.x + blockDim.x * threadIdx.y; k < 25 * 9; k += blockDim.x * blockDim.y)
+        s_pw[k / 9][k % 9] = tab.Pw[k / 9][k % 9];
+    __syncthreads();
     pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int jb = (blockIdx.y * blockDim.y + threadIdx.y) * kProlongRows;
@@ -366,7 +374,7 @@ __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c
         v[r].x = v[r].y = T(0);
         if (act[r]) {
             v[r] = reinterpret_cast<const V2*>(x)[(size_t)j * f.Lx + i];
-            prolong_node<T, false>(f, c, tab, xc, i, j, a0[r], a1[r]);
+            prolong_node<T, false>(f, c, s_pw, xc, i, j, a0[r], a1[r]);
         }
     }
 #pragma unroll

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_vcycle_kernel(const Tail
             const int i = node % L.g.Lx, j = node / L.g.Lx;
             if (L.g.fixed(i, j)) continue;
             double a0, a1;
-            prolong_node<T, true>(L.g, C.g, A.tab, cur[t + 1], i, j, a0, a1);
+            prolong_node<T, true>(L.g, C.g, A.tab.Pw, cur[t + 1], i, j, a0, a1);
             const typename Vec2<T>::type xv = tail_ld2<T>(x, node);
             tail_st2<T>(x, node, (T)((double)xv.x + a0), (T)((double)xv.y + a1));
         }
