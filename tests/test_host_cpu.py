@@ -295,28 +295,34 @@ def test_bench_reference_arm_line(repo_root):
 
 
 def test_committed_bench_lines_keep_the_contract(repo_root):
-    """The JSON line bench.py printed on the B200 (committed under profiles/) carries every key of the
+    """The JSON lines bench.py printed on the B200 (committed under profiles/) carry every key of the
     measurement contract; guards the schema against edits of bench.py made without a GPU at hand."""
     import json
 
-    full = json.load(open(os.path.join(repo_root, "profiles", "r1j_bench.json")))
-    last = json.load(open(os.path.join(repo_root, "profiles", "r1l_bench_nocpu.json")))
-    for line in (full, last):
+    one = json.loads(open(os.path.join(repo_root, "profiles", "r2i_bench.json")).read().strip().splitlines()[-1])
+    eight = json.loads(open(os.path.join(repo_root, "profiles", "r2h_bench_8gpu.json")).read().strip().splitlines()[-1])
+    for line in (one, eight):
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
-                    "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+                    "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline",
+                    "parity", "cpu_baseline"):
             assert key in line, key
-        assert line["metric"] == "mirror_descent_iters_per_sec" and line["dtype"] == "f64"
-        assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["vs_baseline"] is None
+        assert line["metric"] == "mirror_descent_iters_per_sec" and line["higher_is_better"] is True
         assert "workload" in line["config"] and "model" not in line["config"]
-        assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
-        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] != line["value"]
-        roof = line["roofline"]
-        assert set(roof) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
-        assert roof["bound"] == "hbm" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+        r = line["roofline"]
+        for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "step", "survey_pcg_figure"):
+            assert key in r, key
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+        assert 0.0 < r["step"]["frac"] < 1.0 and line["gpu_launches"] > 0
+        assert set(line["e2e"]) == {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
         assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-        assert line["gpu_launches"] > 0
-    cpu = full["cpu_baseline"]
-    assert set(cpu) >= {"value", "unit", "cores", "kind", "sample"} and cpu["kind"] in ("port", "reference")
+        assert line["parity"]["ok"] is True
+    assert (one["n_gpus"], eight["n_gpus"]) == (1, 8)
+    assert "bridge.json N=2048" in one["config"]["workload"] and "cantilever.json N=16384" in eight["config"]["workload"]
+    cb = one["cpu_baseline"]
+    assert set(cb) >= {"value", "unit", "cores", "kind", "sample", "same_config_pair"} and cb["kind"] == "port"
+    assert one["secondary"]["parity"]["ok"] is True and "N=512" in one["secondary"]["config"]["workload"]
+    assert eight["cpu_baseline"] is None and eight["roofline"]["phases_by_rank_ms"] and len(eight["roofline"]["phases_by_rank_ms"]) == 8
 
 
 def test_fluid_solver_variants_stay_off_unless_named(repo_root):
