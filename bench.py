@@ -875,7 +875,10 @@ def run_cuda_arm(args):
             if engine.peer_memory_active else "NCCL halo exchange + all-reduce") +
         f", {engine.dist_levels} sharded multigrid levels",
         "value_normalisation": f"iter/s x (global dofs / dofs of the 1-GPU workload {base_design} N={base_n}) = "
-                               f"x{size_factor:.4f}",
+                               f"x{size_factor:.4f}" + (
+            "" if world == 1 else "; BASELINE.json's configs are DIFFERENT designs (PCG iterations per solve: bridge ~45, "
+            "triangle ~19, cantilever ~29), so value(N) / (N value(1)) is a size-normalised rate ratio, not a scaling "
+            "efficiency: the like-for-like figure is single_gpu_comparison.strong_scaling_speedup (same mesh on one GPU)"),
         "l2": f"working set of a state solve ~{10 * nu * esize / 1e6:.0f} MB of lattice vectors per GPU, larger than "
               f"the 126 MB L2",
         "md_iterations_timed": [args.warmup, args.warmup + args.steps],
