@@ -613,6 +613,8 @@ def run_cuda_arm(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (CUDA arm) needs a GPU; use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    # host-side staging copies of the end-to-end leg: torchrun pins OMP_NUM_THREADS to 1 per rank
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // max(1, world))))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

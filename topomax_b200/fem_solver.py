@@ -241,7 +241,8 @@ class FEMSolver(Solver):
             self._pinned_out = torch.empty(n, dtype=tensor.dtype).pin_memory()
         self._pinned_out.copy_(tensor.detach().reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return self._pinned_out.numpy().copy()  # the staging buffer is reused
+        # the staging buffer is reused: hand out a copy (torch's copy is threaded, numpy's is not)
+        return torch.empty(n, dtype=tensor.dtype).copy_(self._pinned_out).numpy()
 
     def to_array(self, rho: Function) -> np.ndarray:
         return self._d2h(rho.tensor)

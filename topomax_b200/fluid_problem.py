@@ -111,7 +111,7 @@ class FluidProblem(Problem):
                  domain_parameters: DomainParameters, *, control_space: FunctionSpace | None = None,
                  state_rtol: float = 1e-10, state_max_iterations: int = 200000, projection_rtol: float = 1e-12,
                  preconditioner: str = "auto", warm_start: bool = False,
-                 device_scalars: bool = False, deterministic: bool = False, graph: bool | None = None,
+                 device_scalars: bool = False, deterministic: bool | None = None, graph: bool | None = None,
                  device=None):
         """``preconditioner``: "diagonal", "multigrid" (V-cycles on per-triangle Galerkin matrices for the
         velocity block and the pressure's Darcy Laplacian; needs cell counts with enough factors of two) or
@@ -119,7 +119,10 @@ class FluidProblem(Problem):
         64 cells on the short side that can be coarsened far enough -- measured on the B200
         (profiles/r2d_fluid_bench.txt): diffuser N=128 104 ms against 403 ms per mirror-descent iteration
         (126 against ~5900 MINRES iterations), N=256 144 ms against 1211 ms -- and the diagonal preconditioner
-        on small meshes, which stay launch bound.  ``graph`` None follows the preconditioner choice."""
+        on small meshes, which stay launch bound.  ``graph`` None follows the preconditioner choice.
+        ``deterministic`` None: the gather kernels (no atomics, bit-reproducible) on meshes below 64 cells per
+        side, where they cost nothing (launch bound), the scatter-with-atomics kernels above (1.5x faster at
+        N=256: 144 against 223 ms per iteration, summation order then varies at round-off level)."""
         self.parameters = fluid_parameters
         self.mesh = mesh
         self.domain_size = (domain_parameters.width, domain_parameters.height)
@@ -167,6 +170,8 @@ class FluidProblem(Problem):
         self.device_scalars = bool(device_scalars)  # MINRES recurrences on the device, no sync per iteration
         if self.device_scalars:
             _lib.check(self.lib.tm_fluid_set_option(self._h, 5, 1.0))
+        if deterministic is None:
+            deterministic = min(mesh.nx, mesh.ny) < 64
         self.deterministic = bool(deterministic)  # gather kernels instead of scatter + atomics
         if self.deterministic:
             _lib.check(self.lib.tm_fluid_set_option(self._h, 7, 1.0))
