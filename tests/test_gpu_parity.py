@@ -430,6 +430,32 @@ def test_tiled_restriction_is_bit_identical_to_the_gather(nx, ny, fixed):
         assert np.array_equal(gather, tiled), (nx, ny, l, np.abs(gather - tiled).max())
 
 
+@pytest.mark.parametrize("nx,ny,fixed,degree", [(96, 40, ["Left"], 3), (130, 70, ["Left", "Right"], 2), (61, 33, ["Bottom"], 3)])
+def test_fused_first_two_smoothing_steps_equal_the_separate_ones(nx, ny, fixed, degree):
+    """EP_CHEB0 (option 131): the coarse levels' first two Chebyshev-Jacobi steps from the zero guess in one
+    operator pass (x1 = D^-1 b / theta formed on the fly) against the separate first-step kernel followed by
+    an EP_CHEB pass: the same V-cycle to round-off, the same PCG iteration counts."""
+    W, H = 0.05 * nx, 0.05 * ny
+    rng = np.random.default_rng(nx * 7 + ny)
+    mesh = StructuredMesh(W, H, nx, ny)
+    xi = _t(0.03 + 0.95 * rng.random(mesh.n1))
+    r = rng.standard_normal(mesh.nu)
+    r[mesh.dirichlet_mask(fixed)] = 0.0
+    b = rng.standard_normal(mesh.nu)
+    out = {}
+    for fused in (0, 1):
+        eng = _engine(nx, ny, W, H, lame_lambda=1.1, lame_mu=0.7, fixed_sides=_sides(fixed))
+        eng.set_option(109, degree)
+        eng.set_option(119, 0)      # no cluster tail: every coarse level runs the launch-per-phase smoother
+        eng.set_option(131, fused)
+        z = eng.mg_debug(xi, 3, 0, _t(r), mesh.nu).cpu().numpy()
+        u, info = eng.state_solve(xi, _t(b), rtol=1e-11, maxit=500)
+        out[fused] = (z, u.cpu().numpy(), info.iterations)
+    assert _rel(out[1][0], out[0][0]) < 1e-12
+    assert out[1][2] == out[0][2]
+    assert np.linalg.norm(out[1][1] - out[0][1]) / np.linalg.norm(out[0][1]) < 1e-9
+
+
 def test_golden_triangle_end_to_end(repo_root, golden_dir, tmp_path):
     """reference tests/test_elasticity_solver.py:30-55 on the CUDA path."""
     import pickle

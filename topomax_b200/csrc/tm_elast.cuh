@@ -22,6 +22,9 @@
 //   EP_CHEBDOT  EP_CHEB + the dot product b . y of the owned nodes (r . z of the PCG)
 //   EP_RESID0 x = c2 D^-1 b evaluated on the fly at the 9 nodes (the first smoothing step from a
 //             zero guess, never materialised before the operator); y = b - A x, x stored to d
+//   EP_CHEB0  the first TWO Chebyshev-Jacobi steps from a zero guess in one pass: x1 = c0 D^-1 b on the fly
+//             (its direction d1 = x1), then r = b - A x1; d = c1 x1 + c2 D^-1 r; y = x1 + d
+//             (saves the separate first-step kernel of the coarse levels: a launch and four vector passes)
 // Dirichlet nodes are identity rows/columns (symmetric elimination; same solution as the
 // reference's bc.apply because the prescribed value is zero).
 #pragma once
@@ -31,7 +34,9 @@
 
 namespace tmx {
 
-enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3, EP_RESID0 = 4, EP_CHEBDOT = 5 };
+enum Epilogue { EP_PLAIN = 0, EP_DOT = 1, EP_RESID = 2, EP_CHEB = 3, EP_RESID0 = 4, EP_CHEBDOT = 5, EP_CHEB0 = 6 };
+// the variants whose INPUT is formed on the fly from b and D^-1 (scale: c2 for EP_RESID0, c0 for EP_CHEB0)
+__host__ __device__ constexpr bool ep_on_the_fly(int ep) { return ep == EP_RESID0 || ep == EP_CHEB0; }
 // EP_CHEBDOT: EP_CHEB that also accumulates  b . y  -- on the last smoothing step of a V-cycle b is
 // the PCG residual r and y the preconditioned residual z, so r.z costs no extra pass over r and z
 __host__ __device__ constexpr bool ep_is_cheb(int ep) { return ep == EP_CHEB || ep == EP_CHEBDOT; }
@@ -55,6 +60,7 @@ struct ApplyArgs {
     const T* dinv;  // EP_CHEB: inverse diagonal
     T* d;           // EP_CHEB: Chebyshev direction, updated in place
     T c1, c2;       // EP_CHEB coefficients; EP_RESID0: c2 scales D^-1 b
+    T c0;           // EP_CHEB0: scale of the on-the-fly first step x1 = c0 D^-1 b
     int store_d;    // EP_CHEB: 0 = the updated direction is not needed any more (last step)
     ReduceScratch rs;
     double* dot_out;  // EP_DOT, EP_CHEBDOT
@@ -75,7 +81,8 @@ struct EpiOps {
 template <typename T, int EP>
 __device__ __forceinline__ void load_epi_ops(const ApplyArgs<T>& a, size_t n, EpiOps<T>& o) {
     using V2 = typename Vec2<T>::type;
-    if (EP == EP_RESID || EP == EP_RESID0 || ep_is_cheb(EP)) o.b = reinterpret_cast<const V2*>(a.b)[n];
+    if (EP == EP_RESID || ep_on_the_fly(EP) || ep_is_cheb(EP)) o.b = reinterpret_cast<const V2*>(a.b)[n];
+    if (EP == EP_CHEB0) o.dinv = reinterpret_cast<const V2*>(a.dinv)[n];
     if (ep_is_cheb(EP)) {
         o.dinv = reinterpret_cast<const V2*>(a.dinv)[n];
         if (a.c1 != T(0)) o.d = reinterpret_cast<const V2*>(a.d)[n];
@@ -87,7 +94,7 @@ template <typename T, int EP>
 __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, bool fixed, T v0, T v1,
                                                T x0, T x1, double& dot, const EpiOps<T>& ops) {
     using V2 = typename Vec2<T>::type;
-    if (fixed && EP == EP_RESID0) {  // x = c2 D^-1 b vanishes on Dirichlet nodes (b_D = 0)
+    if (fixed && ep_on_the_fly(EP)) {  // x = c D^-1 b vanishes on Dirichlet nodes (b_D = 0)
         x0 = x1 = v0 = v1 = T(0);
     } else if (fixed) {  // identity row: the registers hold the masked input (0), fetch the raw value
         const V2 xr = reinterpret_cast<const V2*>(a.x)[n];
@@ -116,7 +123,10 @@ __device__ __forceinline__ void apply_epilogue(const ApplyArgs<T>& a, size_t n, 
             V2 dd;
             dd.x = a.c2 * di.x * r0;
             dd.y = a.c2 * di.y * r1;
-            if (a.c1 != T(0)) {
+            if (EP == EP_CHEB0) {  // the previous direction IS the on-the-fly first iterate
+                dd.x += a.c1 * x0;
+                dd.y += a.c1 * x1;
+            } else if (a.c1 != T(0)) {
                 dd.x += a.c1 * ops.d.x;
                 dd.y += a.c1 * ops.d.y;
             }
@@ -152,6 +162,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
     const bool own_c1 = owner && ix < g.nx;
 
     double dot = 0.0;
+    const T cfly = EP == EP_CHEB0 ? a.c0 : a.c2;  // scale of an on-the-fly input
 
     if (warp_active) {
         const V2* __restrict__ xv = reinterpret_cast<const V2*>(a.x);
@@ -179,11 +190,11 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             for (int c = 0; c < 3; ++c)
                 if (colok[c]) {
                     V2 v;
-                    if (EP == EP_RESID0) {
+                    if (ep_on_the_fly(EP)) {
                         const V2 bv = reinterpret_cast<const V2*>(a.b)[row + i0 + c];
                         const V2 dv = reinterpret_cast<const V2*>(a.dinv)[row + i0 + c];
-                        v.x = a.c2 * dv.x * bv.x;
-                        v.y = a.c2 * dv.y * bv.y;
+                        v.x = cfly * dv.x * bv.x;
+                        v.y = cfly * dv.y * bv.y;
                     } else {
                         v = xv[row + i0 + c];
                     }
@@ -213,7 +224,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                     if (colok[c]) {  // raw values: nothing may consume them before the next step
-                        if (EP == EP_RESID0) {
+                        if (ep_on_the_fly(EP)) {
                             const V2 bv = reinterpret_cast<const V2*>(a.b)[row + i0 + c];
                             const V2 dv = reinterpret_cast<const V2*>(a.dinv)[row + i0 + c];
                             Xn[3 * r + c][0] = bv.x;
@@ -233,7 +244,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             }
         };
         auto prefetch_epilogue = [&](int iy_e) {
-            if (!(PF && colok[0] && (EP == EP_RESID || ep_is_cheb(EP))) || iy_e < iy0) return;
+            if (!(PF && colok[0] && (EP == EP_RESID || (ep_is_cheb(EP) && EP != EP_CHEB0))) || iy_e < iy0) return;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t n = (size_t)(2 * iy_e + r) * Lx + i0;
@@ -262,9 +273,9 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const bool f = rowfix || colfix[c];
-                    if (EP == EP_RESID0) {
-                        X[3 + 3 * r + c][0] = f ? T(0) : a.c2 * Dn[3 * r + c][0] * Xn[3 * r + c][0];
-                        X[3 + 3 * r + c][1] = f ? T(0) : a.c2 * Dn[3 * r + c][1] * Xn[3 * r + c][1];
+                    if (ep_on_the_fly(EP)) {
+                        X[3 + 3 * r + c][0] = f ? T(0) : cfly * Dn[3 * r + c][0] * Xn[3 * r + c][0];
+                        X[3 + 3 * r + c][1] = f ? T(0) : cfly * Dn[3 * r + c][1] * Xn[3 * r + c][1];
                     } else {
                         X[3 + 3 * r + c][0] = f ? T(0) : Xn[3 * r + c][0];
                         X[3 + 3 * r + c][1] = f ? T(0) : Xn[3 * r + c][1];
@@ -283,7 +294,7 @@ elast_apply_kernel(const LevelGeom<T> g, const ApplyArgs<T> a) {
             // (fine level only: the stored-moment kernels of the coarse levels are better off with
             // the registers, i.e. a third resident block per SM, and load them where they are used)
             EpiOps<T> eo[2][2];
-            if (!STORED_W && (EP == EP_RESID || EP == EP_RESID0 || ep_is_cheb(EP))) {
+            if (!STORED_W && (EP == EP_RESID || ep_on_the_fly(EP) || ep_is_cheb(EP))) {
                 if (iy >= iy0 && owner) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {

@@ -281,6 +281,7 @@ class Engine : public EngineBase {
             case 127: fuse_rz_ = (int)value; graph_dirty_ = true; break;
             case 128: restrict_tiled_ = value != 0.0; graph_dirty_ = true; break;
             case 129: wave_aware_ = value != 0.0; graph_dirty_ = true; break;
+            case 131: fuse_cheb0_ = value != 0.0; graph_dirty_ = true; break;
             case TM_OPT_P2P:  // collective: every rank must set it alike
                 p2p_want_ = value != 0.0;
                 graph_dirty_ = true;
@@ -1725,7 +1726,7 @@ class Engine : public EngineBase {
             if (stored_cap_ == 0) {
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                        &per_sm, elast_apply_kernel<T, true, EP_CHEB, 2, false>, kApplyWarps * 32, 0) != cudaSuccess ||
+                        &per_sm, elast_apply_kernel<T, true, EP_CHEB, 3, false>, kApplyWarps * 32, 0) != cudaSuccess ||
                     per_sm < 1) {
                     cudaGetLastError();
                     per_sm = 3;
@@ -1755,7 +1756,7 @@ class Engine : public EngineBase {
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         const bool timed = profile_ == 2 || (profile_ == 1 && fine);
         // statistics file the fused variants under their base epilogue
-        const int ep_slot = ep == EP_RESID0 ? (int)EP_RESID : (ep == EP_CHEBDOT ? (int)EP_CHEB : ep);
+        const int ep_slot = ep == EP_RESID0 ? (int)EP_RESID : ((ep == EP_CHEBDOT || ep == EP_CHEB0) ? (int)EP_CHEB : ep);
         if (timed) {
             if (prof_free_.empty()) {
                 TM_CUDA(cudaEventCreate(&ev.first));
@@ -1774,10 +1775,11 @@ class Engine : public EngineBase {
         case EP_RESID: TM_LAUNCH_APPLY(ST, EP_RESID, MB, PFV); break;   \
         case EP_RESID0: TM_LAUNCH_APPLY(ST, EP_RESID0, MB, PFV); break; \
         case EP_CHEBDOT: TM_LAUNCH_APPLY(ST, EP_CHEBDOT, MB, PFV); break; \
+        case EP_CHEB0: TM_LAUNCH_APPLY(ST, EP_CHEB0, MB, PFV); break;   \
         default: TM_LAUNCH_APPLY(ST, EP_CHEB, MB, PFV); break;          \
     }
         if (stored) {
-            TM_LAUNCH_APPLY_EP(true, 2, false)
+            TM_LAUNCH_APPLY_EP(true, 3, false)
         } else if (apply_minb_ >= 4) {
             TM_LAUNCH_APPLY_EP(false, 4, true)
         } else {
@@ -1791,9 +1793,11 @@ class Engine : public EngineBase {
             double vecs = 2.0;  // EP_PLAIN, EP_DOT: read x, write y
             if (ep == EP_RESID) vecs = 3.0;  // + b
             else if (ep == EP_RESID0) vecs = 4.0;  // read b, D^-1; write x, r
+            else if (ep == EP_CHEB0) vecs = 3.0 + (a.store_d ? 1.0 : 0.0);  // read b, D^-1; write y (, d)
             else if (ep_is_cheb(ep)) vecs = 4.0 + (a.c1 != T(0) ? 1.0 : 0.0) + (a.store_d ? 1.0 : 0.0);
             const double coef = stored ? 12.0 * g.nx * g.ny : (double)(g.nx + 1) * (g.ny + 1);
-            acct(fine ? LC_FINE_PLAIN + ep : LC_COARSE1 + std::min(level, 14) - 1, (vecs * nuv + coef) * sizeof(T));
+            const int fine_cat = ep == EP_CHEB0 ? (int)LC_FINE_CHEB : LC_FINE_PLAIN + ep;
+            acct(fine ? fine_cat : LC_COARSE1 + std::min(level, 14) - 1, (vecs * nuv + coef) * sizeof(T));
         }
         if (timed) {
             TM_CUDA(cudaEventRecord(ev.second, stream_));
@@ -2365,6 +2369,7 @@ class Engine : public EngineBase {
         in.fuse_first_ = fuse_first_;
         in.restrict_tiled_ = restrict_tiled_;
         in.wave_aware_ = wave_aware_;
+        in.fuse_cheb0_ = fuse_cheb0_;
         in.set_penalty(spec_.p);
         in.fuse_rz_ = 0;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
@@ -2402,7 +2407,23 @@ class Engine : public EngineBase {
         double rho = 1.0 / sigma;
         T* cur;
         int k0 = 0;
-        if (!xin) {
+        const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
+        if (!xin && degree >= 2 && fuse_first_ && fuse_cheb0_) {
+            // steps 0 and 1 from the zero guess in ONE operator pass (EP_CHEB0): x1 = D^-1 b / theta is formed
+            // on the fly at the nodes the operator touches, so b's halo rows must be current
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            exchange_p2(l, const_cast<T*>(b));
+            ApplyArgs<T> a = apply_args();
+            a.y = L.x.p; a.b = b; a.dinv = L.dinv.p; a.d = L.d.p;
+            a.c0 = (T)(1.0 / theta);
+            a.c1 = (T)(rho_new * rho);
+            a.c2 = (T)(2.0 * rho_new / delta);
+            a.store_d = degree > 2 ? 1 : 0;
+            launch_apply(L.g, l > 0, EP_CHEB0, a);
+            rho = rho_new;
+            cur = L.x.p;
+            k0 = 2;
+        } else if (!xin) {
             launch_chain(cheb_first_kernel<T>, dim3(grid1d(L.cnt)), dim3(kVecThreads), L.cnt, 1.0 / theta,
                          (const T*)(L.dinv.p + L.off), b + L.off, L.d.p + L.off, L.x.p + L.off);
             TM_CHECK_LAUNCH();
@@ -2412,7 +2433,6 @@ class Engine : public EngineBase {
         } else {
             cur = xin;
         }
-        const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
         for (int k = k0; k < degree; ++k) {
             double c1, c2;
             if (k == 0) {
@@ -2649,6 +2669,7 @@ class Engine : public EngineBase {
     bool pdl_ = true, pdl_active_ = false;  // option 126: programmatic dependent launch in V-cycles
     bool restrict_tiled_ = true;            // option 128: shared-memory tiled restriction on the large levels
     bool wave_aware_ = true;                // option 129: strip heights of the stored-moment levels fill whole waves
+    bool fuse_cheb0_ = true;                // option 131: first two smoothing steps from zero in one operator pass
     long stored_cap_ = 0;                   // resident blocks of the stored-moment operator kernel (whole GPU)
     bool warm_guard_ = true;   // option 125: drop a warm start whose residual exceeds the zero guess's
     int stats_warm_used_ = 0;  // last state solve: 1 if the caller's initial guess was kept
