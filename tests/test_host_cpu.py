@@ -299,8 +299,8 @@ def test_committed_bench_lines_keep_the_contract(repo_root):
     measurement contract; guards the schema against edits of bench.py made without a GPU at hand."""
     import json
 
-    one = json.loads(open(os.path.join(repo_root, "profiles", "r2i_bench.json")).read().strip().splitlines()[-1])
-    eight = json.loads(open(os.path.join(repo_root, "profiles", "r2h_bench_8gpu.json")).read().strip().splitlines()[-1])
+    one = json.loads(open(os.path.join(repo_root, "profiles", "r2o_bench.json")).read().strip().splitlines()[-1])
+    eight = json.loads(open(os.path.join(repo_root, "profiles", "r2n_bench_8gpu.json")).read().strip().splitlines()[-1])
     for line in (one, eight):
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                     "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline",
@@ -323,6 +323,9 @@ def test_committed_bench_lines_keep_the_contract(repo_root):
     assert set(cb) >= {"value", "unit", "cores", "kind", "sample", "same_config_pair"} and cb["kind"] == "port"
     assert one["secondary"]["parity"]["ok"] is True and "N=512" in one["secondary"]["config"]["workload"]
     assert eight["cpu_baseline"] is None and eight["roofline"]["phases_by_rank_ms"] and len(eight["roofline"]["phases_by_rank_ms"]) == 8
+    # the north-star line: every lattice row of the 6.4e9-dof mesh went through the independent CPU operator
+    assert eight["parity"]["coverage"] == "every lattice row" and eight["parity"]["compliance_rel_diff"] < 1e-6
+    assert eight["roofline"]["step"]["frac"] >= 0.6
 
 
 def test_fluid_solver_variants_stay_off_unless_named(repo_root):
