@@ -430,6 +430,29 @@ def test_tiled_restriction_is_bit_identical_to_the_gather(nx, ny, fixed):
         assert np.array_equal(gather, tiled), (nx, ny, l, np.abs(gather - tiled).max())
 
 
+@pytest.mark.parametrize("nx,ny,fixed", [(8, 8, ["Left"]), (13, 7, ["Left", "Right"]), (22, 9, ["Bottom", "Top"]),
+                                         (150, 37, ["Left"]), (260, 131, []), (129, 70, ["Left", "Right", "Bottom", "Top"]),
+                                         (256, 64, ["Right", "Top"])])
+def test_tiled_prolongation_is_bit_identical_to_the_gather(nx, ny, fixed):
+    """mg_prolong_tiled_kernel (x tile and coarse window staged in shared memory, one interpolation class per
+    warp, far-edge nodes addressed as class 0 of the next coarse cell) against mg_prolong_add_kernel on every
+    level pair: EQUAL bits -- tile edges, odd sizes (overhanging coarse cells), even sizes (nodes on the last
+    coarse cell's far edge), Dirichlet sides and meshes narrower than one tile included."""
+    W, H = 0.1 * nx, 0.1 * ny
+    rng = np.random.default_rng(3 * nx + ny)
+    mesh = StructuredMesh(W, H, nx, ny)
+    xi = _t(0.05 + 0.9 * rng.random(mesh.n1))
+    eng = _engine(nx, ny, W, H, lame_lambda=1.2, lame_mu=0.9, fixed_sides=_sides(fixed))
+    levels = eng.mg_levels()
+    for l in range(len(levels) - 2):
+        (fx, fy, *_), (cx, cy, *_) = levels[l], levels[l + 1]
+        nf, nc = 2 * (2 * fx + 1) * (2 * fy + 1), 2 * (2 * cx + 1) * (2 * cy + 1)
+        vc = _t(rng.standard_normal(nc))
+        gather = eng.mg_debug(xi, 1, l, vc, nf).cpu().numpy()
+        tiled = eng.mg_debug(xi, 8, l, vc, nf).cpu().numpy()
+        assert np.array_equal(gather, tiled), (nx, ny, l, np.abs(gather - tiled).max())
+
+
 @pytest.mark.parametrize("nx,ny,fixed,degree", [(96, 40, ["Left"], 3), (130, 70, ["Left", "Right"], 2), (61, 33, ["Bottom"], 3)])
 def test_fused_first_two_smoothing_steps_equal_the_separate_ones(nx, ny, fixed, degree):
     """EP_CHEB0 (option 131): the coarse levels' first two Chebyshev-Jacobi steps from the zero guess in one

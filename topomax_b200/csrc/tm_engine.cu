@@ -282,6 +282,7 @@ class Engine : public EngineBase {
             case 128: restrict_tiled_ = value != 0.0; graph_dirty_ = true; break;
             case 129: wave_aware_ = value != 0.0; graph_dirty_ = true; break;
             case 131: fuse_cheb0_ = value != 0.0; graph_dirty_ = true; break;
+            case 132: prolong_tiled_ = value != 0.0; graph_dirty_ = true; break;
             case TM_OPT_P2P:  // collective: every rank must set it alike
                 p2p_want_ = value != 0.0;
                 graph_dirty_ = true;
@@ -1337,6 +1338,13 @@ class Engine : public EngineBase {
             dim3 grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
             mg_restrict_kernel<T><<<grd, blk, 0, stream_>>>(L.g, C.g, tr_tab_, in, out);
             TM_CHECK_LAUNCH();
+        } else if (op == 8) {  // the shared-memory tiled prolongation, whatever the level size (out += P in)
+            if (level + 1 >= nl) throw Invalid{"no coarser level"};
+            Level& C = levels_[level + 1];
+            TM_CUDA(cudaMemsetAsync(out, 0, L.nu * sizeof(T), stream_));
+            mg_prolong_tiled_kernel<T><<<dim3(ceil_div(L.g.Lx, kPtTI), ceil_div(L.g.Ly, kPtTJ)), kPtThreads, 0, stream_>>>(
+                L.g, C.g, in, out);
+            TM_CHECK_LAUNCH();
         } else if (op == 7) {  // the shared-memory tiled restriction, whatever the level size
             if (level + 1 >= nl) throw Invalid{"no coarser level"};
             Level& C = levels_[level + 1];
@@ -1977,6 +1985,8 @@ class Engine : public EngineBase {
         {   // stencil lists of the tiled restriction (tm_mg.cuh)
             const RestrictLists rl = make_restrict_lists(tr_tab_);
             TM_CUDA(cudaMemcpyToSymbol(c_restrict_lists, &rl, sizeof(rl)));
+            const ProlongLists pl = make_prolong_lists(tr_tab_);
+            TM_CUDA(cudaMemcpyToSymbol(c_prolong_lists, &pl, sizeof(pl)));
         }
         plan_tail();
     }
@@ -2370,6 +2380,7 @@ class Engine : public EngineBase {
         in.restrict_tiled_ = restrict_tiled_;
         in.wave_aware_ = wave_aware_;
         in.fuse_cheb0_ = fuse_cheb0_;
+        in.prolong_tiled_ = prolong_tiled_;
         in.set_penalty(spec_.p);
         in.fuse_rz_ = 0;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
@@ -2588,7 +2599,11 @@ class Engine : public EngineBase {
             Level& C = levels_[l + 1];
             exchange_p2(l + 1, xs[l + 1]);
             dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8 * kProlongRows));
-            launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
+            if (prolong_tiled_ && (long)L.g.Lx * L.g.Ly >= 16384)
+                launch_chain(mg_prolong_tiled_kernel<T>, dim3(ceil_div(L.g.Lx, kPtTI), ceil_div(L.g.Ly, kPtTJ)),
+                             dim3(kPtThreads), L.g, C.g, (const T*)xs[l + 1], xs[l]);
+            else
+                launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
             TM_CHECK_LAUNCH();
             acct(LC_PROLONG, 2 * sz(L.cnt) + sz(C.nu));
             // the V-cycle ends with the level-0 post-smoothing: its last step also returns r . z
@@ -2670,6 +2685,7 @@ class Engine : public EngineBase {
     bool restrict_tiled_ = true;            // option 128: shared-memory tiled restriction on the large levels
     bool wave_aware_ = true;                // option 129: strip heights of the stored-moment levels fill whole waves
     bool fuse_cheb0_ = true;                // option 131: first two smoothing steps from zero in one operator pass
+    bool prolong_tiled_ = true;             // option 132: shared-memory tiled prolongation on the large levels
     long stored_cap_ = 0;                   // resident blocks of the stored-moment operator kernel (whole GPU)
     bool warm_guard_ = true;   // option 125: drop a warm start whose residual exceeds the zero guess's
     int stats_warm_used_ = 0;  // last state solve: 1 if the caller's initial guess was kept

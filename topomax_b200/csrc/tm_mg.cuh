@@ -387,6 +387,112 @@ __global__ void mg_prolong_add_kernel(const LevelGeom<T> f, const LevelGeom<T> c
         }
 }
 
+// The same prolongation through shared-memory tiles (the large levels).  ncu on the 2e8-dof level showed the
+// node-per-thread kernel above bound by its per-node WEIGHT fetches, not by bytes: a warp holds four column
+// classes, so every indexed load of a weight replays (constant bank: ADU / IDC 88 % busy, 3.4 TB/s; from
+// shared memory: short-scoreboard stalls, 3.5 TB/s; profiles/r2i_ncu_prolong_constant_table.txt).  Here a
+// block stages its 128 x 8 tile of x (four planes by column mod 4) and the coarse window under it (two
+// planes by column parity) with cp.async, and every warp then updates 32 fine nodes of ONE class
+// (a, b) = (i mod 4, j mod 4): i = i0 + 4 lane + a.  Its <= 5 non-zero weights come from a constant-memory
+// list with warp-uniform addresses, its coarse and x reads are 32 consecutive 16-byte shared words, and the
+// tile goes back with coalesced stores.  A node on a coarse cell's far edge is addressed as class 0 of the
+// NEXT cell (i >> 2 unclipped): the interpolation is continuous, the weights are the same numbers in the
+// same order, so the result is bit-identical to prolong_node (test_tiled_prolongation_is_bit_identical...).
+constexpr int kPtTI = 128, kPtTJ = 8, kPtThreads = 256;
+constexpr int kPtCW = 36;                  // entries per coarse-window plane and row (65 columns: 33 + 32; = 4 mod 8)
+constexpr int kPtCRows = 7;                // coarse rows under 8 fine rows, whatever the alignment
+constexpr int kPtXW = kPtTI / 4 + 2;       // entries per x-tile plane and row (32, padded: = 2 mod 8)
+
+struct ProlongLists {
+    int n[16];
+    int off[16][6];     // relative to &cw[(2 (cy - cy_lo)) * 2 kPtCW + lane]
+    double w[16][6];
+};
+
+inline ProlongLists make_prolong_lists(const TransferTable& tab) {
+    ProlongLists L;
+    std::memset(&L, 0, sizeof(L));
+    for (int b = 0; b < 4; ++b)
+        for (int a = 0; a < 4; ++a) {
+            const int cls = 4 * b + a;
+            for (int q = 0; q < 9; ++q) {
+                const double w = tab.Pw[5 * b + a][q];
+                if (w == 0.0) continue;
+                const int qc = q % 3, qr = q / 3;
+                int& k = L.n[cls];
+                L.off[cls][k] = qr * (2 * kPtCW) + (qc & 1) * kPtCW + (qc >> 1);
+                L.w[cls][k] = w;
+                ++k;
+            }
+        }
+    return L;
+}
+
+__constant__ ProlongLists c_prolong_lists;
+
+template <typename T>
+__global__ void __launch_bounds__(kPtThreads)
+mg_prolong_tiled_kernel(const LevelGeom<T> f, const LevelGeom<T> c, const T* __restrict__ xc, T* __restrict__ x) {
+    using V2 = typename MgVec2<T>::type;
+    __shared__ V2 xs[kPtTJ * 4 * kPtXW];
+    __shared__ V2 cw[kPtCRows * 2 * kPtCW];
+    pdl_prologue();
+    const int i0 = blockIdx.x * kPtTI, j0 = blockIdx.y * kPtTJ;
+    const int jg0 = j0 + f.j_off;       // global fine row of the tile's first row
+    const int cx0 = i0 >> 2, cy_lo = jg0 >> 2;
+    // x tile: xs[row][col & 3][col >> 2]
+    for (int e = threadIdx.x; e < kPtTJ * kPtTI; e += kPtThreads) {
+        const int row = e / kPtTI, col = e - row * kPtTI;
+        const int i = i0 + col, j = j0 + row;
+        const bool ok = i < f.Lx && j < f.Ly;
+        const V2* src = reinterpret_cast<const V2*>(x) + (ok ? (size_t)j * f.Lx + i : (size_t)0);
+        cp_async_zfill<sizeof(V2)>(&xs[row * (4 * kPtXW) + (col & 3) * kPtXW + (col >> 2)], src, ok);
+    }
+    // coarse window: cw[row][col & 1][col >> 1], coarse columns 2 cx0 .. 2 cx0 + 64, rows 2 cy_lo .. + 6
+    for (int e = threadIdx.x; e < kPtCRows * 65; e += kPtThreads) {
+        const int row = e / 65, col = e - row * 65;
+        const int I = 2 * cx0 + col, J = 2 * cy_lo + row - c.j_off;  // local coarse lattice position
+        const bool ok = I < c.Lx && J >= 0 && J < c.Ly;
+        const V2* src = reinterpret_cast<const V2*>(xc) + (ok ? (size_t)J * c.Lx + I : (size_t)0);
+        cp_async_zfill<sizeof(V2)>(&cw[row * (2 * kPtCW) + (col & 1) * kPtCW + (col >> 1)], src, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < (4 * kPtTJ) / (kPtThreads / 32); ++k) {
+        const int task = warp + (kPtThreads / 32) * k;
+        const int jr = task >> 2, a = task & 3;
+        const int i = i0 + 4 * lane + a, j = j0 + jr;
+        if (j >= f.Ly) continue;  // warp-uniform
+        const int jg = j + f.j_off;
+        const int cls = 4 * (jg & 3) + a;  // one class per warp
+        const V2* base = cw + (2 * ((jg >> 2) - cy_lo)) * (2 * kPtCW) + lane;
+        const int n = c_prolong_lists.n[cls];
+        double a0 = 0.0, a1 = 0.0;
+        for (int q = 0; q < n; ++q) {
+            const V2 v = base[c_prolong_lists.off[cls][q]];
+            const double w = c_prolong_lists.w[cls][q];
+            a0 += w * (double)v.x;
+            a1 += w * (double)v.y;
+        }
+        if (i < f.Lx && f.owns_row(j) && !f.fixed(i, j)) {
+            V2* xp = &xs[jr * (4 * kPtXW) + a * kPtXW + lane];
+            V2 o = *xp;
+            o.x = (T)((double)o.x + a0);
+            o.y = (T)((double)o.y + a1);
+            *xp = o;
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kPtTJ * kPtTI; e += kPtThreads) {
+        const int row = e / kPtTI, col = e - row * kPtTI;
+        const int i = i0 + col, j = j0 + row;
+        if (i < f.Lx && j < f.Ly && f.owns_row(j))
+            reinterpret_cast<V2*>(x)[(size_t)j * f.Lx + i] = xs[row * (4 * kPtXW) + (col & 3) * kPtXW + (col >> 2)];
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // coarsest level: dense Cholesky in one block (n = 2*Lx*Ly <= kCoarseMaxDofs)
 // ---------------------------------------------------------------------------------------
