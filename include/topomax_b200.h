@@ -39,10 +39,15 @@ enum {
     TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
     TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 1; coarse levels 3) */
     TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
-    TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (default 2)     */
+    TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (1..4, default 4) */
     TM_OPT_PROFILE = 5,      /* 1: time every fine-level operator launch with CUDA events; 2: the operator
                                 launches of every multigrid level; 3: every launch, by ledger category
                                 (tm_ledger_read).  2 and 3 switch CUDA-graph replay off: diagnostics only */
+    TM_OPT_CYCLE_FIRST = 133, /* multigrid cycle: levels [CYCLE_FIRST, CYCLE_LAST] are cycled CYCLE_GAMMA times per  */
+    TM_OPT_CYCLE_LAST = 134,  /* visit of their parent (a W-cycle on that window, a V-cycle elsewhere; pre- and post-  */
+    TM_OPT_CYCLE_GAMMA = 135, /* smoother are the same polynomial, so the cycle stays symmetric).  GAMMA 0 (default):  */
+                              /* automatic window = the levels whose short side has 8..16 cells (4..32 on meshes of    */
+                              /* >= 2^24 dofs); 1: plain V-cycle; 2..4: explicit window                               */
     TM_OPT_P2P = 130         /* sharded runs: halo exchange and scalar all-reduce by our own kernels over
                                 peer-mapped memory (NVLink) instead of NCCL calls; collective, set alike
                                 on every rank (default 1 since round 2; env TM_P2P=0 selects NCCL,
@@ -172,7 +177,8 @@ int tm_sample_field(tm_handle h, int degree, const void* field, int nsx, int nsy
  * operator applications, [3] levels, [4] lambda_max estimate of level 0, [5..8] cumulative
  * level-0 operator launches per epilogue, [9] first level of the cluster tail (-1: none), [10] its
  * cluster size, [11] 1 if the caller's initial guess was kept (a warm start whose residual
- * exceeds that of the zero guess is dropped) */
+ * exceeds that of the zero guess is dropped), [12..14] first / last multigrid level cycled more than
+ * once per visit of its parent and the number of cycles (-1, -1, 1: plain V-cycle) */
 int tm_last_solve_stats(tm_handle h, double* out, int n);
 
 /* Measurement support (bench.py): with TM_OPT_PROFILE on, out[0..3] = milliseconds spent in the

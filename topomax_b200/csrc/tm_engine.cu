@@ -186,7 +186,7 @@ class Engine : public EngineBase {
         if (rank_ < 0 || rank_ >= nranks_) throw Invalid{"rank out of range"};
         hx_ = cfg.width / nx_;
         hy_ = cfg.height / nyg_;
-        coarse_cells_ = 2;
+        coarse_cells_ = 4;
         plan_levels(cfg.mg_dist_levels);
         derive_local_sizes();
 
@@ -283,6 +283,12 @@ class Engine : public EngineBase {
             case 129: wave_aware_ = value != 0.0; graph_dirty_ = true; break;
             case 131: fuse_cheb0_ = value != 0.0; graph_dirty_ = true; break;
             case 132: prolong_tiled_ = value != 0.0; graph_dirty_ = true; break;
+            case 133:  // cycle window: first level whose visits are repeated (with 134, 135)
+                cycle_first_ = std::max(1, (int)value); graph_dirty_ = true; break;
+            case 134: cycle_last_ = (int)value; graph_dirty_ = true; break;
+            case 136: light_levels_ = (int)value; graph_dirty_ = true; break;
+            case 135:  // 0 = automatic window (default), 1 = V-cycle, 2.. = cycles per visit inside [133, 134]
+                cycle_gamma_ = std::min(4, std::max(0, (int)value)); graph_dirty_ = true; break;
             case TM_OPT_P2P:  // collective: every rank must set it alike
                 p2p_want_ = value != 0.0;
                 graph_dirty_ = true;
@@ -1104,9 +1110,17 @@ class Engine : public EngineBase {
         };
         auto precond = [&](T* r) -> T* { return !use_mg ? nullptr : (mixed ? mixed_vcycle(r) : vcycle(r)); };
         int check = check_every_;
-        if (check <= 0) check = use_mg ? 1 : 25;
+        // automatic: with the multigrid preconditioner every iteration is checked, but only from where the
+        // previous solve of this engine stopped (consecutive designs of a run need about the same count; the
+        // host then enqueues the earlier iterations without waiting for the device)
+        int check_from = 0;
+        if (check <= 0) {
+            check = use_mg ? 1 : 25;
+            if (use_mg && warm && expected_iters_ > 3) check_from = expected_iters_ - 2;
+        }
         SolveStats st = pcg(p2_off_, p2_cnt_, s_b_.p, u, s_r_.p, s_p_.p, s_Ap_.p, dinv, apply_dot, precond,
-                            !use_mg, rtol, maxit, check);
+                            !use_mg, rtol, maxit, check, false, check_from);
+        expected_iters_ = st.converged ? st.iters : 0;
         exchange_p2(0, u);
         stats_iters_ = st.iters;
         if (mixed) {
@@ -1239,10 +1253,19 @@ class Engine : public EngineBase {
         // [9]: first level of the cluster tail (-1: none), [10]: its cluster size
         const int tf = inner_ ? inner_->tail_first_ : tail_first_;
         const int tc = inner_ ? inner_->tail_cluster_used_ : tail_cluster_used_;
-        const double v[12] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
+        // [12..14]: the levels cycled more than once per visit of their parent (first, last, cycles; -1 -1 1: V-cycle)
+        int cf = -1, cl = -1, cg = 1;
+        for (int l = 1; l + 1 < nlevels_; ++l)
+            if (repeats(l) > 1) {
+                if (cf < 0) cf = l;
+                cl = l;
+                cg = repeats(l);
+            }
+        const double v[15] = {(double)stats_iters_, (double)stats_vcycles_, (double)stats_fine_applies_,
                               (double)nlevels_, lmax0, (double)epc[0], (double)epc[1], (double)epc[2],
-                              (double)epc[3], (double)tf, (double)(tf >= 0 ? tc : 0), (double)stats_warm_used_};
-        for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
+                              (double)epc[3], (double)tf, (double)(tf >= 0 ? tc : 0), (double)stats_warm_used_,
+                              (double)cf, (double)cl, (double)cg};
+        for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
     }
 
     // CUDA-event timing of every fine-level operator launch (TM_OPT_PROFILE), per epilogue
@@ -1846,7 +1869,7 @@ class Engine : public EngineBase {
     template <class ApplyDot, class Precond>
     SolveStats pcg(size_t off, size_t n, const T* b, T* x, T* r, T* p, T* Ap, const T* dinv,
                    ApplyDot apply_dot, Precond precond, bool jacobi, double rtol, int maxit, int check,
-                   bool filter_solve = false) {
+                   bool filter_solve = false, int check_from = 0) {
         SolveStats st;
         const int g1 = grid1d(n);
         const T* dv = dinv ? dinv + off : nullptr;
@@ -1898,7 +1921,9 @@ class Engine : public EngineBase {
                 sum_ranks(sc_ + SC_RR, 1);
             }
             st.iters = k + 1;
-            const bool do_check = ((k + 1) % check == 0) || (k + 1 == maxit);
+            // check_from: no residual read-back (a host synchronisation) before that iteration, apart from a
+            // sparse safety net -- the caller expects about as many iterations as its previous solve took
+            const bool do_check = (k + 1 >= check_from && (k + 1) % check == 0) || (k + 1) % 16 == 0 || (k + 1 == maxit);
             if (do_check) {
                 read_scalars();
                 st.relres = std::sqrt(h_sc_[SC_RR] / bb);
@@ -2179,6 +2204,7 @@ class Engine : public EngineBase {
             V.xb = L.xalt.p;
             V.d = L.d.p;
             V.r = L.tmp.p;
+            V.gamma = repeats(tail_first_ + t);
             if (t + 1 == A.nt) {  // coarsest level: only its lattice and the transfer split are used
                 if (V.G == 0) tail_plan_level(V, tail_cluster_used_, 0);
                 break;
@@ -2198,8 +2224,9 @@ class Engine : public EngineBase {
         TM_CUDA(cudaMemcpyAsync(tail_dev_.p, &A, sizeof(A), cudaMemcpyHostToDevice, stream_));
         TM_CUDA(cudaStreamSynchronize(stream_));
     }
-    // x of level tail_first_ after the kernel: the ping-pong buffer the last step wrote
-    T* launch_tail() {
+    // x of level tail_first_ after the kernel: the ping-pong buffer the last step wrote.  x0 != nullptr:
+    // the cycle starts from that guess (one of the level's two iterate buffers) and returns in the same buffer
+    T* launch_tail(T* x0 = nullptr) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(tail_cluster_used_);
         cfg.blockDim = dim3(kTailThreads);
@@ -2212,13 +2239,16 @@ class Engine : public EngineBase {
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
+        Level& L = levels_[tail_first_];
+        if (x0 && x0 != L.x.p && x0 != L.xalt.p) throw Invalid{"tail: the initial guess is not an iterate buffer"};
+        const int warm = !x0 ? 0 : (x0 == L.x.p ? 1 : 2);
         TM_CUDA(cudaLaunchKernelEx(&cfg, tail_vcycle_kernel<T>,
-                                   reinterpret_cast<const TailArgs<T>*>(tail_dev_.p)));
+                                   reinterpret_cast<const TailArgs<T>*>(tail_dev_.p), warm));
         TM_CHECK_LAUNCH();
         acct(LC_TAIL, 2 * sz(levels_[tail_first_].nu));
+        if (x0) return x0;  // D pre- and D post-smoothing steps: an even number of buffer flips
         const int D = tail_host_.degree;
         const int flips = std::max(D - 2, 0) + D;
-        Level& L = levels_[tail_first_];
         return (flips & 1) ? L.xalt.p : L.x.p;
     }
 
@@ -2381,6 +2411,8 @@ class Engine : public EngineBase {
         in.wave_aware_ = wave_aware_;
         in.fuse_cheb0_ = fuse_cheb0_;
         in.prolong_tiled_ = prolong_tiled_;
+        in.cycle_first_ = cycle_first_; in.cycle_last_ = cycle_last_; in.cycle_gamma_ = cycle_gamma_;
+        in.light_levels_ = light_levels_;
         in.set_penalty(spec_.p);
         in.fuse_rz_ = 0;  // r . z is taken in fp64 on the converted vectors
         if (in.tail_max_nodes_ != tail_max_nodes_ || in.tail_cluster_ != tail_cluster_) in.levels_.clear();
@@ -2418,7 +2450,7 @@ class Engine : public EngineBase {
         double rho = 1.0 / sigma;
         T* cur;
         int k0 = 0;
-        const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
+        const int degree = level_degree(l);
         if (!xin && degree >= 2 && fuse_first_ && fuse_cheb0_) {
             // steps 0 and 1 from the zero guess in ONE operator pass (EP_CHEB0): x1 = D^-1 b / theta is formed
             // on the fly at the nodes the operator touches, so b's halo rows must be current
@@ -2540,37 +2572,93 @@ class Engine : public EngineBase {
             PdlScope(bool& f, bool on) : flag(f) { flag = on; }
             ~PdlScope() { flag = false; }
         } pdl_scope(pdl_active_, pdl_ && nranks_ == 1);
-        const int nl = nlevels_;
         vcycle_rz_ = false;
-        std::vector<T*> xs(nl, nullptr);
-        std::vector<const T*> bs(nl, nullptr);
-        bs[0] = r;
-        int lbot = tail_first_ >= 0 ? tail_first_ : nl - 1;  // first level the loops do not visit
+        int lbot = tail_first_ >= 0 ? tail_first_ : nlevels_ - 1;  // first level the recursion does not visit
         const bool truncated = depth_limit_ > 0 && depth_limit_ < lbot;  // timing studies only
         if (truncated) lbot = depth_limit_;
-        for (int l = 0; l < lbot; ++l) {
-            Level& L = levels_[l];
-            Level& C = levels_[l + 1];
-            const int degree = (l > 0 && coarse_degree_ > 0) ? coarse_degree_ : cheb_degree_;
-            if (degree == 1 && fuse_first_) {
-                // x = (1/theta) D^-1 b and r = b - A x in ONE pass: x is formed on the fly from b and
-                // D^-1 at the nodes the operator touches (saves the separate first-step kernel)
-                const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
-                exchange_p2(l, const_cast<T*>(bs[l]));
-                ApplyArgs<T> a = apply_args();
-                a.y = L.tmp.p; a.b = bs[l]; a.dinv = L.dinv.p; a.d = L.x.p;
-                a.c2 = (T)(1.0 / (0.5 * (hi + lo)));
-                launch_apply(L.g, l > 0, EP_RESID0, a);
-                xs[l] = L.x.p;
-            } else {
-                xs[l] = smooth(l, bs[l], nullptr);
-                exchange_p2(l, xs[l]);
-                ApplyArgs<T> a = apply_args();
-                a.x = xs[l]; a.y = L.tmp.p; a.b = bs[l];
-                launch_apply(L.g, l > 0, EP_RESID, a);
-            }
-            exchange_p2(l, L.tmp.p);
-            const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
+        T* z = cycle(0, r, nullptr, lbot, truncated);
+        ++stats_vcycles_;
+        return z;
+    }
+
+    // How often the coarse-grid correction of level l is repeated (options 133 / 134: levels
+    // [cycle_first_, cycle_last_] are visited cycle_gamma_ times per visit of their parent: a W-cycle on
+    // that window of levels, a V-cycle elsewhere).  Why: on SIMP designs (stiffness contrast 1e6 inside
+    // coarse cells) the V-cycle's error grows with every level below the current one -- the scipy study
+    // tools/studies/elast_smoother_study.py needs 52 PCG iterations with V against 25-27 with the
+    // coarse levels cycled twice, and repeating ANY one level gains about the same, so the window sits
+    // on the small levels whose visits cost microseconds.
+    // Chebyshev-Jacobi steps before and after the coarse-grid correction of level l: cheb_degree_ on the finest
+    // level, coarse_degree_ below -- except that levels 1..light_levels_ (option 136; automatic: levels 1-2
+    // whenever a window of levels is cycled twice) take two: under the W window the PCG iteration count is set
+    // by the smoothing of the small levels, not of these (bridge N=2048: 19 iterations either way, 265 -> 235 ms
+    // per solve since levels 1-2 carry a third of the step's bytes; short_cantilever N=512: 24 -> 23
+    // iterations, 17.8 -> 16.3 ms; profiles/r2t_cycle_study_*.jsonl).
+    int level_degree(int l) const {
+        if (l == 0 || coarse_degree_ <= 0) return cheb_degree_;
+        int light = light_levels_ >= 0 ? light_levels_ : (repeats_any() ? 2 : 0);
+        if (tail_first_ >= 0) light = std::min(light, tail_first_ - 1);
+        return l <= light ? std::min(2, coarse_degree_) : coarse_degree_;
+    }
+    bool repeats_any() const {
+        for (int l = 1; l + 1 < nlevels_; ++l)
+            if (repeats(l) > 1) return true;
+        return false;
+    }
+
+    int repeats(int l) const {
+        if (l < 1 || l + 1 >= nlevels_) return 1;  // the coarsest level is solved exactly
+        if (cycle_gamma_ > 0) return (cycle_gamma_ > 1 && l >= cycle_first_ && l <= cycle_last_) ? cycle_gamma_ : 1;
+        // automatic (option 135 = 0, the default): cycle twice the levels whose short side has 8..16 cells
+        // (4..32 on a bandwidth-bound mesh, where a visit of those levels is noise next to the fine level).
+        // Measured on the designs real runs reach after 25 iterations (profiles/r2r_cycle_study_*.jsonl):
+        // bridge N=2048 634 ms / 50 PCG iterations per solve with the V-cycle, 284 ms / 20 with levels 6-9
+        // (192 x 32 ... 24 x 4 cells) cycled twice; short_cantilever N=512 25.2 ms / 46 against 18.5 ms / 24
+        // with levels 5-6 (32 x 16, 16 x 8).  Wider windows gain at most two more iterations and pay for
+        // them in visits of the latency-bound levels (N=512, levels 4-6: 20 iterations, 21.9 ms).
+        const bool big = 2.0 * (2.0 * nx_ + 1.0) * (2.0 * nyg_ + 1.0) >= (double)((size_t)1 << 24);
+        const int m = std::min(lv_nx_[l], lv_ny_[l]);
+        return (m >= (big ? 4 : 8) && m <= (big ? 32 : 16)) ? 2 : 1;
+    }
+
+    // One multigrid cycle on level l for A x = b from the guess x0 (nullptr = zero): pre-smoothing,
+    // coarse-grid correction (repeated repeats(l + 1) times, each visit starting from the last), post-smoothing.
+    // Pre- and post-smoother are the same polynomial, so the cycle is a symmetric operator for any window.
+    T* cycle(int l, const T* b, T* x0, int lbot, bool truncated) {
+        const int nl = nlevels_;
+        if (l == lbot) {
+            if (truncated) return smooth(l, b, x0);
+            if (tail_first_ >= 0) return launch_tail(x0);
+            Level& C = levels_[nl - 1];
+            mg_coarse_apply_inverse_kernel<T><<<1, 192, 0, stream_>>>((int)C.nu, coarse_Ainv_.p, b, C.x.p);
+            TM_CHECK_LAUNCH();
+            acct(LC_COARSE_SOLVE, 8.0 * C.nu * C.nu);
+            return C.x.p;
+        }
+        Level& L = levels_[l];
+        Level& C = levels_[l + 1];
+        const int degree = level_degree(l);
+        T* x;
+        if (!x0 && degree == 1 && fuse_first_) {
+            // x = (1/theta) D^-1 b and r = b - A x in ONE pass: x is formed on the fly from b and
+            // D^-1 at the nodes the operator touches (saves the separate first-step kernel)
+            const double hi = eig_safety_ * L.lmax, lo = hi / cheb_ratio_;
+            exchange_p2(l, const_cast<T*>(b));
+            ApplyArgs<T> a = apply_args();
+            a.y = L.tmp.p; a.b = b; a.dinv = L.dinv.p; a.d = L.x.p;
+            a.c2 = (T)(1.0 / (0.5 * (hi + lo)));
+            launch_apply(L.g, l > 0, EP_RESID0, a);
+            x = L.x.p;
+        } else {
+            x = smooth(l, b, x0);
+            exchange_p2(l, x);
+            ApplyArgs<T> a = apply_args();
+            a.x = x; a.y = L.tmp.p; a.b = b;
+            launch_apply(L.g, l > 0, EP_RESID, a);
+        }
+        exchange_p2(l, L.tmp.p);
+        const bool gather = nranks_ > 1 && (l + 1) == dist_levels_;
+        {
             dim3 blk(32, 8), grd(ceil_div(C.g.Lx, 32), ceil_div(C.g.Ly, 8));
             if (restrict_tiled_ && (long)C.g.Lx * C.g.Ly >= 16384)
                 launch_chain(mg_restrict_tiled_kernel<T>, dim3(ceil_div(C.g.Lx, kRtTI), ceil_div(C.g.Ly, kRtTJ)),
@@ -2581,37 +2669,23 @@ class Engine : public EngineBase {
             TM_CHECK_LAUNCH();
             acct(LC_RESTRICT, sz(L.nu) + sz(gather ? (size_t)(C.gpiece.own_j1 - C.gpiece.own_j0) * C.g.Lx * 2 : C.cnt));
             if (gather) gather_rows(l + 1, C.b.p, (size_t)C.g.Lx * 2, false);
-            bs[l + 1] = C.b.p;
         }
-        if (truncated) {
-            xs[lbot] = smooth(lbot, bs[lbot], nullptr);
-        } else if (tail_first_ >= 0) {
-            xs[lbot] = launch_tail();
-        } else {
-            Level& C = levels_[nl - 1];
-            mg_coarse_apply_inverse_kernel<T><<<1, 192, 0, stream_>>>((int)C.nu, coarse_Ainv_.p, bs[nl - 1], C.x.p);
-            TM_CHECK_LAUNCH();
-            acct(LC_COARSE_SOLVE, 8.0 * C.nu * C.nu);
-            xs[nl - 1] = C.x.p;
-        }
-        for (int l = lbot; l-- > 0;) {
-            Level& L = levels_[l];
-            Level& C = levels_[l + 1];
-            exchange_p2(l + 1, xs[l + 1]);
+        T* xc = cycle(l + 1, C.b.p, nullptr, lbot, truncated);
+        for (int rep = 1, n = repeats(l + 1); rep < n; ++rep) xc = cycle(l + 1, C.b.p, xc, lbot, truncated);
+        exchange_p2(l + 1, xc);
+        {
             dim3 blk(32, 8), grd(ceil_div(L.g.Lx, 32), ceil_div(L.g.Ly, 8 * kProlongRows));
             if (prolong_tiled_ && (long)L.g.Lx * L.g.Ly >= 16384)
                 launch_chain(mg_prolong_tiled_kernel<T>, dim3(ceil_div(L.g.Lx, kPtTI), ceil_div(L.g.Ly, kPtTJ)),
-                             dim3(kPtThreads), L.g, C.g, (const T*)xs[l + 1], xs[l]);
+                             dim3(kPtThreads), L.g, C.g, (const T*)xc, x);
             else
-                launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xs[l + 1], xs[l]);
+                launch_chain(mg_prolong_add_kernel<T>, grd, blk, L.g, C.g, tr_tab_, (const T*)xc, x);
             TM_CHECK_LAUNCH();
             acct(LC_PROLONG, 2 * sz(L.cnt) + sz(C.nu));
-            // the V-cycle ends with the level-0 post-smoothing: its last step also returns r . z
-            xs[l] = smooth(l, bs[l], xs[l], (l == 0 && (fuse_rz_ > 0 || (fuse_rz_ < 0 && p2_cnt_ >= ((size_t)1 << 24)))) ? sc_ + SC_RZV
-                                                                                                 : nullptr);
         }
-        ++stats_vcycles_;
-        return xs[0];
+        // the outermost cycle ends with the level-0 post-smoothing: its last step also returns r . z
+        const bool rz = l == 0 && (fuse_rz_ > 0 || (fuse_rz_ < 0 && p2_cnt_ >= ((size_t)1 << 24)));
+        return smooth(l, b, x, rz ? sc_ + SC_RZV : nullptr);
     }
 
     // ------------------------------------------------------------------ state
@@ -2636,7 +2710,7 @@ class Engine : public EngineBase {
     double* eig_sc_ = nullptr;
     double* h_sc_ = nullptr;
 
-    int precond_ = TM_PRECOND_MULTIGRID, cheb_degree_ = 1, check_every_ = 0, coarse_cells_ = 2;
+    int precond_ = TM_PRECOND_MULTIGRID, cheb_degree_ = 1, check_every_ = 0, coarse_cells_ = 4;
     double cheb_ratio_ = 30.0, eig_safety_ = 1.1;
 
     DevBuf<T> f_r_, f_p_, f_Ap_, f_dinv_, f_rhs_, f_p2_;
@@ -2686,6 +2760,8 @@ class Engine : public EngineBase {
     bool wave_aware_ = true;                // option 129: strip heights of the stored-moment levels fill whole waves
     bool fuse_cheb0_ = true;                // option 131: first two smoothing steps from zero in one operator pass
     bool prolong_tiled_ = true;             // option 132: shared-memory tiled prolongation on the large levels
+    int light_levels_ = -1;  // option 136: levels 1..k smooth with two steps (-1: automatic, level_degree())
+    int cycle_first_ = 1, cycle_last_ = 1 << 20, cycle_gamma_ = 0;  // options 133-135: W-cycle window (repeats())
     long stored_cap_ = 0;                   // resident blocks of the stored-moment operator kernel (whole GPU)
     bool warm_guard_ = true;   // option 125: drop a warm start whose residual exceeds the zero guess's
     int stats_warm_used_ = 0;  // last state solve: 1 if the caller's initial guess was kept
@@ -2712,6 +2788,7 @@ class Engine : public EngineBase {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free_;
     int stats_iters_ = 0;
+    int expected_iters_ = 0;  // iterations of the previous converged state solve (0: unknown)
     Ledger led_, graph_led_, fgraph_led_, setup_graph_led_;
     bool capturing_ = false;
     std::vector<std::pair<int, cudaEvent_t>> ev_marks_;

@@ -47,6 +47,7 @@ struct TailLevel {
     // A task is one warp's work: npt = 32 / G nodes of ONE type (parity of i + 2 * parity of j)
     // times G lanes per node; lane = sub * npt + ln handles entries k = u * G + sub of node ln.
     int G, U, npt;
+    int gamma;       // cycles of THIS level per visit of its parent (1 = V-cycle; the coarsest level is exact)
     int nxp[2], nyp[2];  // nodes per parity along x and y
     int toff[5];         // task prefix per type
     int ecnt[4];         // structural entries per type
@@ -344,10 +345,15 @@ __device__ __forceinline__ void tail_restrict(const TailLevel<T>& F, const TailL
     }
 }
 
-// z_tail = V(b_tail): launched as ONE cluster; every thread takes part in every barrier.
+// z_tail = cycle(b_tail): launched as ONE cluster; every thread takes part in every barrier.
 // Dynamic shared memory: the argument block, then this CTA's stencil image.
+// The cycle is the recursion of Engine::cycle run as a state machine (control flow is uniform over the
+// cluster): level t+1 is cycled lv[t+1].gamma times per visit of level t, the first time from a zero
+// guess, then from its own last iterate (a W-cycle where gamma = 2).  warm = 1 / 2: the first tail
+// level starts from the guess in its xa / xb instead of zero (the engine repeating the tail's first
+// level); the result then lands in the buffer the guess came in.
 template <typename T>
-__global__ void __launch_bounds__(kTailThreads, 1) tail_vcycle_kernel(const TailArgs<T>* __restrict__ ap) {
+__global__ void __launch_bounds__(kTailThreads, 1) tail_vcycle_kernel(const TailArgs<T>* __restrict__ ap, int warm) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char tail_smem[];
     constexpr int kArgBytes = (int)((sizeof(TailArgs<T>) + 15) / 16 * 16);
@@ -382,67 +388,95 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_vcycle_kernel(const Tail
         __syncthreads();
     }
     const T* cur[kTailMaxLevels];
+    int done[kTailMaxLevels];  // cycles of level t+1 completed in the current visit of level t
+    int t = 0;
+    bool descending = true, have_guess = warm != 0;
+    if (have_guess) cur[0] = warm == 2 ? A.lv[0].xb : A.lv[0].xa;
 
-    for (int t = 0; t + 1 < nt; ++t) {
-        const TailLevel<T>& L = A.lv[t];
-        const TailLevel<T>& C = A.lv[t + 1];
-        const T* sl = simg + L.img_base;
-        const T c0 = L.c2[0];
-        if (D == 1) {
-            tail_phase<T, false, true>(L, sl, nullptr, L.r, L.xa, c0, T(0), T(0), false, me);
-            cur[t] = L.xa;
-        } else {
-            tail_phase<T, true, true>(L, sl, nullptr, L.xa, nullptr, c0, L.c1[1], L.c2[1], D > 2, me);
+    while (true) {
+        if (descending && t == nt - 1) {  // coarsest level: x = Ainv b, one warp per row
+            const TailLevel<T>& C = A.lv[nt - 1];
+            const int nc = A.nc;
+            for (int row = gwarp; row < nc; row += nwarps) {
+                double s = 0.0;
+                for (int k = me.lane; k < nc; k += 32)
+                    s += __ldg(A.Ainv + (size_t)row * nc + k) * (double)__ldcg(C.b + k);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (me.lane == 0) __stcg(C.xa + row, (T)s);
+            }
+            cur[nt - 1] = C.xa;
             cluster.sync();
-            T* x = L.xa;
-            for (int k = 2; k < D; ++k) {
-                T* other = (x == L.xa) ? L.xb : L.xa;
-                tail_phase<T, true, false>(L, sl, x, other, nullptr, c0, L.c1[k], L.c2[k], k + 1 < D, me);
+            descending = false;
+            --t;
+        } else if (descending) {  // pre-smoothing, residual, restriction; then down
+            const TailLevel<T>& L = A.lv[t];
+            const TailLevel<T>& C = A.lv[t + 1];
+            const T* sl = simg + L.img_base;
+            const T c0 = L.c2[0];
+            if (have_guess) {
+                T* x = const_cast<T*>(cur[t]);
+                for (int k = 0; k < D; ++k) {
+                    T* other = (x == L.xa) ? L.xb : L.xa;
+                    tail_phase<T, true, false>(L, sl, x, other, nullptr, T(0), L.c1[k], L.c2[k], k + 1 < D, me);
+                    cluster.sync();
+                    x = other;
+                }
+                tail_phase<T, false, false>(L, sl, x, L.r, nullptr, c0, T(0), T(0), false, me);
+                cur[t] = x;
+            } else if (D == 1) {
+                tail_phase<T, false, true>(L, sl, nullptr, L.r, L.xa, c0, T(0), T(0), false, me);
+                cur[t] = L.xa;
+            } else {
+                tail_phase<T, true, true>(L, sl, nullptr, L.xa, nullptr, c0, L.c1[1], L.c2[1], D > 2, me);
                 cluster.sync();
+                T* x = L.xa;
+                for (int k = 2; k < D; ++k) {
+                    T* other = (x == L.xa) ? L.xb : L.xa;
+                    tail_phase<T, true, false>(L, sl, x, other, nullptr, c0, L.c1[k], L.c2[k], k + 1 < D, me);
+                    cluster.sync();
+                    x = other;
+                }
+                tail_phase<T, false, false>(L, sl, x, L.r, nullptr, c0, T(0), T(0), false, me);
+                cur[t] = x;
+            }
+            cluster.sync();
+            tail_restrict<T>(L, C, A.tab, gwarp, nwarps, me.lane);
+            cluster.sync();
+            done[t] = 0;
+            have_guess = false;
+            ++t;
+        } else {  // a cycle of level t+1 has finished, its iterate is cur[t+1]
+            ++done[t];
+            if (t + 1 < nt - 1 && done[t] < A.lv[t + 1].gamma) {  // cycle the child again, from its iterate
+                have_guess = true;
+                descending = true;
+                ++t;
+                continue;
+            }
+            const TailLevel<T>& L = A.lv[t];
+            const TailLevel<T>& C = A.lv[t + 1];
+            const T* sl = simg + L.img_base;
+            T* x = const_cast<T*>(cur[t]);
+            for (int node = gtid; node < L.n; node += nthreads) {
+                const int i = node % L.g.Lx, j = node / L.g.Lx;
+                if (L.g.fixed(i, j)) continue;
+                double a0, a1;
+                prolong_node<T, true>(L.g, C.g, A.tab.Pw, cur[t + 1], i, j, a0, a1);
+                const typename Vec2<T>::type xv = tail_ld2<T>(x, node);
+                tail_st2<T>(x, node, (T)((double)xv.x + a0), (T)((double)xv.y + a1));
+            }
+            cluster.sync();
+            for (int k = 0; k < D; ++k) {
+                T* other = (x == L.xa) ? L.xb : L.xa;
+                tail_phase<T, true, false>(L, sl, x, other, nullptr, T(0), L.c1[k], L.c2[k], k + 1 < D, me);
+                if (t > 0 || k + 1 < D) cluster.sync();
                 x = other;
             }
-            tail_phase<T, false, false>(L, sl, x, L.r, nullptr, c0, T(0), T(0), false, me);
             cur[t] = x;
+            if (t == 0) break;
+            --t;
         }
-        cluster.sync();
-        tail_restrict<T>(L, C, A.tab, gwarp, nwarps, me.lane);
-        cluster.sync();
-    }
-    {  // coarsest level: x = Ainv b, one warp per row
-        const TailLevel<T>& C = A.lv[nt - 1];
-        const int nc = A.nc;
-        for (int row = gwarp; row < nc; row += nwarps) {
-            double s = 0.0;
-            for (int k = me.lane; k < nc; k += 32)
-                s += __ldg(A.Ainv + (size_t)row * nc + k) * (double)__ldcg(C.b + k);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (me.lane == 0) __stcg(C.xa + row, (T)s);
-        }
-        cur[nt - 1] = C.xa;
-        cluster.sync();
-    }
-    for (int t = nt - 1; t-- > 0;) {
-        const TailLevel<T>& L = A.lv[t];
-        const TailLevel<T>& C = A.lv[t + 1];
-        const T* sl = simg + L.img_base;
-        T* x = const_cast<T*>(cur[t]);
-        for (int node = gtid; node < L.n; node += nthreads) {
-            const int i = node % L.g.Lx, j = node / L.g.Lx;
-            if (L.g.fixed(i, j)) continue;
-            double a0, a1;
-            prolong_node<T, true>(L.g, C.g, A.tab.Pw, cur[t + 1], i, j, a0, a1);
-            const typename Vec2<T>::type xv = tail_ld2<T>(x, node);
-            tail_st2<T>(x, node, (T)((double)xv.x + a0), (T)((double)xv.y + a1));
-        }
-        cluster.sync();
-        for (int k = 0; k < D; ++k) {
-            T* other = (x == L.xa) ? L.xb : L.xa;
-            tail_phase<T, true, false>(L, sl, x, other, nullptr, T(0), L.c1[k], L.c2[k], k + 1 < D, me);
-            if (t > 0 || k + 1 < D) cluster.sync();
-            x = other;
-        }
-        cur[t] = x;
     }
 }
 

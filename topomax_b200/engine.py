@@ -267,14 +267,16 @@ class Engine:
         return out
 
     def last_solve_stats(self) -> dict:
-        buf = (c_double * 12)()
-        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 12))
+        buf = (c_double * 15)()
+        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 15))
         return {"iterations": int(buf[0]), "vcycles": int(buf[1]), "fine_applies": int(buf[2]),
                 "levels": int(buf[3]), "lambda_max": buf[4],
                 "fine_launches_total": {"plain": int(buf[5]), "dot": int(buf[6]), "resid": int(buf[7]),
                                         "cheb": int(buf[8])},
                 "tail_first_level": int(buf[9]), "tail_cluster": int(buf[10]),
-                "warm_start_used": bool(buf[11])}
+                "warm_start_used": bool(buf[11]),
+                # multigrid levels cycled `cycles` times per visit of their parent (W-cycle window; V-cycle: [-1, -1, 1])
+                "cycle_window": [int(buf[12]), int(buf[13]), int(buf[14])]}
 
     def profile_read(self) -> dict:
         """Milliseconds / launch counts of the fine-level operator kernel per epilogue since the
