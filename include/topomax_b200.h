@@ -38,7 +38,9 @@ enum { TM_PRECOND_JACOBI = 0, TM_PRECOND_MULTIGRID = 1 };
 enum {
     TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
     TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 1; coarse levels 3) */
-    TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0=auto) */
+    TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0 = automatic: every iteration with
+                                the multigrid preconditioner, from two iterations before the count of this engine's
+                                previous warm-started solve; every 25 with Jacobi) */
     TM_OPT_MG_COARSE_CELLS = 4, /* stop coarsening at max(nx,ny) <= this (1..4, default 4) */
     TM_OPT_PROFILE = 5,      /* 1: time every fine-level operator launch with CUDA events; 2: the operator
                                 launches of every multigrid level; 3: every launch, by ledger category
@@ -48,6 +50,10 @@ enum {
     TM_OPT_CYCLE_GAMMA = 135, /* smoother are the same polynomial, so the cycle stays symmetric).  GAMMA 0 (default):  */
                               /* automatic window = the levels whose short side has 8..16 cells (4..32 on meshes of    */
                               /* >= 2^24 dofs); 1: plain V-cycle; 2..4: explicit window                               */
+    TM_OPT_FP_FLOOR_FACTOR = 137, /* state solves that start from an initial guess stop at max(rtol, factor x floor),     */
+                              /* floor = ||K (u o delta)|| / ||b||, delta_i = +-eps/2: the relative residual fp arithmetic */
+                              /* cannot resolve on this mesh, estimated by one operator pass (default 0.5; 0 = off:       */
+                              /* iterate until the RECURSIVE residual meets rtol).  tm_last_solve_stats [15], [16]        */
     TM_OPT_P2P = 130         /* sharded runs: halo exchange and scalar all-reduce by our own kernels over
                                 peer-mapped memory (NVLink) instead of NCCL calls; collective, set alike
                                 on every rank (default 1 since round 2; env TM_P2P=0 selects NCCL,
@@ -132,7 +138,10 @@ int tm_elast_matvec(tm_handle h, void* xi, double penalty, void* x, void* y);
 int tm_elast_diag(tm_handle h, void* xi, double penalty, void* dinv);
 
 /* u = K(xi)^-1 b with u = 0 on the fixed sides, by preconditioned CG to ||r|| <= rtol ||b||.
- * flags bit 0: use the incoming u as initial guess.
+ * flags bit 0: use the incoming u as initial guess.  With an initial guess the iteration also stops once the
+ * recursive residual is below half the level fp arithmetic can resolve on this mesh (TM_OPT_FP_FLOOR_FACTOR):
+ * at 2e8 dofs that level is 2.6e-9 in fp64, i.e. a direct solver's residual (what the reference's MUMPS returns);
+ * *relres then reports the recursive residual at the stop, and tm_last_solve_stats the floor and the tolerance used.
  * reference: ElasticityProblem.forward, FEM_src/elasisity_problem.py:168-169 ->
  * SmartMumpsSolver.solve, FEM_src/pde_solver.py:106-133 (LUSolver("mumps")). */
 int tm_state_solve(tm_handle h, void* xi, double penalty, const void* b, void* u,
@@ -178,7 +187,8 @@ int tm_sample_field(tm_handle h, int degree, const void* field, int nsx, int nsy
  * level-0 operator launches per epilogue, [9] first level of the cluster tail (-1: none), [10] its
  * cluster size, [11] 1 if the caller's initial guess was kept (a warm start whose residual
  * exceeds that of the zero guess is dropped), [12..14] first / last multigrid level cycled more than
- * once per visit of its parent and the number of cycles (-1, -1, 1: plain V-cycle) */
+ * once per visit of its parent and the number of cycles (-1, -1, 1: plain V-cycle), [15] the relative
+ * fp floor estimated for this solve (0: none), [16] the tolerance the iteration stopped at */
 int tm_last_solve_stats(tm_handle h, double* out, int n);
 
 /* Measurement support (bench.py): with TM_OPT_PROFILE on, out[0..3] = milliseconds spent in the

@@ -631,6 +631,48 @@ def test_cluster_tail_equals_launch_per_phase_vcycle(repo_root, design, N, degre
     assert np.linalg.norm(out[0][0] - out[1][0]) / np.linalg.norm(out[0][0]) < 1e-9
 
 
+def test_state_solve_stops_at_the_attainable_accuracy(repo_root):
+    """Option 137: a warm-started solve estimates the relative residual fp64 cannot resolve (one operator pass
+    on the half-ulp perturbation of the guess) and stops the PCG at max(rtol, 0.5 x that).  Asking for 1e-14
+    then costs fewer iterations than iterating the recursive residual down, and the TRUE residual (oracle
+    matrix) is no worse; the estimate agrees with the same quantity computed with the oracle's matrix."""
+    d, prm, mesh, lam, mu = _state_case("bridge", 40, repo_root)
+    X, Y = np.meshgrid(mesh.xv, mesh.yv, indexing="xy")
+    xi = np.where((np.mod(X + 0.3 * Y, 1.0) < 0.3) | (np.mod(Y, 0.5) < 0.15), 1.0, 1e-3).ravel()
+    xi2 = np.clip(xi * (1.0 + 0.01 * np.sin(3 * X.ravel())), 1e-3, 1.0)  # the "next design" of a run
+    b = mesh.load_vector(d["body_force"], d["tractions"])
+    fix = mesh.dirichlet_mask(d["fixed_sides"])
+    bm = np.where(fix, 0.0, b)
+    K2 = mesh.elasticity_matrix(xi2, lam, mu)
+    free = (~fix).astype(float)
+
+    def true_relres(u):
+        return np.linalg.norm(free * (bm - K2 @ u)) / np.linalg.norm(bm)
+
+    out = {}
+    for factor in (0.0, 0.5):
+        eng = _engine(mesh.nx, mesh.ny, mesh.W, mesh.H, lame_lambda=lam, lame_mu=mu, fixed_sides=prm.fixed_sides)
+        eng.set_option(137, factor)
+        bt = eng.load_vector(prm.body_force, prm.tractions)
+        u, _ = eng.state_solve(_t(xi), bt, rtol=1e-10, maxit=2000)
+        assert eng.last_solve_stats()["fp_floor_estimate"] == 0.0  # no initial guess, no estimate
+        u2, info = eng.state_solve(_t(xi2), bt, rtol=1e-14, maxit=2000, u=u.clone(), warm_start=True)
+        st = eng.last_solve_stats()
+        out[factor] = (info.iterations, true_relres(u2.cpu().numpy()), st, u2.cpu().numpy())
+    (it_off, res_off, st_off, u_off), (it_on, res_on, st_on, u_on) = out[0.0], out[0.5]
+    rng = np.random.default_rng(3)
+    delta = np.where(rng.random(mesh.nu) < 0.5, -1.0, 1.0) * 2.0 ** -53
+    floor_oracle = np.linalg.norm(free * (K2 @ (u_off * delta))) / np.linalg.norm(bm)
+    print(f"iterations off/on {it_off}/{it_on}, true residual off/on {res_off:.2e}/{res_on:.2e}, "
+          f"floor estimate {st_on['fp_floor_estimate']:.2e} (oracle matrix {floor_oracle:.2e}), stopped at {st_on['rtol_used']:.2e}")
+    assert st_off["fp_floor_estimate"] == 0.0 and st_off["rtol_used"] == 1e-14
+    assert 0.5 * floor_oracle < st_on["fp_floor_estimate"] < 2.0 * floor_oracle
+    assert st_on["rtol_used"] == pytest.approx(0.5 * st_on["fp_floor_estimate"])
+    assert it_on < it_off
+    assert res_on < 2.0 * res_off + 0.5 * floor_oracle
+    assert np.linalg.norm(u_on - u_off) / np.linalg.norm(u_off) < 1e-6  # north_star's per-solve bar
+
+
 @pytest.mark.parametrize("design,N,tail", [("bridge", 30, 0), ("bridge", 64, 1), ("short_cantilever", 70, 1)])
 def test_cycle_window_is_a_symmetric_preconditioner_with_fewer_iterations(repo_root, design, N, tail):
     """Options 133-135 repeat the coarse-grid correction on a window of levels (W-cycle there).  The cycle

@@ -494,29 +494,44 @@ mg_prolong_tiled_kernel(const LevelGeom<T> f, const LevelGeom<T> c, const T* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// coarsest level: dense Cholesky in one block (n = 2*Lx*Ly <= kCoarseMaxDofs)
+// coarsest level: dense inverse in one block (n = 2*Lx*Ly <= kCoarseMaxDofs)
 // ---------------------------------------------------------------------------------------
 constexpr int kCoarseMaxDofs = 2 * 9 * 9;
 
-// A (n x n, row-major, double) <- dense K of the coarsest level, then A = L L^T in place (lower)
+// Ainv (n x n, row-major, symmetric) <- inverse of the dense K of the coarsest level, in ONE block with the
+// matrix in shared memory (n <= kCoarseMaxDofs: 210 KB of dynamic shared memory at most): assembly column by
+// column, then in-place Gauss-Jordan elimination without pivoting (the matrix is
+// symmetric positive definite), 2 block barriers per pivot, and a final symmetrisation.  (The first version,
+// a Cholesky factor and one triangular solve pair per column walking global memory from one thread per
+// column, took 0.65 ms per kernel for the 90 dofs of a 4 x 2-cell level, once per state solve.)
+constexpr int kCoarseInvThreads = 1024;
 template <typename T>
-__global__ void mg_coarse_factor_kernel(const LevelGeom<T> g, double* __restrict__ A) {
+__global__ void __launch_bounds__(kCoarseInvThreads, 1)
+mg_coarse_inverse_kernel(const LevelGeom<T> g, double* __restrict__ Ainv) {
+    extern __shared__ __align__(16) unsigned char coarse_smem[];
+    double* A = reinterpret_cast<double*>(coarse_smem);  // n x n
     const int n = 2 * g.Lx * g.Ly;
+    double* prow = A + (size_t)n * n;  // pivot row / column of the current step
+    double* pcol = prow + n;
     Material<double> mat;
     mat.A11 = (double)g.mat.A11; mat.A22 = (double)g.mat.A22; mat.A12 = (double)g.mat.A12;
     mat.A33 = (double)g.mat.A33; mat.kappa = (double)g.mat.kappa;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) A[e] = 0.0;
+    __syncthreads();
+    // column `col` = K applied to the unit vector of (node, comp), cell by cell (<= 4 cells touch a node);
+    // a thread owns whole columns, so the additions need no atomics
     for (int col = threadIdx.x; col < n; col += blockDim.x) {
-        for (int row = 0; row < n; ++row) A[(size_t)row * n + col] = 0.0;
         const int node = col >> 1, comp = col & 1;
         const int ni = node % g.Lx, nj = node / g.Lx;
         if (g.fixed(ni, nj)) {
             A[(size_t)col * n + col] = 1.0;
             continue;
         }
-        for (int cy = 0; cy < g.ny; ++cy)
-            for (int cx = 0; cx < g.nx; ++cx) {
+        const int cx_lo = ni > 0 ? (ni - 1) >> 1 : 0, cx_hi = min(g.nx - 1, ni >> 1);
+        const int cy_lo = nj > 0 ? (nj - 1) >> 1 : 0, cy_hi = min(g.ny - 1, nj >> 1);
+        for (int cy = cy_lo; cy <= cy_hi; ++cy)
+            for (int cx = cx_lo; cx <= cx_hi; ++cx) {
                 const int li = ni - 2 * cx, lj = nj - 2 * cy;
-                if (li < 0 || li > 2 || lj < 0 || lj > 2) continue;
                 double X[9][2] = {}, acc[9][2] = {}, wA[6], wB[6];
                 X[3 * lj + li][comp] = 1.0;
                 const size_t plane = (size_t)g.nx * g.ny, cidx = (size_t)cy * g.nx + cx;
@@ -535,36 +550,28 @@ __global__ void mg_coarse_factor_kernel(const LevelGeom<T> g, double* __restrict
             }
     }
     __syncthreads();
+    // in-place inverse: after step k the leading (k+1) x (k+1) part holds the partial inverse
     for (int k = 0; k < n; ++k) {
-        if (threadIdx.x == 0) A[(size_t)k * n + k] = sqrt(A[(size_t)k * n + k]);
+        const double p = 1.0 / A[(size_t)k * n + k];
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            prow[j] = A[(size_t)k * n + j];
+            pcol[j] = A[(size_t)j * n + k];
+        }
         __syncthreads();
-        const double dk = A[(size_t)k * n + k];
-        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + k] /= dk;
-        __syncthreads();
-        const int m = n - k - 1;
-        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            if (j <= i) A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e / n, j = e - i * n;
+            double v;
+            if (i == k && j == k) v = p;
+            else if (i == k) v = prow[j] * p;
+            else if (j == k) v = -pcol[i] * p;
+            else v = A[e] - pcol[i] * prow[j] * p;
+            A[e] = v;
         }
         __syncthreads();
     }
-}
-
-// Ainv (n x n) from the Cholesky factor L (lower, in A): column c of the inverse by one thread
-__global__ void mg_coarse_invert_kernel(int n, const double* __restrict__ L, double* __restrict__ Ainv) {
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        double* y = Ainv + (size_t)c * n;  // column c, stored contiguously (the inverse is symmetric)
-        for (int i = 0; i < n; ++i) y[i] = i == c ? 1.0 : 0.0;
-        for (int k = 0; k < n; ++k) {
-            y[k] /= L[(size_t)k * n + k];
-            const double yk = y[k];
-            for (int i = k + 1; i < n; ++i) y[i] -= L[(size_t)i * n + k] * yk;
-        }
-        for (int k = n - 1; k >= 0; --k) {
-            y[k] /= L[(size_t)k * n + k];
-            const double yk = y[k];
-            for (int i = 0; i < k; ++i) y[i] -= L[(size_t)k * n + i] * yk;
-        }
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e - i * n;
+        Ainv[e] = 0.5 * (A[e] + A[(size_t)j * n + i]);
     }
 }
 
@@ -581,30 +588,6 @@ __global__ void mg_coarse_apply_inverse_kernel(int n, const double* __restrict__
         for (int k = 0; k < n; ++k) acc += row[k] * sb[k];
         x[i] = (T)acc;
     }
-}
-
-// x = (L L^T)^-1 b, one block
-template <typename T>
-__global__ void mg_coarse_solve_kernel(int n, const double* __restrict__ L,
-                                       const T* __restrict__ b, T* __restrict__ x) {
-    __shared__ double y[kCoarseMaxDofs];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = (double)b[i];
-    __syncthreads();
-    for (int k = 0; k < n; ++k) {  // forward: L y = b
-        if (threadIdx.x == 0) y[k] /= L[(size_t)k * n + k];
-        __syncthreads();
-        const double yk = y[k];
-        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) y[i] -= L[(size_t)i * n + k] * yk;
-        __syncthreads();
-    }
-    for (int k = n - 1; k >= 0; --k) {  // backward: L^T x = y
-        if (threadIdx.x == 0) y[k] /= L[(size_t)k * n + k];
-        __syncthreads();
-        const double yk = y[k];
-        for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] -= L[(size_t)k * n + i] * yk;
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = (T)y[i];
 }
 
 // deterministic pseudo-random start vector for the power iteration (zero on Dirichlet nodes)

@@ -15,7 +15,7 @@ namespace tmx {
 // SC_RZV: r . z delivered by the V-cycle's last smoothing step (EP_CHEBDOT); a fixed slot, so that
 // the captured V-cycle graph can be replayed whichever of SC_RZ0/1 is current
 // SC_NEWTON: {c, done, iterations, status} of the device-resident volume projection (md_newton_update_kernel)
-enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RR = 3, SC_BB = 4, SC_TMP = 5, SC_RZV = 8, SC_NEWTON = 10, SC_COUNT = 16 };
+enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RR = 3, SC_BB = 4, SC_TMP = 5, SC_RZV = 8, SC_FLOOR = 9, SC_NEWTON = 10, SC_COUNT = 16 };
 
 constexpr int kVecThreads = 256;
 
@@ -101,6 +101,18 @@ __global__ void axpby_kernel(size_t n, double a, const T* __restrict__ x, double
 }
 
 // z = a x + b y   (z may alias x or y)
+// w_i = +-(eps/2) u_i with a pseudo-random sign per entry (eps = machine epsilon of T): the perturbation
+// rounding u to T may cause; K w then samples the residual no solver can resolve (Engine::state_solve)
+template <typename T>
+__global__ void half_ulp_kernel(size_t n, size_t index_offset, const T* __restrict__ u, T* __restrict__ w) {
+    const double half_eps = sizeof(T) == 8 ? 1.1102230246251565e-16 : 5.9604644775390625e-08;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long h = (unsigned long long)(i + index_offset) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+        w[i] = (T)(((h & 1ull) ? half_eps : -half_eps) * (double)u[i]);
+    }
+}
+
 template <typename T>
 __global__ void waxpby_kernel(size_t n, double a, const T* x, double b, const T* y, T* z) {
     TM_GRID_STRIDE(i, n) z[i] = (T)(a * (double)x[i] + b * (double)y[i]);

@@ -267,8 +267,8 @@ class Engine:
         return out
 
     def last_solve_stats(self) -> dict:
-        buf = (c_double * 15)()
-        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 15))
+        buf = (c_double * 17)()
+        _lib.check(self.lib.tm_last_solve_stats(self._h, buf, 17))
         return {"iterations": int(buf[0]), "vcycles": int(buf[1]), "fine_applies": int(buf[2]),
                 "levels": int(buf[3]), "lambda_max": buf[4],
                 "fine_launches_total": {"plain": int(buf[5]), "dot": int(buf[6]), "resid": int(buf[7]),
@@ -276,7 +276,10 @@ class Engine:
                 "tail_first_level": int(buf[9]), "tail_cluster": int(buf[10]),
                 "warm_start_used": bool(buf[11]),
                 # multigrid levels cycled `cycles` times per visit of their parent (W-cycle window; V-cycle: [-1, -1, 1])
-                "cycle_window": [int(buf[12]), int(buf[13]), int(buf[14])]}
+                "cycle_window": [int(buf[12]), int(buf[13]), int(buf[14])],
+                # estimate of the relative residual fp arithmetic cannot resolve (0.0: not estimated: no initial
+                # guess, or option 137 = 0) and the tolerance the PCG stopped at, max(rtol, 0.5 x that estimate)
+                "fp_floor_estimate": buf[15], "rtol_used": buf[16]}
 
     def profile_read(self) -> dict:
         """Milliseconds / launch counts of the fine-level operator kernel per epilogue since the
