@@ -66,6 +66,7 @@ class Hierarchy:
         self.A.append(A)
         self.free.append(free)
         nx, ny = mesh.nx, mesh.ny
+        self.cells = [(nx, ny)]
         sides_fixed = fixed
         while nx % 2 == 0 and ny % 2 == 0 and min(nx, ny) // 2 >= 1 and max(nx, ny) > min_cells:
             nxc, nyc = nx // 2, ny // 2
@@ -77,6 +78,7 @@ class Hierarchy:
             Ac = (P.T @ self.A[-1] @ P + sp.diags(1.0 - freec)).tocsr()
             self.P.append(P); self.A.append(Ac); self.free.append(freec)
             nx, ny = nxc, nyc
+            self.cells.append((nx, ny))
         self.coarse = spla.splu(self.A[-1].tocsc())
         self.dinv = [1.0 / A.diagonal() for A in self.A]
         self.binv = [block_inverse(A) for A in self.A]
@@ -148,7 +150,7 @@ def smooth(A, apply_B, lmax, b, x, degree, kind, ratio=30.0, safety=1.1):
 
 
 def make_vcycle(h, kind="cheb1", fine_degree=1, coarse_degree=3, block=False, ratio=30.0, safety=1.1, gamma=1,
-                gamma_from=2, fine_kind=None, gamma_levels=None, count=None):
+                gamma_from=2, fine_kind=None, gamma_levels=None, count=None, window=None, light=0):
     nl = len(h.A)
 
     def B(l):
@@ -161,12 +163,15 @@ def make_vcycle(h, kind="cheb1", fine_degree=1, coarse_degree=3, block=False, ra
     def cyc(l, b):
         if l == nl - 1:
             return h.coarse.solve(b)
-        deg = fine_degree if l == 0 else coarse_degree
+        deg = fine_degree if l == 0 else (min(2, coarse_degree) if l <= light else coarse_degree)
         knd = (fine_kind or kind) if l == 0 else kind
         x = smooth(h.A[l], B(l), lm[l], b, None, deg, knd, ratio, safety)
         reps = gamma if l + 1 >= gamma_from and l + 1 < nl - 1 else 1
         if gamma_levels is not None:
             reps = gamma if (l + 1) in gamma_levels and l + 1 < nl - 1 else 1
+        if window is not None:  # the library's automatic rule: cells on the short side of level l + 1
+            m = min(h.cells[l + 1])
+            reps = 2 if (window[0] <= m <= window[1] and l + 1 < nl - 1) else 1
         if count is not None:
             count[l] = count.get(l, 0) + 1
         for _ in range(reps):
@@ -198,6 +203,14 @@ def pcg(A, b, M, rtol=1e-10, maxit=400, x0=None):
     return x, maxit
 
 
+VARIANTS3 = {  # the library's automatic choices (tm_engine.cu: repeats(), level_degree())
+    "V-cycle, 1/3 steps (round-2 start)": dict(),
+    "window 8..16 cells": dict(window=(8, 16)),
+    "window 8..16, levels 1-2 two steps": dict(window=(8, 16), light=2),
+    "window 4..32 cells": dict(window=(4, 32)),
+    "window 4..32, levels 1-2 two steps": dict(window=(4, 32), light=2),
+    "W on every level": dict(gamma=2, gamma_from=1),
+}
 VARIANTS2 = {
     "library: cheb1 1/3 V": dict(),
     "W all levels >= 2": dict(gamma=2, gamma_from=2),
@@ -271,7 +284,7 @@ def main():
         sel = {0: 0, its // 2: 1, its: 2}
         us = None
     Hierarchy.fixed_sides = s.design["fixed_sides"]
-    variants = VARIANTS2 if os.environ.get("STUDY_SET") == "2" else {
+    variants = VARIANTS3 if os.environ.get("STUDY_SET") == "3" else VARIANTS2 if os.environ.get("STUDY_SET") == "2" else {
         "library: cheb1 1/3": dict(),
         "cheb1 1/3 ratio 10": dict(ratio=10.0),
         "cheb1 1/3 ratio 100": dict(ratio=100.0),
