@@ -37,7 +37,8 @@ enum { TM_PRECOND_JACOBI = 0, TM_PRECOND_MULTIGRID = 1 };
 /* integer / real options for tm_set_option */
 enum {
     TM_OPT_PRECOND = 1,      /* TM_PRECOND_*                      (default MULTIGRID)   */
-    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 1; coarse levels 3) */
+    TM_OPT_CHEB_DEGREE = 2,  /* Chebyshev-Jacobi smoothing steps on the finest level (default 1; levels 1-2: 2 when a cycle
+                                window is active, the other coarse levels 3) */
     TM_OPT_CHECK_EVERY = 3,  /* PCG iterations between residual read-backs (default 0 = automatic: every iteration with
                                 the multigrid preconditioner, from two iterations before the count of this engine's
                                 previous warm-started solve; every 25 with Jacobi) */
