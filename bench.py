@@ -880,6 +880,10 @@ def run_cuda_arm(args):
     cfg = workload_description(design, run_n, nx, ny, args.dtype)
     cfg.update({
         "preconditioner": args.preconditioner, "state_rtol": args.state_rtol,
+        "state_stop_rule": "recursive PCG residual <= max(state_rtol, 0.5 x fp64 floor); the floor (relative residual fp64 "
+                           "cannot resolve on this mesh) is estimated on the device by one operator pass per solve "
+                           "(pcg.fp_floor_estimate_last_solve) and measured independently by the CPU operator "
+                           "(parity.fp64_floor); the TRUE residual of the checked solve is parity.relative_residual",
         "parallelism": "1 GPU" if world == 1 else
         f"{world} GPUs, row strips of cells, " + (
             "halo rows and scalar sums by the library's own kernels over peer-mapped NVLink windows (TM_OPT_P2P)"
@@ -887,7 +891,7 @@ def run_cuda_arm(args):
         f", {engine.dist_levels} sharded multigrid levels",
         "value_normalisation": f"iter/s x (global dofs / dofs of the 1-GPU workload {base_design} N={base_n}) = "
                                f"x{size_factor:.4f}" + (
-            "" if world == 1 else "; BASELINE.json's configs are DIFFERENT designs (PCG iterations per solve: bridge ~45, "
+            "" if world == 1 else "; BASELINE.json's configs are DIFFERENT designs (PCG iterations per solve with the V-cycle of mid-round 2: bridge ~45, "
             "triangle ~19, cantilever ~29), so value(N) / (N value(1)) is a size-normalised rate ratio, not a scaling "
             "efficiency: the like-for-like figure is single_gpu_comparison.strong_scaling_speedup (same mesh on one GPU)"),
         "l2": f"working set of a state solve ~{10 * nu * esize / 1e6:.0f} MB of lattice vectors per GPU, larger than "
