@@ -87,3 +87,30 @@ def test_cycling_the_small_levels_twice_cuts_pcg_iterations_on_a_high_contrast_d
         assert np.linalg.norm(b - h.A[0] @ x) <= 2e-8 * np.linalg.norm(b)
     print(its)
     assert its["W window"] <= 0.8 * its["V"] and its["W window, light levels"] <= 0.85 * its["V"]  # seen: 72 / 54 / 58
+
+
+def test_windowed_cycle_is_a_symmetric_positive_definite_operator():
+    """PCG needs a fixed SPD preconditioner.  The cycle with a W window (repeated visits start from the last
+    iterate, pre- and post-smoother are the same polynomial) applied to every unit vector of a small mesh gives
+    a symmetric matrix with positive spectrum, and so does the variant with two smoothing steps on levels 1-2."""
+    import elast_smoother_study as st
+
+    mesh = StructuredMesh(4.0, 1.0, 32, 8)
+    X, Y = np.meshgrid(mesh.xv, mesh.yv, indexing="xy")
+    xi = np.where((np.mod(X + 0.3 * Y, 1.0) < 0.3) | (np.mod(Y, 0.5) < 0.15), 1.0, 1e-3).ravel()
+    lam, mu = lame(2.0e5, 0.3)
+    fixed = mesh.dirichlet_mask(["Left"])
+    st.Hierarchy.fixed_sides = ["Left"]
+    h = st.Hierarchy(mesh, mesh.elasticity_matrix(xi, lam, mu), fixed)
+    free = np.flatnonzero(~fixed)
+    for kw in (dict(window=(2, 8)), dict(window=(2, 8), light=2), dict(gamma=3, gamma_levels={1, 2})):
+        M = st.make_vcycle(h, **kw)
+        B = np.empty((mesh.nu, free.size))
+        e = np.zeros(mesh.nu)
+        for c, j in enumerate(free):
+            e[j] = 1.0
+            B[:, c] = M(e)
+            e[j] = 0.0
+        B = B[free]
+        assert np.abs(B - B.T).max() <= 1e-10 * np.abs(B).max(), kw
+        assert np.linalg.eigvalsh(0.5 * (B + B.T)).min() > 0.0, kw
