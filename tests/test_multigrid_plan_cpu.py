@@ -114,3 +114,24 @@ def test_windowed_cycle_is_a_symmetric_positive_definite_operator():
         B = B[free]
         assert np.abs(B - B.T).max() <= 1e-10 * np.abs(B).max(), kw
         assert np.linalg.eigvalsh(0.5 * (B + B.T)).min() > 0.0, kw
+
+
+def test_cycle_and_stop_options_are_named_alike_in_header_and_python_seam():
+    """The option numbers of include/topomax_b200.h, of the ctypes layer and the keyword arguments of
+    ElasticityProblem that select them (defaults leave the library's automatic choices untouched)."""
+    import inspect
+    import re
+
+    from topomax_b200 import _lib
+    from topomax_b200.elasticity_problem import ElasticityProblem
+
+    header = open(os.path.join(ROOT, "include", "topomax_b200.h")).read()
+    for name, value in (("TM_OPT_CYCLE_FIRST", _lib.OPT_CYCLE_FIRST), ("TM_OPT_CYCLE_LAST", _lib.OPT_CYCLE_LAST),
+                        ("TM_OPT_CYCLE_GAMMA", _lib.OPT_CYCLE_GAMMA), ("TM_OPT_FP_FLOOR_FACTOR", _lib.OPT_FP_FLOOR_FACTOR)):
+        m = re.search(name + r"\s*=\s*(\d+)", header)
+        assert m and int(m.group(1)) == value, name
+    params = inspect.signature(ElasticityProblem.__init__).parameters
+    assert params["multigrid_cycle"].default == "auto" and params["attainable_accuracy_stop"].default is None
+    src = open(os.path.join(ROOT, "topomax_b200", "csrc", "tm_engine.cu")).read()
+    for opt in ("case 133:", "case 134:", "case 135:", "case 137:"):
+        assert opt in src

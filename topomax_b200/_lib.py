@@ -18,6 +18,7 @@ PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
 OPT_PRECOND, OPT_CHEB_DEGREE, OPT_CHECK_EVERY, OPT_MG_COARSE_CELLS = 1, 2, 3, 4
 OPT_PROFILE = 5
 OPT_P2P = 130
+OPT_CYCLE_FIRST, OPT_CYCLE_LAST, OPT_CYCLE_GAMMA, OPT_FP_FLOOR_FACTOR = 133, 134, 135, 137
 LEDGER_CATEGORIES = 40
 OPT_CHEB_RATIO, OPT_EIG_SAFETY = 100, 101
 

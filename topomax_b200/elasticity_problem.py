@@ -26,7 +26,8 @@ class ElasticityProblem(Problem):
                  *, state_rtol: float = 1e-10, state_max_iterations: int = 200000,
                  filter_rtol: float = 1e-11, preconditioner: str = "multigrid",
                  warm_start: bool = True, engine: Engine | None = None, mixed_precision: bool = False,
-                 warm_start_extrapolation: bool = False):
+                 warm_start_extrapolation: bool = False, multigrid_cycle="auto",
+                 attainable_accuracy_stop: float | None = None):
         self.parameters = elasticity_parameters
         self.domain_size = (domain_parameters.width, domain_parameters.height)
         self.mesh = mesh
@@ -54,6 +55,21 @@ class ElasticityProblem(Problem):
         self.mixed_precision = mixed_precision
         if mixed_precision:
             self.engine.set_option(117, 1)
+        # shape of the multigrid cycle: "auto" (the library's window of small levels cycled twice), "v" (plain
+        # V-cycle) or (first_level, last_level, cycles); None / "auto" leaves the library default untouched
+        if multigrid_cycle not in (None, "auto"):
+            if multigrid_cycle == "v":
+                self.engine.set_option(_lib.OPT_CYCLE_GAMMA, 1)
+            else:
+                first, last, cycles = multigrid_cycle
+                self.engine.set_option(_lib.OPT_CYCLE_FIRST, int(first))
+                self.engine.set_option(_lib.OPT_CYCLE_LAST, int(last))
+                self.engine.set_option(_lib.OPT_CYCLE_GAMMA, int(cycles))
+        self.multigrid_cycle = multigrid_cycle
+        # warm-started solves stop at max(state_rtol, factor x the residual level fp64 cannot resolve on this
+        # mesh); None keeps the library default (0.5), 0 iterates until the recursive residual meets state_rtol
+        if attainable_accuracy_stop is not None:
+            self.engine.set_option(_lib.OPT_FP_FLOOR_FACTOR, float(attainable_accuracy_stop))
         self.state_rtol = state_rtol
         self.state_max_iterations = state_max_iterations
         self.warm_start = warm_start
